@@ -1,0 +1,353 @@
+"""CPU oracle for the constant-memory-waveglow flow hot path.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``, ``__graft_entry__.smoke()``
+and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The product
+package (``constant_memory_waveglow_b200``) never imports anything from ``oracle/``.
+
+What it is: a functional, state-dict driven restatement in plain fp32 (or fp64) PyTorch-on-CPU of
+the reference algorithm for the path named in BASELINE.json ``north_star``.  Every function cites
+the reference ``file:line`` (relative to the reference repo root) whose arithmetic it follows.
+Weights are taken from a flat ``dict[str, Tensor]`` with the reference's state-dict keys
+(``SURVEY.md`` section 8b), so the oracle, the reference and the CUDA product can share one set of
+random-init weights.
+
+Parity pin: ``tests/golden/make_golden.py`` imports the unmodified reference from
+``/root/reference`` (CPU, fp32), runs it on seeded inputs in BOTH memory modes and stores
+inputs / weights / outputs / gradients under ``tests/golden/*.pt``;
+``tests/test_oracle_golden.py`` checks every function below against those fixtures.  The reference
+itself ships no golden vectors (its tests are self-consistency checks), so the fixtures generated
+from the reference are the pin.
+
+Gradients: the reference's constant-memory backward (``model/efficient_modules.py:118-154,
+176-212,230-244,263-279``) computes exactly the autograd gradient of the naive formulation; the
+oracle therefore differentiates the naive restatement with ``torch.autograd`` and, separately,
+restates the input reconstruction step (``coupling_restore_input`` / ``conv1x1_restore_input``)
+that the reversible backward performs.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+State = Dict[str, Tensor]
+
+
+# --------------------------------------------------------------------------------------------
+# weight handling
+# --------------------------------------------------------------------------------------------
+def weight_norm_weight(g: Tensor, v: Tensor) -> Tensor:
+    """w = g * v / ||v|| with the norm over every dim except 0 (``utils.py:14-16`` ->
+    ``nn.utils.weight_norm`` default ``dim=0``)."""
+    norm = v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+    return v * (g / norm)
+
+
+def resolve_weight(sd: State, prefix: str) -> Tensor:
+    """Return the effective conv weight for ``prefix`` whether or not weight-norm is attached
+    (``weight_g``/``weight_v`` pair vs plain ``weight`` after ``remove_weight_norms``,
+    ``utils.py:9-16``)."""
+    if prefix + "weight_g" in sd:
+        return weight_norm_weight(sd[prefix + "weight_g"], sd[prefix + "weight_v"])
+    return sd[prefix + "weight"]
+
+
+def resolve_bias(sd: State, prefix: str) -> Optional[Tensor]:
+    return sd.get(prefix + "bias")
+
+
+def wn_depth(sd: State, prefix: str) -> int:
+    n = 0
+    while (prefix + f"layers.{n}.W.weight_g" in sd) or (prefix + f"layers.{n}.W.weight" in sd):
+        n += 1
+    return n
+
+
+# --------------------------------------------------------------------------------------------
+# WN transform (model/waveglow.py:13-105)
+# --------------------------------------------------------------------------------------------
+def fused_gate(x1: Tensor, x2: Tensor) -> Tensor:
+    """``model/waveglow.py:13-15``."""
+    return torch.tanh(x1) * torch.sigmoid(x2)
+
+
+def wn_forward(sd: State, prefix: str, x: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
+    """WN.forward (``model/waveglow.py:98-105``) with NonCausalLayer.forward (``:41-46``).
+
+    x: (B, in_channels, T) ; y: (B, aux_channels, T) -> (log_s, t) each (B, in_channels, T).
+    Dilation of layer i is 2**i and the padding is dilation*(radix-1)//2 (``:27,61``).
+    """
+    depth = wn_depth(sd, prefix)
+    h = F.conv1d(x, resolve_weight(sd, prefix + "start."), resolve_bias(sd, prefix + "start."))
+    v_all = F.conv1d(y, resolve_weight(sd, prefix + "V."), resolve_bias(sd, prefix + "V."))
+    cum_skip = None
+    for i, v in enumerate(v_all.chunk(depth, 1)):
+        w = resolve_weight(sd, prefix + f"layers.{i}.W.")
+        radix = w.shape[2]
+        dil = 2 ** i
+        xy = F.conv1d(h, w, resolve_bias(sd, prefix + f"layers.{i}.W."),
+                      padding=dil * (radix - 1) // 2, dilation=dil) + v
+        zw, zf = xy.chunk(2, 1)
+        g = fused_gate(zw, zf)
+        wo = resolve_weight(sd, prefix + f"layers.{i}.W_o.")
+        ro = F.conv1d(g, wo, resolve_bias(sd, prefix + f"layers.{i}.W_o."))
+        if i < depth - 1:
+            res_ch = h.shape[1]
+            h = ro[:, :res_ch] + h
+            skip = ro[:, res_ch:]
+        else:
+            skip = ro
+        cum_skip = skip if cum_skip is None else cum_skip + skip
+    out = F.conv1d(cum_skip, sd[prefix + "end.weight"], sd.get(prefix + "end.bias"))
+    log_s, t = out.chunk(2, 1)
+    return log_s, t
+
+
+# --------------------------------------------------------------------------------------------
+# affine coupling (model/efficient_modules.py:57-212)
+# --------------------------------------------------------------------------------------------
+def coupling_forward(sd: State, prefix: str, x: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
+    """``model/efficient_modules.py:77-82`` (naive) == ``:105-111`` (efficient forward)."""
+    xa, xb = x.chunk(2, 1)
+    log_s, t = wn_forward(sd, prefix, xa, y)
+    zb = xb * log_s.exp() + t
+    return torch.cat((xa, zb), 1), log_s
+
+
+def coupling_reverse(sd: State, prefix: str, z: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
+    """``model/efficient_modules.py:91-96`` == ``:163-172``; returns (x, -log_s)."""
+    za, zb = z.chunk(2, 1)
+    log_s, t = wn_forward(sd, prefix, za, y)
+    xb = (zb - t) / log_s.exp()
+    return torch.cat((za, xb), 1), -log_s
+
+
+def coupling_restore_input(sd: State, prefix: str, z: Tensor, y: Tensor) -> Tensor:
+    """Input reconstruction done inside the reversible backward
+    (``model/efficient_modules.py:127-136``): x = cat(za, (zb - t)/exp(log_s))."""
+    return coupling_reverse(sd, prefix, z, y)[0]
+
+
+# --------------------------------------------------------------------------------------------
+# invertible 1x1 convolution (model/efficient_modules.py:17-54, 215-279)
+# --------------------------------------------------------------------------------------------
+def conv1x1_forward(weight: Tensor, x: Tensor) -> Tuple[Tensor, Tensor]:
+    """``model/efficient_modules.py:36-41`` / ``:218-226``: z = W x, logdet = T * logdet(W)."""
+    n = x.shape[-1]
+    return F.conv1d(x, weight), n * weight.squeeze(-1).logdet()
+
+
+def conv1x1_reverse(weight: Tensor, z: Tensor) -> Tuple[Tensor, Tensor]:
+    """``model/efficient_modules.py:49-54`` / ``:250-259``: x = W^-1 z, logdet = -T*logdet(W)."""
+    n = z.shape[-1]
+    w = weight.squeeze(-1)
+    return F.conv1d(z, w.inverse().unsqueeze(-1)), -n * w.logdet()
+
+
+def conv1x1_restore_input(weight: Tensor, z: Tensor) -> Tensor:
+    """``model/efficient_modules.py:235-237``: x = W^-1 z written back into the freed storage."""
+    return F.conv1d(z, weight.squeeze(-1).inverse().unsqueeze(-1))
+
+
+def conv1x1_backward(weight: Tensor, x: Tensor, dz: Tensor, dlogdet: Tensor) -> Tuple[Tensor, Tensor]:
+    """Closed form of ``Conv1x1Func.backward`` (``model/efficient_modules.py:230-244``):
+    dx = W^T dz ; dW = sum_{b,t} dz x^T + W^-T * dlogdet * T."""
+    n = x.shape[-1]
+    w = weight.squeeze(-1)
+    dx = F.conv1d(dz, w.t().unsqueeze(-1))
+    dw = torch.einsum("bot,bit->oi", dz, x) + w.inverse().t() * dlogdet * n
+    return dx, dw.unsqueeze(-1)
+
+
+def invconv1x1_backward(weight: Tensor, x: Tensor, dz: Tensor, dlogdet: Tensor) -> Tuple[Tensor, Tensor]:
+    """Closed form of ``InvConv1x1Func.backward`` (``model/efficient_modules.py:263-279``) where
+    forward was z = W^-1 x, L = -T logdet W and ``x`` here is that forward's INPUT:
+    dx = W^-T dz ; dM = sum dz (W z)^T = sum dz x^T ; dW = -W^-T dM W^-T - W^-T dlogdet T."""
+    n = x.shape[-1]
+    w = weight.squeeze(-1)
+    wt_inv = w.inverse().t()
+    dx = F.conv1d(dz, wt_inv.unsqueeze(-1))
+    dm = torch.einsum("bot,bit->oi", dz, x)
+    dw = -wt_inv @ dm @ wt_inv - wt_inv * dlogdet * n
+    return dx, dw.unsqueeze(-1)
+
+
+# --------------------------------------------------------------------------------------------
+# WaveGlow model glue (model/waveglow.py:108-212), loss (model/loss.py:10-15), infer (base.py:42-55)
+# --------------------------------------------------------------------------------------------
+class WaveGlowSpec:
+    """Structural hyper-parameters of ``WaveGlow.__init__`` (``model/waveglow.py:108-148``)."""
+
+    def __init__(self, flows: int, n_group: int, n_early_every: int, n_early_size: int,
+                 hop_size: int, n_mels: int):
+        self.flows = flows
+        self.n_group = n_group
+        self.n_early_every = n_early_every
+        self.n_early_size = n_early_size
+        self.hop_size = hop_size
+        self.n_mels = n_mels
+        self.upsample_factor = hop_size // n_group
+        self.sub_win = self.upsample_factor * 2 + 1
+        self.up_pad = self.sub_win // 2 - self.upsample_factor // 2
+        rem = n_group
+        self.channels: List[int] = []
+        self.z_split_sizes: List[int] = []
+        for k in range(flows):
+            if k % n_early_every == 0 and k:
+                rem -= n_early_size
+                self.z_split_sizes.append(n_early_size)
+            self.channels.append(rem)
+        self.z_split_sizes.append(rem)
+
+
+def upsample_h(sd: State, spec: WaveGlowSpec, h: Tensor) -> Tensor:
+    """``model/waveglow.py:126-130,210-212``: weight-normed depthwise ConvTranspose1d with bias."""
+    w = resolve_weight(sd, "upsampler.")
+    return F.conv_transpose1d(h, w, sd.get("upsampler.bias"), stride=spec.upsample_factor,
+                              padding=spec.up_pad, groups=spec.n_mels)
+
+
+def squeeze(x: Tensor, n_group: int) -> Tensor:
+    """``model/waveglow.py:153``: (B, T) -> (B, n_group, T/n_group)."""
+    return x.view(x.size(0), -1, n_group).transpose(1, 2).contiguous()
+
+
+def unsqueeze(x: Tensor) -> Tensor:
+    """``model/waveglow.py:179,207``: (B, C, T') -> (B, C*T')."""
+    return x.transpose(1, 2).contiguous().view(x.size(0), -1)
+
+
+def waveglow_forward(sd: State, spec: WaveGlowSpec, x: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
+    """``WaveGlow.forward_computation`` (``model/waveglow.py:150-179``)."""
+    y = upsample_h(sd, spec, h)
+    x = squeeze(x, spec.n_group)
+    assert x.size(2) <= y.size(2)
+    y = y[..., :x.size(2)]
+    outs = []
+    logdet = 0
+    for k in range(spec.flows):
+        if k % spec.n_early_every == 0 and k:
+            outs.append(x[:, :spec.n_early_size])
+            x = x[:, spec.n_early_size:]
+        x, ldw = conv1x1_forward(sd[f"invconv1x1.{k}.weight"], x)
+        x, log_s = coupling_forward(sd, f"WNs.{k}.F.", x, y)
+        logdet = logdet + ldw + log_s.sum((1, 2))
+    outs.append(x)
+    return unsqueeze(torch.cat(outs, 1)), logdet
+
+
+def waveglow_reverse(sd: State, spec: WaveGlowSpec, z: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
+    """``WaveGlow.reverse_computation`` (``model/waveglow.py:181-208``)."""
+    y = upsample_h(sd, spec, h)
+    z = squeeze(z, spec.n_group)
+    assert z.size(2) <= y.size(2)
+    y = y[..., :z.size(2)]
+    *remained, z = z.split(spec.z_split_sizes, 1)
+    remained = list(remained)
+    logdet = 0
+    for k in range(spec.flows - 1, -1, -1):
+        z, log_s = coupling_reverse(sd, f"WNs.{k}.F.", z, y)
+        z, ldw = conv1x1_reverse(sd[f"invconv1x1.{k}.weight"], z)
+        logdet = logdet + ldw + log_s.sum((1, 2))
+        if k % spec.n_early_every == 0 and k:
+            z = torch.cat((remained.pop(), z), 1)
+    return unsqueeze(z), logdet
+
+
+def waveglow_loss(z: Tensor, logdet: Tensor, sigma: float = 1.0, elementwise_mean: bool = True) -> Tensor:
+    """``WaveGlowLoss.forward`` (``model/loss.py:10-15``)."""
+    loss = 0.5 * z.pow(2).sum(1) / (sigma ** 2) - logdet
+    loss = loss.mean()
+    if elementwise_mean:
+        loss = loss / z.size(1)
+    return loss
+
+
+def waveglow_infer(sd: State, spec: WaveGlowSpec, h: Tensor, z: Tensor) -> Tensor:
+    """``FlowBase.infer`` (``model/base.py:42-55``) with the noise ``z`` supplied by the caller
+    (already scaled by sigma) so that oracle and product consume identical samples."""
+    x, _ = waveglow_reverse(sd, spec, z, h)
+    return x.squeeze()
+
+
+# --------------------------------------------------------------------------------------------
+# gradients (autograd over the naive restatement == the reference's reversible backward)
+# --------------------------------------------------------------------------------------------
+def _leafify(sd: State) -> State:
+    return {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+
+
+def waveglow_train_step(sd: State, spec: WaveGlowSpec, x: Tensor, h: Tensor, sigma: float
+                        ) -> Tuple[Tensor, Tensor, Tensor, State]:
+    """One fwd + loss + bwd; returns (z, logdet, loss, grads keyed like the state dict)."""
+    leaf = _leafify(sd)
+    z, logdet = waveglow_forward(leaf, spec, x, h)
+    loss = waveglow_loss(z, logdet, sigma)
+    keys = [k for k, v in leaf.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys], allow_unused=True)
+    return z.detach(), logdet.detach(), loss.detach(), {k: g for k, g in zip(keys, grads) if g is not None}
+
+
+def coupling_grads(sd: State, prefix: str, x: Tensor, y: Tensor, dz: Tensor, dlog_s: Tensor,
+                   reverse: bool = False, need_dy: bool = False):
+    """Gradient of <z,dz> + <log_s,dlog_s> w.r.t. (x, params[, y]) for the coupling block in the
+    forward (``AffineCouplingFunc``) or reverse (``InvAffineCouplingFunc``) direction."""
+    leaf = _leafify({k: v for k, v in sd.items() if k.startswith(prefix)})
+    xx = x.detach().clone().requires_grad_(True)
+    yy = y.detach().clone().requires_grad_(need_dy)
+    fn = coupling_reverse if reverse else coupling_forward
+    out, ls = fn(leaf, prefix, xx, yy)
+    obj = (out * dz).sum() + (ls * dlog_s).sum()
+    keys = list(leaf.keys())
+    wrt = [xx] + [leaf[k] for k in keys] + ([yy] if need_dy else [])
+    g = torch.autograd.grad(obj, wrt)
+    dx = g[0]
+    dparams = {k: gi for k, gi in zip(keys, g[1:1 + len(keys)])}
+    dy = g[-1] if need_dy else None
+    return out.detach(), ls.detach(), dx, dparams, dy
+
+
+def random_state(spec: WaveGlowSpec, wn_channels: int, depth: int, seed: int = 0,
+                 radix: int = 3, end_std: Optional[float] = None, dtype=torch.float32) -> State:
+    """Random-init weights with the reference's key layout and init distributions
+    (Conv1d default init = kaiming_uniform(a=sqrt(5)); weight_norm sets g = ||v||; the 1x1 conv is
+    a QR orthogonal matrix with positive determinant, ``model/efficient_modules.py:22-26``;
+    ``end`` keeps the default Conv1d init when ``zero_init=False``, ``model/waveglow.py:92-96``).
+    Used where the reference cannot be imported (GPU box); the distributions matter only for
+    conditioning of the problem, not for parity."""
+    gen = torch.Generator().manual_seed(seed)
+
+    def conv_v(out_c, in_c, k):
+        bound = 1.0 / (in_c * k) ** 0.5
+        return (torch.rand(out_c, in_c, k, generator=gen, dtype=dtype) * 2 - 1) * bound
+
+    sd: State = {}
+    sd["upsampler.bias"] = (torch.rand(spec.n_mels, generator=gen, dtype=dtype) * 2 - 1) / spec.sub_win ** 0.5
+    v = conv_v(spec.n_mels, 1, spec.sub_win)
+    sd["upsampler.weight_g"] = v.flatten(1).norm(dim=1).view(-1, 1, 1)
+    sd["upsampler.weight_v"] = v
+    for k, c in enumerate(spec.channels):
+        q = torch.linalg.qr(torch.randn(c, c, generator=gen, dtype=torch.float64))[0]
+        if torch.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        sd[f"invconv1x1.{k}.weight"] = q.to(dtype).contiguous().unsqueeze(-1)
+    for k, c in enumerate(spec.channels):
+        p = f"WNs.{k}.F."
+
+        def put(name, out_c, in_c, ks):
+            vv = conv_v(out_c, in_c, ks)
+            sd[p + name + ".weight_g"] = vv.flatten(1).norm(dim=1).view(-1, 1, 1)
+            sd[p + name + ".weight_v"] = vv
+
+        put("V", 2 * wn_channels * depth, spec.n_mels, 1)
+        put("start", wn_channels, c // 2, 1)
+        for i in range(depth):
+            put(f"layers.{i}.W", 2 * wn_channels, wn_channels, radix)
+            put(f"layers.{i}.W_o", wn_channels * (2 if i < depth - 1 else 1), wn_channels, 1)
+        if end_std is None:
+            sd[p + "end.weight"] = conv_v(c, wn_channels, 1)
+        else:
+            sd[p + "end.weight"] = torch.randn(c, wn_channels, 1, generator=gen, dtype=dtype) * end_std
+    return sd

@@ -1,0 +1,141 @@
+"""Generate golden fixtures by running the UNMODIFIED reference (CPU, fp32).
+
+Run in the authoring container only (``/root/reference`` does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference is imported from ``/root/reference`` with an in-memory stub for the missing
+``pytorch_lightning`` module (only ``model/lightning.py`` needs it; none of the flow code does).
+Every fixture stores the seeded inputs, the reference state-dict, the reference outputs and the
+gradients produced by the reference's *memory-efficient* (constant-memory) path, so the oracle
+(and through it the CUDA product) is pinned against the real reversible backward.
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+warnings.filterwarnings("ignore")
+REF = os.environ.get("CMWG_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    pl = types.ModuleType("pytorch_lightning")
+
+    class _LM(torch.nn.Module):
+        def save_hyperparameters(self, *a, **k):
+            pass
+
+    pl.LightningModule = _LM
+    pl.Callback = object
+    pl.Trainer = object
+    sys.modules["pytorch_lightning"] = pl
+    # the reference must win over this repo's drop-in ``model`` package
+    sys.path.insert(0, REF)
+    for name in list(sys.modules):
+        if name == "model" or name.startswith("model.") or name == "utils":
+            del sys.modules[name]
+    from model.efficient_modules import AffineCouplingBlock, InvertibleConv1x1
+    from model.waveglow import WN, WaveGlow
+    from model.loss import WaveGlowLoss
+    assert sys.modules["model.waveglow"].__file__.startswith(REF)
+    return AffineCouplingBlock, InvertibleConv1x1, WN, WaveGlow, WaveGlowLoss
+
+
+def set_seed(seed):
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def cpu_state(m):
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def main():
+    torch.set_num_threads(4)
+    AffineCouplingBlock, InvertibleConv1x1, WN, WaveGlow, WaveGlowLoss = import_reference()
+
+    # ---- 1. invertible 1x1 conv, both directions, efficient mode --------------------------------
+    for c in (2, 4, 8):
+        set_seed(100 + c)
+        B, T = 3, 257
+        m = InvertibleConv1x1(c, True)
+        sd = cpu_state(m)
+        x = torch.rand(B, c, T) * 2 - 1
+        loss_fn = WaveGlowLoss(0.7)
+        fx = {"state": sd, "x": x, "sigma": 0.7}
+        for direction in ("forward", "reverse"):
+            m.zero_grad()
+            xin = x.clone().requires_grad_(True)
+            xc = xin.clone()
+            y, ld = (m(xc) if direction == "forward" else m.reverse(xc))
+            loss = loss_fn(y.reshape(B, -1), ld)
+            loss.backward()
+            fx[direction] = {"out": y.detach().clone(), "logdet": ld.detach().clone(),
+                             "loss": loss.detach().clone(), "dx": xin.grad.clone(),
+                             "dweight": m.weight.grad.clone()}
+        torch.save(fx, os.path.join(OUT, f"conv1x1_c{c}.pt"))
+
+    # ---- 2. affine coupling block with WN transform --------------------------------------------
+    for name, ch, wn_ch, depth, aux, T in (("a", 16, 32, 2, 20, 300), ("b", 8, 32, 3, 12, 211)):
+        set_seed(7 + depth)
+        B = 2
+        kw = dict(in_channels=ch // 2, aux_channels=aux, zero_init=False, dilation_channels=wn_ch,
+                  residual_channels=wn_ch, skip_channels=wn_ch, depth=depth)
+        m = AffineCouplingBlock(WN, True, **kw)
+        sd = cpu_state(m)
+        x = torch.rand(B, ch, T) * 2 - 1
+        y = torch.randn(B, aux, T)
+        loss_fn = WaveGlowLoss(1.0)
+        fx = {"state": sd, "x": x, "y": y, "kwargs": kw, "param_order": [n for n, _ in m.F.named_parameters()]}
+        for direction in ("forward", "reverse"):
+            m.zero_grad()
+            xin = x.clone().requires_grad_(True)
+            yin = y.clone().requires_grad_(True)
+            xc = xin.clone()
+            out, ls = (m(xc, yin) if direction == "forward" else m.reverse(xc, yin))
+            loss = loss_fn(out.reshape(B, -1), ls.sum((1, 2)))
+            loss.backward()
+            fx[direction] = {"out": out.detach().clone(), "log_s": ls.detach().clone(),
+                             "loss": loss.detach().clone(), "dx": xin.grad.clone(), "dy": yin.grad.clone(),
+                             "dparams": {"F." + n: p.grad.clone() for n, p in m.F.named_parameters()}}
+        torch.save(fx, os.path.join(OUT, f"coupling_{name}.pt"))
+
+    # ---- 3. tiny WaveGlow: forward, loss, reversible backward, reverse, infer ---------------------
+    set_seed(0)
+    arch = dict(flows=4, n_group=8, n_early_every=2, n_early_size=2, hop_size=256, n_mels=8)
+    wkw = dict(dilation_channels=32, residual_channels=32, skip_channels=32, depth=3, radix=3,
+               bias=False, zero_init=False)
+    B, T, frames = 2, 2048, 8
+    m = WaveGlow(memory_efficient=True, **arch, **wkw)
+    sd = cpu_state(m)
+    x = torch.rand(B, T) * 2 - 1
+    h = torch.randn(B, arch["n_mels"], frames)
+    loss_fn = WaveGlowLoss(0.7)
+    m.zero_grad()
+    z, logdet = m(x.clone(), h)
+    loss = loss_fn(z, logdet)
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in m.named_parameters()}
+    with torch.no_grad():
+        m2 = WaveGlow(memory_efficient=False, **arch, **wkw)
+        m2.load_state_dict(sd)
+        xr, logdet_r = m2.reverse(z.detach().clone(), h)
+        zs = torch.randn(B, frames * arch["hop_size"]) * 0.6
+        audio, _ = m2.reverse_computation(zs.clone(), h)
+    torch.save({"state": sd, "arch": arch, "wn_kwargs": wkw, "x": x, "h": h, "sigma": 0.7,
+                "z": z.detach().clone(), "logdet": logdet.detach().clone(), "loss": loss.detach().clone(),
+                "grads": grads, "x_roundtrip": xr, "logdet_reverse": logdet_r,
+                "infer_z": zs, "infer_audio": audio},
+               os.path.join(OUT, "waveglow_tiny.pt"))
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".pt"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
