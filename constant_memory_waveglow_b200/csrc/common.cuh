@@ -1,0 +1,115 @@
+// Shared helpers for the cmwg_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cmwg_b200.h"
+
+namespace cmwg {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing: no exceptions cross the C ABI; every entry point returns an int and leaves a
+// message retrievable through cmwg_last_error().
+// ------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define CMWG_CHECK_CUDA(expr)                                                                \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::cmwg::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                   \
+                        cudaGetErrorString(_e));                                             \
+      return CMWG_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+#define CMWG_REQUIRE(cond, ...)                                                              \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      ::cmwg::set_error(__VA_ARGS__);                                                        \
+      return CMWG_ERR_ARG;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+#define CMWG_PROPAGATE(expr)                                                                 \
+  do {                                                                                       \
+    int _r = (expr);                                                                         \
+    if (_r != CMWG_OK) return _r;                                                            \
+  } while (0)
+
+#define CMWG_LAUNCH_CHECK() CMWG_CHECK_CUDA(cudaGetLastError())
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+int num_sms();
+
+// optional per-kernel-class event timing (bench.py's roofline leg); no-ops unless enabled
+void prof_begin(cudaStream_t st, int cls);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  ProfScope(cudaStream_t s, int cls) : st(s) { prof_begin(s, cls); }
+  ~ProfScope() { prof_end(st); }
+};
+
+// kernel launch counter (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+#define CMWG_COUNT_LAUNCH() (++::cmwg::g_launch_count)
+
+// ------------------------------------------------------------------------------------------
+// operand element types: the WN GEMM operands are stored either as fp32 (exact CUDA-core engine)
+// or as 16-bit (bf16 / fp16) for the tcgen05 engine.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t f32_to_op16(float v, int is_fp16) {
+  if (is_fp16) {
+    // saturate instead of producing inf
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    return __half_as_ushort(__float2half_rn(v));
+  }
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float op16_to_f32(uint16_t u, int is_fp16) {
+  if (is_fp16) return __half2float(__ushort_as_half(u));
+  return __bfloat162float(__ushort_as_bfloat16(u));
+}
+
+template <typename T> struct OpTraits;
+template <> struct OpTraits<float> {
+  static constexpr bool is16 = false;
+  __device__ __forceinline__ static float load(const float* p, int) { return *p; }
+  __device__ __forceinline__ static void store(float* p, float v, int) { *p = v; }
+};
+template <> struct OpTraits<uint16_t> {
+  static constexpr bool is16 = true;
+  __device__ __forceinline__ static float load(const uint16_t* p, int f16) { return op16_to_f32(*p, f16); }
+  __device__ __forceinline__ static void store(uint16_t* p, float v, int f16) { *p = f32_to_op16(v, f16); }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// accurate (fp32 mode) and fast (tensor-core modes) gate non-linearities
+template <bool FAST> __device__ __forceinline__ float tanh_f(float x) {
+  if (FAST) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  }
+  return tanhf(x);
+}
+template <bool FAST> __device__ __forceinline__ float sigmoid_f(float x) {
+  if (FAST) return fmaf(0.5f, tanh_f<true>(0.5f * x), 0.5f);
+  return 1.f / (1.f + expf(-x));
+}
+
+}  // namespace cmwg

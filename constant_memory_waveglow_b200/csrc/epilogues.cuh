@@ -1,0 +1,226 @@
+// Epilogue functors shared by the FFMA engine (fp32 operands, NC = 4 columns per call) and the
+// tcgen05 engine (16-bit operands, NC = 32 columns per call).  Each call covers one output ROW
+// (= one (batch, time) column of the reference's NCL tensors) and NC consecutive channels, so all
+// global accesses are NC*sizeof contiguous.
+#pragma once
+#include "common.cuh"
+
+namespace cmwg {
+
+template <typename OpT, int NC>
+__device__ __forceinline__ void store_ops(OpT* dst, const float (&v)[NC], int f16) {
+  if constexpr (sizeof(OpT) == 4) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 4)
+      *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+    if constexpr (NC % 8 == 0) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 8) {
+        uint4 u;
+        u.x = (uint32_t)f32_to_op16(v[j + 0], f16) | ((uint32_t)f32_to_op16(v[j + 1], f16) << 16);
+        u.y = (uint32_t)f32_to_op16(v[j + 2], f16) | ((uint32_t)f32_to_op16(v[j + 3], f16) << 16);
+        u.z = (uint32_t)f32_to_op16(v[j + 4], f16) | ((uint32_t)f32_to_op16(v[j + 5], f16) << 16);
+        u.w = (uint32_t)f32_to_op16(v[j + 6], f16) | ((uint32_t)f32_to_op16(v[j + 7], f16) << 16);
+        *reinterpret_cast<uint4*>(dst + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        uint2 u;
+        u.x = (uint32_t)f32_to_op16(v[j + 0], f16) | ((uint32_t)f32_to_op16(v[j + 1], f16) << 16);
+        u.y = (uint32_t)f32_to_op16(v[j + 2], f16) | ((uint32_t)f32_to_op16(v[j + 3], f16) << 16);
+        *reinterpret_cast<uint2*>(dst + j) = u;
+      }
+    }
+  }
+}
+
+template <typename OpT, int NC>
+__device__ __forceinline__ void load_ops(const OpT* src, float (&v)[NC], int f16) {
+  if constexpr (sizeof(OpT) == 4) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      float4 q = *reinterpret_cast<const float4*>(src + j);
+      v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      uint2 u = *reinterpret_cast<const uint2*>(src + j);
+      v[j + 0] = op16_to_f32((uint16_t)(u.x & 0xffff), f16);
+      v[j + 1] = op16_to_f32((uint16_t)(u.x >> 16), f16);
+      v[j + 2] = op16_to_f32((uint16_t)(u.y & 0xffff), f16);
+      v[j + 3] = op16_to_f32((uint16_t)(u.y >> 16), f16);
+    }
+  }
+}
+
+template <int NC>
+__device__ __forceinline__ void load_f32(const float* src, float (&v)[NC]) {
+#pragma unroll
+  for (int j = 0; j < NC; j += 4) {
+    float4 q = *reinterpret_cast<const float4*>(src + j);
+    v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
+  }
+}
+template <int NC>
+__device__ __forceinline__ void store_f32(float* dst, const float (&v)[NC]) {
+#pragma unroll
+  for (int j = 0; j < NC; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+
+// ---- 1. gate: g = tanh(pre_t) * sigmoid(pre_s)  (model/waveglow.py:13-15,42-44) -----------------
+// The gate GEMM's weight rows are permuted so that the partner pre-activations of gate channel ch
+// sit G columns apart inside one N tile; the engine hands both halves to pair().
+template <typename OpT, bool FAST>
+struct GateEpi {
+  OpT* g;          // [rows][Cd]
+  OpT* a_save;     // [rows][Cd] or nullptr: tanh(pre_t)   (kept for the backward)
+  OpT* b_save;     // [rows][Cd] or nullptr: sigmoid(pre_s)
+  const float* bias;  // nullptr or [2][Cd]
+  int Cd;
+  int f16;
+  template <int NC>
+  __device__ __forceinline__ void pair(long long row, int ch0, const float (&lo)[NC], const float (&hi)[NC]) const {
+    if (ch0 >= Cd) return;  // Cd % 4 == 0 and NC | (Cd - ch0) for both engines' tilings
+    float gv[NC], av[NC], bv[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      float pt = lo[j], ps = hi[j];
+      if (bias) { pt += bias[ch0 + j]; ps += bias[Cd + ch0 + j]; }
+      av[j] = tanh_f<FAST>(pt);
+      bv[j] = sigmoid_f<FAST>(ps);
+      gv[j] = av[j] * bv[j];
+    }
+    long long o = row * Cd + ch0;
+    store_ops<OpT, NC>(g + o, gv, f16);
+    if (a_save) {
+      store_ops<OpT, NC>(a_save + o, av, f16);
+      store_ops<OpT, NC>(b_save + o, bv, f16);
+    }
+  }
+};
+
+// ---- 2. residual / skip: W_o output split (model/waveglow.py:45-46,104) -------------------------
+template <typename OpT>
+struct ResSkipEpi {
+  const float* res_src;  // [rows][Cr] fp32 layer input (nullptr when OpT==float and res_src_op is used)
+  const OpT* res_src_op; // alternative residual source in operand type (ff training path)
+  float* res_dst32;      // [rows][Cr] fp32 or nullptr
+  OpT* res_dst_op;       // [rows][Cr] operand copy for the next layer or nullptr
+  float* skip;           // [rows][Cs] fp32 cumulative skip
+  const float* bias;     // nullptr or [nb]
+  int Cr, Cs, cr_eff, first_layer, f16;
+  template <int NC>
+  __device__ __forceinline__ void op(long long row, int col0, const float (&v)[NC]) const {
+    float w[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) w[j] = v[j] + (bias ? bias[col0 + j] : 0.f);
+    if (col0 < cr_eff) {
+      float r[NC];
+      long long o = row * Cr + col0;
+      if (res_src) load_f32<NC>(res_src + o, r);
+      else load_ops<OpT, NC>(res_src_op + o, r, f16);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) w[j] += r[j];
+      if (res_dst32) store_f32<NC>(res_dst32 + o, w);
+      if (res_dst_op) store_ops<OpT, NC>(res_dst_op + o, w, f16);
+    } else {
+      int k = col0 - cr_eff;
+      if (k >= Cs) return;
+      long long o = row * Cs + k;
+      if (!first_layer) {
+        float s[NC];
+        load_f32<NC>(skip + o, s);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) w[j] += s[j];
+      }
+      store_f32<NC>(skip + o, w);
+    }
+  }
+};
+
+// ---- 3. gate backward: dpre = dg * d(tanh*sigmoid) ----------------------------------------------
+template <typename OpT>
+struct GateBwdEpi {
+  const OpT* a_save;  // tanh values
+  const OpT* b_save;  // sigmoid values
+  OpT* dpre;          // [rows][ld]: columns [0,Cd) tanh-half grads, [Cd,2Cd) sigmoid-half grads
+  int Cd, ld, f16;
+  template <int NC>
+  __device__ __forceinline__ void op(long long row, int col0, const float (&v)[NC]) const {
+    if (col0 >= Cd) return;
+    float a[NC], b[NC], dt[NC], ds[NC];
+    long long o = row * Cd + col0;
+    load_ops<OpT, NC>(a_save + o, a, f16);
+    load_ops<OpT, NC>(b_save + o, b, f16);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      dt[j] = v[j] * b[j] * (1.f - a[j] * a[j]);
+      ds[j] = v[j] * a[j] * b[j] * (1.f - b[j]);
+    }
+    long long p = row * ld + col0;
+    store_ops<OpT, NC>(dpre + p, dt, f16);
+    store_ops<OpT, NC>(dpre + p + Cd, ds, f16);
+  }
+};
+
+// ---- 4. dx of the dilated conv + residual gradient ----------------------------------------------
+template <typename OpT>
+struct DxEpi {
+  const float* src;  // [rows][Cr] fp32 upstream residual gradient or nullptr (last layer)
+  float* dst32;      // [rows][Cr]
+  OpT* dst_op;       // operand copy or nullptr
+  int Cr, f16;
+  template <int NC>
+  __device__ __forceinline__ void op(long long row, int col0, const float (&v)[NC]) const {
+    if (col0 >= Cr) return;
+    float w[NC];
+    long long o = row * Cr + col0;
+    if (src) {
+      load_f32<NC>(src + o, w);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) w[j] += v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) w[j] = v[j];
+    }
+    store_f32<NC>(dst32 + o, w);
+    if (dst_op) store_ops<OpT, NC>(dst_op + o, w, f16);
+  }
+};
+
+// ---- 5. accumulate into an fp32 slab (conditioning gradient) ------------------------------------
+struct AccumEpi {
+  float* dst;  // [rows][ld]
+  int ld, n_valid, first;
+  template <int NC>
+  __device__ __forceinline__ void op(long long row, int col0, const float (&v)[NC]) const {
+    if (col0 >= n_valid) return;
+    float w[NC];
+    long long o = row * ld + col0;
+    if (!first) {
+      load_f32<NC>(dst + o, w);
+#pragma unroll
+      for (int j = 0; j < NC; ++j) w[j] += v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) w[j] = v[j];
+    }
+    store_f32<NC>(dst + o, w);
+  }
+};
+
+// ---- 6. plain fp32 store (self tests, weight-gradient partials) ---------------------------------
+struct StoreEpi {
+  float* dst;  // [rows][ld]
+  int ld, n_valid;
+  template <int NC>
+  __device__ __forceinline__ void op(long long row, int col0, const float (&v)[NC]) const {
+    if (col0 >= n_valid) return;
+    store_f32<NC>(dst + row * ld + col0, v);
+  }
+};
+
+}  // namespace cmwg

@@ -1,0 +1,210 @@
+// Dimension bookkeeping and HBM buffer layouts of the WN pipeline (host side).
+//
+// Slab layout: every activation between WN layers is stored channel-last, [B*T rows][C channels],
+// so that (a) a dilated-conv tap is a pure ROW SHIFT of the GEMM A operand (TMA coordinate offset,
+// zero fill outside [0,T) gives the 'same' padding for free), (b) the K dimension of every GEMM is
+// contiguous (K-major operands, 128B-swizzle friendly), (c) weight-gradient GEMMs read the very same
+// buffers as MN-major operands with K = time.
+#pragma once
+#include "common.cuh"
+
+namespace cmwg {
+
+constexpr int MAX_SEG = 8;  // radix taps + conditioning segment
+constexpr int TC_MAX_WG_REDUCE = 8;  // weight-gradient problems reduced per launch
+
+struct WnDims {
+  int cin, aux, Cd, Cr, Cs, depth, R, bias, prec;
+  bool tc;      // tcgen05 engine (16-bit operands) vs FFMA engine (fp32 operands)
+  int opsize;   // bytes per operand element
+  int kb;       // K granule every GEMM segment is padded to: 64 (tc) / 16 (ff)
+  int auxp;     // padded conditioning channels
+  int Crp, Cdp, Csp, Cd2p;  // channel counts rounded up to kb (Cd2p: 2*Cd)
+  int bn_gate;  // N tile of the gate GEMM; tanh/sigmoid partner channels are G = bn_gate/2 apart
+  int G;
+  int npadA;    // padded rows of the gate GEMM weight matrix
+  int KA;       // K of the gate GEMM: R*Crp + auxp
+  __host__ __device__ int nb(int i) const { return (i < depth - 1) ? Cr + Cs : Cs; }     // rows of W_o[i]
+  __host__ __device__ int cr_eff(int i) const { return (i < depth - 1) ? Cr : 0; }       // residual rows of W_o[i]
+  __host__ __device__ int k1(int i) const { return (i < depth - 1) ? Crp + Csp : Csp; }  // K of the dgate GEMM
+};
+
+inline bool wn_tc_shapes_ok(const cmwg_wn_config& c) {
+  return c.dil_channels % 64 == 0 && c.res_channels % 64 == 0 && c.skip_channels % 64 == 0 &&
+         c.radix <= MAX_SEG - 1 && c.dil_channels >= 64;
+}
+
+inline int make_dims(const cmwg_wn_config* c, WnDims* d) {
+  CMWG_REQUIRE(c != nullptr, "null cmwg_wn_config");
+  CMWG_REQUIRE(c->depth >= 1 && c->depth <= CMWG_MAX_DEPTH, "WN depth %d out of range [1,%d]", c->depth,
+               CMWG_MAX_DEPTH);
+  CMWG_REQUIRE(c->radix >= 1 && (c->radix % 2) == 1 && c->radix <= MAX_SEG - 1,
+               "WN radix %d unsupported (odd, <= %d)", c->radix, MAX_SEG - 1);
+  CMWG_REQUIRE(c->in_channels >= 1 && c->in_channels <= 64, "WN in_channels %d out of range [1,64]",
+               c->in_channels);
+  CMWG_REQUIRE(c->aux_channels >= 1, "WN aux_channels %d invalid", c->aux_channels);
+  CMWG_REQUIRE(c->dil_channels % 4 == 0 && c->res_channels % 4 == 0 && c->skip_channels % 4 == 0 &&
+                   c->dil_channels > 0 && c->res_channels > 0 && c->skip_channels > 0,
+               "WN channel counts (dil %d, res %d, skip %d) must be positive multiples of 4", c->dil_channels,
+               c->res_channels, c->skip_channels);
+  CMWG_REQUIRE(c->precision == CMWG_PREC_FP32 || c->precision == CMWG_PREC_BF16 || c->precision == CMWG_PREC_FP16,
+               "unknown precision %d", c->precision);
+  d->cin = c->in_channels; d->aux = c->aux_channels; d->Cd = c->dil_channels; d->Cr = c->res_channels;
+  d->Cs = c->skip_channels; d->depth = c->depth; d->R = c->radix; d->bias = c->has_bias ? 1 : 0;
+  d->prec = c->precision;
+  d->tc = c->precision != CMWG_PREC_FP32;
+  if (d->tc && !wn_tc_shapes_ok(*c)) {
+    set_error("tensor-core precision requested but WN channels (dil %d, res %d, skip %d) are not multiples of 64",
+              c->dil_channels, c->res_channels, c->skip_channels);
+    return CMWG_ERR_UNSUPPORTED;
+  }
+  d->opsize = d->tc ? 2 : 4;
+  d->kb = d->tc ? 64 : 16;
+  d->auxp = round_up(d->aux, d->kb);
+  d->Crp = round_up(d->Cr, d->kb);
+  d->Cdp = round_up(d->Cd, d->kb);
+  d->Csp = round_up(d->Cs, d->kb);
+  d->Cd2p = round_up(2 * d->Cd, d->kb);
+  d->bn_gate = (d->tc && d->Cd % 128 == 0) ? 256 : 128;
+  d->G = d->bn_gate / 2;
+  d->npadA = ceil_div(d->Cd, d->G) * d->bn_gate;
+  d->KA = d->R * d->Crp + d->auxp;
+  return CMWG_OK;
+}
+
+// ---- packed weights ----------------------------------------------------------------------------
+struct PackedLayout {
+  // fp32, natural PyTorch layouts (effective weights after weight norm) + 1/||v|| per out channel
+  size_t wV, wStart, wEnd, wW[CMWG_MAX_DEPTH], wWo[CMWG_MAX_DEPTH];
+  size_t nV, nStart, nW[CMWG_MAX_DEPTH], nWo[CMWG_MAX_DEPTH];
+  // fp32 bias vectors in engine order (only when has_bias)
+  size_t biasA[CMWG_MAX_DEPTH];  // [2][Cd]: tanh-half bias, sigmoid-half bias (W bias + V bias)
+  size_t biasB[CMWG_MAX_DEPTH];  // [nb(i)]
+  size_t biasStart, biasEnd;
+  // GEMM operand matrices (operand element type), row-major [N][K]
+  size_t PA[CMWG_MAX_DEPTH];  // gate GEMM      [npadA][KA]
+  size_t PB[CMWG_MAX_DEPTH];  // res/skip GEMM  [nb(i)][Cdp]
+  size_t Q1[CMWG_MAX_DEPTH];  // dgate GEMM     [Cd][k1(i)]          = W_o^T
+  size_t Q2[CMWG_MAX_DEPTH];  // dx GEMM        [Cr][R*Cd2p]         = W^T per tap
+  size_t QV[CMWG_MAX_DEPTH];  // dy GEMM        [auxp][Cd2p]         = V_i^T
+  size_t total;
+};
+
+inline PackedLayout make_packed_layout(const WnDims& d) {
+  PackedLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.wV = take((size_t)2 * d.Cd * d.depth * d.aux * 4);
+  L.wStart = take((size_t)d.Cr * d.cin * 4);
+  L.wEnd = take((size_t)2 * d.cin * d.Cs * 4);
+  L.nV = take((size_t)2 * d.Cd * d.depth * 4);
+  L.nStart = take((size_t)d.Cr * 4);
+  L.biasStart = take((size_t)d.Cr * 4);
+  L.biasEnd = take((size_t)2 * d.cin * 4);
+  for (int i = 0; i < d.depth; ++i) {
+    L.wW[i] = take((size_t)2 * d.Cd * d.Cr * d.R * 4);
+    L.wWo[i] = take((size_t)d.nb(i) * d.Cd * 4);
+    L.nW[i] = take((size_t)2 * d.Cd * 4);
+    L.nWo[i] = take((size_t)d.nb(i) * 4);
+    L.biasA[i] = take((size_t)2 * d.Cd * 4);
+    L.biasB[i] = take((size_t)d.nb(i) * 4);
+    L.PA[i] = take((size_t)d.npadA * d.KA * d.opsize);
+    L.PB[i] = take((size_t)d.nb(i) * d.Cdp * d.opsize);
+    L.Q1[i] = take((size_t)d.Cd * d.k1(i) * d.opsize);
+    L.Q2[i] = take((size_t)d.Cr * d.R * d.Cd2p * d.opsize);
+    L.QV[i] = take((size_t)d.auxp * d.Cd2p * d.opsize);
+  }
+  L.total = off;
+  return L;
+}
+
+// ---- forward workspace / saved activations -----------------------------------------------------
+struct FwdLayout {
+  // workspace
+  size_t h32;     // [rows][Cr] fp32 residual stream
+  size_t skip32;  // [rows][Cs] fp32 cumulative skip
+  size_t hop;     // [rows][Cr] operand copy of the layer input (tc inference only; ff aliases h32)
+  size_t gop;     // [rows][Cd] operand gate output (inference)
+  size_t ws_total;
+  // saved (training): per layer
+  size_t s_hin[CMWG_MAX_DEPTH], s_g[CMWG_MAX_DEPTH], s_a[CMWG_MAX_DEPTH], s_b[CMWG_MAX_DEPTH];
+  size_t s_skip;  // final cumulative skip fp32 (for d end.weight)
+  size_t saved_total;
+};
+
+// ---- backward workspace ------------------------------------------------------------------------
+struct BwdLayout {
+  size_t dskip_op;   // [rows][Cs] operand
+  size_t dh32;       // [rows][Cr] fp32
+  size_t dh_op;      // [rows][Cr] operand (tc only; ff aliases dh32)
+  size_t dpre_op;    // [rows][2Cd] operand
+  size_t partial;    // split-K partials / block partials
+  size_t partial_bytes;
+  size_t dweff;      // fp32 scratch for one conv's effective-weight gradient (largest conv)
+  size_t total;
+};
+
+inline void make_fwd_layout(const WnDims& d, int B, int T, FwdLayout* L) {
+  size_t rows = (size_t)B * T;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  L->h32 = take(rows * d.Cr * 4);
+  L->skip32 = take(rows * d.Cs * 4);
+  L->hop = d.tc ? take(rows * d.Cr * d.opsize) : L->h32;
+  L->gop = take(rows * d.Cd * d.opsize);
+  L->ws_total = off;
+  off = 0;
+  for (int i = 0; i < d.depth; ++i) {
+    L->s_hin[i] = take(rows * d.Cr * d.opsize);
+    L->s_g[i] = take(rows * d.Cd * d.opsize);
+    L->s_a[i] = take(rows * d.Cd * d.opsize);
+    L->s_b[i] = take(rows * d.Cd * d.opsize);
+  }
+  L->s_skip = take(rows * d.Cs * 4);
+  L->saved_total = off;
+}
+
+// time-chunk length of one split of the weight-gradient GEMMs
+inline int wgrad_chunk_len(int B, int T) {
+  // aim for >= ~300 work items with a 4x2..4x6 tile grid per problem; keep chunks long to bound the
+  // partial-sum traffic
+  int target_splits = 24;
+  int per_batch = ceil_div(target_splits, B);
+  int lc = ceil_div(T, per_batch);
+  lc = round_up(lc < 256 ? 256 : lc, 64);
+  return lc;
+}
+
+inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
+  size_t rows = (size_t)B * T;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  L->dskip_op = take(rows * d.Cs * d.opsize);
+  L->dh32 = take(rows * d.Cr * 4);
+  L->dh_op = d.tc ? take(rows * d.Cr * d.opsize) : L->dh32;
+  L->dpre_op = take(rows * 2 * d.Cd * d.opsize);
+  int lc = wgrad_chunk_len(B, T);
+  size_t splits = (size_t)B * ceil_div(T, lc);
+  // largest simultaneous partial set: all weight-gradient problems of one layer
+  size_t per_layer = (size_t)2 * d.Cd * d.Cr * d.R + (size_t)(d.Cr + d.Cs) * d.Cd + (size_t)2 * d.Cd * d.auxp;
+  size_t p1 = splits * per_layer * 4;
+  // start / end conv and bias-gradient block partials (32-row blocks)
+  size_t blocks32 = (size_t)B * ceil_div(T, 32) + 1;
+  size_t per_block = (size_t)d.Cr * d.cin + d.Cr;
+  size_t pe = (size_t)2 * d.cin * d.Cs + 2 * d.cin;
+  if (pe > per_block) per_block = pe;
+  if ((size_t)2 * d.Cd > per_block) per_block = 2 * d.Cd;
+  size_t p2 = blocks32 * per_block * 4;
+  L->partial_bytes = p1 > p2 ? p1 : p2;
+  L->partial = take(L->partial_bytes);
+  // scratch for effective-weight gradients: one layer's dW_o, dW, dV_i side by side
+  size_t big = (size_t)(d.Cr + d.Cs) * d.Cd + (size_t)2 * d.Cd * d.Cr * d.R + (size_t)2 * d.Cd * d.aux;
+  size_t se = (size_t)2 * d.cin * d.Cs;
+  if (se > big) big = se;
+  size_t ss = (size_t)d.Cr * d.cin;
+  if (ss > big) big = ss;
+  L->dweff = take(big * 4 + 4096);
+  L->total = off;
+}
+
+}  // namespace cmwg

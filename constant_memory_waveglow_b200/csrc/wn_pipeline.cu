@@ -1,0 +1,556 @@
+// WN transform: forward, backward, weight packing.  Orchestrates the GEMM engines (engine_tc.cuh /
+// engine_ff.cuh) and the CUDA-core kernels of wn_kernels.cuh; exported through the C ABI.
+//
+// Per NonCausalLayer i (model/waveglow.py:41-46), forward:
+//   gate GEMM   pre[row][2Cd] = sum_tap h_i[row + (tap-c)*2^i] W_tap^T  +  ycond[row] V_i^T
+//               (the conditioning 1x1 conv V is folded in as extra K rows, so its (B, 2*Cd*depth, T)
+//               output -- 786 MB per flow at the LJ config -- never exists), epilogue = fused_gate
+//   res/skip GEMM  ro = g W_o^T ; epilogue: h_{i+1} = h_i + ro[:, :Cr] (fp32 stream + operand copy),
+//               skip += ro[:, Cr:] (fp32)
+// backward (reverse layer order), given d(end output):
+//   dgate GEMM  dg = [dh_{i+1} | dskip] W_o ; epilogue: dpre = dg * d(tanh*sigmoid)
+//   wgrad GEMMs dW_o, dW (per tap), dV_i: MN-major reads of the same slabs, split-K over time
+//   dcond GEMM  dycond += dpre V_i
+//   dx GEMM     dh_i = dh_{i+1} + sum_tap dpre[row - (tap-c)*2^i] W_tap
+#include "engine_ff.cuh"
+#include "engine_tc.cuh"
+#include "epilogues.cuh"
+#include "wn_kernels.cuh"
+
+namespace cmwg {
+
+template <typename OpT> struct EngineSel;
+template <> struct EngineSel<float> {
+  static constexpr bool kTc = false;
+  template <bool PAIRED, class Epi>
+  static int gemm(const GemmDesc& d, const Epi& e, cudaStream_t st) { return ff_gemm_launch<Epi, PAIRED>(d, e, st); }
+};
+template <> struct EngineSel<uint16_t> {
+  static constexpr bool kTc = true;
+  template <bool PAIRED, class Epi>
+  static int gemm(const GemmDesc& d, const Epi& e, cudaStream_t st) { return tc_gemm_launch<PAIRED, Epi>(d, e, st); }
+};
+
+static inline int pick_bn(int N) { return N >= 256 ? 256 : 128; }
+
+static inline const uint8_t* cu8(const void* p) { return reinterpret_cast<const uint8_t*>(p); }
+static inline uint8_t* u8(void* p) { return reinterpret_cast<uint8_t*>(p); }
+
+// ------------------------------------------------------------------------------------------------
+// pack
+// ------------------------------------------------------------------------------------------------
+static int wn_pack_impl(const WnDims& d, const cmwg_wn_params* prm, void* packed, cudaStream_t st) {
+  PackedLayout L = make_packed_layout(d);
+  uint8_t* base = u8(packed);
+  WeffTable tb;
+  int n = 0, rows = 0;
+  auto add = [&](const cmwg_conv_param& c, size_t w_off, size_t n_off, int O, int Lr) {
+    WeffEntry& e = tb.e[n++];
+    e.g = c.g; e.v = c.v;
+    e.w = reinterpret_cast<float*>(base + w_off);
+    e.inv_norm = c.g ? reinterpret_cast<float*>(base + n_off) : nullptr;
+    e.O = O; e.L = Lr; e.row_begin = rows;
+    rows += O;
+  };
+  CMWG_REQUIRE(prm->V.v && prm->start.v && prm->end.v, "cmwg_wn_pack: missing V/start/end weights");
+  add(prm->V, L.wV, L.nV, 2 * d.Cd * d.depth, d.aux);
+  add(prm->start, L.wStart, L.nStart, d.Cr, d.cin);
+  add(prm->end, L.wEnd, 0, 2 * d.cin, d.Cs);
+  for (int i = 0; i < d.depth; ++i) {
+    CMWG_REQUIRE(prm->W[i].v && prm->W_o[i].v, "cmwg_wn_pack: missing layer %d weights", i);
+    add(prm->W[i], L.wW[i], L.nW[i], 2 * d.Cd, d.Cr * d.R);
+    add(prm->W_o[i], L.wWo[i], L.nWo[i], d.nb(i), d.Cd);
+  }
+  tb.n = n;
+  weight_eff_kernel<<<rows, 128, 0, st>>>(tb);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+
+  PackParams pp;
+  pp.d = d;
+  pp.wV = reinterpret_cast<const float*>(base + L.wV);
+  pp.is_fp16 = d.prec == CMWG_PREC_FP16;
+  for (int i = 0; i < d.depth; ++i) {
+    pp.wW[i] = reinterpret_cast<const float*>(base + L.wW[i]);
+    pp.wWo[i] = reinterpret_cast<const float*>(base + L.wWo[i]);
+    pp.PA[i] = base + L.PA[i]; pp.PB[i] = base + L.PB[i]; pp.Q1[i] = base + L.Q1[i];
+    pp.Q2[i] = base + L.Q2[i]; pp.QV[i] = base + L.QV[i];
+  }
+  long long biggest = (long long)d.npadA * d.KA;
+  long long q2 = (long long)d.Cr * d.R * d.Cd2p;
+  if (q2 > biggest) biggest = q2;
+  int gx = (int)std::min<long long>(ceil_div_ll(biggest, 256 * 4), 1024);
+  dim3 grid(gx, d.depth, 5);
+  if (d.tc) pack_operands_kernel<uint16_t><<<grid, 256, 0, st>>>(pp);
+  else pack_operands_kernel<float><<<grid, 256, 0, st>>>(pp);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+
+  if (d.bias) {
+    BiasPackParams bp;
+    bp.d = d;
+    CMWG_REQUIRE(prm->V.bias && prm->start.bias && prm->end.bias, "cmwg_wn_pack: has_bias set but bias pointers missing");
+    bp.bV = prm->V.bias; bp.bStart = prm->start.bias; bp.bEnd = prm->end.bias;
+    bp.biasStart = reinterpret_cast<float*>(base + L.biasStart);
+    bp.biasEnd = reinterpret_cast<float*>(base + L.biasEnd);
+    for (int i = 0; i < d.depth; ++i) {
+      CMWG_REQUIRE(prm->W[i].bias && prm->W_o[i].bias, "cmwg_wn_pack: layer %d bias missing", i);
+      bp.bW[i] = prm->W[i].bias; bp.bWo[i] = prm->W_o[i].bias;
+      bp.biasA[i] = reinterpret_cast<float*>(base + L.biasA[i]);
+      bp.biasB[i] = reinterpret_cast<float*>(base + L.biasB[i]);
+    }
+    pack_bias_kernel<<<dim3(4, d.depth), 256, 0, st>>>(bp);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+  }
+  return CMWG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <typename OpT>
+static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, long long x_bs, const void* ycl, int B,
+                           int T, void* workspace, void* saved, float* lst, cudaStream_t st) {
+  using E = EngineSel<OpT>;
+  constexpr bool TC = E::kTc;
+  const int f16 = d.prec == CMWG_PREC_FP16;
+  PackedLayout PL = make_packed_layout(d);
+  FwdLayout FL;
+  make_fwd_layout(d, B, T, &FL);
+  const uint8_t* pk = cu8(packed);
+  uint8_t* ws = u8(workspace);
+  uint8_t* sv = u8(saved);
+  const bool save = saved != nullptr;
+  CMWG_REQUIRE(!(save && f16), "fp16 operands are forward/inverse only; training needs bf16 or fp32");
+
+  float* h32 = reinterpret_cast<float*>(ws + FL.h32);
+  float* skip32 = save ? reinterpret_cast<float*>(sv + FL.s_skip) : reinterpret_cast<float*>(ws + FL.skip32);
+  auto hin_op = [&](int i) -> OpT* {
+    if (save) return reinterpret_cast<OpT*>(sv + FL.s_hin[i]);
+    return reinterpret_cast<OpT*>(ws + FL.hop);  // ff: aliases h32
+  };
+  auto g_op = [&](int i) -> OpT* {
+    return save ? reinterpret_cast<OpT*>(sv + FL.s_g[i]) : reinterpret_cast<OpT*>(ws + FL.gop);
+  };
+  const int bpb = ceil_div(T, ROWS_PER_BLOCK);
+
+  // ---- start conv
+  {
+    // tc: fp32 stream in h32 + operand copy; ff inference: h32 only (operand aliases it);
+    // ff training: operand (fp32) copy per layer only
+    float* o32 = (TC || !save) ? h32 : nullptr;
+    OpT* oop = (TC || save) ? hin_op(0) : nullptr;
+    size_t smem = ((size_t)d.cin * ROWS_PER_BLOCK + (size_t)d.Cr * d.cin) * sizeof(float);
+    start_fwd_kernel<OpT><<<B * bpb, 256, smem, st>>>(
+        x, x_bs, reinterpret_cast<const float*>(pk + PL.wStart),
+        d.bias ? reinterpret_cast<const float*>(pk + PL.biasStart) : nullptr, d.cin, d.Cr, T, bpb, o32, oop, f16);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+  }
+
+  for (int i = 0; i < d.depth; ++i) {
+    const int dil = 1 << i;
+    // ---- gate GEMM
+    {
+      GemmDesc g;
+      memset(&g, 0, sizeof(g));
+      for (int s = 0; s < d.R; ++s) {
+        g.seg[s].a = hin_op(i); g.seg[s].lda = d.Cr; g.seg[s].K = d.Cr;
+        g.seg[s].shift = (s - (d.R - 1) / 2) * dil; g.seg[s].koff = s * d.Crp;
+      }
+      g.seg[d.R].a = ycl; g.seg[d.R].lda = d.auxp; g.seg[d.R].K = d.auxp; g.seg[d.R].shift = 0;
+      g.seg[d.R].koff = d.R * d.Crp;
+      g.nseg = d.R + 1;
+      g.w = pk + PL.PA[i]; g.ldw = d.KA; g.N = d.npadA; g.n_rows_w = d.npadA;
+      g.B = B; g.T = T; g.bn = d.bn_gate; g.is_fp16 = f16; g.tag = CMWG_KCLASS_GATE;
+      GateEpi<OpT, TC> epi;
+      epi.g = g_op(i);
+      epi.a_save = save ? reinterpret_cast<OpT*>(sv + FL.s_a[i]) : nullptr;
+      epi.b_save = save ? reinterpret_cast<OpT*>(sv + FL.s_b[i]) : nullptr;
+      epi.bias = d.bias ? reinterpret_cast<const float*>(pk + PL.biasA[i]) : nullptr;
+      epi.Cd = d.Cd; epi.f16 = f16;
+      CMWG_PROPAGATE((E::template gemm<true>(g, epi, st)));
+    }
+    // ---- residual / skip GEMM
+    {
+      GemmDesc g;
+      memset(&g, 0, sizeof(g));
+      g.seg[0].a = g_op(i); g.seg[0].lda = d.Cd; g.seg[0].K = d.Cd; g.seg[0].shift = 0; g.seg[0].koff = 0;
+      g.nseg = 1;
+      g.w = pk + PL.PB[i]; g.ldw = d.Cdp; g.N = d.nb(i); g.n_rows_w = d.nb(i);
+      g.B = B; g.T = T; g.bn = pick_bn(d.nb(i)); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
+      ResSkipEpi<OpT> epi;
+      const bool last = (i == d.depth - 1);
+      if (TC || !save) {
+        epi.res_src = h32; epi.res_src_op = nullptr; epi.res_dst32 = h32;
+        epi.res_dst_op = (TC && !last) ? hin_op(i + 1) : nullptr;
+      } else {
+        epi.res_src = nullptr; epi.res_src_op = hin_op(i); epi.res_dst32 = nullptr;
+        epi.res_dst_op = last ? nullptr : hin_op(i + 1);
+      }
+      epi.skip = skip32;
+      epi.bias = d.bias ? reinterpret_cast<const float*>(pk + PL.biasB[i]) : nullptr;
+      epi.Cr = d.Cr; epi.Cs = d.Cs; epi.cr_eff = d.cr_eff(i); epi.first_layer = (i == 0); epi.f16 = f16;
+      CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+    }
+  }
+  // ---- end conv
+  {
+    size_t smem = (size_t)ROWS_PER_BLOCK * (d.Cs + 1) * sizeof(float);
+    if (smem > 48 * 1024)
+      CMWG_CHECK_CUDA(cudaFuncSetAttribute(end_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    end_fwd_kernel<<<B * bpb, 256, smem, st>>>(skip32, reinterpret_cast<const float*>(pk + PL.wEnd),
+                                               d.bias ? reinterpret_cast<const float*>(pk + PL.biasEnd) : nullptr,
+                                               2 * d.cin, d.Cs, T, bpb, lst);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+  }
+  return CMWG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+static int reduce_and_wn_bwd(const float* partial, int nblocks, int O, int Lr, float* dweff, const cmwg_conv_param& prm,
+                             const float* inv_norm, const cmwg_conv_grad& gr, cudaStream_t st) {
+  if (!gr.g && !gr.v) return CMWG_OK;
+  int P = O * Lr;
+  reduce_blocks_kernel<<<ceil_div(P, 128), 128, 0, st>>>(partial, nblocks, P, dweff);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+  weight_norm_bwd_kernel<<<O, 128, 0, st>>>(dweff, prm.v, prm.g, inv_norm, Lr, gr.g, gr.v);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+  return CMWG_OK;
+}
+
+template <typename OpT>
+static int colsum_to(const OpT* a, int ld, int C, long long rows, float* partial, float* out, int f16,
+                     cudaStream_t st) {
+  int nblocks = (int)ceil_div_ll(rows, ROWS_PER_BLOCK);
+  colsum_partial_kernel<OpT><<<nblocks, 256, 0, st>>>(a, ld, C, rows, partial, f16);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+  reduce_blocks_kernel<<<ceil_div(C, 128), 128, 0, st>>>(partial, nblocks, C, out);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+  return CMWG_OK;
+}
+
+template <typename OpT>
+static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const void* packed, const float* x,
+                            long long x_bs, const void* ycl, int B, int T, void* workspace, const void* saved,
+                            const float* dlst, float* dx, long long dx_bs, float* dycl, const cmwg_wn_grads* gr,
+                            cudaStream_t st) {
+  using E = EngineSel<OpT>;
+  constexpr bool TC = E::kTc;
+  const int f16 = 0;  // training never uses fp16 operands
+  CMWG_REQUIRE(d.prec != CMWG_PREC_FP16, "fp16 operands are forward/inverse only; training needs bf16 or fp32");
+  PackedLayout PL = make_packed_layout(d);
+  FwdLayout FL;
+  make_fwd_layout(d, B, T, &FL);
+  BwdLayout BL;
+  make_bwd_layout(d, B, T, &BL);
+  const uint8_t* pk = cu8(packed);
+  const uint8_t* sv = cu8(saved);
+  uint8_t* ws = u8(workspace);
+  const long long rows = (long long)B * T;
+  const int bpb = ceil_div(T, ROWS_PER_BLOCK);
+  const int nblk = B * bpb;
+  const int cout = 2 * d.cin;
+
+  OpT* dskip_op = reinterpret_cast<OpT*>(ws + BL.dskip_op);
+  float* dh32 = reinterpret_cast<float*>(ws + BL.dh32);
+  OpT* dh_op = reinterpret_cast<OpT*>(ws + BL.dh_op);  // ff: aliases dh32
+  OpT* dpre_op = reinterpret_cast<OpT*>(ws + BL.dpre_op);
+  float* partial = reinterpret_cast<float*>(ws + BL.partial);
+  float* dweff = reinterpret_cast<float*>(ws + BL.dweff);
+  const float* skip32 = reinterpret_cast<const float*>(sv + FL.s_skip);
+  const float* wEnd = reinterpret_cast<const float*>(pk + PL.wEnd);
+  const float* wStart = reinterpret_cast<const float*>(pk + PL.wStart);
+
+  // ---- end conv backward: dskip, d end.weight, d end.bias
+  {
+    size_t smem = (size_t)cout * ROWS_PER_BLOCK * sizeof(float);
+    end_bwd_dskip_kernel<OpT><<<nblk, 256, smem, st>>>(dlst, wEnd, cout, d.Cs, T, bpb, dskip_op, f16);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+    if (gr->end.v || gr->end.bias) {
+      size_t smem2 = ((size_t)cout * ROWS_PER_BLOCK + (size_t)ROWS_PER_BLOCK * d.Cs) * sizeof(float);
+      float* pw = partial;
+      float* pb = partial + (size_t)nblk * cout * d.Cs;
+      end_bwd_dw_kernel<<<nblk, 256, smem2, st>>>(dlst, skip32, cout, d.Cs, T, bpb, pw, gr->end.bias ? pb : nullptr);
+      CMWG_COUNT_LAUNCH();
+      CMWG_LAUNCH_CHECK();
+      cmwg_conv_grad ge = gr->end;
+      ge.g = nullptr;
+      CMWG_PROPAGATE(reduce_and_wn_bwd(pw, nblk, cout, d.Cs, dweff, prm->end, nullptr, ge, st));
+      if (gr->end.bias) {
+        reduce_blocks_kernel<<<ceil_div(cout, 128), 128, 0, st>>>(pb, nblk, cout, gr->end.bias);
+        CMWG_COUNT_LAUNCH();
+        CMWG_LAUNCH_CHECK();
+      }
+    }
+  }
+
+  const int Lc = wgrad_chunk_len(B, T);
+  const int splits = B * ceil_div(T, Lc);
+
+  for (int i = d.depth - 1; i >= 0; --i) {
+    const int dil = 1 << i;
+    const bool last = (i == d.depth - 1);
+    const OpT* hin = reinterpret_cast<const OpT*>(sv + FL.s_hin[i]);
+    const OpT* gsv = reinterpret_cast<const OpT*>(sv + FL.s_g[i]);
+    // ---- dgate GEMM + gate backward epilogue -> dpre
+    {
+      GemmDesc g;
+      memset(&g, 0, sizeof(g));
+      int ns = 0;
+      if (!last) {
+        g.seg[ns].a = dh_op; g.seg[ns].lda = d.Cr; g.seg[ns].K = d.Cr; g.seg[ns].shift = 0; g.seg[ns].koff = 0;
+        ++ns;
+      }
+      g.seg[ns].a = dskip_op; g.seg[ns].lda = d.Cs; g.seg[ns].K = d.Cs; g.seg[ns].shift = 0;
+      g.seg[ns].koff = last ? 0 : d.Crp;
+      ++ns;
+      g.nseg = ns;
+      g.w = pk + PL.Q1[i]; g.ldw = d.k1(i); g.N = d.Cd; g.n_rows_w = d.Cd;
+      g.B = B; g.T = T; g.bn = pick_bn(d.Cd); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DGATE;
+      GateBwdEpi<OpT> epi;
+      epi.a_save = reinterpret_cast<const OpT*>(sv + FL.s_a[i]);
+      epi.b_save = reinterpret_cast<const OpT*>(sv + FL.s_b[i]);
+      epi.dpre = dpre_op; epi.Cd = d.Cd; epi.ld = 2 * d.Cd; epi.f16 = f16;
+      CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+    }
+    // ---- weight gradients of this layer: W_o (res rows, skip rows), W per tap, V_i
+    {
+      WgradProblem pr[TC_MAX_WG];
+      WgReduceTable rt;
+      int np = 0;
+      float* pcur = partial;
+      auto add = [&](const void* a, int lda, int M, const void* b, int ldb, int N, int shift) {
+        WgradProblem& q = pr[np];
+        q.a = a; q.lda = lda; q.a_c0 = 0; q.M = M; q.b = b; q.ldb = ldb; q.b_c0 = 0; q.N = N; q.shift = shift;
+        q.partial = pcur;
+        pcur += (size_t)splits * M * N;
+        return np++;
+      };
+      // destinations live in dweff, laid out as three consecutive natural-layout matrices
+      float* dWo = dweff;
+      float* dW = dWo + (size_t)d.nb(i) * d.Cd;
+      float* dV = dW + (size_t)2 * d.Cd * d.Cr * d.R;
+      int nr = 0;
+      auto red = [&](int pi, float* out, long long sm, long long sn, long long off, int n_valid) {
+        WgReduceEntry& e = rt.e[nr++];
+        e.partial = pr[pi].partial; e.M = pr[pi].M; e.N = pr[pi].N; e.n_valid = n_valid;
+        e.out = out; e.sm = sm; e.sn = sn; e.off = off;
+      };
+      const bool want_wo = gr->W_o[i].g || gr->W_o[i].v;
+      const bool want_w = gr->W[i].g || gr->W[i].v;
+      const bool want_v = gr->V.g || gr->V.v;
+      if (want_wo) {
+        if (!last) red(add(dh_op, d.Cr, d.Cr, gsv, d.Cd, d.Cd, 0), dWo, d.Cd, 1, 0, d.Cd);
+        red(add(dskip_op, d.Cs, d.Cs, gsv, d.Cd, d.Cd, 0), dWo, d.Cd, 1, (long long)d.cr_eff(i) * d.Cd, d.Cd);
+      }
+      if (want_w)
+        for (int s = 0; s < d.R; ++s)
+          red(add(dpre_op, 2 * d.Cd, 2 * d.Cd, hin, d.Cr, d.Cr, (s - (d.R - 1) / 2) * dil), dW,
+              (long long)d.Cr * d.R, d.R, s, d.Cr);
+      if (want_v) red(add(dpre_op, 2 * d.Cd, 2 * d.Cd, ycl, d.auxp, d.auxp, 0), dV, d.aux, 1, 0, d.aux);
+      CMWG_REQUIRE((size_t)((uint8_t*)pcur - (uint8_t*)partial) <= BL.partial_bytes, "wgrad partial buffer overflow");
+      if (np) {
+        if (TC) {
+          CMWG_PROPAGATE(tc_wgrad_launch(pr, np, B, T, Lc, f16, st));
+        } else {
+          for (int k = 0; k < np; ++k) CMWG_PROPAGATE(ff_wgrad_launch(pr[k], B, T, Lc, st));
+        }
+        rt.n = nr; rt.splits = splits;
+        wgrad_reduce_kernel<<<dim3(64, nr), 256, 0, st>>>(rt);
+        CMWG_COUNT_LAUNCH();
+        CMWG_LAUNCH_CHECK();
+        if (want_wo) {
+          weight_norm_bwd_kernel<<<d.nb(i), 128, 0, st>>>(dWo, prm->W_o[i].v, prm->W_o[i].g,
+                                                         reinterpret_cast<const float*>(pk + PL.nWo[i]), d.Cd,
+                                                         gr->W_o[i].g, gr->W_o[i].v);
+          CMWG_COUNT_LAUNCH();
+          CMWG_LAUNCH_CHECK();
+        }
+        if (want_w) {
+          weight_norm_bwd_kernel<<<2 * d.Cd, 128, 0, st>>>(dW, prm->W[i].v, prm->W[i].g,
+                                                          reinterpret_cast<const float*>(pk + PL.nW[i]), d.Cr * d.R,
+                                                          gr->W[i].g, gr->W[i].v);
+          CMWG_COUNT_LAUNCH();
+          CMWG_LAUNCH_CHECK();
+        }
+        if (want_v) {
+          size_t ro = (size_t)i * 2 * d.Cd;
+          weight_norm_bwd_kernel<<<2 * d.Cd, 128, 0, st>>>(
+              dV, prm->V.v + ro * d.aux, prm->V.g ? prm->V.g + ro : nullptr,
+              reinterpret_cast<const float*>(pk + PL.nV) + ro, d.aux, gr->V.g ? gr->V.g + ro : nullptr,
+              gr->V.v ? gr->V.v + ro * d.aux : nullptr);
+          CMWG_COUNT_LAUNCH();
+          CMWG_LAUNCH_CHECK();
+        }
+      }
+    }
+    // ---- bias gradients (bias=True only)
+    if (d.bias) {
+      // W_i.bias and V.bias[i] both receive the column sums of dpre
+      if (gr->W[i].bias) CMWG_PROPAGATE(colsum_to<OpT>(dpre_op, 2 * d.Cd, 2 * d.Cd, rows, partial, gr->W[i].bias, f16, st));
+      if (gr->V.bias)
+        CMWG_PROPAGATE(colsum_to<OpT>(dpre_op, 2 * d.Cd, 2 * d.Cd, rows, partial, gr->V.bias + (size_t)i * 2 * d.Cd, f16, st));
+      if (gr->W_o[i].bias) {
+        if (!last) CMWG_PROPAGATE(colsum_to<OpT>(dh_op, d.Cr, d.Cr, rows, partial, gr->W_o[i].bias, f16, st));
+        CMWG_PROPAGATE(colsum_to<OpT>(dskip_op, d.Cs, d.Cs, rows, partial, gr->W_o[i].bias + d.cr_eff(i), f16, st));
+      }
+    }
+    // ---- conditioning gradient
+    if (dycl) {
+      GemmDesc g;
+      memset(&g, 0, sizeof(g));
+      g.seg[0].a = dpre_op; g.seg[0].lda = 2 * d.Cd; g.seg[0].K = 2 * d.Cd; g.seg[0].shift = 0; g.seg[0].koff = 0;
+      g.nseg = 1;
+      g.w = pk + PL.QV[i]; g.ldw = d.Cd2p; g.N = d.auxp; g.n_rows_w = d.auxp;
+      g.B = B; g.T = T; g.bn = pick_bn(d.auxp); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DCOND;
+      AccumEpi epi{dycl, d.auxp, d.auxp, last ? 1 : 0};
+      CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+    }
+    // ---- dx GEMM: dh_i = dh_{i+1} + conv^T(dpre)
+    {
+      GemmDesc g;
+      memset(&g, 0, sizeof(g));
+      for (int s = 0; s < d.R; ++s) {
+        g.seg[s].a = dpre_op; g.seg[s].lda = 2 * d.Cd; g.seg[s].K = 2 * d.Cd;
+        g.seg[s].shift = -(s - (d.R - 1) / 2) * dil; g.seg[s].koff = s * d.Cd2p;
+      }
+      g.nseg = d.R;
+      g.w = pk + PL.Q2[i]; g.ldw = d.R * d.Cd2p; g.N = d.Cr; g.n_rows_w = d.Cr;
+      g.B = B; g.T = T; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DX;
+      DxEpi<OpT> epi;
+      epi.src = last ? nullptr : dh32; epi.dst32 = dh32; epi.dst_op = TC ? dh_op : nullptr;
+      epi.Cr = d.Cr; epi.f16 = f16;
+      CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+    }
+  }
+
+  // ---- start conv backward
+  {
+    size_t smem = ((size_t)ROWS_PER_BLOCK * (d.Cr + 1) + (size_t)d.cin * ROWS_PER_BLOCK) * sizeof(float);
+    float* pw = partial;
+    float* pb = partial + (size_t)nblk * d.Cr * d.cin;
+    start_bwd_kernel<<<nblk, 256, smem, st>>>(dh32, x, x_bs, wStart, d.cin, d.Cr, T, bpb, dx, dx_bs, pw,
+                                              (d.bias && gr->start.bias) ? pb : nullptr);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+    CMWG_PROPAGATE(reduce_and_wn_bwd(pw, nblk, d.Cr, d.cin, dweff, prm->start,
+                                     reinterpret_cast<const float*>(pk + PL.nStart), gr->start, st));
+    if (d.bias && gr->start.bias) {
+      reduce_blocks_kernel<<<ceil_div(d.Cr, 128), 128, 0, st>>>(pb, nblk, d.Cr, gr->start.bias);
+      CMWG_COUNT_LAUNCH();
+      CMWG_LAUNCH_CHECK();
+    }
+  }
+  return CMWG_OK;
+}
+
+}  // namespace cmwg
+
+using namespace cmwg;
+
+extern "C" {
+
+int cmwg_wn_tc_supported(const cmwg_wn_config* cfg) { return cfg && wn_tc_shapes_ok(*cfg) ? 1 : 0; }
+
+int cmwg_wn_aux_padded(const cmwg_wn_config* cfg) {
+  WnDims d;
+  if (make_dims(cfg, &d) != CMWG_OK) return -1;
+  return d.auxp;
+}
+
+size_t cmwg_wn_packed_bytes(const cmwg_wn_config* cfg) {
+  WnDims d;
+  if (make_dims(cfg, &d) != CMWG_OK) return 0;
+  return make_packed_layout(d).total;
+}
+
+size_t cmwg_wn_workspace_bytes(const cmwg_wn_config* cfg, int B, int T) {
+  WnDims d;
+  if (make_dims(cfg, &d) != CMWG_OK) return 0;
+  FwdLayout FL;
+  make_fwd_layout(d, B, T, &FL);
+  BwdLayout BL;
+  make_bwd_layout(d, B, T, &BL);
+  return (FL.ws_total > BL.total ? FL.ws_total : BL.total) + 1024;
+}
+
+size_t cmwg_wn_saved_bytes(const cmwg_wn_config* cfg, int B, int T) {
+  WnDims d;
+  if (make_dims(cfg, &d) != CMWG_OK) return 0;
+  FwdLayout FL;
+  make_fwd_layout(d, B, T, &FL);
+  return FL.saved_total + 1024;
+}
+
+int cmwg_wn_pack(const cmwg_wn_config* cfg, const cmwg_wn_params* params, void* packed, void* stream) {
+  WnDims d;
+  CMWG_PROPAGATE(make_dims(cfg, &d));
+  CMWG_REQUIRE(params && packed, "cmwg_wn_pack: null argument");
+  return wn_pack_impl(d, params, packed, (cudaStream_t)stream);
+}
+
+int cmwg_cond_pack(const cmwg_wn_config* cfg, const float* y, long long y_bstride, long long y_cstride,
+                   long long y_tstride, int B, int T, void* ycl, void* stream) {
+  WnDims d;
+  CMWG_PROPAGATE(make_dims(cfg, &d));
+  if (B == 0 || T == 0) return CMWG_OK;
+  dim3 grid(ceil_div(T, 32), ceil_div(d.auxp, 32), B);
+  if (d.tc)
+    cond_pack_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>(y, y_bstride, y_cstride, y_tstride, d.aux, d.auxp,
+                                                                       T, (uint16_t*)ycl, d.prec == CMWG_PREC_FP16);
+  else
+    cond_pack_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(y, y_bstride, y_cstride, y_tstride, d.aux, d.auxp, T,
+                                                                    (float*)ycl, 0);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+  return CMWG_OK;
+}
+
+int cmwg_cond_unpack_grad(const cmwg_wn_config* cfg, const float* dycl, int B, int T, float* dy, void* stream) {
+  WnDims d;
+  CMWG_PROPAGATE(make_dims(cfg, &d));
+  if (B == 0 || T == 0) return CMWG_OK;
+  dim3 grid(ceil_div(T, 32), ceil_div(d.auxp, 32), B);
+  cond_unpack_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dycl, d.aux, d.auxp, T, dy);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+  return CMWG_OK;
+}
+
+int cmwg_wn_forward(const cmwg_wn_config* cfg, const void* packed, const float* x, long long x_bstride,
+                    const void* ycl, int B, int T, void* workspace, void* saved, float* lst, void* stream) {
+  WnDims d;
+  CMWG_PROPAGATE(make_dims(cfg, &d));
+  CMWG_REQUIRE(packed && x && ycl && workspace && lst, "cmwg_wn_forward: null argument");
+  if (B == 0 || T == 0) return CMWG_OK;
+  if (d.tc) return wn_forward_impl<uint16_t>(d, packed, x, x_bstride, ycl, B, T, workspace, saved, lst, (cudaStream_t)stream);
+  return wn_forward_impl<float>(d, packed, x, x_bstride, ycl, B, T, workspace, saved, lst, (cudaStream_t)stream);
+}
+
+int cmwg_wn_backward(const cmwg_wn_config* cfg, const cmwg_wn_params* params, const void* packed, const float* x,
+                     long long x_bstride, const void* ycl, int B, int T, void* workspace, const void* saved,
+                     const float* dlst, float* dx, long long dx_bstride, float* dycl, const cmwg_wn_grads* grads,
+                     void* stream) {
+  WnDims d;
+  CMWG_PROPAGATE(make_dims(cfg, &d));
+  CMWG_REQUIRE(params && packed && x && ycl && workspace && saved && dlst && dx && grads,
+               "cmwg_wn_backward: null argument");
+  if (B == 0 || T == 0) return CMWG_OK;
+  if (d.tc)
+    return wn_backward_impl<uint16_t>(d, params, packed, x, x_bstride, ycl, B, T, workspace, saved, dlst, dx, dx_bstride,
+                                      dycl, grads, (cudaStream_t)stream);
+  return wn_backward_impl<float>(d, params, packed, x, x_bstride, ycl, B, T, workspace, saved, dlst, dx, dx_bstride, dycl,
+                                 grads, (cudaStream_t)stream);
+}
+
+}  // extern "C"

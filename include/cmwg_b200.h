@@ -1,0 +1,236 @@
+/*
+ * cmwg_b200 -- C ABI of the B200-native flow hot path of constant-memory-waveglow.
+ *
+ * The reference (yoyololicon/constant-memory-waveglow) is pure PyTorch and has no FFI of its own;
+ * each entry point below replaces the stock-library kernels that one reference call site
+ * dispatches to.  The reference file:line each one stands in for is cited (paths relative to the
+ * reference repository root).  The Python host side (constant_memory_waveglow_b200/*.py) binds
+ * these with ctypes and mirrors the reference's nn.Module / autograd.Function surface.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - every function returns CMWG_OK (0) or a negative error code and never throws;
+ *     cmwg_last_error() returns a thread-local, NUL-terminated description of the last failure;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *   - "NCL" = (batch, channel, time) with time contiguous, the layout PyTorch's Conv1d uses;
+ *     *_bstride arguments are the batch stride in elements so channel-slices of a larger tensor
+ *     can be passed without a copy;
+ *   - "slab" = the internal channel-last layout [batch][time][channel] used between WN layers.
+ */
+#ifndef CMWG_B200_H
+#define CMWG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMWG_OK 0
+#define CMWG_ERR_ARG (-1)
+#define CMWG_ERR_CUDA (-2)
+#define CMWG_ERR_UNSUPPORTED (-3)
+
+#define CMWG_MAX_DEPTH 16
+
+/* precision of the WN GEMM operands (accumulation, flow state, coupling and log-det are fp32) */
+#define CMWG_PREC_FP32 0 /* exact: CUDA-core FFMA engine                                   */
+#define CMWG_PREC_BF16 1 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM       */
+#define CMWG_PREC_FP16 2 /* tcgen05 kind::f16, fp16 operands (forward/inverse only)         */
+
+const char* cmwg_last_error(void);
+int cmwg_version(void);
+/* cumulative number of kernels this library has launched in this process */
+unsigned long long cmwg_launch_count(void);
+void cmwg_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Invertible 1x1 convolution  (model/efficient_modules.py:17-54, 215-279)
+ * ------------------------------------------------------------------------------------------- */
+
+/* LU of a c x c fp32 matrix on the device (c <= 64): w_inv = W^-1, *logdet = log(det W), NaN when
+ * det W <= 0 exactly like Tensor.logdet().  Replaces weight.squeeze().logdet() / .inverse()
+ * (model/efficient_modules.py:39,52-53,221,235,254-256,272). */
+int cmwg_small_inverse_logdet(const float* w, int c, float* w_inv, float* logdet, void* stream);
+
+/* z[b,:,t] = M x[b,:,t] with M = W (transpose_w = 0) or W^T (transpose_w = 1); W is c x c row
+ * major.  Replaces F.conv1d(x, weight) with kernel size 1
+ * (model/efficient_modules.py:40,53,223,237,239,256,269,273). */
+int cmwg_conv1x1_apply(const float* w, int transpose_w, const float* x, long long x_bstride, float* z,
+                       long long z_bstride, int B, int C, int T, void* stream);
+
+/* dm[o][i] = sum_{b,t} dz[b,o,t] * x[b,i,t]   (model/efficient_modules.py:240-241,274-275).
+ * Deterministic two-pass reduction; `workspace` must hold cmwg_conv1x1_wgrad_workspace(B,C,T) bytes. */
+size_t cmwg_conv1x1_wgrad_workspace(int B, int C, int T);
+int cmwg_conv1x1_wgrad(const float* dz, long long dz_bstride, const float* x, long long x_bstride, int B, int C,
+                       int T, float* dm, void* workspace, void* stream);
+
+/* dW from dm (model/efficient_modules.py:242 and :276-277):
+ *   inverse_mode = 0:  dW = dm + W^-T * (*dlogdet) * T
+ *   inverse_mode = 1:  dW = -W^-T dm W^-T - W^-T * (*dlogdet) * T
+ * w_inv is the c x c inverse; dlogdet points at one device float. */
+int cmwg_conv1x1_dw_finalize(const float* dm, const float* w_inv, const float* dlogdet, int c, int T,
+                             int inverse_mode, float* dw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Affine coupling  (model/efficient_modules.py:57-212)
+ * `lst` is the WN output, NCL (B, 2*cin, T): channels [0,cin) = log_s, [cin,2cin) = t.
+ * ------------------------------------------------------------------------------------------- */
+
+/* inverse = 0 (:105-111): z = cat(xa, xb*exp(log_s)+t)
+ * inverse = 1 (:163-169): z = cat(xa, (xb-t)/exp(log_s)); neg_log_s (B,cin,T contiguous, may be
+ * NULL) receives -log_s. */
+int cmwg_coupling_apply(const float* x, long long x_bstride, const float* lst, float* z, long long z_bstride,
+                        float* neg_log_s, int B, int cin, int T, int inverse, void* stream);
+
+/* The elementwise half of AffineCouplingFunc.backward (:132-148, inverse = 0) and of
+ * InvAffineCouplingFunc.backward (:190-207, inverse = 1).  Given the saved OUTPUT `out` of the
+ * forward call, the recomputed `lst`, and the incoming cotangents (dout for the tensor output,
+ * dls for the returned +-log_s), it
+ *   - re-materialises the forward call's INPUT into `restored` (B, 2cin, T contiguous),
+ *   - writes the cotangent of the WN output into `dlst` (B, 2cin, T contiguous),
+ *   - writes din[:, cin:] (the 'b' half of the input gradient) and copies dout[:, :cin] into
+ *     din[:, :cin] (the WN backward later ACCUMULATES its dxa into that half). */
+int cmwg_coupling_bwd(const float* out, long long out_bstride, const float* lst, const float* dout,
+                      long long dout_bstride, const float* dls, long long dls_bstride, float* restored, float* dlst,
+                      float* din, int B, int cin, int T, int inverse, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * WN transform  (model/waveglow.py:13-105), weight norm (utils.py:9-16)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int in_channels;   /* cin: channels of xa and of each of log_s / t  (WN in_channels)   */
+  int aux_channels;  /* conditioning channels                                              */
+  int dil_channels;  /* Cd (gate channels; W produces 2*Cd)                                */
+  int res_channels;  /* Cr                                                                 */
+  int skip_channels; /* Cs                                                                 */
+  int depth;         /* number of NonCausalLayers, dilation 2^i                            */
+  int radix;         /* kernel size of W (odd)                                             */
+  int has_bias;      /* bias=True in the reference constructor                             */
+  int precision;     /* CMWG_PREC_*                                                        */
+} cmwg_wn_config;
+
+/* One convolution's parameters.  With weight norm attached: g = weight_g (out,1,1), v = weight_v;
+ * after remove_weight_norms (or for `end`, which never has weight norm): g = NULL, v = weight. */
+typedef struct {
+  const float* g;
+  const float* v;
+  const float* bias; /* NULL when has_bias == 0 */
+} cmwg_conv_param;
+
+typedef struct {
+  cmwg_conv_param V;     /* (2*Cd*depth, aux, 1)                   model/waveglow.py:70-72 */
+  cmwg_conv_param start; /* (Cr, cin, 1)                           model/waveglow.py:74-75 */
+  cmwg_conv_param W[CMWG_MAX_DEPTH];   /* (2*Cd, Cr, radix)        model/waveglow.py:29-30 */
+  cmwg_conv_param W_o[CMWG_MAX_DEPTH]; /* (Cr+Cs | Cs, Cd, 1)      model/waveglow.py:33-38 */
+  cmwg_conv_param end;   /* (2*cin, Cs, 1), never weight-normed    model/waveglow.py:92    */
+} cmwg_wn_params;
+
+/* gradient destinations, same shapes as the parameters; any pointer may be NULL (skipped) */
+typedef struct {
+  float* g;
+  float* v;
+  float* bias;
+} cmwg_conv_grad;
+
+typedef struct {
+  cmwg_conv_grad V, start, W[CMWG_MAX_DEPTH], W_o[CMWG_MAX_DEPTH], end;
+} cmwg_wn_grads;
+
+/* Is the tcgen05 engine usable for this configuration (channel counts multiples of 64, ...)?
+ * Returns 1/0.  When 0, precision must be CMWG_PREC_FP32. */
+int cmwg_wn_tc_supported(const cmwg_wn_config* cfg);
+
+/* Padded channel count of the slab-layout conditioning tensor for this config/precision. */
+int cmwg_wn_aux_padded(const cmwg_wn_config* cfg);
+
+/* y (B, aux, T) fp32 with arbitrary element strides -> slab [B][T][aux_padded] in the operand type
+ * of cfg->precision (zero padded).  Done once per conditioning tensor and shared by all flows.
+ * Replaces nothing in the reference (its V conv reads y directly, model/waveglow.py:100); it is the
+ * layout change that lets V be folded into the dilated-conv GEMM as extra K rows. */
+int cmwg_cond_pack(const cmwg_wn_config* cfg, const float* y, long long y_bstride, long long y_cstride,
+                   long long y_tstride, int B, int T, void* ycl, void* stream);
+/* dy (B, aux, T) contiguous fp32 <- slab gradient [B][T][aux_padded] fp32 */
+int cmwg_cond_unpack_grad(const cmwg_wn_config* cfg, const float* dycl, int B, int T, float* dy, void* stream);
+
+/* Effective weights (g*v/||v||, utils.py:14-16 -> torch weight_norm) packed for the GEMM engines. */
+size_t cmwg_wn_packed_bytes(const cmwg_wn_config* cfg);
+int cmwg_wn_pack(const cmwg_wn_config* cfg, const cmwg_wn_params* params, void* packed, void* stream);
+
+size_t cmwg_wn_workspace_bytes(const cmwg_wn_config* cfg, int B, int T);
+/* bytes of per-layer activations kept between cmwg_wn_forward(save != NULL) and cmwg_wn_backward */
+size_t cmwg_wn_saved_bytes(const cmwg_wn_config* cfg, int B, int T);
+
+/* (log_s, t) = WN(xa, y)   (model/waveglow.py:98-105 with NonCausalLayer.forward :41-46 and
+ * fused_gate :13-15).  xa = first cin channels of x (NCL, batch stride x_bstride);
+ * lst (B, 2cin, T) contiguous.  `saved` = NULL for inference, else a buffer of
+ * cmwg_wn_saved_bytes() that cmwg_wn_backward consumes. */
+int cmwg_wn_forward(const cmwg_wn_config* cfg, const void* packed, const float* x, long long x_bstride,
+                    const void* ycl, int B, int T, void* workspace, void* saved, float* lst, void* stream);
+
+/* Gradient of WN given dlst (B, 2cin, T): the autograd.grad call of
+ * model/efficient_modules.py:139-144 / :198-203 for F = WN.
+ *   dxa: ACCUMULATED (+=) into dx (NCL, batch stride dx_bstride, first cin channels);
+ *   dycl: NULL or slab fp32 [B][T][aux_padded], OVERWRITTEN with the conditioning gradient;
+ *   grads: weight gradients in the reference's parameterisation (weight_g / weight_v or weight),
+ *          OVERWRITTEN. */
+int cmwg_wn_backward(const cmwg_wn_config* cfg, const cmwg_wn_params* params, const void* packed,
+                     const float* x, long long x_bstride, const void* ycl, int B, int T, void* workspace,
+                     const void* saved, const float* dlst, float* dx, long long dx_bstride, float* dycl,
+                     const cmwg_wn_grads* grads, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Conditioning upsampler (model/waveglow.py:126-130, 210-212): depthwise ConvTranspose1d with
+ * weight norm and bias.  h (B, C, F) -> y (B, C, (F-1)*stride - 2*pad + K).
+ * ------------------------------------------------------------------------------------------- */
+int cmwg_upsample_fwd(const float* h, const float* g, const float* v, const float* bias, int B, int C, int F,
+                      int K, int stride, int pad, float* y, void* stream);
+/* dy (B, C, Tout) with element strides -> dg (C), dv (C,K), dbias (C); g == NULL => dv is d(weight) */
+size_t cmwg_upsample_bwd_workspace(int B, int C, int K);
+int cmwg_upsample_bwd(const float* h, const float* g, const float* v, const float* dy, long long dy_bstride,
+                      long long dy_cstride, int B, int C, int F, int K, int stride, int pad, int Tvalid, float* dg,
+                      float* dv, float* dbias, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Model glue (model/waveglow.py:153,179; model/loss.py:10-15)
+ * ------------------------------------------------------------------------------------------- */
+/* squeeze: x (B, T) -> out (B, n_group, T/n_group);  unsqueeze is the inverse permutation */
+int cmwg_squeeze(const float* x, float* out, int B, int T, int n_group, int inverse, void* stream);
+
+/* loss = mean_b(0.5*sum_t z^2/sigma^2 - logdet_b) / (mean ? T : 1); also dz = dloss/dz (may be NULL).
+ * Deterministic. workspace >= (B + 1) floats. */
+int cmwg_nll_loss(const float* z, const float* logdet, int B, int T, float sigma, int elementwise_mean,
+                  float* loss, float* dz, void* workspace, void* stream);
+
+/* per-batch sum over (channel, time) of an NCL tensor: the log_s.sum((1,2)) of model/waveglow.py:175 */
+int cmwg_sum_per_batch(const float* a, long long a_bstride, int B, int N, float* out, int accumulate, float scale,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-kernel-class device timing (CUDA events recorded on the launching stream around each GEMM
+ * launch).  Off by default; bench.py turns it on for its roofline leg.
+ * ------------------------------------------------------------------------------------------- */
+#define CMWG_KCLASS_GATE 0    /* dilated conv + conditioning GEMM with fused gate epilogue */
+#define CMWG_KCLASS_RESSKIP 1 /* W_o GEMM with residual/skip epilogue                      */
+#define CMWG_KCLASS_DGATE 2   /* W_o^T GEMM with gate-backward epilogue                    */
+#define CMWG_KCLASS_DX 3      /* transposed dilated conv GEMM                              */
+#define CMWG_KCLASS_DCOND 4   /* conditioning gradient GEMM                                */
+#define CMWG_KCLASS_WGRAD 5   /* weight-gradient GEMMs                                     */
+#define CMWG_KCLASS_COUNT 8
+/* on != 0: start recording (drops earlier records); on == 0: stop */
+int cmwg_profile_enable(int on);
+/* waits for the recorded events; fills ms[CMWG_KCLASS_COUNT], launches[CMWG_KCLASS_COUNT]; clears records */
+int cmwg_profile_collect(double* ms, long long* launches);
+
+/* ---------------------------------------------------------------------------------------------
+ * Self-test hooks used by tests/: a plain GEMM through each engine.
+ *   D[m][n] = sum_k A[m][k] * Bm[n][k]      (A: M x K, Bm: N x K, both row major, 16-bit operands)
+ * ------------------------------------------------------------------------------------------- */
+int cmwg_selftest_tc_gemm(const void* a, const void* b, float* d, int M, int N, int K, int is_fp16, int variant,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMWG_B200_H */

@@ -1,0 +1,119 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares, the host
+modules keep the reference's structure (state-dict keys, parameter order, channel schedule) and the
+product path fails loudly without a GPU."""
+import os
+import re
+
+import pytest
+import torch
+
+import constant_memory_waveglow_b200 as cm
+from constant_memory_waveglow_b200 import _lib, precision
+from tests._util import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "cmwg_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cmwg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), s
+        assert s in _lib.SIGNATURES, f"{s} declared in the header but not bound in _lib.SIGNATURES"
+    for s in _lib.SIGNATURES:
+        assert s in syms, f"{s} bound in _lib but not declared in include/cmwg_b200.h"
+    assert lib.cmwg_version() >= 100
+    assert lib.cmwg_launch_count() >= 0
+
+
+def test_size_queries_need_no_gpu():
+    import ctypes as C
+    lib = _lib.load()
+    cfg = _lib.WnConfig(4, 80, 256, 256, 256, 8, 3, 0, _lib.PREC_BF16)
+    assert lib.cmwg_wn_tc_supported(C.byref(cfg)) == 1
+    assert lib.cmwg_wn_aux_padded(C.byref(cfg)) == 128
+    assert lib.cmwg_wn_packed_bytes(C.byref(cfg)) > 0
+    assert lib.cmwg_wn_saved_bytes(C.byref(cfg), 2, 2000) > lib.cmwg_wn_saved_bytes(C.byref(cfg), 1, 2000)
+    small = _lib.WnConfig(8, 20, 32, 32, 32, 2, 3, 0, _lib.PREC_FP32)
+    assert lib.cmwg_wn_tc_supported(C.byref(small)) == 0
+    assert lib.cmwg_wn_aux_padded(C.byref(small)) == 32
+    bad = _lib.WnConfig(8, 20, 32, 32, 32, 2, 3, 0, _lib.PREC_BF16)  # tensor cores need multiples of 64
+    assert lib.cmwg_wn_packed_bytes(C.byref(bad)) == 0
+    assert b"multiples of 64" in lib.cmwg_last_error()
+
+
+def test_state_dict_layout_matches_reference_fixture():
+    fx = load_golden("waveglow_tiny.pt")
+    m = cm.WaveGlow(memory_efficient=True, **fx["arch"], **fx["wn_kwargs"])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(fx["state"].keys())
+    for k in sd:
+        assert sd[k].shape == fx["state"][k].shape, k
+    m.load_state_dict(fx["state"])
+    assert m.z_split_sizes == [2, 6]
+    fc = load_golden("coupling_a.pt")
+    blk = cm.AffineCouplingBlock(cm.WN, True, **fc["kwargs"])
+    assert [n for n, _ in blk.F.named_parameters()] == fc["param_order"]
+    blk.load_state_dict(fc["state"])
+    # remove_weight_norms collapses g/v pairs to .weight (inference.py:17)
+    blk.apply(cm.remove_weight_norms)
+    names = [n for n, _ in blk.F.named_parameters()]
+    assert "V.weight" in names and not any(n.endswith("weight_g") for n in names)
+
+
+def test_lj_channel_schedule():
+    m = cm.WaveGlow(12, 8, 4, 2, 256, 80, True, dilation_channels=64, residual_channels=64, skip_channels=64, depth=1)
+    assert [c.in_channels for c in m.invconv1x1] == [8] * 4 + [6] * 4 + [4] * 4
+    assert m.z_split_sizes == [2, 2, 4]
+    assert m.upsampler.weight_v.shape == (80, 1, 65) and m.upsampler.bias.shape == (80,)
+    w = m.invconv1x1[0].weight.squeeze(-1)
+    assert torch.det(w) > 0
+    assert torch.allclose(w @ w.t(), torch.eye(8), atol=1e-5)
+
+
+def test_product_path_fails_loudly_on_cpu():
+    conv = cm.InvertibleConv1x1(4, True)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        conv(torch.randn(1, 4, 16))
+    blk = cm.AffineCouplingBlock(cm.WN, True, in_channels=2, aux_channels=4, dilation_channels=8,
+                                 residual_channels=8, skip_channels=8, depth=1)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        blk(torch.randn(1, 4, 16), torch.randn(1, 4, 16))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        cm.WaveGlowLoss()(torch.randn(2, 8), torch.zeros(2))
+
+
+def test_precision_resolution():
+    old = precision.get_precision()
+    flag = torch.backends.cudnn.allow_tf32
+    try:
+        precision.set_precision("auto")
+        torch.backends.cudnn.allow_tf32 = False
+        assert precision.resolve(True, False) == "fp32"
+        torch.backends.cudnn.allow_tf32 = True
+        assert precision.resolve(True, True) == "bf16"
+        assert precision.resolve(False, True) == "fp32"
+        precision.set_precision("fp16")
+        assert precision.resolve(True, False) == "fp16"
+        assert precision.resolve(True, True) == "bf16"
+        with pytest.raises(ValueError):
+            precision.set_precision("int8")
+    finally:
+        precision.set_precision(old)
+        torch.backends.cudnn.allow_tf32 = flag
+
+
+def test_no_product_import_of_oracle():
+    pkg = os.path.join(ROOT, "constant_memory_waveglow_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
