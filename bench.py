@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the flow hot path (BASELINE.json metric: WaveGlow train segments/s at 1/2/4/8 B200,
+synthesis kHz/GPU, % of roofline, next to the reference CPU path).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the CPU oracle port of the reference
+
+A "step" = one constant-memory training step (forward + NLL loss + reversible backward + gradient
+all-reduce + Adam) of the WaveGlow LJ configuration (256 channels, 12 flows, 8 WN layers, 80 mel) on a
+batch of 24 synthetic 16000-sample segments PER GPU (weak scaling).  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+LJ = dict(flows=12, n_group=8, n_early_every=4, n_early_size=2, hop_size=256, n_mels=80)
+LJ_WN = dict(dilation_channels=256, residual_channels=256, skip_channels=256, depth=8, radix=3, bias=False)
+SEGMENT = 16000
+FRAMES = 63                      # MelSpec frames of a 16000-sample segment
+PER_GPU_BATCH = 24
+SIGMA = 0.7
+FWD_GFLOP_PER_SEGMENT = 214.023  # algorithmic, counted on the reference
+TRAIN_GFLOP_PER_SEGMENT = 4 * FWD_GFLOP_PER_SEGMENT
+SYNTH_FRAMES = 862               # 10 s at 22.05 kHz -> 220672 samples (model/base.py:47-48)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tflops_burst=d["bf16_tflops"], tflops_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_oracle_train(batch: int, steps: int, warmup: int):
+    from oracle import flow_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = O.WaveGlowSpec(**LJ)
+    sd = O.random_state(spec, 256, 8, seed=0)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(batch, SEGMENT, generator=g) * 2 - 1
+    h = torch.randn(batch, LJ["n_mels"], FRAMES, generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.waveglow_train_step(sd, spec, x, h, SIGMA)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return batch / (sum(times) / len(times)), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 1
+    value, times = cpu_oracle_train(batch, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "waveglow_lj_train_segments_per_s", "value": value, "unit": "segments/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "waveglow_lj_train_fwd+reversible_bwd", "per_gpu_batch": PER_GPU_BATCH,
+                   "segment": SEGMENT, "n_mels": 80, "channels": 256, "flows": 12, "wn_layers": 8},
+        "cpu_baseline": {"value": value, "unit": "segments/s", "cores": cores, "kind": "port",
+                         "sample": f"oracle port of the reference (torch CPU fp32, autograd over the naive flow), "
+                                   f"batch {batch} x {SEGMENT} samples per step, forward + loss + backward, no optimizer"},
+        "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    import constant_memory_waveglow_b200 as cm
+    from constant_memory_waveglow_b200 import _lib, precision
+    from constant_memory_waveglow_b200.parallel import FlowGradSync, flow_buckets
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    precision.set_precision(args.precision)
+    lib = _lib.load()
+
+    torch.manual_seed(0)
+    model = cm.WaveGlow(memory_efficient=True, zero_init=False, **LJ, **LJ_WN).to(dev).train()
+    loss_fn = cm.WaveGlowLoss(SIGMA)
+    sync = FlowGradSync(flow_buckets(model))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+
+    B = args.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = (torch.rand(B, SEGMENT, generator=g) * 2 - 1).pin_memory()
+    h_host = torch.randn(B, LJ["n_mels"], FRAMES, generator=g).pin_memory()
+    x_dev, h_dev = x_host.to(dev), h_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(x, h):
+        sync.zero_grad()
+        z, logdet = model(x, h)
+        loss = loss_fn(z, logdet)
+        loss.backward()
+        sync.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, e2e):
+        total_ms = 0.0
+        last = None
+        for _ in range(nsteps):
+            flush.zero_()                                  # evict L2 between timed iterations
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record()
+            if e2e:
+                x = x_host.to(dev, non_blocking=True)
+                h = h_host.to(dev, non_blocking=True)
+                last = step(x, h).item()                   # D2H read of the step's result
+            else:
+                last = step(x_dev, h_dev)
+            b.record()
+            barrier()
+            total_ms += a.elapsed_time(b)
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), last
+
+    for _ in range(args.warmup):
+        step(x_dev, h_dev)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.cmwg_reset_launch_count()
+    ms, loss = timed(args.steps, e2e=False)
+    launches = int(lib.cmwg_launch_count())
+    ms_e2e, loss_e2e = timed(args.steps, e2e=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline leg: device time of every GEMM class over one more step (events on the launching stream)
+    import ctypes as C
+    lib.cmwg_profile_enable(1)
+    step(x_dev, h_dev)
+    torch.cuda.synchronize()
+    kms = (C.c_double * 8)()
+    kn = (C.c_longlong * 8)()
+    _lib.check(lib.cmwg_profile_collect(kms, kn), "profile_collect")
+    lib.cmwg_profile_enable(0)
+    names = ["gate", "resskip", "dgate", "dx", "dcond", "wgrad"]
+    kern = {n: {"ms": kms[i], "launches": int(kn[i])} for i, n in enumerate(names)}
+
+    # ---- synthesis (config 3): sigma 0.6, 10 s utterances, utterance-sharded, no collective
+    synth = None
+    if not args.no_synth:
+        model.eval()
+        sb = args.synth_batch
+        hs = torch.randn(sb, LJ["n_mels"], SYNTH_FRAMES, device=dev)
+        zs = torch.randn(sb, SYNTH_FRAMES * LJ["hop_size"], device=dev) * 0.6
+        with torch.no_grad():
+            for _ in range(2):
+                model.infer(hs, 0.6, z=zs)
+            reps = 3
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record()
+            for _ in range(reps):
+                audio = model.infer(hs, 0.6, z=zs)
+            b.record()
+            barrier()
+        t = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        samples = sb * SYNTH_FRAMES * LJ["hop_size"]
+        khz = world * samples / (t.item() * 1e-3) / 1e3
+        pk = peaks()
+        synth = {"value": khz, "unit": "kHz (all GPUs)", "per_gpu_khz": khz / world, "batch_per_gpu": sb,
+                 "utterance_samples": SYNTH_FRAMES * LJ["hop_size"], "sigma": 0.6, "ms": t.item(),
+                 "tflops_per_gpu": samples * 13.3764e6 / (t.item() * 1e-3) / 1e12,
+                 "frac_of_bf16_peak": samples * 13.3764e6 / (t.item() * 1e-3) / 1e12 / pk["tflops_sustained"]}
+        model.train()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    segs = world * B * args.steps
+    value = segs / (ms * 1e-3)
+    value_e2e = segs / (ms_e2e * 1e-3)
+    rows = B * (SEGMENT // LJ["n_group"])
+    gate_flops = 2.0 * rows * 512 * (3 * 256 + 80)          # algorithmic: 80 mel rows, not the padded 128
+    gate = kern["gate"]
+    gate_ms = gate["ms"] / max(gate["launches"], 1)
+    achieved = gate_flops / (gate_ms * 1e-3) / 1e12 if gate_ms > 0 else 0.0
+    total_kernel_ms = sum(v["ms"] for v in kern.values())
+    line = {
+        "metric": "waveglow_lj_train_segments_per_s", "value": value, "unit": "segments/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"bf16": "bf16", "fp32": "f32", "fp16": "bf16", "auto": "bf16"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": "waveglow_lj_train_fwd+reversible_bwd+adam", "per_gpu_batch": B, "segment": SEGMENT,
+                   "n_mels": 80, "channels": 256, "flows": 12, "wn_layers": 8, "precision": args.precision,
+                   "l2": "256 MiB flush between timed steps; per-step working set >> 126 MB L2",
+                   "parallelism": f"dp{world}", "loss": float(loss)},
+        "e2e": {"value": value_e2e, "unit": "segments/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + h_host.numel() * 4),
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "train_tflops_per_gpu": B * TRAIN_GFLOP_PER_SEGMENT / (ms / args.steps),
+        "roofline": {"bound": "tensor", "kernel": "tc_gemm_kernel<gate epilogue> (dilated conv + conditioning GEMM)",
+                     "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"],
+                     "flops_per_launch": gate_flops, "ms_per_launch": gate_ms, "launches_per_step": gate["launches"],
+                     "share_of_gemm_time": gate["ms"] / total_kernel_ms if total_kernel_ms else None,
+                     "kernel_classes_ms_per_step": {k: round(v["ms"], 3) for k, v in kern.items()}},
+        "clocks": clocks,
+        "synth": synth,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, times = cpu_oracle_train(1, 1, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "segments/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "oracle port (torch CPU fp32), LJ config, batch 1 x 16000 samples, "
+                                          "1 warm-up + 1 timed forward+loss+backward"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp16", "auto"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--synth-batch", type=int, default=4)
+    ap.add_argument("--no-synth", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -111,5 +111,9 @@ template <bool FAST> __device__ __forceinline__ float sigmoid_f(float x) {
   if (FAST) return fmaf(0.5f, tanh_f<true>(0.5f * x), 0.5f);
   return 1.f / (1.f + expf(-x));
 }
+// MUFU.EX2 + MUFU.RCP forms: ~1e-7 absolute error (tanh.approx is ~5e-4), used with fp16 operands
+// whose 11-bit mantissa would otherwise be wasted on the gate approximation
+__device__ __forceinline__ float tanh_ex2(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+__device__ __forceinline__ float sigmoid_ex2(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 }  // namespace cmwg

@@ -89,8 +89,13 @@ struct GateEpi {
     for (int j = 0; j < NC; ++j) {
       float pt = lo[j], ps = hi[j];
       if (bias) { pt += bias[ch0 + j]; ps += bias[Cd + ch0 + j]; }
-      av[j] = tanh_f<FAST>(pt);
-      bv[j] = sigmoid_f<FAST>(ps);
+      if (FAST && f16) {
+        av[j] = tanh_ex2(pt);
+        bv[j] = sigmoid_ex2(ps);
+      } else {
+        av[j] = tanh_f<FAST>(pt);
+        bv[j] = sigmoid_f<FAST>(ps);
+      }
       gv[j] = av[j] * bv[j];
     }
     long long o = row * Cd + ch0;

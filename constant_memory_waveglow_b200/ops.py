@@ -49,6 +49,7 @@ def small_inverse_logdet(w2d: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]
 def conv1x1_apply(w2d: torch.Tensor, x: torch.Tensor, transpose: bool = False,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     L.require_cuda(w2d, x, op="conv1x1_apply")
+    w2d = w2d.contiguous()  # row-major c x c (QR factors come out column-major)
     x = _ncl(x)
     B, Cc, T = x.shape
     if out is None:

@@ -1,0 +1,133 @@
+"""Data-parallel gradient exchange for the reversible backward (one process per GPU).
+
+The reference gets data parallelism from Lightning's DDPPlugin (``train.py:51-53,73-78``): every rank
+holds a full replica, the only exchange is one sum of fp32 gradients per step.  Here the exchange is
+organised around the structure of the constant-memory backward: flows finish in the order
+K-1 ... 0, and each coupling / 1x1-conv Function returns ALL gradients of its flow at once, so the
+natural bucket is "one flow" (~17.9 MB fp32 at the LJ config) plus one bucket for the upsampler.
+
+  * every bucket owns one flat fp32 buffer; the parameters' ``.grad`` tensors are VIEWS into it, so
+    autograd accumulates straight into the communication buffer (no gather / scatter copies);
+  * a post-accumulate-grad hook counts arrivals; when a bucket is complete its all-reduce is issued
+    immediately with ``async_op=True`` -- NCCL runs it on its own stream over NVLink/NVSwitch while
+    the compute stream proceeds with the next flow's recompute + gradient GEMMs;
+  * ``finish()`` waits for the outstanding collectives and averages.
+
+Works with any process group backend (``nccl`` on the B200 box, ``gloo`` in the CPU tests).
+Inference shards independent utterances across ranks and needs no collective (``shard_utterances``).
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def flow_buckets(model) -> List[List[torch.nn.Parameter]]:
+    """One bucket per flow (1x1 conv + coupling WN), in BACKWARD completion order, then the rest."""
+    buckets: List[List[torch.nn.Parameter]] = []
+    seen = set()
+    if hasattr(model, "WNs") and hasattr(model, "invconv1x1"):
+        for k in range(len(model.WNs) - 1, -1, -1):
+            ps = [p for p in list(model.WNs[k].parameters()) + list(model.invconv1x1[k].parameters())
+                  if p.requires_grad]
+            for p in ps:
+                seen.add(id(p))
+            if ps:
+                buckets.append(ps)
+    rest = [p for p in model.parameters() if p.requires_grad and id(p) not in seen]
+    if rest:
+        buckets.append(rest)
+    return buckets
+
+
+class FlowGradSync:
+    def __init__(self, buckets: Sequence[Sequence[torch.nn.Parameter]], process_group=None):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.buckets = [list(b) for b in buckets]
+        self.flat: List[torch.Tensor] = []
+        self._pending: List[int] = []
+        self._works = []
+        self._launch_order: List[int] = []
+        self._handles = []
+        for bi, params in enumerate(self.buckets):
+            n = sum(p.numel() for p in params)
+            p0 = params[0]
+            flat = torch.zeros(n, device=p0.device, dtype=p0.dtype)
+            self.flat.append(flat)
+            off = 0
+            for p in params:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+            self._pending.append(len(params))
+
+    def _make_hook(self, bi: int):
+        def hook(param):
+            self._pending[bi] -= 1
+            if self._pending[bi] == 0:
+                self._launch(bi)
+        return hook
+
+    def _launch(self, bi: int) -> None:
+        self._launch_order.append(bi)
+        if self.world > 1:
+            self._works.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def zero_grad(self) -> None:
+        """Zero the flat buffers and (re)attach the gradient views; call before every backward."""
+        self._works.clear()
+        self._launch_order.clear()
+        for bi, params in enumerate(self.buckets):
+            self.flat[bi].zero_()
+            off = 0
+            for p in params:
+                if p.grad is None or p.grad.data_ptr() != self.flat[bi].data_ptr() + off * self.flat[bi].element_size():
+                    p.grad = self.flat[bi][off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self._pending[bi] = len(params)
+
+    def finish(self) -> None:
+        """Wait for the collectives issued during backward and turn sums into means."""
+        for bi, left in enumerate(self._pending):
+            if left != 0 and left != len(self.buckets[bi]):
+                raise RuntimeError(f"FlowGradSync: bucket {bi} received only part of its gradients")
+            if left == len(self.buckets[bi]) and self.world > 1:
+                # bucket untouched this step (unused parameters): still reduce so ranks stay in step
+                self._launch(bi)
+        for w in self._works:
+            w.wait()
+        self._works.clear()
+        if self.world > 1:
+            inv = 1.0 / self.world
+            for f in self.flat:
+                f.mul_(inv)
+
+    @property
+    def launch_order(self) -> List[int]:
+        return list(self._launch_order)
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles.clear()
+
+
+def shard_utterances(n_items: int, rank: Optional[int] = None, world: Optional[int] = None) -> List[int]:
+    """Round-robin utterance -> rank assignment for synthesis (no data-path collective)."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    return list(range(rank, n_items, world))
+
+
+def allreduce_scalars(values: Iterable[float], device) -> List[float]:
+    """Mean of a few python scalars across ranks (the metric sync of model/lightning.py:58-64)."""
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+        t /= dist.get_world_size()
+    return t.tolist()
