@@ -19,6 +19,7 @@ recompute + gradient pipeline is fused (``F._cmwg_forward`` / ``F._cmwg_backward
 """
 from __future__ import annotations
 
+import threading
 from typing import Tuple
 
 import torch
@@ -42,6 +43,28 @@ try:  # torch >= 2.4
         return _cb(fn, device_type='cuda')
 except ImportError:  # pragma: no cover
     from torch.cuda.amp import custom_bwd, custom_fwd
+
+
+# ---------------------------------------------------------------------------------------------
+# Inside Function.forward grad mode is always off and ctx.needs_input_grad only mirrors
+# requires_grad flags, so the module wrappers record whether a graph is being built at all
+# (torch.no_grad() synthesis must neither keep activations nor be forced onto the training precision).
+# ---------------------------------------------------------------------------------------------
+_tls = threading.local()
+
+
+class grad_hint:
+    def __enter__(self):
+        self.prev = getattr(_tls, "grad", None)
+        _tls.grad = torch.is_grad_enabled()
+
+    def __exit__(self, *exc):
+        _tls.grad = self.prev
+
+
+def graph_possible() -> bool:
+    g = getattr(_tls, "grad", None)
+    return True if g is None else g
 
 
 # ---------------------------------------------------------------------------------------------
@@ -167,18 +190,20 @@ class InvertibleConv1x1(Reversible, nn.Conv1d):
             self._efficient_reverse = InvConv1x1Func.apply
 
     def forward_computation(self, x: Tensor) -> Tuple[Tensor, Tensor]:
-        if hasattr(self, '_efficient_forward'):
-            z, log_det_w = self._efficient_forward(x, self.weight)
-            _free_storage(x)
-            return z, log_det_w
-        return _StoredConv1x1Func.apply(x, self.weight, False)
+        with grad_hint():
+            if hasattr(self, '_efficient_forward'):
+                z, log_det_w = self._efficient_forward(x, self.weight)
+                _free_storage(x)
+                return z, log_det_w
+            return _StoredConv1x1Func.apply(x, self.weight, False)
 
     def reverse_computation(self, z: Tensor) -> Tuple[Tensor, Tensor]:
-        if hasattr(self, '_efficient_reverse'):
-            x, log_det_w = self._efficient_reverse(z, self.weight)
-            _free_storage(z)
-            return x, log_det_w
-        return _StoredConv1x1Func.apply(z, self.weight, True)
+        with grad_hint():
+            if hasattr(self, '_efficient_reverse'):
+                x, log_det_w = self._efficient_reverse(z, self.weight)
+                _free_storage(z)
+                return x, log_det_w
+            return _StoredConv1x1Func.apply(z, self.weight, True)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -204,7 +229,7 @@ def _coupling_fwd(ctx, x, y, F, inverse: bool, recompute: bool):
     xd = ops._ncl(x.detach())
     yd = y.detach()
     ctx.F, ctx.inverse, ctx.recompute = F, inverse, recompute
-    need = any(ctx.needs_input_grad)
+    need = any(ctx.needs_input_grad) and graph_possible()
     if _is_fused(F):
         from . import precision
         prec = precision.resolve(F._tc_supported(), training=need)
@@ -344,15 +369,17 @@ class AffineCouplingBlock(Reversible):
             self._efficient_reverse = InvAffineCouplingFunc.apply
 
     def forward_computation(self, x: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
-        if hasattr(self, '_efficient_forward'):
-            z, log_s = self._efficient_forward(x, y, self.F, *self.F.parameters())
-            _free_storage(x)
-            return z, log_s
-        return _StoredCouplingFunc.apply(x, y, self.F, False, *self.F.parameters())
+        with grad_hint():
+            if hasattr(self, '_efficient_forward'):
+                z, log_s = self._efficient_forward(x, y, self.F, *self.F.parameters())
+                _free_storage(x)
+                return z, log_s
+            return _StoredCouplingFunc.apply(x, y, self.F, False, *self.F.parameters())
 
     def reverse_computation(self, z: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
-        if hasattr(self, '_efficient_reverse'):
-            x, log_s = self._efficient_reverse(z, y, self.F, *self.F.parameters())
-            _free_storage(z)
-            return x, log_s
-        return _StoredCouplingFunc.apply(z, y, self.F, True, *self.F.parameters())
+        with grad_hint():
+            if hasattr(self, '_efficient_reverse'):
+                x, log_s = self._efficient_reverse(z, y, self.F, *self.F.parameters())
+                _free_storage(z)
+                return x, log_s
+            return _StoredCouplingFunc.apply(z, y, self.F, True, *self.F.parameters())

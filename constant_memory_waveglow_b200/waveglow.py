@@ -22,7 +22,7 @@ from torch import Tensor
 from . import _lib as L
 from . import ops, precision
 from .base import FlowBase
-from .efficient_modules import AffineCouplingBlock, InvertibleConv1x1
+from .efficient_modules import AffineCouplingBlock, InvertibleConv1x1, grad_hint, graph_possible
 from .utils import add_weight_norms
 
 
@@ -255,7 +255,8 @@ class WN(nn.Module):
         return out, dy
 
     def forward(self, x, y):
-        lst = _WNFunction.apply(x, y, self, *self.parameters())
+        with grad_hint():
+            lst = _WNFunction.apply(x, y, self, *self.parameters())
         return lst.chunk(2, 1)
 
 
@@ -265,7 +266,7 @@ class _WNFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, y, wn, *params):
-        need = any(ctx.needs_input_grad)
+        need = any(ctx.needs_input_grad) and graph_possible()
         xd = ops._ncl(x.detach())
         lst, st = wn._cmwg_forward(xd, y.detach(), save=need)
         ctx.wn, ctx.st = wn, st
