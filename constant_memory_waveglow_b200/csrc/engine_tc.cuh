@@ -5,7 +5,7 @@
 //                      B (packed weight) tiles into a STAGES-deep shared-memory ring, 128B swizzle
 //   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN, K = 16 per
 //                      instruction, fp32 accumulators in TMEM, double buffered (2 x BN columns)
-//   warps 2..5         epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue
+//   warps 2..9         epilogue (two warps per TMEM lane quadrant, half of the columns each): tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue
 //                      functor (gate / residual+skip / gate-backward / ...) -> global
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA) and TMEM full/empty mbarriers
 // (MMA <-> epilogue) so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -27,7 +27,8 @@ namespace cmwg {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                 // 64 x 16-bit = 128 B = one swizzle row
 constexpr int TC_A_BYTES = TC_BM * 128;   // 16 KB
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;            // 2 per TMEM lane quadrant, each owning half of the tile's columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_MAX_WG = 8;              // weight-gradient problems per launch
 
 struct alignas(64) TcGemmParams {
@@ -203,7 +204,7 @@ __device__ __forceinline__ void tc_setup(const TcSmem& s, int warp, int lane) {
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], 4); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], TC_EPI_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -283,7 +284,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access (hardware: warp id % 4)
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       if constexpr (PAIRED) {
         constexpr int G = BN / 2;
 #pragma unroll 1
-        for (int c = 0; c < G; c += 32) {
+        for (int c = half * (G / 2); c < (half + 1) * (G / 2); c += 32) {
           float lo[32], hi[32];
           tmem_ld32(taddr + c, lo);
           tmem_ld32(taddr + G + c, hi);
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         }
       } else {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
           float v[32];
           tmem_ld32(taddr + c, v);
           if (valid && (n0 + c) < p.N) epi.template op<32>(row, n0 + c, v);
@@ -416,6 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
@@ -428,7 +431,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       float* out = p.partial[pr] + ((long long)split * p.M[pr] + m) * p.N[pr];
       uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
         float v[32];
         tmem_ld32(taddr + c, v);
         if (valid && (n0 + c) < p.N[pr]) {

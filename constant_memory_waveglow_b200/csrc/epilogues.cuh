@@ -7,6 +7,18 @@
 
 namespace cmwg {
 
+// two floats -> one packed 16-bit pair with a single cvt.rn.{bf16x2,f16x2}.f32
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, int f16) {
+  if (f16) {
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&b);
+}
+
 template <typename OpT, int NC>
 __device__ __forceinline__ void store_ops(OpT* dst, const float (&v)[NC], int f16) {
   if constexpr (sizeof(OpT) == 4) {
@@ -18,18 +30,18 @@ __device__ __forceinline__ void store_ops(OpT* dst, const float (&v)[NC], int f1
 #pragma unroll
       for (int j = 0; j < NC; j += 8) {
         uint4 u;
-        u.x = (uint32_t)f32_to_op16(v[j + 0], f16) | ((uint32_t)f32_to_op16(v[j + 1], f16) << 16);
-        u.y = (uint32_t)f32_to_op16(v[j + 2], f16) | ((uint32_t)f32_to_op16(v[j + 3], f16) << 16);
-        u.z = (uint32_t)f32_to_op16(v[j + 4], f16) | ((uint32_t)f32_to_op16(v[j + 5], f16) << 16);
-        u.w = (uint32_t)f32_to_op16(v[j + 6], f16) | ((uint32_t)f32_to_op16(v[j + 7], f16) << 16);
+        u.x = pack2(v[j + 0], v[j + 1], f16);
+        u.y = pack2(v[j + 2], v[j + 3], f16);
+        u.z = pack2(v[j + 4], v[j + 5], f16);
+        u.w = pack2(v[j + 6], v[j + 7], f16);
         *reinterpret_cast<uint4*>(dst + j) = u;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < NC; j += 4) {
         uint2 u;
-        u.x = (uint32_t)f32_to_op16(v[j + 0], f16) | ((uint32_t)f32_to_op16(v[j + 1], f16) << 16);
-        u.y = (uint32_t)f32_to_op16(v[j + 2], f16) | ((uint32_t)f32_to_op16(v[j + 3], f16) << 16);
+        u.x = pack2(v[j + 0], v[j + 1], f16);
+        u.y = pack2(v[j + 2], v[j + 3], f16);
         *reinterpret_cast<uint2*>(dst + j) = u;
       }
     }

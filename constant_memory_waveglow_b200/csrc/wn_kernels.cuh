@@ -434,16 +434,35 @@ struct WgReduceTable {
 
 static __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgReduceTable tb) {
   const WgReduceEntry& e = tb.e[blockIdx.y];
-  long long total = (long long)e.M * e.n_valid;
+  const int nv4 = (e.n_valid + 3) >> 2;  // stored N is a multiple of 4, so the float4 loads stay in bounds
+  long long total = (long long)e.M * nv4;
+  const long long stride = (long long)e.M * e.N;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    int m = (int)(idx / e.n_valid), n = (int)(idx % e.n_valid);
+    int m = (int)(idx / nv4), n = (int)(idx % nv4) * 4;
     const float* p = e.partial + (long long)m * e.N + n;
-    long long stride = (long long)e.M * e.N;
-    double s = 0.0;
-    for (int j = 0; j < tb.splits; ++j) s += (double)p[j * stride];
-    e.out[e.off + m * e.sm + n * e.sn] = (float)s;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < tb.splits; ++j) {  // fixed order: deterministic
+      float4 v = *reinterpret_cast<const float4*>(p + j * stride);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* o = e.out + e.off + m * e.sm + n * e.sn;
+    o[0] = s.x;
+    if (n + 1 < e.n_valid) o[e.sn] = s.y;
+    if (n + 2 < e.n_valid) o[2 * e.sn] = s.z;
+    if (n + 3 < e.n_valid) o[3 * e.sn] = s.w;
   }
+}
+
+// two-level fixed-order reduction of block partials: [nblocks][P] -> [ceil(nblocks/64)][P]
+static __global__ void __launch_bounds__(128) reduce_blocks_stage_kernel(const float* __restrict__ partial, int nblocks,
+                                                                         int P, float* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int j0 = blockIdx.y * 64, j1 = min(j0 + 64, nblocks);
+  float s = 0.f;
+  for (int j = j0; j < j1; ++j) s += partial[(long long)j * P + p];
+  out[(long long)blockIdx.y * P + p] = s;
 }
 
 // column sums of a slab (bias gradients): block partials over 32 rows

@@ -194,7 +194,7 @@ inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
   size_t pe = (size_t)2 * d.cin * d.Cs + 2 * d.cin;
   if (pe > per_block) per_block = pe;
   if ((size_t)2 * d.Cd > per_block) per_block = 2 * d.Cd;
-  size_t p2 = blocks32 * per_block * 4;
+  size_t p2 = (blocks32 + blocks32 / 64 + 2) * per_block * 4;  // + second-stage scratch
   L->partial_bytes = p1 > p2 ? p1 : p2;
   L->partial = take(L->partial_bytes);
   // scratch for effective-weight gradients: one layer's dW_o, dW, dV_i side by side

@@ -212,13 +212,27 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-static int reduce_and_wn_bwd(const float* partial, int nblocks, int O, int Lr, float* dweff, const cmwg_conv_param& prm,
-                             const float* inv_norm, const cmwg_conv_grad& gr, cudaStream_t st) {
-  if (!gr.g && !gr.v) return CMWG_OK;
-  int P = O * Lr;
-  reduce_blocks_kernel<<<ceil_div(P, 128), 128, 0, st>>>(partial, nblocks, P, dweff);
+// fixed-order reduction of [nblocks][P] block partials into out[P]; `scratch` holds ceil(nblocks/64)*P floats
+static int reduce_blocks(const float* partial, int nblocks, int P, float* scratch, float* out, cudaStream_t st) {
+  if (nblocks > 128) {
+    int stages = ceil_div(nblocks, 64);
+    reduce_blocks_stage_kernel<<<dim3(ceil_div(P, 128), stages), 128, 0, st>>>(partial, nblocks, P, scratch);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+    partial = scratch;
+    nblocks = stages;
+  }
+  reduce_blocks_kernel<<<ceil_div(P, 128), 128, 0, st>>>(partial, nblocks, P, out);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
+  return CMWG_OK;
+}
+
+static int reduce_and_wn_bwd(const float* partial, int nblocks, int O, int Lr, float* scratch, float* dweff,
+                             const cmwg_conv_param& prm, const float* inv_norm, const cmwg_conv_grad& gr,
+                             cudaStream_t st) {
+  if (!gr.g && !gr.v) return CMWG_OK;
+  CMWG_PROPAGATE(reduce_blocks(partial, nblocks, O * Lr, scratch, dweff, st));
   weight_norm_bwd_kernel<<<O, 128, 0, st>>>(dweff, prm.v, prm.g, inv_norm, Lr, gr.g, gr.v);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
@@ -232,10 +246,7 @@ static int colsum_to(const OpT* a, int ld, int C, long long rows, float* partial
   colsum_partial_kernel<OpT><<<nblocks, 256, 0, st>>>(a, ld, C, rows, partial, f16);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
-  reduce_blocks_kernel<<<ceil_div(C, 128), 128, 0, st>>>(partial, nblocks, C, out);
-  CMWG_COUNT_LAUNCH();
-  CMWG_LAUNCH_CHECK();
-  return CMWG_OK;
+  return reduce_blocks(partial, nblocks, C, partial + (size_t)nblocks * C, out, st);
 }
 
 template <typename OpT>
@@ -280,16 +291,15 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       size_t smem2 = ((size_t)cout * ROWS_PER_BLOCK + (size_t)ROWS_PER_BLOCK * d.Cs) * sizeof(float);
       float* pw = partial;
       float* pb = partial + (size_t)nblk * cout * d.Cs;
+      float* scratch = pb + (size_t)nblk * cout;
       end_bwd_dw_kernel<<<nblk, 256, smem2, st>>>(dlst, skip32, cout, d.Cs, T, bpb, pw, gr->end.bias ? pb : nullptr);
       CMWG_COUNT_LAUNCH();
       CMWG_LAUNCH_CHECK();
       cmwg_conv_grad ge = gr->end;
       ge.g = nullptr;
-      CMWG_PROPAGATE(reduce_and_wn_bwd(pw, nblk, cout, d.Cs, dweff, prm->end, nullptr, ge, st));
+      CMWG_PROPAGATE(reduce_and_wn_bwd(pw, nblk, cout, d.Cs, scratch, dweff, prm->end, nullptr, ge, st));
       if (gr->end.bias) {
-        reduce_blocks_kernel<<<ceil_div(cout, 128), 128, 0, st>>>(pb, nblk, cout, gr->end.bias);
-        CMWG_COUNT_LAUNCH();
-        CMWG_LAUNCH_CHECK();
+        CMWG_PROPAGATE(reduce_blocks(pb, nblk, cout, scratch, gr->end.bias, st));
       }
     }
   }
@@ -366,7 +376,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
           for (int k = 0; k < np; ++k) CMWG_PROPAGATE(ff_wgrad_launch(pr[k], B, T, Lc, st));
         }
         rt.n = nr; rt.splits = splits;
-        wgrad_reduce_kernel<<<dim3(64, nr), 256, 0, st>>>(rt);
+        wgrad_reduce_kernel<<<dim3(num_sms(), nr), 256, 0, st>>>(rt);
         CMWG_COUNT_LAUNCH();
         CMWG_LAUNCH_CHECK();
         if (want_wo) {
@@ -439,16 +449,15 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     size_t smem = ((size_t)ROWS_PER_BLOCK * (d.Cr + 1) + (size_t)d.cin * ROWS_PER_BLOCK) * sizeof(float);
     float* pw = partial;
     float* pb = partial + (size_t)nblk * d.Cr * d.cin;
+    float* scratch = pb + (size_t)nblk * d.Cr;
     start_bwd_kernel<<<nblk, 256, smem, st>>>(dh32, x, x_bs, wStart, d.cin, d.Cr, T, bpb, dx, dx_bs, pw,
                                               (d.bias && gr->start.bias) ? pb : nullptr);
     CMWG_COUNT_LAUNCH();
     CMWG_LAUNCH_CHECK();
-    CMWG_PROPAGATE(reduce_and_wn_bwd(pw, nblk, d.Cr, d.cin, dweff, prm->start,
+    CMWG_PROPAGATE(reduce_and_wn_bwd(pw, nblk, d.Cr, d.cin, scratch, dweff, prm->start,
                                      reinterpret_cast<const float*>(pk + PL.nStart), gr->start, st));
     if (d.bias && gr->start.bias) {
-      reduce_blocks_kernel<<<ceil_div(d.Cr, 128), 128, 0, st>>>(pb, nblk, d.Cr, gr->start.bias);
-      CMWG_COUNT_LAUNCH();
-      CMWG_LAUNCH_CHECK();
+      CMWG_PROPAGATE(reduce_blocks(pb, nblk, d.Cr, scratch, gr->start.bias, st));
     }
   }
   return CMWG_OK;
