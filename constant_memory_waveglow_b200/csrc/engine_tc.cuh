@@ -178,7 +178,28 @@ struct TcSmem {
   uint64_t* tmem_full;
   uint64_t* tmem_empty;
   uint32_t* tmem_ptr;
+  float* stage;  // TC_EPI_WARPS x (32 rows x 32 fp32) transposition buffers of the epilogue warps
 };
+
+constexpr int TC_STAGE_FLOATS = 32 * 32;
+
+// Epilogue transposition.  tcgen05.ld hands every thread ONE accumulator row (TMEM lane), so direct
+// global accesses would touch 32 different 128-byte lines per warp instruction and saturate the L1
+// tag stage.  Each warp therefore bounces its 32x32 fp32 chunk through shared memory (16-byte slots
+// XOR-swizzled by row, conflict free both ways) and continues with the mapping
+//   lane -> rows 4*i + lane/8 (i = 0..7), columns 4*(lane%8) .. +3
+// in which 8 consecutive lanes cover one contiguous 128-byte row segment.
+__device__ __forceinline__ void stage_write(float* sbuf, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(sbuf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void stage_read(const float* sbuf, int lane, int i, float (&o)[4]) {
+  int r = 4 * i + (lane >> 3);
+  float4 q = *reinterpret_cast<const float4*>(sbuf + r * 32 + (((lane & 7) ^ (r & 7)) << 2));
+  o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+}
 
 template <int BN, int STAGES>
 __device__ __forceinline__ TcSmem tc_carve(uint8_t* raw) {
@@ -192,11 +213,12 @@ __device__ __forceinline__ TcSmem tc_carve(uint8_t* raw) {
   s.tmem_full = bars + 2 * STAGES;
   s.tmem_empty = bars + 2 * STAGES + 2;
   s.tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  s.stage = reinterpret_cast<float*>(bars + 2 * STAGES + 6);  // 16-byte aligned: stages are 1 KB multiples
   return s;
 }
 template <int BN, int STAGES>
 constexpr size_t tc_smem_bytes() {
-  return (size_t)STAGES * (TC_A_BYTES + BN * 128) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  return (size_t)STAGES * (TC_A_BYTES + BN * 128) + (2 * STAGES + 6) * 8 + TC_EPI_WARPS * TC_STAGE_FLOATS * 4 + 1024;
 }
 
 template <int BN, int STAGES>
@@ -293,25 +315,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       int b = rt / p.tiles_per_batch, t0 = (rt % p.tiles_per_batch) * TC_BM, n0 = nt * BN;
       mbar_wait(&s.tmem_full[acc], acc_phase);
       tc_fence_after();
-      int t = t0 + q * 32 + lane;
-      bool valid = t < p.T;
-      long long row = (long long)b * p.T + t;
       uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      float* sbuf = s.stage + (warp - 2) * TC_STAGE_FLOATS;
+      const int tq = t0 + q * 32;                  // first row of this warp's quadrant
+      const long long row0 = (long long)b * p.T + tq;
+      const int cl = (lane & 7) * 4;                 // column offset inside a 32-wide chunk
       if constexpr (PAIRED) {
         constexpr int G = BN / 2;
 #pragma unroll 1
         for (int c = half * (G / 2); c < (half + 1) * (G / 2); c += 32) {
-          float lo[32], hi[32];
-          tmem_ld32(taddr + c, lo);
-          tmem_ld32(taddr + G + c, hi);
-          if (valid) epi.template pair<32>(row, nt * G + c, lo, hi);
+          float v[32], lo[8][4];
+          tmem_ld32(taddr + c, v);
+          stage_write(sbuf, lane, v);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) stage_read(sbuf, lane, i, lo[i]);
+          __syncwarp();
+          tmem_ld32(taddr + G + c, v);
+          stage_write(sbuf, lane, v);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float hi[4];
+            stage_read(sbuf, lane, i, hi);
+            int r = 4 * i + (lane >> 3);
+            if (tq + r < p.T) epi.template pair<4>(row0 + r, nt * G + c + cl, lo[i], hi);
+          }
+          __syncwarp();
         }
       } else {
 #pragma unroll 1
         for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
           float v[32];
           tmem_ld32(taddr + c, v);
-          if (valid && (n0 + c) < p.N) epi.template op<32>(row, n0 + c, v);
+          stage_write(sbuf, lane, v);
+          __syncwarp();
+          if (n0 + c + cl < p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float o[4];
+              stage_read(sbuf, lane, i, o);
+              int r = 4 * i + (lane >> 3);
+              if (tq + r < p.T) epi.template op<4>(row0 + r, n0 + c + cl, o);
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -426,24 +474,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       decode(w, pr, m0, n0, split);
       mbar_wait(&s.tmem_full[acc], acc_phase);
       tc_fence_after();
-      int m = m0 + q * 32 + lane;
-      bool valid = m < p.M[pr];
-      float* out = p.partial[pr] + ((long long)split * p.M[pr] + m) * p.N[pr];
+      const int mq = m0 + q * 32;
+      const int M = p.M[pr], N = p.N[pr];
+      float* out = p.partial[pr] + (long long)split * M * N;
       uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+      float* sbuf = s.stage + (warp - 2) * TC_STAGE_FLOATS;
+      const int cl = (lane & 7) * 4;
 #pragma unroll 1
       for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
         float v[32];
         tmem_ld32(taddr + c, v);
-        if (valid && (n0 + c) < p.N[pr]) {
-          int nrem = p.N[pr] - (n0 + c);
-          if (nrem >= 32) {
+        stage_write(sbuf, lane, v);
+        __syncwarp();
+        int n = n0 + c + cl;
+        if (n < N) {  // N is a multiple of 4
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(out + n0 + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < nrem; ++j) out[n0 + c + j] = v[j];
+          for (int i = 0; i < 8; ++i) {
+            float o[4];
+            stage_read(sbuf, lane, i, o);
+            int m = mq + 4 * i + (lane >> 3);
+            if (m < M) *reinterpret_cast<float4*>(out + (long long)m * N + n) = make_float4(o[0], o[1], o[2], o[3]);
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
