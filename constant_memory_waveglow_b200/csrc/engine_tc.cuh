@@ -346,20 +346,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       } else {
 #pragma unroll 1
         for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+          // issue the epilogue's global reads first (8 independent 16-byte loads per lane) so that
+          // they fly while the accumulator chunk is pulled out of TMEM and transposed
+          float aux[8][4 * Epi::kAux];
+          const bool col_ok = n0 + c + cl < p.N;
+          if (col_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              int r = 4 * i + (lane >> 3);
+              if (tq + r < p.T) epi.template load<4>(row0 + r, n0 + c + cl, aux[i]);
+            }
+          }
           float v[32];
           tmem_ld32(taddr + c, v);
           stage_write(sbuf, lane, v);
           __syncwarp();
-          if (n0 + c + cl < p.N) {
+          float o[8][4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) stage_read(sbuf, lane, i, o[i]);
+          __syncwarp();
+          if (col_ok) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float o[4];
-              stage_read(sbuf, lane, i, o);
               int r = 4 * i + (lane >> 3);
-              if (tq + r < p.T) epi.template op<4>(row0 + r, n0 + c + cl, o);
+              if (tq + r < p.T) epi.template apply<4>(row0 + r, n0 + c + cl, o[i], aux[i]);
             }
           }
-          __syncwarp();
         }
       }
       tc_fence_before();
