@@ -313,14 +313,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
       int b = rt / p.tiles_per_batch, t0 = (rt % p.tiles_per_batch) * TC_BM, n0 = nt * BN;
-      mbar_wait(&s.tmem_full[acc], acc_phase);
-      tc_fence_after();
       uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
       float* sbuf = s.stage + (warp - 2) * TC_STAGE_FLOATS;
       const int tq = t0 + q * 32;                  // first row of this warp's quadrant
       const long long row0 = (long long)b * p.T + tq;
       const int cl = (lane & 7) * 4;                 // column offset inside a 32-wide chunk
       if constexpr (PAIRED) {
+        mbar_wait(&s.tmem_full[acc], acc_phase);
+        tc_fence_after();
         constexpr int G = BN / 2;
 #pragma unroll 1
         for (int c = half * (G / 2); c < (half + 1) * (G / 2); c += 32) {
@@ -344,32 +344,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           __syncwarp();
         }
       } else {
-#pragma unroll 1
-        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
-          // issue the epilogue's global reads first (8 independent 16-byte loads per lane) so that
-          // they fly while the accumulator chunk is pulled out of TMEM and transposed
-          float aux[8][4 * Epi::kAux];
-          const bool col_ok = n0 + c + cl < p.N;
-          if (col_ok) {
+        // The epilogue's global reads (residual / skip / saved gate values) are issued one chunk
+        // AHEAD of the accumulator drain -- the first chunk even before the MMA of this tile has
+        // finished -- so each lane keeps 8..16 independent 16-byte loads in flight.
+        constexpr int NCH = (BN / 2) / 32;           // chunks per warp
+        constexpr int AW = 4 * Epi::kAux;
+        constexpr bool AHEAD = (Epi::kAux == 1);     // two aux sets fit the register budget
+        float aux[AHEAD ? 2 : 1][8][AW];
+        const int cbase = half * (BN / 2);
+        auto issue = [&](int k, float (&dst)[8][AW]) {
+          int col = n0 + cbase + 32 * k + cl;
+          if (col < p.N) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               int r = 4 * i + (lane >> 3);
-              if (tq + r < p.T) epi.template load<4>(row0 + r, n0 + c + cl, aux[i]);
+              if (tq + r < p.T) epi.template load<4>(row0 + r, col, dst[i]);
             }
           }
+        };
+        if constexpr (AHEAD) issue(0, aux[0]);
+        mbar_wait(&s.tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          if constexpr (AHEAD) {
+            if (k + 1 < NCH) issue(k + 1, aux[(k + 1) & 1]);
+          } else {
+            issue(k, aux[0]);
+          }
           float v[32];
-          tmem_ld32(taddr + c, v);
+          tmem_ld32(taddr + cbase + 32 * k, v);
           stage_write(sbuf, lane, v);
           __syncwarp();
           float o[8][4];
 #pragma unroll
           for (int i = 0; i < 8; ++i) stage_read(sbuf, lane, i, o[i]);
           __syncwarp();
-          if (col_ok) {
+          int col = n0 + cbase + 32 * k + cl;
+          if (col < p.N) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               int r = 4 * i + (lane >> 3);
-              if (tq + r < p.T) epi.template apply<4>(row0 + r, n0 + c + cl, o[i], aux[i]);
+              if (tq + r < p.T) epi.template apply<4>(row0 + r, col, o[i], aux[AHEAD ? (k & 1) : 0][i]);
             }
           }
         }

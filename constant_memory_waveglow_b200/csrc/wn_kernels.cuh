@@ -98,7 +98,8 @@ struct PackParams {
   void* PB[CMWG_MAX_DEPTH];
   void* Q1[CMWG_MAX_DEPTH];
   void* Q2[CMWG_MAX_DEPTH];
-  void* QV[CMWG_MAX_DEPTH];
+  void* QV;  // shared [auxp][ldQV]
+  void* PS;  // [Cs][ldPS] (tc)
   int is_fp16;
 };
 
@@ -106,15 +107,16 @@ template <typename OpT>
 static __global__ void __launch_bounds__(256) pack_operands_kernel(const PackParams p) {
   const WnDims& d = p.d;
   const int i = blockIdx.y;     // layer
-  const int kind = blockIdx.z;  // 0 PA, 1 PB, 2 Q1, 3 Q2, 4 QV
+  const int kind = blockIdx.z;  // 0 PA, 1 PB, 2 Q1, 3 Q2, 4 QV, 5 PS
   const int nb = d.nb(i), k1 = d.k1(i), cr_eff = d.cr_eff(i);
   long long size;
   switch (kind) {
     case 0: size = (long long)d.npadA * d.KA; break;
-    case 1: size = (long long)nb * d.Cdp; break;
+    case 1: size = (long long)nb * d.ldPB; break;
     case 2: size = (long long)d.Cd * k1; break;
-    case 3: size = (long long)d.Cr * d.R * d.Cd2p; break;
-    default: size = (long long)d.auxp * d.Cd2p; break;
+    case 3: size = (long long)d.Cr * d.ldQ2; break;
+    case 4: size = (long long)d.auxp * d.Cd2p; break;
+    default: size = d.tc ? (long long)d.Cs * d.Cdp : 0; break;
   }
   const float* wW = p.wW[i];
   const float* wWo = p.wWo[i];
@@ -122,6 +124,7 @@ static __global__ void __launch_bounds__(256) pack_operands_kernel(const PackPar
        idx += (long long)gridDim.x * blockDim.x) {
     float val = 0.f;
     OpT* dst;
+    long long didx = idx;  // destination element index (differs from idx for the K-concatenated matrices)
     if (kind == 0) {
       int n = (int)(idx / d.KA), k = (int)(idx % d.KA);
       int tile = n / d.bn_gate, r = n % d.bn_gate;
@@ -138,8 +141,10 @@ static __global__ void __launch_bounds__(256) pack_operands_kernel(const PackPar
       }
       dst = reinterpret_cast<OpT*>(p.PA[i]);
     } else if (kind == 1) {
-      int n = (int)(idx / d.Cdp), k = (int)(idx % d.Cdp);
+      int n = (int)(idx / d.ldPB), k = (int)(idx % d.ldPB);
       if (k < d.Cd) val = wWo[(long long)n * d.Cd + k];
+      // tc: identity columns add the (hi, lo) halves of the layer input to the residual rows
+      else if (k >= d.Cdp && n < cr_eff && ((k - d.Cdp) == n || (k - d.Cdp - d.Crp) == n)) val = 1.f;
       dst = reinterpret_cast<OpT*>(p.PB[i]);
     } else if (kind == 2) {
       int n = (int)(idx / k1), k = (int)(idx % k1);
@@ -153,17 +158,28 @@ static __global__ void __launch_bounds__(256) pack_operands_kernel(const PackPar
       if (ro >= 0) val = wWo[(long long)ro * d.Cd + n];
       dst = reinterpret_cast<OpT*>(p.Q1[i]);
     } else if (kind == 3) {
-      int ld = d.R * d.Cd2p;
+      int ld = d.ldQ2;
       int n = (int)(idx / ld), k = (int)(idx % ld);
-      int tap = k / d.Cd2p, oc = k % d.Cd2p;
-      if (oc < 2 * d.Cd) val = wW[((long long)oc * d.Cr + n) * d.R + tap];
+      if (k < d.R * d.Cd2p) {
+        int tap = k / d.Cd2p, oc = k % d.Cd2p;
+        if (oc < 2 * d.Cd) val = wW[((long long)oc * d.Cr + n) * d.R + tap];
+      } else {
+        int kk = k - d.R * d.Cd2p;  // tc: identity columns carry the (hi, lo) upstream residual gradient
+        if (kk == n || kk - d.Crp == n) val = 1.f;
+      }
       dst = reinterpret_cast<OpT*>(p.Q2[i]);
-    } else {
+    } else if (kind == 4) {
       int n = (int)(idx / d.Cd2p), k = (int)(idx % d.Cd2p);
       if (n < d.aux && k < 2 * d.Cd) val = p.wV[((long long)i * 2 * d.Cd + k) * d.aux + n];
-      dst = reinterpret_cast<OpT*>(p.QV[i]);
+      dst = reinterpret_cast<OpT*>(p.QV);
+      didx = (long long)n * d.ldQV + (long long)i * d.Cd2p + k;
+    } else {
+      int n = (int)(idx / d.Cdp), k = (int)(idx % d.Cdp);
+      if (k < d.Cd) val = wWo[((long long)cr_eff + n) * d.Cd + k];
+      dst = reinterpret_cast<OpT*>(p.PS);
+      didx = (long long)n * d.ldPS + (long long)i * d.Cdp + k;
     }
-    OpTraits<OpT>::store(dst + idx, val, p.is_fp16);
+    OpTraits<OpT>::store(dst + didx, val, p.is_fp16);
   }
 }
 
@@ -178,6 +194,7 @@ struct BiasPackParams {
   float* biasB[CMWG_MAX_DEPTH];
   float* biasStart;
   float* biasEnd;
+  float* biasS;
 };
 static __global__ void __launch_bounds__(256) pack_bias_kernel(const BiasPackParams p) {
   const WnDims& d = p.d;
@@ -191,6 +208,11 @@ static __global__ void __launch_bounds__(256) pack_bias_kernel(const BiasPackPar
       p.biasStart[idx] = p.bStart[idx];
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * d.cin; idx += gridDim.x * blockDim.x)
       p.biasEnd[idx] = p.bEnd[idx];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < d.Cs; idx += gridDim.x * blockDim.x) {
+      float sacc = 0.f;
+      for (int l = 0; l < d.depth; ++l) sacc += p.bWo[l][d.cr_eff(l) + idx];
+      p.biasS[idx] = sacc;
+    }
   }
 }
 
@@ -242,7 +264,7 @@ static __global__ void __launch_bounds__(256) start_fwd_kernel(const float* __re
                                                                const float* __restrict__ bias, int cin, int Cr,
                                                                int T, int blocks_per_batch,
                                                                float* __restrict__ h32, OpT* __restrict__ hop,
-                                                               int is_fp16) {
+                                                               OpT* __restrict__ hlo, int is_fp16) {
   extern __shared__ float sm[];
   float* xs = sm;                          // [cin][32]
   float* wsm = sm + cin * ROWS_PER_BLOCK;  // [Cr][cin]
@@ -264,11 +286,17 @@ static __global__ void __launch_bounds__(256) start_fwd_kernel(const float* __re
     long long off = ((long long)b * T + t) * Cr + o;
     if (h32) h32[off] = acc;
     if (hop) OpTraits<OpT>::store(hop + off, acc, is_fp16);
+    if (hlo) {  // tc: residual stream as hi + lo
+      float hi = OpTraits<OpT>::load(hop + off, is_fp16);
+      OpTraits<OpT>::store(hlo + off, acc - hi, is_fp16);
+    }
   }
 }
 
 // start conv backward: dx[:, :cin] += Ws^T dh0 ; block partials of dWs (and dbias)
 static __global__ void __launch_bounds__(256) start_bwd_kernel(const float* __restrict__ dh0,
+                                                               const uint16_t* __restrict__ dh_hi,
+                                                               const uint16_t* __restrict__ dh_lo,
                                                                const float* __restrict__ x, long long x_bs,
                                                                const float* __restrict__ ws, int cin, int Cr, int T,
                                                                int blocks_per_batch, float* __restrict__ dx,
@@ -283,7 +311,13 @@ static __global__ void __launch_bounds__(256) start_bwd_kernel(const float* __re
   for (int idx = threadIdx.x; idx < ROWS_PER_BLOCK * Cr; idx += 256) {
     int r = idx / Cr, o = idx % Cr;
     int t = t0 + r;
-    dhs[r * LD + o] = (t < T) ? dh0[((long long)b * T + t) * Cr + o] : 0.f;
+    float val = 0.f;
+    if (t < T) {
+      long long off = ((long long)b * T + t) * Cr + o;
+      // tc engine: dh_0 arrives as a (hi, lo) bf16 pair
+      val = dh0 ? dh0[off] : (op16_to_f32(dh_hi[off], 0) + op16_to_f32(dh_lo[off], 0));
+    }
+    dhs[r * LD + o] = val;
   }
   for (int idx = threadIdx.x; idx < cin * ROWS_PER_BLOCK; idx += 256) {
     int i = idx / ROWS_PER_BLOCK, r = idx % ROWS_PER_BLOCK;

@@ -10,7 +10,7 @@
 
 namespace cmwg {
 
-constexpr int MAX_SEG = 8;  // radix taps + conditioning segment
+constexpr int MAX_SEG = 16;  // K segments of one GEMM: radix taps + conditioning / hi+lo identity blocks / one per layer
 constexpr int TC_MAX_WG_REDUCE = 8;  // weight-gradient problems reduced per launch
 
 struct WnDims {
@@ -24,6 +24,10 @@ struct WnDims {
   int G;
   int npadA;    // padded rows of the gate GEMM weight matrix
   int KA;       // K of the gate GEMM: R*Crp + auxp
+  int ldPB;     // K of the res GEMM: Cdp (+ 2*Crp identity columns carrying the hi/lo residual, tc)
+  int ldQ2;     // K of the dx GEMM: R*Cd2p (+ 2*Crp identity columns, tc)
+  int ldQV;     // K of the conditioning-gradient GEMM: depth*Cd2p (all layers concatenated)
+  int ldPS;     // K of the skip GEMM (tc): depth*Cdp
   __host__ __device__ int nb(int i) const { return (i < depth - 1) ? Cr + Cs : Cs; }     // rows of W_o[i]
   __host__ __device__ int cr_eff(int i) const { return (i < depth - 1) ? Cr : 0; }       // residual rows of W_o[i]
   __host__ __device__ int k1(int i) const { return (i < depth - 1) ? Crp + Csp : Csp; }  // K of the dgate GEMM
@@ -31,15 +35,15 @@ struct WnDims {
 
 inline bool wn_tc_shapes_ok(const cmwg_wn_config& c) {
   return c.dil_channels % 64 == 0 && c.res_channels % 64 == 0 && c.skip_channels % 64 == 0 &&
-         c.radix <= MAX_SEG - 1 && c.dil_channels >= 64;
+         c.radix <= 7 && c.dil_channels >= 64;
 }
 
 inline int make_dims(const cmwg_wn_config* c, WnDims* d) {
   CMWG_REQUIRE(c != nullptr, "null cmwg_wn_config");
   CMWG_REQUIRE(c->depth >= 1 && c->depth <= CMWG_MAX_DEPTH, "WN depth %d out of range [1,%d]", c->depth,
                CMWG_MAX_DEPTH);
-  CMWG_REQUIRE(c->radix >= 1 && (c->radix % 2) == 1 && c->radix <= MAX_SEG - 1,
-               "WN radix %d unsupported (odd, <= %d)", c->radix, MAX_SEG - 1);
+  CMWG_REQUIRE(c->radix >= 1 && (c->radix % 2) == 1 && c->radix <= 7, "WN radix %d unsupported (odd, <= 7)",
+               c->radix);
   CMWG_REQUIRE(c->in_channels >= 1 && c->in_channels <= 64, "WN in_channels %d out of range [1,64]",
                c->in_channels);
   CMWG_REQUIRE(c->aux_channels >= 1, "WN aux_channels %d invalid", c->aux_channels);
@@ -69,6 +73,10 @@ inline int make_dims(const cmwg_wn_config* c, WnDims* d) {
   d->G = d->bn_gate / 2;
   d->npadA = ceil_div(d->Cd, d->G) * d->bn_gate;
   d->KA = d->R * d->Crp + d->auxp;
+  d->ldPB = d->Cdp + (d->tc ? 2 * d->Crp : 0);
+  d->ldQ2 = d->R * d->Cd2p + (d->tc ? 2 * d->Crp : 0);
+  d->ldQV = d->depth * d->Cd2p;
+  d->ldPS = d->depth * d->Cdp;
   return CMWG_OK;
 }
 
@@ -81,12 +89,14 @@ struct PackedLayout {
   size_t biasA[CMWG_MAX_DEPTH];  // [2][Cd]: tanh-half bias, sigmoid-half bias (W bias + V bias)
   size_t biasB[CMWG_MAX_DEPTH];  // [nb(i)]
   size_t biasStart, biasEnd;
+  size_t biasS;               // [Cs] sum over layers of the skip rows' biases (tc skip GEMM)
+  size_t PS;                  // skip GEMM      [Cs][depth*Cdp]      = skip rows of every W_o, K-concatenated (tc)
   // GEMM operand matrices (operand element type), row-major [N][K]
   size_t PA[CMWG_MAX_DEPTH];  // gate GEMM      [npadA][KA]
-  size_t PB[CMWG_MAX_DEPTH];  // res/skip GEMM  [nb(i)][Cdp]
+  size_t PB[CMWG_MAX_DEPTH];  // res/skip GEMM  [nb(i)][ldPB]
   size_t Q1[CMWG_MAX_DEPTH];  // dgate GEMM     [Cd][k1(i)]          = W_o^T
-  size_t Q2[CMWG_MAX_DEPTH];  // dx GEMM        [Cr][R*Cd2p]         = W^T per tap
-  size_t QV[CMWG_MAX_DEPTH];  // dy GEMM        [auxp][Cd2p]         = V_i^T
+  size_t Q2[CMWG_MAX_DEPTH];  // dx GEMM        [Cr][ldQ2]           = W^T per tap (+ identity blocks)
+  size_t QV[CMWG_MAX_DEPTH];  // dy GEMM        [auxp][ldQV] shared; QV[i] points at column i*Cd2p
   size_t total;
 };
 
@@ -101,6 +111,9 @@ inline PackedLayout make_packed_layout(const WnDims& d) {
   L.nStart = take((size_t)d.Cr * 4);
   L.biasStart = take((size_t)d.Cr * 4);
   L.biasEnd = take((size_t)2 * d.cin * 4);
+  L.biasS = take((size_t)d.Cs * 4);
+  L.PS = take((size_t)d.Cs * d.ldPS * d.opsize);
+  size_t qv_base = take((size_t)d.auxp * d.ldQV * d.opsize);
   for (int i = 0; i < d.depth; ++i) {
     L.wW[i] = take((size_t)2 * d.Cd * d.Cr * d.R * 4);
     L.wWo[i] = take((size_t)d.nb(i) * d.Cd * 4);
@@ -109,10 +122,10 @@ inline PackedLayout make_packed_layout(const WnDims& d) {
     L.biasA[i] = take((size_t)2 * d.Cd * 4);
     L.biasB[i] = take((size_t)d.nb(i) * 4);
     L.PA[i] = take((size_t)d.npadA * d.KA * d.opsize);
-    L.PB[i] = take((size_t)d.nb(i) * d.Cdp * d.opsize);
+    L.PB[i] = take((size_t)d.nb(i) * d.ldPB * d.opsize);
     L.Q1[i] = take((size_t)d.Cd * d.k1(i) * d.opsize);
-    L.Q2[i] = take((size_t)d.Cr * d.R * d.Cd2p * d.opsize);
-    L.QV[i] = take((size_t)d.auxp * d.Cd2p * d.opsize);
+    L.Q2[i] = take((size_t)d.Cr * d.ldQ2 * d.opsize);
+    L.QV[i] = qv_base + (size_t)i * d.Cd2p * d.opsize;
   }
   L.total = off;
   return L;
@@ -125,6 +138,11 @@ struct FwdLayout {
   size_t skip32;  // [rows][Cs] fp32 cumulative skip
   size_t hop;     // [rows][Cr] operand copy of the layer input (tc inference only; ff aliases h32)
   size_t gop;     // [rows][Cd] operand gate output (inference)
+  // tc engine: the residual stream lives as a (hi, lo) pair of 16-bit slabs, h = hi + lo, so that
+  // the residual add rides through the tensor core (identity K columns) and the epilogue is store-only
+  size_t hi2[2];  // ping-pong [rows][Cr] (inference; training keeps hi per layer in `saved`)
+  size_t lo2[2];  // ping-pong [rows][Cr]
+  size_t gl[CMWG_MAX_DEPTH];  // per-layer gate outputs (inference; the skip GEMM reads all of them at the end)
   size_t ws_total;
   // saved (training): per layer
   size_t s_hin[CMWG_MAX_DEPTH], s_g[CMWG_MAX_DEPTH], s_a[CMWG_MAX_DEPTH], s_b[CMWG_MAX_DEPTH];
@@ -138,6 +156,8 @@ struct BwdLayout {
   size_t dh32;       // [rows][Cr] fp32
   size_t dh_op;      // [rows][Cr] operand (tc only; ff aliases dh32)
   size_t dpre_op;    // [rows][2Cd] operand
+  size_t dhi2[2], dlo2[2];          // tc: (hi, lo) residual-gradient pairs, ping-pong
+  size_t dprel[CMWG_MAX_DEPTH];     // tc: per-layer dpre
   size_t partial;    // split-K partials / block partials
   size_t partial_bytes;
   size_t dweff;      // fp32 scratch for one conv's effective-weight gradient (largest conv)
@@ -152,6 +172,10 @@ inline void make_fwd_layout(const WnDims& d, int B, int T, FwdLayout* L) {
   L->skip32 = take(rows * d.Cs * 4);
   L->hop = d.tc ? take(rows * d.Cr * d.opsize) : L->h32;
   L->gop = take(rows * d.Cd * d.opsize);
+  if (d.tc) {
+    for (int j = 0; j < 2; ++j) { L->hi2[j] = take(rows * d.Cr * 2); L->lo2[j] = take(rows * d.Cr * 2); }
+    for (int i = 0; i < d.depth; ++i) L->gl[i] = take(rows * d.Cd * 2);
+  }
   L->ws_total = off;
   off = 0;
   for (int i = 0; i < d.depth; ++i) {
@@ -183,6 +207,13 @@ inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
   L->dh32 = take(rows * d.Cr * 4);
   L->dh_op = d.tc ? take(rows * d.Cr * d.opsize) : L->dh32;
   L->dpre_op = take(rows * 2 * d.Cd * d.opsize);
+  if (d.tc) {
+    // residual-gradient stream as (hi, lo) 16-bit pairs, ping-pong; per-layer dpre for the deferred
+    // conditioning-gradient GEMM (K-concatenated over layers)
+    for (int j = 0; j < 2; ++j) { L->dhi2[j] = take(rows * d.Cr * 2); L->dlo2[j] = take(rows * d.Cr * 2); }
+    L->dprel[0] = L->dpre_op;
+    for (int i = 1; i < d.depth; ++i) L->dprel[i] = take(rows * 2 * d.Cd * 2);
+  }
   int lc = wgrad_chunk_len(B, T);
   size_t splits = (size_t)B * ceil_div(T, lc);
   // largest simultaneous partial set: all weight-gradient problems of one layer

@@ -74,13 +74,15 @@ static int wn_pack_impl(const WnDims& d, const cmwg_wn_params* prm, void* packed
     pp.wW[i] = reinterpret_cast<const float*>(base + L.wW[i]);
     pp.wWo[i] = reinterpret_cast<const float*>(base + L.wWo[i]);
     pp.PA[i] = base + L.PA[i]; pp.PB[i] = base + L.PB[i]; pp.Q1[i] = base + L.Q1[i];
-    pp.Q2[i] = base + L.Q2[i]; pp.QV[i] = base + L.QV[i];
+    pp.Q2[i] = base + L.Q2[i];
   }
+  pp.QV = base + L.QV[0];
+  pp.PS = base + L.PS;
   long long biggest = (long long)d.npadA * d.KA;
-  long long q2 = (long long)d.Cr * d.R * d.Cd2p;
+  long long q2 = (long long)d.Cr * d.ldQ2;
   if (q2 > biggest) biggest = q2;
   int gx = (int)std::min<long long>(ceil_div_ll(biggest, 256 * 4), 1024);
-  dim3 grid(gx, d.depth, 5);
+  dim3 grid(gx, d.depth, d.tc ? 6 : 5);
   if (d.tc) pack_operands_kernel<uint16_t><<<grid, 256, 0, st>>>(pp);
   else pack_operands_kernel<float><<<grid, 256, 0, st>>>(pp);
   CMWG_COUNT_LAUNCH();
@@ -93,6 +95,7 @@ static int wn_pack_impl(const WnDims& d, const cmwg_wn_params* prm, void* packed
     bp.bV = prm->V.bias; bp.bStart = prm->start.bias; bp.bEnd = prm->end.bias;
     bp.biasStart = reinterpret_cast<float*>(base + L.biasStart);
     bp.biasEnd = reinterpret_cast<float*>(base + L.biasEnd);
+    bp.biasS = reinterpret_cast<float*>(base + L.biasS);
     for (int i = 0; i < d.depth; ++i) {
       CMWG_REQUIRE(prm->W[i].bias && prm->W_o[i].bias, "cmwg_wn_pack: layer %d bias missing", i);
       bp.bW[i] = prm->W[i].bias; bp.bWo[i] = prm->W_o[i].bias;
@@ -126,31 +129,37 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
 
   float* h32 = reinterpret_cast<float*>(ws + FL.h32);
   float* skip32 = save ? reinterpret_cast<float*>(sv + FL.s_skip) : reinterpret_cast<float*>(ws + FL.skip32);
+  // operand (16-bit hi half on the tc engine) of layer i's input
   auto hin_op = [&](int i) -> OpT* {
     if (save) return reinterpret_cast<OpT*>(sv + FL.s_hin[i]);
+    if (TC) return reinterpret_cast<OpT*>(ws + FL.hi2[i & 1]);
     return reinterpret_cast<OpT*>(ws + FL.hop);  // ff: aliases h32
   };
+  auto hlo_op = [&](int i) -> OpT* { return reinterpret_cast<OpT*>(ws + FL.lo2[i & 1]); };  // tc only
   auto g_op = [&](int i) -> OpT* {
-    return save ? reinterpret_cast<OpT*>(sv + FL.s_g[i]) : reinterpret_cast<OpT*>(ws + FL.gop);
+    if (save) return reinterpret_cast<OpT*>(sv + FL.s_g[i]);
+    if (TC) return reinterpret_cast<OpT*>(ws + FL.gl[i]);
+    return reinterpret_cast<OpT*>(ws + FL.gop);
   };
   const int bpb = ceil_div(T, ROWS_PER_BLOCK);
 
   // ---- start conv
   {
-    // tc: fp32 stream in h32 + operand copy; ff inference: h32 only (operand aliases it);
-    // ff training: operand (fp32) copy per layer only
-    float* o32 = (TC || !save) ? h32 : nullptr;
+    // tc: (hi, lo) 16-bit pair; ff inference: h32 only (operand aliases it); ff training: fp32 copy per layer
+    float* o32 = (!TC && !save) ? h32 : nullptr;
     OpT* oop = (TC || save) ? hin_op(0) : nullptr;
+    OpT* olo = TC ? hlo_op(0) : nullptr;
     size_t smem = ((size_t)d.cin * ROWS_PER_BLOCK + (size_t)d.Cr * d.cin) * sizeof(float);
     start_fwd_kernel<OpT><<<B * bpb, 256, smem, st>>>(
         x, x_bs, reinterpret_cast<const float*>(pk + PL.wStart),
-        d.bias ? reinterpret_cast<const float*>(pk + PL.biasStart) : nullptr, d.cin, d.Cr, T, bpb, o32, oop, f16);
+        d.bias ? reinterpret_cast<const float*>(pk + PL.biasStart) : nullptr, d.cin, d.Cr, T, bpb, o32, oop, olo, f16);
     CMWG_COUNT_LAUNCH();
     CMWG_LAUNCH_CHECK();
   }
 
   for (int i = 0; i < d.depth; ++i) {
     const int dil = 1 << i;
+    const bool last = (i == d.depth - 1);
     // ---- gate GEMM
     {
       GemmDesc g;
@@ -172,19 +181,34 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
       epi.Cd = d.Cd; epi.f16 = f16;
       CMWG_PROPAGATE((E::template gemm<true>(g, epi, st)));
     }
-    // ---- residual / skip GEMM
-    {
+    if constexpr (TC) {
+      // ---- residual GEMM: h_{i+1} = g W_res^T + hi_i + lo_i (identity K columns), store-only epilogue
+      if (!last) {
+        GemmDesc g;
+        memset(&g, 0, sizeof(g));
+        g.seg[0].a = g_op(i); g.seg[0].lda = d.Cd; g.seg[0].K = d.Cd; g.seg[0].koff = 0;
+        g.seg[1].a = hin_op(i); g.seg[1].lda = d.Cr; g.seg[1].K = d.Cr; g.seg[1].koff = d.Cdp;
+        g.seg[2].a = hlo_op(i); g.seg[2].lda = d.Cr; g.seg[2].K = d.Cr; g.seg[2].koff = d.Cdp + d.Crp;
+        g.nseg = 3;
+        g.w = pk + PL.PB[i]; g.ldw = d.ldPB; g.N = d.Cr; g.n_rows_w = d.nb(i);
+        g.B = B; g.T = T; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
+        SplitEpi<OpT> epi;
+        epi.hi = hin_op(i + 1); epi.lo = hlo_op(i + 1);
+        epi.bias = d.bias ? reinterpret_cast<const float*>(pk + PL.biasB[i]) : nullptr;
+        epi.ld = d.Cr; epi.n_valid = d.Cr; epi.f16 = f16;
+        CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+      }
+    } else {
+      // ---- residual / skip GEMM (fp32 engine: read-modify-write epilogue)
       GemmDesc g;
       memset(&g, 0, sizeof(g));
       g.seg[0].a = g_op(i); g.seg[0].lda = d.Cd; g.seg[0].K = d.Cd; g.seg[0].shift = 0; g.seg[0].koff = 0;
       g.nseg = 1;
-      g.w = pk + PL.PB[i]; g.ldw = d.Cdp; g.N = d.nb(i); g.n_rows_w = d.nb(i);
+      g.w = pk + PL.PB[i]; g.ldw = d.ldPB; g.N = d.nb(i); g.n_rows_w = d.nb(i);
       g.B = B; g.T = T; g.bn = pick_bn(d.nb(i)); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
       ResSkipEpi<OpT> epi;
-      const bool last = (i == d.depth - 1);
-      if (TC || !save) {
-        epi.res_src = h32; epi.res_src_op = nullptr; epi.res_dst32 = h32;
-        epi.res_dst_op = (TC && !last) ? hin_op(i + 1) : nullptr;
+      if (!save) {
+        epi.res_src = h32; epi.res_src_op = nullptr; epi.res_dst32 = h32; epi.res_dst_op = nullptr;
       } else {
         epi.res_src = nullptr; epi.res_src_op = hin_op(i); epi.res_dst32 = nullptr;
         epi.res_dst_op = last ? nullptr : hin_op(i + 1);
@@ -194,6 +218,22 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
       epi.Cr = d.Cr; epi.Cs = d.Cs; epi.cr_eff = d.cr_eff(i); epi.first_layer = (i == 0); epi.f16 = f16;
       CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
     }
+  }
+  if constexpr (TC) {
+    // ---- skip GEMM: cum_skip = sum_i g_i W_skip,i^T as ONE GEMM with the layers concatenated along K
+    // (accumulation across layers happens in TMEM; the fp32 result is written once)
+    GemmDesc g;
+    memset(&g, 0, sizeof(g));
+    for (int i = 0; i < d.depth; ++i) {
+      g.seg[i].a = g_op(i); g.seg[i].lda = d.Cd; g.seg[i].K = d.Cd; g.seg[i].shift = 0; g.seg[i].koff = i * d.Cdp;
+    }
+    g.nseg = d.depth;
+    g.w = pk + PL.PS; g.ldw = d.ldPS; g.N = d.Cs; g.n_rows_w = d.Cs;
+    g.B = B; g.T = T; g.bn = pick_bn(d.Cs); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
+    StoreEpi epi;
+    epi.dst = skip32; epi.ld = d.Cs; epi.n_valid = d.Cs;
+    epi.bias = d.bias ? reinterpret_cast<const float*>(pk + PL.biasS) : nullptr;
+    CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
   }
   // ---- end conv
   {
@@ -275,6 +315,10 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   float* dh32 = reinterpret_cast<float*>(ws + BL.dh32);
   OpT* dh_op = reinterpret_cast<OpT*>(ws + BL.dh_op);  // ff: aliases dh32
   OpT* dpre_op = reinterpret_cast<OpT*>(ws + BL.dpre_op);
+  // tc: per-layer dpre (deferred conditioning-gradient GEMM) and (hi, lo) residual-gradient pairs
+  auto dpre_l = [&](int i) -> OpT* { return TC ? reinterpret_cast<OpT*>(ws + BL.dprel[i]) : dpre_op; };
+  auto dhi = [&](int i) -> OpT* { return TC ? reinterpret_cast<OpT*>(ws + BL.dhi2[i & 1]) : dh_op; };
+  auto dlo = [&](int i) -> OpT* { return reinterpret_cast<OpT*>(ws + BL.dlo2[i & 1]); };
   float* partial = reinterpret_cast<float*>(ws + BL.partial);
   float* dweff = reinterpret_cast<float*>(ws + BL.dweff);
   const float* skip32 = reinterpret_cast<const float*>(sv + FL.s_skip);
@@ -312,13 +356,15 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     const bool last = (i == d.depth - 1);
     const OpT* hin = reinterpret_cast<const OpT*>(sv + FL.s_hin[i]);
     const OpT* gsv = reinterpret_cast<const OpT*>(sv + FL.s_g[i]);
+    OpT* dpre_i = dpre_l(i);
+    const OpT* dh_next = dhi(i + 1);  // operand view of dh_{i+1} (unused for the last layer)
     // ---- dgate GEMM + gate backward epilogue -> dpre
     {
       GemmDesc g;
       memset(&g, 0, sizeof(g));
       int ns = 0;
       if (!last) {
-        g.seg[ns].a = dh_op; g.seg[ns].lda = d.Cr; g.seg[ns].K = d.Cr; g.seg[ns].shift = 0; g.seg[ns].koff = 0;
+        g.seg[ns].a = dh_next; g.seg[ns].lda = d.Cr; g.seg[ns].K = d.Cr; g.seg[ns].shift = 0; g.seg[ns].koff = 0;
         ++ns;
       }
       g.seg[ns].a = dskip_op; g.seg[ns].lda = d.Cs; g.seg[ns].K = d.Cs; g.seg[ns].shift = 0;
@@ -330,7 +376,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       GateBwdEpi<OpT> epi;
       epi.a_save = reinterpret_cast<const OpT*>(sv + FL.s_a[i]);
       epi.b_save = reinterpret_cast<const OpT*>(sv + FL.s_b[i]);
-      epi.dpre = dpre_op; epi.Cd = d.Cd; epi.ld = 2 * d.Cd; epi.f16 = f16;
+      epi.dpre = dpre_i; epi.Cd = d.Cd; epi.ld = 2 * d.Cd; epi.f16 = f16;
       CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
     }
     // ---- weight gradients of this layer: W_o (res rows, skip rows), W per tap, V_i
@@ -360,14 +406,14 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       const bool want_w = gr->W[i].g || gr->W[i].v;
       const bool want_v = gr->V.g || gr->V.v;
       if (want_wo) {
-        if (!last) red(add(dh_op, d.Cr, d.Cr, gsv, d.Cd, d.Cd, 0), dWo, d.Cd, 1, 0, d.Cd);
+        if (!last) red(add(dh_next, d.Cr, d.Cr, gsv, d.Cd, d.Cd, 0), dWo, d.Cd, 1, 0, d.Cd);
         red(add(dskip_op, d.Cs, d.Cs, gsv, d.Cd, d.Cd, 0), dWo, d.Cd, 1, (long long)d.cr_eff(i) * d.Cd, d.Cd);
       }
       if (want_w)
         for (int s = 0; s < d.R; ++s)
-          red(add(dpre_op, 2 * d.Cd, 2 * d.Cd, hin, d.Cr, d.Cr, (s - (d.R - 1) / 2) * dil), dW,
+          red(add(dpre_i, 2 * d.Cd, 2 * d.Cd, hin, d.Cr, d.Cr, (s - (d.R - 1) / 2) * dil), dW,
               (long long)d.Cr * d.R, d.R, s, d.Cr);
-      if (want_v) red(add(dpre_op, 2 * d.Cd, 2 * d.Cd, ycl, d.auxp, d.auxp, 0), dV, d.aux, 1, 0, d.aux);
+      if (want_v) red(add(dpre_i, 2 * d.Cd, 2 * d.Cd, ycl, d.auxp, d.auxp, 0), dV, d.aux, 1, 0, d.aux);
       CMWG_REQUIRE((size_t)((uint8_t*)pcur - (uint8_t*)partial) <= BL.partial_bytes, "wgrad partial buffer overflow");
       if (np) {
         if (TC) {
@@ -407,21 +453,21 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     // ---- bias gradients (bias=True only)
     if (d.bias) {
       // W_i.bias and V.bias[i] both receive the column sums of dpre
-      if (gr->W[i].bias) CMWG_PROPAGATE(colsum_to<OpT>(dpre_op, 2 * d.Cd, 2 * d.Cd, rows, partial, gr->W[i].bias, f16, st));
+      if (gr->W[i].bias) CMWG_PROPAGATE(colsum_to<OpT>(dpre_i, 2 * d.Cd, 2 * d.Cd, rows, partial, gr->W[i].bias, f16, st));
       if (gr->V.bias)
-        CMWG_PROPAGATE(colsum_to<OpT>(dpre_op, 2 * d.Cd, 2 * d.Cd, rows, partial, gr->V.bias + (size_t)i * 2 * d.Cd, f16, st));
+        CMWG_PROPAGATE(colsum_to<OpT>(dpre_i, 2 * d.Cd, 2 * d.Cd, rows, partial, gr->V.bias + (size_t)i * 2 * d.Cd, f16, st));
       if (gr->W_o[i].bias) {
-        if (!last) CMWG_PROPAGATE(colsum_to<OpT>(dh_op, d.Cr, d.Cr, rows, partial, gr->W_o[i].bias, f16, st));
+        if (!last) CMWG_PROPAGATE(colsum_to<OpT>(dh_next, d.Cr, d.Cr, rows, partial, gr->W_o[i].bias, f16, st));
         CMWG_PROPAGATE(colsum_to<OpT>(dskip_op, d.Cs, d.Cs, rows, partial, gr->W_o[i].bias + d.cr_eff(i), f16, st));
       }
     }
-    // ---- conditioning gradient
-    if (dycl) {
+    // ---- conditioning gradient (fp32 engine: accumulate per layer; tc: one deferred GEMM after the loop)
+    if (dycl && !TC) {
       GemmDesc g;
       memset(&g, 0, sizeof(g));
-      g.seg[0].a = dpre_op; g.seg[0].lda = 2 * d.Cd; g.seg[0].K = 2 * d.Cd; g.seg[0].shift = 0; g.seg[0].koff = 0;
+      g.seg[0].a = dpre_i; g.seg[0].lda = 2 * d.Cd; g.seg[0].K = 2 * d.Cd; g.seg[0].shift = 0; g.seg[0].koff = i * d.Cd2p;
       g.nseg = 1;
-      g.w = pk + PL.QV[i]; g.ldw = d.Cd2p; g.N = d.auxp; g.n_rows_w = d.auxp;
+      g.w = pk + PL.QV[0]; g.ldw = d.ldQV; g.N = d.auxp; g.n_rows_w = d.auxp;
       g.B = B; g.T = T; g.bn = pick_bn(d.auxp); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DCOND;
       AccumEpi epi{dycl, d.auxp, d.auxp, last ? 1 : 0};
       CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
@@ -431,15 +477,45 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       GemmDesc g;
       memset(&g, 0, sizeof(g));
       for (int s = 0; s < d.R; ++s) {
-        g.seg[s].a = dpre_op; g.seg[s].lda = 2 * d.Cd; g.seg[s].K = 2 * d.Cd;
+        g.seg[s].a = dpre_i; g.seg[s].lda = 2 * d.Cd; g.seg[s].K = 2 * d.Cd;
         g.seg[s].shift = -(s - (d.R - 1) / 2) * dil; g.seg[s].koff = s * d.Cd2p;
       }
       g.nseg = d.R;
-      g.w = pk + PL.Q2[i]; g.ldw = d.R * d.Cd2p; g.N = d.Cr; g.n_rows_w = d.Cr;
+      g.w = pk + PL.Q2[i]; g.ldw = d.ldQ2; g.N = d.Cr; g.n_rows_w = d.Cr;
       g.B = B; g.T = T; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DX;
-      DxEpi<OpT> epi;
-      epi.src = last ? nullptr : dh32; epi.dst32 = dh32; epi.dst_op = TC ? dh_op : nullptr;
-      epi.Cr = d.Cr; epi.f16 = f16;
+      if constexpr (TC) {
+        if (!last) {  // upstream residual gradient rides through identity K columns
+          g.seg[d.R].a = dhi(i + 1); g.seg[d.R].lda = d.Cr; g.seg[d.R].K = d.Cr; g.seg[d.R].koff = d.R * d.Cd2p;
+          g.seg[d.R + 1].a = dlo(i + 1); g.seg[d.R + 1].lda = d.Cr; g.seg[d.R + 1].K = d.Cr;
+          g.seg[d.R + 1].koff = d.R * d.Cd2p + d.Crp;
+          g.nseg = d.R + 2;
+        }
+        SplitEpi<OpT> epi;
+        epi.hi = dhi(i); epi.lo = dlo(i); epi.bias = nullptr; epi.ld = d.Cr; epi.n_valid = d.Cr; epi.f16 = f16;
+        CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+      } else {
+        DxEpi<OpT> epi;
+        epi.src = last ? nullptr : dh32; epi.dst32 = dh32; epi.dst_op = nullptr;
+        epi.Cr = d.Cr; epi.f16 = f16;
+        CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+      }
+    }
+  }
+
+  if constexpr (TC) {
+    // ---- conditioning gradient: dy = sum_i dpre_i V_i as ONE GEMM, layers concatenated along K
+    if (dycl) {
+      GemmDesc g;
+      memset(&g, 0, sizeof(g));
+      for (int i = 0; i < d.depth; ++i) {
+        g.seg[i].a = dpre_l(i); g.seg[i].lda = 2 * d.Cd; g.seg[i].K = 2 * d.Cd; g.seg[i].shift = 0;
+        g.seg[i].koff = i * d.Cd2p;
+      }
+      g.nseg = d.depth;
+      g.w = pk + PL.QV[0]; g.ldw = d.ldQV; g.N = d.auxp; g.n_rows_w = d.auxp;
+      g.B = B; g.T = T; g.bn = pick_bn(d.auxp); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DCOND;
+      StoreEpi epi;
+      epi.dst = dycl; epi.ld = d.auxp; epi.n_valid = d.auxp; epi.bias = nullptr;
       CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
     }
   }
@@ -450,7 +526,9 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     float* pw = partial;
     float* pb = partial + (size_t)nblk * d.Cr * d.cin;
     float* scratch = pb + (size_t)nblk * d.Cr;
-    start_bwd_kernel<<<nblk, 256, smem, st>>>(dh32, x, x_bs, wStart, d.cin, d.Cr, T, bpb, dx, dx_bs, pw,
+    start_bwd_kernel<<<nblk, 256, smem, st>>>(TC ? nullptr : dh32, TC ? reinterpret_cast<const uint16_t*>(dhi(0)) : nullptr,
+                                              TC ? reinterpret_cast<const uint16_t*>(dlo(0)) : nullptr, x, x_bs, wStart,
+                                              d.cin, d.Cr, T, bpb, dx, dx_bs, pw,
                                               (d.bias && gr->start.bias) ? pb : nullptr);
     CMWG_COUNT_LAUNCH();
     CMWG_LAUNCH_CHECK();
