@@ -1,10 +1,20 @@
-// Host side of the tcgen05 engine: TMA descriptor construction, weight-gradient launch, self test.
+// Host side of the tcgen05 engine: TMA descriptor construction (cached), pair launches, the
+// weight-gradient launch and the self test.
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "engine_tc.cuh"
-#include "epilogues.cuh"
+#include "epilogues_tc.cuh"
 
 namespace cmwg {
 
-PFN_encodeTiled get_encode_fn() {
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -19,87 +29,139 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-int make_slab_map(CUtensorMap* m, const void* ptr, int C, int T, int B, int box_c, int box_t, int is_fp16) {
+// ---- tensor-map cache: a training step re-encodes the same few hundred descriptors every step -----
+struct MapKey {
+  const void* ptr;
+  int d0, d1, d2, ld, b0, b1, flags;  // dims (d0 innermost), row pitch in elements, box, dtype/swizzle/rank
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld == o.ld && b0 == o.b0 && b1 == o.b1 &&
+           flags == o.flags;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    auto mix = [&](int v) { h ^= (size_t)(unsigned)v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+    mix(k.d0); mix(k.d1); mix(k.d2); mix(k.ld); mix(k.b0); mix(k.b1); mix(k.flags);
+    return h;
+  }
+};
+static std::mutex g_map_mu;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+static bool dbg_flag(const char* name) {
+  const char* v = getenv(name);
+  return v && v[0] == '1';
+}
+
+static int encode_cached(CUtensorMap* m, const MapKey& key, CUtensorMapDataType dt, int esize, int rank,
+                         CUtensorMapSwizzle sw) {
+  static const bool nocache = dbg_flag("CMWG_DEBUG_NOCACHE");
+  if (!nocache) {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+      *m = it->second;
+      return CMWG_OK;
+    }
+  }
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return CMWG_ERR_CUDA;
-  CMWG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (C * 2) % 16 == 0,
-               "make_slab_map: pointer/row pitch not 16-byte aligned (C=%d)", C);
-  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
-  cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_t, 1};
+  CMWG_REQUIRE((reinterpret_cast<uintptr_t>(key.ptr) & 15) == 0 && ((long long)key.ld * esize) % 16 == 0,
+               "tensor map: pointer/row pitch not 16-byte aligned (pitch %d elements)", key.ld);
+  cuuint64_t dims[3] = {(cuuint64_t)key.d0, (cuuint64_t)key.d1, (cuuint64_t)(rank == 3 ? key.d2 : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)key.ld * esize, (cuuint64_t)key.d1 * key.ld * esize};
+  cuuint32_t box[3] = {(cuuint32_t)key.b0, (cuuint32_t)key.b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, is_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
-                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, dt, rank, const_cast<void*>(key.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(slab C=%d T=%d B=%d box=%dx%d) failed with CUresult %d", C, T, B, box_c, box_t,
-              (int)r);
+    set_error("cuTensorMapEncodeTiled(dims %d x %d x %d, box %d x %d, flags %d) failed with CUresult %d", key.d0,
+              key.d1, key.d2, key.b0, key.b1, key.flags, (int)r);
     return CMWG_ERR_CUDA;
   }
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_map_cache.size() > 16384) g_map_cache.clear();
+  g_map_cache.emplace(key, *m);
   return CMWG_OK;
 }
 
-int make_matrix_map(CUtensorMap* m, const void* ptr, int ld, int rows, int box_rows, int is_fp16) {
-  PFN_encodeTiled enc = get_encode_fn();
-  if (!enc) return CMWG_ERR_CUDA;
-  CMWG_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0,
-               "make_matrix_map: pointer/row pitch not 16-byte aligned (ld=%d)", ld);
-  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, is_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(matrix ld=%d rows=%d box_rows=%d) failed with CUresult %d", ld, rows, box_rows,
-              (int)r);
-    return CMWG_ERR_CUDA;
-  }
+int get_slab_map(CUtensorMap* m, const void* ptr, int C, int ld, int T, int B, int box_c, int box_t, int is_fp16,
+                 int kind) {
+  MapKey key{ptr, C, T, B, ld, box_c, box_t, (kind << 4) | (is_fp16 ? 1 : 0) | 2};
+  if (kind == TC_MAP_CHUNK32)
+    return encode_cached(m, key, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 3, CU_TENSOR_MAP_SWIZZLE_128B);
+  return encode_cached(m, key, is_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3,
+                       kind == TC_MAP_CHUNK16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int get_matrix_map(CUtensorMap* m, const void* ptr, int ld, int rows, int box_rows, int is_fp16) {
+  MapKey key{ptr, ld, rows, 1, ld, TC_BK, box_rows, (is_fp16 ? 1 : 0)};
+  return encode_cached(m, key, is_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CMWG_CHECK_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+  static const bool dbg_sync = dbg_flag("CMWG_DEBUG_SYNC");
+  if (dbg_sync) CMWG_CHECK_CUDA(cudaStreamSynchronize(st));
   return CMWG_OK;
 }
 
 template <int BN>
 static int tc_wgrad_launch_bn(const WgradProblem* probs, int nprob, int B, int T, int Lc, int is_fp16, cudaStream_t st,
                               int lbo_override, int sbo_override) {
-  constexpr int STAGES = (BN == 256) ? 4 : 6;
   TcWgradParams p;
   memset(&p, 0, sizeof(p));
   p.nprob = nprob;
-  int tiles = 0;
-  for (int i = 0; i < nprob; ++i) {
-    const WgradProblem& q = probs[i];
-    CMWG_REQUIRE(q.lda % 8 == 0 && q.ldb % 8 == 0 && q.a_c0 % 8 == 0 && q.b_c0 % 8 == 0,
-                 "tc_wgrad: leading dimensions must be multiples of 8");
-    CMWG_PROPAGATE(make_slab_map(&p.a_map[i], q.a, q.lda, T, B, 64, TC_BK, is_fp16));
-    CMWG_PROPAGATE(make_slab_map(&p.b_map[i], q.b, q.ldb, T, B, 64, TC_BK, is_fp16));
-    p.M[i] = q.M; p.N[i] = q.N; p.shift[i] = q.shift; p.a_c0[i] = q.a_c0; p.b_c0[i] = q.b_c0;
-    p.partial[i] = q.partial;
-    p.n_tiles_n[i] = ceil_div(q.N, BN);
-    p.tile_begin[i] = tiles;
-    tiles += ceil_div(q.M, TC_BM) * p.n_tiles_n[i];
-  }
-  p.tile_begin[nprob] = tiles;
   p.B = B; p.T = T; p.Lc = Lc;
   p.chunks_per_batch = ceil_div(T, Lc);
   p.splits = B * p.chunks_per_batch;
+  int tiles = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const WgradProblem& q = probs[i];
+    CMWG_REQUIRE(q.lda % 8 == 0 && q.ldb % 8 == 0 && q.a_c0 % 8 == 0 && q.b_c0 % 8 == 0 && q.N % 4 == 0,
+                 "tc_wgrad: leading dimensions must be multiples of 8");
+    CMWG_PROPAGATE(get_slab_map(&p.a_map[i], q.a, q.lda, q.lda, T, B, 64, TC_BK, is_fp16, TC_MAP_OPERAND));
+    CMWG_PROPAGATE(get_slab_map(&p.b_map[i], q.b, q.ldb, q.ldb, T, B, 64, TC_BK, is_fp16, TC_MAP_OPERAND));
+    CMWG_PROPAGATE(get_slab_map(&p.out_map[i], q.partial, q.N, q.N, q.M, p.splits, 32, 32, 0, TC_MAP_CHUNK32));
+    p.M[i] = q.M; p.N[i] = q.N; p.shift[i] = q.shift; p.a_c0[i] = q.a_c0; p.b_c0[i] = q.b_c0;
+    p.n_tiles_n[i] = ceil_div(q.N, BN);
+    p.tile_begin[i] = tiles;
+    tiles += ceil_div(q.M, 2 * TC_BM) * p.n_tiles_n[i];
+  }
+  p.tile_begin[nprob] = tiles;
   p.total_work = tiles * p.splits;
-  p.idesc = make_idesc(is_fp16, TC_BM, BN, 1, 1);
+  p.idesc = make_idesc(is_fp16, 2 * TC_BM, BN, 1, 1);
   p.desc_lbo = lbo_override >= 0 ? (uint32_t)lbo_override : (8192u >> 4);
   p.desc_sbo = sbo_override >= 0 ? (uint32_t)sbo_override : (1024u >> 4);
   if (p.total_work == 0) return CMWG_OK;
-  auto kern = tc_wgrad_kernel<BN, STAGES>;
-  constexpr size_t smem = tc_smem_bytes<BN, STAGES>();
+  auto kern = tc_wgrad_kernel<BN>;
+  constexpr size_t smem = tc_smem_bytes<BN, WgradEpiShape>();
+  static_assert(smem <= TC_SMEM_LIMIT, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
     CMWG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  int grid = std::min(p.total_work, num_sms());
+  int pairs = std::min(p.total_work, num_sms() / 2);
   ProfScope prof(st, CMWG_KCLASS_WGRAD);
-  kern<<<grid, TC_THREADS, smem, st>>>(p);
+  void* args[1] = {(void*)&p};
+  CMWG_PROPAGATE(tc_launch_pairs((const void*)kern, smem, pairs, args, st));
   CMWG_COUNT_LAUNCH();
-  CMWG_LAUNCH_CHECK();
   return CMWG_OK;
 }
 
@@ -137,8 +199,11 @@ extern "C" int cmwg_selftest_tc_gemm(const void* a, const void* b, float* d, int
     g.seg[0].a = a; g.seg[0].lda = K; g.seg[0].K = K; g.seg[0].shift = 0; g.seg[0].koff = 0;
     g.w = b; g.ldw = K; g.N = N; g.n_rows_w = N; g.B = 1; g.T = M; g.is_fp16 = is_fp16;
     g.bn = ((variant & 2) || N < 256) ? 128 : 256;
-    StoreEpi epi{d, N, N};
-    return tc_gemm_launch<false, StoreEpi>(g, epi, st);
+    TcIo io;
+    memset(&io, 0, sizeof(io));
+    io.out[0] = TcStream{d, N, N, 1};
+    StoreTcEpi epi{nullptr};
+    return tc_gemm_launch<StoreTcEpi>(g, io, epi, st);
   }
   WgradProblem pr;
   pr.a = a; pr.lda = M; pr.a_c0 = 0; pr.M = M;

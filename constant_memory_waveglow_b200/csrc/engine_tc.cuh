@@ -1,14 +1,24 @@
 // tcgen05 / TMEM / TMA GEMM engine for sm_100a (hand-written PTX; no CUTLASS).
 //
-// Persistent, warp-specialised CTAs (one per SM):
-//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor loads of the A (activation slab) and
-//                      B (packed weight) tiles into a STAGES-deep shared-memory ring, 128B swizzle
-//   warp 1 (one lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M = 128, N = BN, K = 16 per
-//                      instruction, fp32 accumulators in TMEM, double buffered (2 x BN columns)
-//   warps 2..9         epilogue (two warps per TMEM lane quadrant, half of the columns each): tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue
-//                      functor (gate / residual+skip / gate-backward / ...) -> global
-// Pipelines: smem full/empty mbarriers (TMA <-> MMA) and TMEM full/empty mbarriers
-// (MMA <-> epilogue) so the epilogue of tile i overlaps the main loop of tile i+1.
+// Persistent, warp-specialised CTAs, launched as CTA PAIRS (clusters of 2, one pair per TPC):
+//   warp 0 (one lane)  TMA producer: cp.async.bulk.tensor loads into a STAGES-deep shared-memory ring
+//                      (128B swizzle).  Each CTA of a pair loads ITS 128 rows of A and ITS HALF of the
+//                      B (weight) tile; both signal the LEADER CTA's full barrier.
+//   warp 1 (one lane)  MMA issuer (leader CTA only): tcgen05.mma.cta_group::2.kind::f16, M = 256
+//                      (128 rows per CTA), N = BN, K = 16 per instruction; fp32 accumulators in the
+//                      TMEM of both SMs, double buffered (2 x BN columns).  Operand traffic per flop
+//                      (L2 -> shared memory and shared memory -> tensor core) is 2/3 of the 1-CTA form,
+//                      which is what bounds a 128 x 256 x 64 1-CTA tile.
+//   warps 2..9         epilogue (two warps per TMEM lane quadrant, half of the columns each):
+//                      tcgen05.ld 32 lanes x 32 columns (one accumulator ROW per thread) -> fused
+//                      epilogue functor -> swizzled shared-memory staging -> TMA store.  Epilogue INPUTS
+//                      (saved gate values, residual hi/lo pairs) arrive the same way in reverse:
+//                      TMA load into per-warp staging, one chunk ahead.  The TMA unit clips rows >= T
+//                      and columns >= C on stores and zero-fills them on loads, so the epilogue has
+//                      no bounds checks and no global address arithmetic.
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA; empty is signalled in both CTAs by a multicast
+// tcgen05.commit) and TMEM full/empty mbarriers (MMA <-> epilogue; the peer's epilogue warps arrive
+// remotely on the leader's tmem_empty barrier).
 //
 // Two operand arrangements:
 //   KMAJOR  (forward / dgrad GEMMs)  A = slab rows x channels (K = channels contiguous),
@@ -24,16 +34,33 @@
 
 namespace cmwg {
 
-constexpr int TC_BM = 128;
+constexpr int TC_BM = 128;                // rows per CTA (the pair covers 256)
 constexpr int TC_BK = 64;                 // 64 x 16-bit = 128 B = one swizzle row
 constexpr int TC_A_BYTES = TC_BM * 128;   // 16 KB
-constexpr int TC_EPI_WARPS = 8;            // 2 per TMEM lane quadrant, each owning half of the tile's columns
+constexpr int TC_EPI_WARPS = 8;           // 2 per TMEM lane quadrant, each owning half of the tile's columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_MAX_WG = 8;              // weight-gradient problems per launch
+constexpr int TC_MAX_OUT = 3;             // output streams of one epilogue
+constexpr int TC_MAX_IN = 2;              // input streams of one epilogue
+constexpr int TC_SMEM_LIMIT = 232448;     // 227 KB opt-in shared memory per CTA
+
+// one epilogue stream: a channel-last slab [B*T][ld] of 16-bit operands or fp32
+struct TcStream {
+  const void* ptr;
+  int ld;      // row pitch in elements
+  int cols;    // valid channels (TMA clips stores / zero-fills loads beyond them)
+  int is_f32;
+};
+struct TcIo {
+  TcStream out[TC_MAX_OUT];
+  TcStream in[TC_MAX_IN];
+};
 
 struct alignas(64) TcGemmParams {
   CUtensorMap a_map[MAX_SEG];
   CUtensorMap b_map;
+  CUtensorMap out_map[TC_MAX_OUT];
+  CUtensorMap in_map[TC_MAX_IN];
   int nseg;
   int seg_nkb[MAX_SEG];
   int seg_shift[MAX_SEG];
@@ -46,11 +73,11 @@ struct alignas(64) TcGemmParams {
 struct alignas(64) TcWgradParams {
   CUtensorMap a_map[TC_MAX_WG];
   CUtensorMap b_map[TC_MAX_WG];
+  CUtensorMap out_map[TC_MAX_WG];  // fp32 partials [splits][M][N]
   int nprob;
   int M[TC_MAX_WG], N[TC_MAX_WG], shift[TC_MAX_WG], a_c0[TC_MAX_WG], b_c0[TC_MAX_WG];
   int tile_begin[TC_MAX_WG + 1];  // prefix sum of (m_tiles * n_tiles) per problem
   int n_tiles_n[TC_MAX_WG];
-  float* partial[TC_MAX_WG];
   int B, T, Lc, chunks_per_batch, splits, total_work;
   uint32_t idesc;
   uint32_t desc_lbo, desc_sbo;
@@ -72,6 +99,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive on the barrier at shared::cluster address `addr` (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   asm volatile(
@@ -86,62 +117,103 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+// TMA loads; `bar` is a shared::cluster mbarrier address (cta_group::2: it may live in the peer CTA)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// CTA-local TMA load (epilogue inputs)
+__device__ __forceinline__ void tma_load_3d_local(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                  int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+          dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// TMA store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
 }
 __device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// completion of all prior tcgen05.mma of this thread -> arrive on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = one accumulator row)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      : "r"(taddr)
+      : "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
@@ -171,118 +243,174 @@ inline uint32_t make_idesc(int is_fp16, int M, int N, int a_mn_major, int b_mn_m
   return d;
 }
 
-struct TcSmem {
-  uint8_t* stages;
-  uint64_t* full;
-  uint64_t* empty;
-  uint64_t* tmem_full;
-  uint64_t* tmem_empty;
-  uint32_t* tmem_ptr;
-  float* stage;  // TC_EPI_WARPS x (32 rows x 32 fp32) transposition buffers of the epilogue warps
+// ------------------------------------------------------------------------------------------------
+// epilogue staging: one 32-row x 32-column chunk per warp, thread `lane` owns row `lane`.
+//   16-bit chunk: 32 x 64 B,  TMA SWIZZLE_64B  (16-byte slot j of row r lives at slot j ^ ((r >> 1) & 3))
+//   fp32 chunk:   32 x 128 B, TMA SWIZZLE_128B (16-byte slot j of row r lives at slot j ^ (r & 7))
+// Both are bank-conflict free for the row-per-thread 16-byte accesses of a quarter warp.
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_CHUNK16_BYTES = 32 * 64;
+constexpr int TC_CHUNK32_BYTES = 32 * 128;
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void stage_store16(uint32_t buf, int lane, const uint32_t (&o)[16]) {
+  const uint32_t base = buf + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) st_shared_v4(base + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+}
+__device__ __forceinline__ void stage_load16(uint32_t buf, int lane, uint32_t (&o)[16]) {
+  const uint32_t base = buf + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ld_shared_v4(base + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+}
+__device__ __forceinline__ void stage_store32(uint32_t buf, int lane, const uint32_t (&o)[32]) {
+  const uint32_t base = buf + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) st_shared_v4(base + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+}
+
+template <class Epi>
+struct TcEpiTraits {
+  static constexpr int kOutChunk = Epi::kOutF32 ? TC_CHUNK32_BYTES : TC_CHUNK16_BYTES;
+  static constexpr int kOutBytes = Epi::kOutBufs * Epi::kOut * kOutChunk;
+  static constexpr int kInBytes = 2 * Epi::kIn * TC_CHUNK16_BYTES;  // inputs: 16-bit, double buffered
+  static constexpr int kWarpBytes = kOutBytes + kInBytes;
 };
 
-constexpr int TC_STAGE_FLOATS = 32 * 32;
+constexpr int TC_BAR_BYTES = 512;  // mbarriers + TMEM pointer
 
-// Epilogue transposition.  tcgen05.ld hands every thread ONE accumulator row (TMEM lane), so direct
-// global accesses would touch 32 different 128-byte lines per warp instruction and saturate the L1
-// tag stage.  Each warp therefore bounces its 32x32 fp32 chunk through shared memory (16-byte slots
-// XOR-swizzled by row, conflict free both ways) and continues with the mapping
-//   lane -> rows 4*i + lane/8 (i = 0..7), columns 4*(lane%8) .. +3
-// in which 8 consecutive lanes cover one contiguous 128-byte row segment.
-__device__ __forceinline__ void stage_write(float* sbuf, int lane, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(sbuf + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+template <int BN, class Epi>
+constexpr int tc_stage_bytes() { return TC_A_BYTES + (BN / 2) * 128; }
+template <int BN, class Epi>
+constexpr int tc_num_stages() {
+  int avail = TC_SMEM_LIMIT - 1024 - TC_BAR_BYTES - TC_EPI_WARPS * TcEpiTraits<Epi>::kWarpBytes;
+  int s = avail / tc_stage_bytes<BN, Epi>();
+  return s > 8 ? 8 : s;
 }
-__device__ __forceinline__ void stage_read(const float* sbuf, int lane, int i, float (&o)[4]) {
-  int r = 4 * i + (lane >> 3);
-  float4 q = *reinterpret_cast<const float4*>(sbuf + r * 32 + (((lane & 7) ^ (r & 7)) << 2));
-  o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+template <int BN, class Epi>
+constexpr size_t tc_smem_bytes() {
+  return (size_t)tc_num_stages<BN, Epi>() * tc_stage_bytes<BN, Epi>() + TC_EPI_WARPS * TcEpiTraits<Epi>::kWarpBytes +
+         TC_BAR_BYTES + 1024;
 }
 
-template <int BN, int STAGES>
-__device__ __forceinline__ TcSmem tc_carve(uint8_t* raw) {
+struct TcSmem {
+  uint8_t* stages;
+  uint8_t* epi;        // TC_EPI_WARPS x per-warp staging (1 KB aligned)
+  uint64_t* full;      // [STAGES]   (leader's is the one in use)
+  uint64_t* empty;     // [STAGES]
+  uint64_t* tmem_full; // [2]
+  uint64_t* tmem_empty;// [2]        (leader's is the one in use)
+  uint64_t* in_bar;    // [TC_EPI_WARPS][2] epilogue input loads
+  uint32_t* tmem_ptr;
+};
+
+template <int STAGES>
+__device__ __forceinline__ TcSmem tc_carve(uint8_t* raw, int stage_bytes, int epi_warp_bytes) {
+  static_assert((2 * STAGES + 4 + 2 * TC_EPI_WARPS) * 8 + 8 <= TC_BAR_BYTES, "barrier area too small");
   TcSmem s;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int STAGE_BYTES = TC_A_BYTES + BN * 128;
   s.stages = base;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
+  s.epi = base + STAGES * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.epi + TC_EPI_WARPS * epi_warp_bytes);
   s.full = bars;
   s.empty = bars + STAGES;
   s.tmem_full = bars + 2 * STAGES;
   s.tmem_empty = bars + 2 * STAGES + 2;
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  s.stage = reinterpret_cast<float*>(bars + 2 * STAGES + 6);  // 16-byte aligned: stages are 1 KB multiples
+  s.in_bar = bars + 2 * STAGES + 4;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * TC_EPI_WARPS);
   return s;
 }
-template <int BN, int STAGES>
-constexpr size_t tc_smem_bytes() {
-  return (size_t)STAGES * (TC_A_BYTES + BN * 128) + (2 * STAGES + 6) * 8 + TC_EPI_WARPS * TC_STAGE_FLOATS * 4 + 1024;
-}
 
-template <int BN, int STAGES>
-__device__ __forceinline__ void tc_setup(const TcSmem& s, int warp, int lane) {
+template <int STAGES>
+__device__ __forceinline__ void tc_setup(const TcSmem& s, int warp, int lane, int tmem_cols) {
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], TC_EPI_WARPS); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], 2 * TC_EPI_WARPS); }
+      for (int i = 0; i < 2 * TC_EPI_WARPS; ++i) mbar_init(&s.in_bar[i], 1);
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(s.tmem_ptr, 2 * BN);
+    tmem_alloc(s.tmem_ptr, tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // both CTAs: barriers initialised, TMEM allocated
   tc_fence_after();
+}
+
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base, int warp, int tmem_cols) {
+  tc_fence_before();
+  __syncwarp();
+  cluster_sync_all();  // every MMA, remote arrive and TMEM read of the pair has finished
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K-major GEMM with fused epilogue
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool PAIRED, class Epi>
+template <int BN, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGemmParams p, const Epi epi) {
   extern __shared__ uint8_t smem_raw[];
-  const TcSmem s = tc_carve<BN, STAGES>(smem_raw);
-  constexpr int STAGE_BYTES = TC_A_BYTES + BN * 128;
+  constexpr int STAGES = tc_num_stages<BN, Epi>();
+  constexpr int STAGE_BYTES = tc_stage_bytes<BN, Epi>();
+  using ET = TcEpiTraits<Epi>;
+  static_assert(STAGES >= 2, "epilogue staging leaves no room for the operand pipeline");
+  const TcSmem s = tc_carve<STAGES>(smem_raw, STAGE_BYTES, ET::kWarpBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nseg; ++i) prefetch_tmap(&p.a_map[i]);
     prefetch_tmap(&p.b_map);
+    for (int i = 0; i < Epi::kOut; ++i) prefetch_tmap(&p.out_map[i]);
+    for (int i = 0; i < Epi::kIn; ++i) prefetch_tmap(&p.in_map[i]);
   }
-  tc_setup<BN, STAGES>(s, warp, lane);
+  tc_setup<STAGES>(s, warp, lane, 2 * BN);
   const uint32_t tmem_base = *s.tmem_ptr;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < p.total_tiles; tile += npairs) {
         int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
-        int b = rt / p.tiles_per_batch, t0 = (rt % p.tiles_per_batch) * TC_BM, n0 = nt * BN;
+        int b = rt / p.tiles_per_batch, t0 = (rt % p.tiles_per_batch) * (2 * TC_BM) + rank * TC_BM;
+        int n0 = nt * BN + rank * (BN / 2);
         for (int sg = 0; sg < p.nseg; ++sg) {
           for (int kb = 0; kb < p.seg_nkb[sg]; ++kb) {
             mbar_wait(&s.empty[stage], phase ^ 1);
-            uint8_t* sa = s.stages + stage * STAGE_BYTES;
-            mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
-            tma_load_3d(sa, &p.a_map[sg], &s.full[stage], kb * TC_BK, t0 + p.seg_shift[sg], b);
-            tma_load_2d(sa + TC_A_BYTES, &p.b_map, &s.full[stage], p.seg_koff[sg] + kb * TC_BK, n0);
+            uint32_t sa = smem_u32(s.stages + stage * STAGE_BYTES);
+            if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * STAGE_BYTES);
+            uint32_t bar = mapa_shared(smem_u32(&s.full[stage]), 0);
+            tma_load_3d(sa, &p.a_map[sg], bar, kb * TC_BK, t0 + p.seg_shift[sg], b);
+            tma_load_2d(sa + TC_A_BYTES, &p.b_map, bar, p.seg_koff[sg] + kb * TC_BK, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int total_kb = 0;
       for (int sg = 0; sg < p.nseg; ++sg) total_kb += p.seg_nkb[sg];
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = pair; tile < p.total_tiles; tile += npairs) {
         mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         uint32_t d_tmem = tmem_base + acc * BN;
@@ -306,119 +434,134 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       }
     }
   } else {
+    const int e = warp - 2;
     const int q = warp & 3;          // TMEM lane quadrant this warp may access (hardware: warp id % 4)
-    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
+    const int half = e >> 2;         // which half of the tile's columns this warp drains
+    constexpr int GW = Epi::kPaired ? BN / 2 : BN;  // epilogue columns of one tile (gate channels when paired)
+    constexpr int NCH = (GW / 2) / 32;              // 32-column chunks per warp per tile
+    const uint32_t wbuf = smem_u32(s.epi + e * ET::kWarpBytes);
+    const uint32_t ibuf0 = wbuf + ET::kOutBytes;
+    uint64_t* ibar = s.in_bar + 2 * e;
+    const uint32_t tmem_empty_addr = mapa_shared(smem_u32(&s.tmem_empty[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int ob = 0;        // output staging buffer in use
+    uint32_t it = 0;   // running chunk counter (input double buffer + phase)
+
+    // coordinates of chunk k of a tile: batch, first row of this warp, first epilogue column
+    auto coords = [&](int tile, int k, int& b, int& r0, int& c0) {
       int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
-      int b = rt / p.tiles_per_batch, t0 = (rt % p.tiles_per_batch) * TC_BM, n0 = nt * BN;
-      uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      float* sbuf = s.stage + (warp - 2) * TC_STAGE_FLOATS;
-      const int tq = t0 + q * 32;                  // first row of this warp's quadrant
-      const long long row0 = (long long)b * p.T + tq;
-      const int cl = (lane & 7) * 4;                 // column offset inside a 32-wide chunk
-      if constexpr (PAIRED) {
-        mbar_wait(&s.tmem_full[acc], acc_phase);
-        tc_fence_after();
-        constexpr int G = BN / 2;
-#pragma unroll 1
-        for (int c = half * (G / 2); c < (half + 1) * (G / 2); c += 32) {
-          float v[32], lo[8][4];
-          tmem_ld32(taddr + c, v);
-          stage_write(sbuf, lane, v);
-          __syncwarp();
+      b = rt / p.tiles_per_batch;
+      r0 = (rt % p.tiles_per_batch) * (2 * TC_BM) + rank * TC_BM + q * 32;
+      c0 = nt * GW + half * (GW / 2) + 32 * k;
+    };
+    auto issue_inputs = [&](int tile, int k, uint32_t n) {
+      if constexpr (Epi::kIn > 0) {
+        if (lane == 0) {
+          int b, r0, c0;
+          coords(tile, k, b, r0, c0);
+          uint32_t buf = ibuf0 + (n & 1) * Epi::kIn * TC_CHUNK16_BYTES;
+          fence_proxy_async();
+          mbar_arrive_expect_tx(&ibar[n & 1], Epi::kIn * TC_CHUNK16_BYTES);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) stage_read(sbuf, lane, i, lo[i]);
-          __syncwarp();
-          tmem_ld32(taddr + G + c, v);
-          stage_write(sbuf, lane, v);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float hi[4];
-            stage_read(sbuf, lane, i, hi);
-            int r = 4 * i + (lane >> 3);
-            if (tq + r < p.T) epi.template pair<4>(row0 + r, nt * G + c + cl, lo[i], hi);
-          }
-          __syncwarp();
-        }
-      } else {
-        // The epilogue's global reads (residual / skip / saved gate values) are issued one chunk
-        // AHEAD of the accumulator drain -- the first chunk even before the MMA of this tile has
-        // finished -- so each lane keeps 8..16 independent 16-byte loads in flight.
-        constexpr int NCH = (BN / 2) / 32;           // chunks per warp
-        constexpr int AW = 4 * Epi::kAux;
-        constexpr bool AHEAD = (Epi::kAux == 1);     // two aux sets fit the register budget
-        float aux[AHEAD ? 2 : 1][8][AW];
-        const int cbase = half * (BN / 2);
-        auto issue = [&](int k, float (&dst)[8][AW]) {
-          int col = n0 + cbase + 32 * k + cl;
-          if (col < p.N) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              int r = 4 * i + (lane >> 3);
-              if (tq + r < p.T) epi.template load<4>(row0 + r, col, dst[i]);
-            }
-          }
-        };
-        if constexpr (AHEAD) issue(0, aux[0]);
-        mbar_wait(&s.tmem_full[acc], acc_phase);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-          if constexpr (AHEAD) {
-            if (k + 1 < NCH) issue(k + 1, aux[(k + 1) & 1]);
-          } else {
-            issue(k, aux[0]);
-          }
-          float v[32];
-          tmem_ld32(taddr + cbase + 32 * k, v);
-          stage_write(sbuf, lane, v);
-          __syncwarp();
-          float o[8][4];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) stage_read(sbuf, lane, i, o[i]);
-          __syncwarp();
-          int col = n0 + cbase + 32 * k + cl;
-          if (col < p.N) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              int r = 4 * i + (lane >> 3);
-              if (tq + r < p.T) epi.template apply<4>(row0 + r, col, o[i], aux[AHEAD ? (k & 1) : 0][i]);
-            }
-          }
+          for (int i = 0; i < Epi::kIn; ++i)
+            tma_load_3d_local(buf + i * TC_CHUNK16_BYTES, &p.in_map[i], smem_u32(&ibar[n & 1]), epi.in_col(i, c0), r0, b);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tmem_empty[acc]);
+    };
+    if (pair < p.total_tiles) issue_inputs(pair, 0, 0);
+
+    for (int tile = pair; tile < p.total_tiles; tile += npairs) {
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + half * (GW / 2);
+      mbar_wait(&s.tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int k = 0; k < NCH; ++k, ++it) {
+        int b, r0, c0;
+        coords(tile, k, b, r0, c0);
+        // epilogue inputs: prefetch the next chunk, wait for this one
+        uint32_t in[Epi::kIn > 0 ? Epi::kIn : 1][16];
+        if constexpr (Epi::kIn > 0) {
+          if (k + 1 < NCH) issue_inputs(tile, k + 1, it + 1);
+          else if (tile + npairs < p.total_tiles) issue_inputs(tile + npairs, 0, it + 1);
+          mbar_wait(&ibar[it & 1], (it >> 1) & 1);
+          uint32_t buf = ibuf0 + (it & 1) * Epi::kIn * TC_CHUNK16_BYTES;
+#pragma unroll
+          for (int i = 0; i < Epi::kIn; ++i) stage_load16(buf + i * TC_CHUNK16_BYTES, lane, in[i]);
+        }
+        // accumulators
+        float v[32];
+        tmem_ld32(taddr + 32 * k, v);
+        uint32_t o[Epi::kOut][Epi::kOutF32 ? 32 : 16];
+        if constexpr (Epi::kPaired) {
+          float w[32];
+          tmem_ld32(taddr + GW + 32 * k, w);
+          if (k == NCH - 1) {  // TMEM buffer drained: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tmem_empty_addr + 8 * acc);
+          }
+          epi.compute(c0, v, w, o);
+        } else {
+          if (k == NCH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tmem_empty_addr + 8 * acc);
+          }
+          if constexpr (Epi::kIn > 0) epi.compute(c0, v, in, o);
+          else epi.compute(c0, v, o);
+        }
+        // staging buffer `ob` must have been read by the TMA store issued Epi::kOutBufs chunks ago
+        if (lane == 0) bulk_wait_read<Epi::kOutBufs - 1>();
+        __syncwarp();
+        const uint32_t obuf = wbuf + ob * Epi::kOut * ET::kOutChunk;
+#pragma unroll
+        for (int i = 0; i < Epi::kOut; ++i) {
+          if constexpr (Epi::kOutF32) stage_store32(obuf + i * ET::kOutChunk, lane, o[i]);
+          else stage_store16(obuf + i * ET::kOutChunk, lane, o[i]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < Epi::kOut; ++i) tma_store_3d(&p.out_map[i], obuf + i * ET::kOutChunk, epi.out_col(i, c0), r0, b);
+          bulk_commit();
+        }
+        if (Epi::kOutBufs > 1) ob ^= 1;
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) bulk_wait_read<0>();  // staging must outlive the last stores' reads
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
-  }
+  tc_teardown(tmem_base, warp, 2 * BN);
 }
 
 // ------------------------------------------------------------------------------------------------
-// MN-major weight-gradient GEMM: D[m][n] = sum_t A[t][m] * B[t+shift][n], split over time chunks
+// MN-major weight-gradient GEMM: D[m][n] = sum_t A[t][m] * B[t+shift][n], split over time chunks.
+// The pair computes a 256 (m) x BN (n) tile: each CTA loads its 128 m-columns of A and its BN/2
+// n-columns of B; fp32 partial tiles leave through the TMA store path.
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+struct WgradEpiShape {  // staging shape of the weight-gradient epilogue (fp32, one stream, double buffered)
+  static constexpr bool kOutF32 = true, kPaired = false;
+  static constexpr int kOut = 1, kIn = 0, kOutBufs = 2;
+};
+
+template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const TcSmem s = tc_carve<BN, STAGES>(smem_raw);
-  constexpr int STAGE_BYTES = TC_A_BYTES + BN * 128;
+  constexpr int STAGES = tc_num_stages<BN, WgradEpiShape>();
+  constexpr int STAGE_BYTES = tc_stage_bytes<BN, WgradEpiShape>();
+  using ET = TcEpiTraits<WgradEpiShape>;
   constexpr int BOX_BYTES = 64 * 128;  // {64 channels, 64 time rows} x 16 bit
+  const TcSmem s = tc_carve<STAGES>(smem_raw, STAGE_BYTES, ET::kWarpBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < p.nprob; ++i) { prefetch_tmap(&p.a_map[i]); prefetch_tmap(&p.b_map[i]); }
+    for (int i = 0; i < p.nprob; ++i) { prefetch_tmap(&p.a_map[i]); prefetch_tmap(&p.b_map[i]); prefetch_tmap(&p.out_map[i]); }
   }
-  tc_setup<BN, STAGES>(s, warp, lane);
+  tc_setup<STAGES>(s, warp, lane, 2 * BN);
   const uint32_t tmem_base = *s.tmem_ptr;
   const int tiles_total = p.tile_begin[p.nprob];
 
@@ -430,7 +573,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     pr = 0;
     while (tl >= p.tile_begin[pr + 1]) ++pr;
     tl -= p.tile_begin[pr];
-    m0 = (tl / p.n_tiles_n[pr]) * TC_BM;
+    m0 = (tl / p.n_tiles_n[pr]) * (2 * TC_BM);
     n0 = (tl % p.n_tiles_n[pr]) * BN;
   };
 
@@ -438,34 +581,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      for (int w = pair; w < p.total_work; w += npairs) {
         int pr, m0, n0, split;
         decode(w, pr, m0, n0, split);
         int b = split / p.chunks_per_batch, tc0 = (split % p.chunks_per_batch) * p.Lc;
         int nkb = (min(p.Lc, p.T - tc0) + TC_BK - 1) / TC_BK;
+        const int ma = p.a_c0[pr] + m0 + rank * TC_BM;
+        const int nb = p.b_c0[pr] + n0 + rank * (BN / 2);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&s.empty[stage], phase ^ 1);
-          uint8_t* sa = s.stages + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&s.full[stage], STAGE_BYTES);
+          uint32_t sa = smem_u32(s.stages + stage * STAGE_BYTES);
+          if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * STAGE_BYTES);
+          uint32_t bar = mapa_shared(smem_u32(&s.full[stage]), 0);
           int t = tc0 + kb * TC_BK;
 #pragma unroll
-          for (int j = 0; j < TC_BM / 64; ++j)
-            tma_load_3d(sa + j * BOX_BYTES, &p.a_map[pr], &s.full[stage], p.a_c0[pr] + m0 + j * 64, t, b);
+          for (int j = 0; j < TC_BM / 64; ++j) tma_load_3d(sa + j * BOX_BYTES, &p.a_map[pr], bar, ma + j * 64, t, b);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_3d(sa + TC_A_BYTES + j * BOX_BYTES, &p.b_map[pr], &s.full[stage], p.b_c0[pr] + n0 + j * 64,
-                        t + p.shift[pr], b);
+          for (int j = 0; j < BN / 128; ++j)
+            tma_load_3d(sa + TC_A_BYTES + j * BOX_BYTES, &p.b_map[pr], bar, nb + j * 64, t + p.shift[pr], b);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      for (int w = pair; w < p.total_work; w += npairs) {
         int pr, m0, n0, split;
         decode(w, pr, m0, n0, split);
         int tc0 = (split % p.chunks_per_batch) * p.Lc;
@@ -493,108 +637,123 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       }
     }
   } else {
+    const int e = warp - 2;
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = e >> 2;
+    constexpr int NCH = (BN / 2) / 32;
+    const uint32_t wbuf = smem_u32(s.epi + e * ET::kWarpBytes);
+    const uint32_t tmem_empty_addr = mapa_shared(smem_u32(&s.tmem_empty[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+    int ob = 0;
+    for (int w = pair; w < p.total_work; w += npairs) {
       int pr, m0, n0, split;
       decode(w, pr, m0, n0, split);
       mbar_wait(&s.tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int mq = m0 + q * 32;
-      const int M = p.M[pr], N = p.N[pr];
-      float* out = p.partial[pr] + (long long)split * M * N;
-      uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-      float* sbuf = s.stage + (warp - 2) * TC_STAGE_FLOATS;
-      const int cl = (lane & 7) * 4;
+      const int mq = m0 + rank * TC_BM + q * 32;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + half * (BN / 2);
 #pragma unroll 1
-      for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+      for (int k = 0; k < NCH; ++k) {
         float v[32];
-        tmem_ld32(taddr + c, v);
-        stage_write(sbuf, lane, v);
-        __syncwarp();
-        int n = n0 + c + cl;
-        if (n < N) {  // N is a multiple of 4
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float o[4];
-            stage_read(sbuf, lane, i, o);
-            int m = mq + 4 * i + (lane >> 3);
-            if (m < M) *reinterpret_cast<float4*>(out + (long long)m * N + n) = make_float4(o[0], o[1], o[2], o[3]);
-          }
+        tmem_ld32(taddr + 32 * k, v);
+        if (k == NCH - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tmem_empty_addr + 8 * acc);
         }
+        uint32_t o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(v[j]);
+        if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
+        const uint32_t obuf = wbuf + ob * TC_CHUNK32_BYTES;
+        stage_store32(obuf, lane, o);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&p.out_map[pr], obuf, n0 + half * (BN / 2) + 32 * k, mq, split);
+          bulk_commit();
+        }
+        ob ^= 1;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) bulk_wait_read<0>();
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
-  }
+  tc_teardown(tmem_base, warp, 2 * BN);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side: tensor maps + launches
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-PFN_encodeTiled get_encode_fn();
-
-// 16-bit tensor map over a slab [B][T][C]: dims (C, T, B), box (box_c, box_t, 1), 128B swizzle, zero OOB fill
-int make_slab_map(CUtensorMap* m, const void* ptr, int C, int T, int B, int box_c, int box_t, int is_fp16);
+enum TcMapKind {
+  TC_MAP_OPERAND = 0,   // 16-bit, 128B swizzle (UMMA operand tiles)
+  TC_MAP_CHUNK16 = 1,   // 16-bit, 64B swizzle, box {32, 32, 1} (epilogue streams)
+  TC_MAP_CHUNK32 = 2,   // fp32,   128B swizzle, box {32, 32, 1}
+};
+// cached tensor map over a slab [B][T][ld] of which the first C channels are valid (dims (C, T, B));
+// box (box_c, box_t, 1); zero OOB fill
+int get_slab_map(CUtensorMap* m, const void* ptr, int C, int ld, int T, int B, int box_c, int box_t, int is_fp16,
+                 int kind);
 // 16-bit tensor map over a matrix [rows][ld]: dims (ld, rows), box (64, box_rows)
-int make_matrix_map(CUtensorMap* m, const void* ptr, int ld, int rows, int box_rows, int is_fp16);
+int get_matrix_map(CUtensorMap* m, const void* ptr, int ld, int rows, int box_rows, int is_fp16);
+int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st);
 
-template <int BN, bool PAIRED, class Epi>
-int tc_gemm_launch_bn(const GemmDesc& d, const Epi& epi, cudaStream_t st, int lbo_override = -1, int sbo_override = -1) {
-  constexpr int STAGES = (BN == 256) ? 4 : 6;
+template <int BN, class Epi>
+int tc_gemm_launch_bn(const GemmDesc& d, const TcIo& io, const Epi& epi, cudaStream_t st, int lbo_override = -1,
+                      int sbo_override = -1) {
   TcGemmParams p;
   memset(&p, 0, sizeof(p));
   p.nseg = d.nseg;
   for (int s = 0; s < d.nseg; ++s) {
     CMWG_REQUIRE(d.seg[s].K % TC_BK == 0, "tc_gemm: segment K=%d not a multiple of %d", d.seg[s].K, TC_BK);
-    CMWG_PROPAGATE(make_slab_map(&p.a_map[s], d.seg[s].a, d.seg[s].lda, d.T, d.B, TC_BK, TC_BM, d.is_fp16));
+    CMWG_PROPAGATE(get_slab_map(&p.a_map[s], d.seg[s].a, d.seg[s].lda, d.seg[s].lda, d.T, d.B, TC_BK, TC_BM, d.is_fp16,
+                                TC_MAP_OPERAND));
     p.seg_nkb[s] = d.seg[s].K / TC_BK;
     p.seg_shift[s] = d.seg[s].shift;
     p.seg_koff[s] = d.seg[s].koff;
   }
-  CMWG_PROPAGATE(make_matrix_map(&p.b_map, d.w, d.ldw, d.n_rows_w, BN, d.is_fp16));
+  CMWG_PROPAGATE(get_matrix_map(&p.b_map, d.w, d.ldw, d.n_rows_w, BN / 2, d.is_fp16));
+  for (int i = 0; i < Epi::kOut; ++i) {
+    CMWG_REQUIRE(io.out[i].ptr != nullptr && (io.out[i].is_f32 != 0) == Epi::kOutF32, "tc_gemm: output stream %d mismatch", i);
+    CMWG_PROPAGATE(get_slab_map(&p.out_map[i], io.out[i].ptr, io.out[i].cols, io.out[i].ld, d.T, d.B, 32, 32, d.is_fp16,
+                                Epi::kOutF32 ? TC_MAP_CHUNK32 : TC_MAP_CHUNK16));
+  }
+  for (int i = 0; i < Epi::kIn; ++i) {
+    CMWG_REQUIRE(io.in[i].ptr != nullptr && !io.in[i].is_f32, "tc_gemm: input stream %d mismatch", i);
+    CMWG_PROPAGATE(get_slab_map(&p.in_map[i], io.in[i].ptr, io.in[i].cols, io.in[i].ld, d.T, d.B, 32, 32, d.is_fp16,
+                                TC_MAP_CHUNK16));
+  }
   p.B = d.B; p.T = d.T; p.N = d.N;
-  p.tiles_per_batch = ceil_div(d.T, TC_BM);
+  p.tiles_per_batch = ceil_div(d.T, 2 * TC_BM);
   p.n_tiles = ceil_div(d.N, BN);
   p.total_tiles = d.B * p.tiles_per_batch * p.n_tiles;
-  p.idesc = make_idesc(d.is_fp16, TC_BM, BN, 0, 0);
+  p.idesc = make_idesc(d.is_fp16, 2 * TC_BM, BN, 0, 0);
   p.desc_lbo = lbo_override >= 0 ? (uint32_t)lbo_override : 1u;
   p.desc_sbo = sbo_override >= 0 ? (uint32_t)sbo_override : (1024u >> 4);
   if (p.total_tiles == 0) return CMWG_OK;
-  auto kern = tc_gemm_kernel<BN, STAGES, PAIRED, Epi>;
-  constexpr size_t smem = tc_smem_bytes<BN, STAGES>();
+  auto kern = tc_gemm_kernel<BN, Epi>;
+  constexpr size_t smem = tc_smem_bytes<BN, Epi>();
+  static_assert(smem <= TC_SMEM_LIMIT, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
     CMWG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  int grid = std::min(p.total_tiles, num_sms());
+  int pairs = std::min(p.total_tiles, num_sms() / 2);
   ProfScope prof(st, d.tag);
-  kern<<<grid, TC_THREADS, smem, st>>>(p, epi);
+  void* args[2] = {(void*)&p, (void*)&epi};
+  CMWG_PROPAGATE(tc_launch_pairs((const void*)kern, smem, pairs, args, st));
   CMWG_COUNT_LAUNCH();
-  CMWG_LAUNCH_CHECK();
   return CMWG_OK;
 }
 
-template <bool PAIRED, class Epi>
-int tc_gemm_launch(const GemmDesc& d, const Epi& epi, cudaStream_t st) {
-  if (d.bn == 256) return tc_gemm_launch_bn<256, PAIRED, Epi>(d, epi, st);
-  return tc_gemm_launch_bn<128, PAIRED, Epi>(d, epi, st);
+template <class Epi>
+int tc_gemm_launch(const GemmDesc& d, const TcIo& io, const Epi& epi, cudaStream_t st) {
+  if (d.bn == 256) return tc_gemm_launch_bn<256, Epi>(d, io, epi, st);
+  return tc_gemm_launch_bn<128, Epi>(d, io, epi, st);
 }
 
 int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int T, int Lc, int is_fp16, cudaStream_t st,

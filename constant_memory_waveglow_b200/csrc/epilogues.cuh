@@ -307,48 +307,4 @@ struct StoreEpi {
   }
 };
 
-// ---- 7. (hi, lo) split store: x = hi + lo with hi = rn16(x), lo = rn16(x - hi) -------------------
-// The tcgen05 pipeline keeps the residual stream (and its gradient) as such a pair of 16-bit slabs:
-// the NEXT GEMM adds hi + lo back through identity K columns of its weight matrix, so the residual
-// add happens inside the tensor core / TMA pipeline and this epilogue never has to READ global
-// memory (a load-dependent epilogue is latency bound: one DRAM round trip per 32-column chunk).
-// hi doubles as the 16-bit GEMM operand of the next dilated conv.  Precision of the pair: 2^-17.
-template <typename OpT>
-struct SplitEpi {
-  static constexpr int kAux = 1;
-  OpT* hi;
-  OpT* lo;
-  const float* bias;
-  int ld, n_valid, f16;
-  template <int NC>
-  __device__ __forceinline__ void load(long long, int, float (&aux)[NC]) const {
-#pragma unroll
-    for (int j = 0; j < NC; ++j) aux[j] = 0.f;
-  }
-  template <int NC>
-  __device__ __forceinline__ void apply(long long row, int col0, const float (&v)[NC], const float (&)[NC]) const {
-    op<NC>(row, col0, v);
-  }
-  template <int NC>
-  __device__ __forceinline__ void op(long long row, int col0, const float (&v)[NC]) const {
-    if (col0 >= n_valid) return;
-    uint32_t ph[NC / 2], pl[NC / 2];
-#pragma unroll
-    for (int j = 0; j < NC; j += 2) {
-      float x0 = v[j] + (bias ? bias[col0 + j] : 0.f), x1 = v[j + 1] + (bias ? bias[col0 + j + 1] : 0.f);
-      uint32_t h = pack2(x0, x1, f16);
-      float h0, h1;
-      unpack2(h, f16, h0, h1);
-      ph[j / 2] = h;
-      pl[j / 2] = pack2(x0 - h0, x1 - h1, f16);
-    }
-    long long o = row * ld + col0;
-#pragma unroll
-    for (int j = 0; j < NC / 2; j += 2) {
-      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hi) + o + 2 * j) = make_uint2(ph[j], ph[j + 1]);
-      *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(lo) + o + 2 * j) = make_uint2(pl[j], pl[j + 1]);
-    }
-  }
-};
-
 }  // namespace cmwg

@@ -143,8 +143,6 @@ static __global__ void __launch_bounds__(256) pack_operands_kernel(const PackPar
     } else if (kind == 1) {
       int n = (int)(idx / d.ldPB), k = (int)(idx % d.ldPB);
       if (k < d.Cd) val = wWo[(long long)n * d.Cd + k];
-      // tc: identity columns add the (hi, lo) halves of the layer input to the residual rows
-      else if (k >= d.Cdp && n < cr_eff && ((k - d.Cdp) == n || (k - d.Cdp - d.Crp) == n)) val = 1.f;
       dst = reinterpret_cast<OpT*>(p.PB[i]);
     } else if (kind == 2) {
       int n = (int)(idx / k1), k = (int)(idx % k1);
@@ -160,13 +158,8 @@ static __global__ void __launch_bounds__(256) pack_operands_kernel(const PackPar
     } else if (kind == 3) {
       int ld = d.ldQ2;
       int n = (int)(idx / ld), k = (int)(idx % ld);
-      if (k < d.R * d.Cd2p) {
-        int tap = k / d.Cd2p, oc = k % d.Cd2p;
-        if (oc < 2 * d.Cd) val = wW[((long long)oc * d.Cr + n) * d.R + tap];
-      } else {
-        int kk = k - d.R * d.Cd2p;  // tc: identity columns carry the (hi, lo) upstream residual gradient
-        if (kk == n || kk - d.Crp == n) val = 1.f;
-      }
+      int tap = k / d.Cd2p, oc = k % d.Cd2p;
+      if (oc < 2 * d.Cd) val = wW[((long long)oc * d.Cr + n) * d.R + tap];
       dst = reinterpret_cast<OpT*>(p.Q2[i]);
     } else if (kind == 4) {
       int n = (int)(idx / d.Cd2p), k = (int)(idx % d.Cd2p);

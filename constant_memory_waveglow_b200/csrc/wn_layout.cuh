@@ -10,7 +10,7 @@
 
 namespace cmwg {
 
-constexpr int MAX_SEG = 16;  // K segments of one GEMM: radix taps + conditioning / hi+lo identity blocks / one per layer
+constexpr int MAX_SEG = 16;  // K segments of one GEMM: radix taps + conditioning / one per layer
 constexpr int TC_MAX_WG_REDUCE = 8;  // weight-gradient problems reduced per launch
 
 struct WnDims {
@@ -24,8 +24,8 @@ struct WnDims {
   int G;
   int npadA;    // padded rows of the gate GEMM weight matrix
   int KA;       // K of the gate GEMM: R*Crp + auxp
-  int ldPB;     // K of the res GEMM: Cdp (+ 2*Crp identity columns carrying the hi/lo residual, tc)
-  int ldQ2;     // K of the dx GEMM: R*Cd2p (+ 2*Crp identity columns, tc)
+  int ldPB;     // K of the res(/skip) GEMM: Cdp
+  int ldQ2;     // K of the dx GEMM: R*Cd2p
   int ldQV;     // K of the conditioning-gradient GEMM: depth*Cd2p (all layers concatenated)
   int ldPS;     // K of the skip GEMM (tc): depth*Cdp
   __host__ __device__ int nb(int i) const { return (i < depth - 1) ? Cr + Cs : Cs; }     // rows of W_o[i]
@@ -73,8 +73,8 @@ inline int make_dims(const cmwg_wn_config* c, WnDims* d) {
   d->G = d->bn_gate / 2;
   d->npadA = ceil_div(d->Cd, d->G) * d->bn_gate;
   d->KA = d->R * d->Crp + d->auxp;
-  d->ldPB = d->Cdp + (d->tc ? 2 * d->Crp : 0);
-  d->ldQ2 = d->R * d->Cd2p + (d->tc ? 2 * d->Crp : 0);
+  d->ldPB = d->Cdp;
+  d->ldQ2 = d->R * d->Cd2p;
   d->ldQV = d->depth * d->Cd2p;
   d->ldPS = d->depth * d->Cdp;
   return CMWG_OK;
@@ -95,7 +95,7 @@ struct PackedLayout {
   size_t PA[CMWG_MAX_DEPTH];  // gate GEMM      [npadA][KA]
   size_t PB[CMWG_MAX_DEPTH];  // res/skip GEMM  [nb(i)][ldPB]
   size_t Q1[CMWG_MAX_DEPTH];  // dgate GEMM     [Cd][k1(i)]          = W_o^T
-  size_t Q2[CMWG_MAX_DEPTH];  // dx GEMM        [Cr][ldQ2]           = W^T per tap (+ identity blocks)
+  size_t Q2[CMWG_MAX_DEPTH];  // dx GEMM        [Cr][ldQ2]           = W^T per tap
   size_t QV[CMWG_MAX_DEPTH];  // dy GEMM        [auxp][ldQV] shared; QV[i] points at column i*Cd2p
   size_t total;
 };
@@ -138,8 +138,8 @@ struct FwdLayout {
   size_t skip32;  // [rows][Cs] fp32 cumulative skip
   size_t hop;     // [rows][Cr] operand copy of the layer input (tc inference only; ff aliases h32)
   size_t gop;     // [rows][Cd] operand gate output (inference)
-  // tc engine: the residual stream lives as a (hi, lo) pair of 16-bit slabs, h = hi + lo, so that
-  // the residual add rides through the tensor core (identity K columns) and the epilogue is store-only
+  // tc engine: the residual stream lives as a (hi, lo) pair of 16-bit slabs, h = hi + lo: hi is the
+  // next GEMM's operand, and the pair is TMA-loaded into the residual GEMM's epilogue for the fp32 add
   size_t hi2[2];  // ping-pong [rows][Cr] (inference; training keeps hi per layer in `saved`)
   size_t lo2[2];  // ping-pong [rows][Cr]
   size_t gl[CMWG_MAX_DEPTH];  // per-layer gate outputs (inference; the skip GEMM reads all of them at the end)

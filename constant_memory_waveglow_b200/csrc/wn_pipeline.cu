@@ -15,6 +15,7 @@
 #include "engine_ff.cuh"
 #include "engine_tc.cuh"
 #include "epilogues.cuh"
+#include "epilogues_tc.cuh"
 #include "wn_kernels.cuh"
 
 namespace cmwg {
@@ -28,8 +29,14 @@ template <> struct EngineSel<float> {
 template <> struct EngineSel<uint16_t> {
   static constexpr bool kTc = true;
   template <bool PAIRED, class Epi>
-  static int gemm(const GemmDesc& d, const Epi& e, cudaStream_t st) { return tc_gemm_launch<PAIRED, Epi>(d, e, st); }
+  static int gemm(const GemmDesc&, const Epi&, cudaStream_t) {  // the tc engine has its own functors (epilogues_tc.cuh)
+    set_error("internal: FFMA epilogue functor routed to the tcgen05 engine");
+    return CMWG_ERR_ARG;
+  }
 };
+
+static inline TcStream op_stream(const void* p, int ld) { return TcStream{p, ld, ld, 0}; }
+static inline TcStream f32_stream(const void* p, int ld) { return TcStream{p, ld, ld, 1}; }
 
 static inline int pick_bn(int N) { return N >= 256 ? 256 : 128; }
 
@@ -173,30 +180,48 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
       g.nseg = d.R + 1;
       g.w = pk + PL.PA[i]; g.ldw = d.KA; g.N = d.npadA; g.n_rows_w = d.npadA;
       g.B = B; g.T = T; g.bn = d.bn_gate; g.is_fp16 = f16; g.tag = CMWG_KCLASS_GATE;
-      GateEpi<OpT, TC> epi;
-      epi.g = g_op(i);
-      epi.a_save = save ? reinterpret_cast<OpT*>(sv + FL.s_a[i]) : nullptr;
-      epi.b_save = save ? reinterpret_cast<OpT*>(sv + FL.s_b[i]) : nullptr;
-      epi.bias = d.bias ? reinterpret_cast<const float*>(pk + PL.biasA[i]) : nullptr;
-      epi.Cd = d.Cd; epi.f16 = f16;
-      CMWG_PROPAGATE((E::template gemm<true>(g, epi, st)));
+      const float* biasA = d.bias ? reinterpret_cast<const float*>(pk + PL.biasA[i]) : nullptr;
+      if constexpr (TC) {
+        TcIo io;
+        memset(&io, 0, sizeof(io));
+        io.out[0] = op_stream(g_op(i), d.Cd);
+        if (save) {
+          io.out[1] = op_stream(sv + FL.s_a[i], d.Cd);
+          io.out[2] = op_stream(sv + FL.s_b[i], d.Cd);
+          GateTcEpi<true> epi{biasA, d.Cd, f16};
+          CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+        } else {
+          GateTcEpi<false> epi{biasA, d.Cd, f16};
+          CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+        }
+      } else {
+        GateEpi<OpT, TC> epi;
+        epi.g = g_op(i);
+        epi.a_save = save ? reinterpret_cast<OpT*>(sv + FL.s_a[i]) : nullptr;
+        epi.b_save = save ? reinterpret_cast<OpT*>(sv + FL.s_b[i]) : nullptr;
+        epi.bias = biasA;
+        epi.Cd = d.Cd; epi.f16 = f16;
+        CMWG_PROPAGATE((E::template gemm<true>(g, epi, st)));
+      }
     }
     if constexpr (TC) {
-      // ---- residual GEMM: h_{i+1} = g W_res^T + hi_i + lo_i (identity K columns), store-only epilogue
+      // ---- residual GEMM: h_{i+1} = g W_res^T + (hi_i + lo_i); the (hi, lo) pair of the layer input is
+      // TMA-loaded into the epilogue and the new pair is TMA-stored
       if (!last) {
         GemmDesc g;
         memset(&g, 0, sizeof(g));
         g.seg[0].a = g_op(i); g.seg[0].lda = d.Cd; g.seg[0].K = d.Cd; g.seg[0].koff = 0;
-        g.seg[1].a = hin_op(i); g.seg[1].lda = d.Cr; g.seg[1].K = d.Cr; g.seg[1].koff = d.Cdp;
-        g.seg[2].a = hlo_op(i); g.seg[2].lda = d.Cr; g.seg[2].K = d.Cr; g.seg[2].koff = d.Cdp + d.Crp;
-        g.nseg = 3;
+        g.nseg = 1;
         g.w = pk + PL.PB[i]; g.ldw = d.ldPB; g.N = d.Cr; g.n_rows_w = d.nb(i);
         g.B = B; g.T = T; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
-        SplitEpi<OpT> epi;
-        epi.hi = hin_op(i + 1); epi.lo = hlo_op(i + 1);
-        epi.bias = d.bias ? reinterpret_cast<const float*>(pk + PL.biasB[i]) : nullptr;
-        epi.ld = d.Cr; epi.n_valid = d.Cr; epi.f16 = f16;
-        CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+        TcIo io;
+        memset(&io, 0, sizeof(io));
+        io.in[0] = op_stream(hin_op(i), d.Cr);
+        io.in[1] = op_stream(hlo_op(i), d.Cr);
+        io.out[0] = op_stream(hin_op(i + 1), d.Cr);
+        io.out[1] = op_stream(hlo_op(i + 1), d.Cr);
+        SplitTcEpi<true> epi{d.bias ? reinterpret_cast<const float*>(pk + PL.biasB[i]) : nullptr, f16};
+        CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
       }
     } else {
       // ---- residual / skip GEMM (fp32 engine: read-modify-write epilogue)
@@ -230,10 +255,11 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
     g.nseg = d.depth;
     g.w = pk + PL.PS; g.ldw = d.ldPS; g.N = d.Cs; g.n_rows_w = d.Cs;
     g.B = B; g.T = T; g.bn = pick_bn(d.Cs); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
-    StoreEpi epi;
-    epi.dst = skip32; epi.ld = d.Cs; epi.n_valid = d.Cs;
-    epi.bias = d.bias ? reinterpret_cast<const float*>(pk + PL.biasS) : nullptr;
-    CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+    TcIo io;
+    memset(&io, 0, sizeof(io));
+    io.out[0] = f32_stream(skip32, d.Cs);
+    StoreTcEpi epi{d.bias ? reinterpret_cast<const float*>(pk + PL.biasS) : nullptr};
+    CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
   }
   // ---- end conv
   {
@@ -373,11 +399,24 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       g.nseg = ns;
       g.w = pk + PL.Q1[i]; g.ldw = d.k1(i); g.N = d.Cd; g.n_rows_w = d.Cd;
       g.B = B; g.T = T; g.bn = pick_bn(d.Cd); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DGATE;
-      GateBwdEpi<OpT> epi;
-      epi.a_save = reinterpret_cast<const OpT*>(sv + FL.s_a[i]);
-      epi.b_save = reinterpret_cast<const OpT*>(sv + FL.s_b[i]);
-      epi.dpre = dpre_i; epi.Cd = d.Cd; epi.ld = 2 * d.Cd; epi.f16 = f16;
-      CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+      if constexpr (TC) {
+        TcIo io;
+        memset(&io, 0, sizeof(io));
+        io.in[0] = op_stream(sv + FL.s_a[i], d.Cd);
+        io.in[1] = op_stream(sv + FL.s_b[i], d.Cd);
+        // two column windows of the dpre slab: each map exposes only its own Cd channels, so a partial
+        // N tile (Cd < BN) is clipped instead of spilling into the other half
+        io.out[0] = TcStream{dpre_i, 2 * d.Cd, d.Cd, 0};
+        io.out[1] = TcStream{dpre_i + d.Cd, 2 * d.Cd, d.Cd, 0};
+        GateBwdTcEpi epi{d.Cd, f16};
+        CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+      } else {
+        GateBwdEpi<OpT> epi;
+        epi.a_save = reinterpret_cast<const OpT*>(sv + FL.s_a[i]);
+        epi.b_save = reinterpret_cast<const OpT*>(sv + FL.s_b[i]);
+        epi.dpre = dpre_i; epi.Cd = d.Cd; epi.ld = 2 * d.Cd; epi.f16 = f16;
+        CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+      }
     }
     // ---- weight gradients of this layer: W_o (res rows, skip rows), W per tap, V_i
     {
@@ -484,15 +523,19 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       g.w = pk + PL.Q2[i]; g.ldw = d.ldQ2; g.N = d.Cr; g.n_rows_w = d.Cr;
       g.B = B; g.T = T; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DX;
       if constexpr (TC) {
-        if (!last) {  // upstream residual gradient rides through identity K columns
-          g.seg[d.R].a = dhi(i + 1); g.seg[d.R].lda = d.Cr; g.seg[d.R].K = d.Cr; g.seg[d.R].koff = d.R * d.Cd2p;
-          g.seg[d.R + 1].a = dlo(i + 1); g.seg[d.R + 1].lda = d.Cr; g.seg[d.R + 1].K = d.Cr;
-          g.seg[d.R + 1].koff = d.R * d.Cd2p + d.Crp;
-          g.nseg = d.R + 2;
+        TcIo io;
+        memset(&io, 0, sizeof(io));
+        io.out[0] = op_stream(dhi(i), d.Cr);
+        io.out[1] = op_stream(dlo(i), d.Cr);
+        if (!last) {  // the upstream residual gradient (hi, lo) is added in the epilogue
+          io.in[0] = op_stream(dhi(i + 1), d.Cr);
+          io.in[1] = op_stream(dlo(i + 1), d.Cr);
+          SplitTcEpi<true> epi{nullptr, f16};
+          CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+        } else {
+          SplitTcEpi<false> epi{nullptr, f16};
+          CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
         }
-        SplitEpi<OpT> epi;
-        epi.hi = dhi(i); epi.lo = dlo(i); epi.bias = nullptr; epi.ld = d.Cr; epi.n_valid = d.Cr; epi.f16 = f16;
-        CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
       } else {
         DxEpi<OpT> epi;
         epi.src = last ? nullptr : dh32; epi.dst32 = dh32; epi.dst_op = nullptr;
@@ -514,9 +557,11 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       g.nseg = d.depth;
       g.w = pk + PL.QV[0]; g.ldw = d.ldQV; g.N = d.auxp; g.n_rows_w = d.auxp;
       g.B = B; g.T = T; g.bn = pick_bn(d.auxp); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DCOND;
-      StoreEpi epi;
-      epi.dst = dycl; epi.ld = d.auxp; epi.n_valid = d.auxp; epi.bias = nullptr;
-      CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
+      TcIo io;
+      memset(&io, 0, sizeof(io));
+      io.out[0] = f32_stream(dycl, d.auxp);
+      StoreTcEpi epi{nullptr};
+      CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
     }
   }
 
