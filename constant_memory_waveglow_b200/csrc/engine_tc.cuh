@@ -9,13 +9,14 @@
 //                      TMEM of both SMs, double buffered (2 x BN columns).  Operand traffic per flop
 //                      (L2 -> shared memory and shared memory -> tensor core) is 2/3 of the 1-CTA form,
 //                      which is what bounds a 128 x 256 x 64 1-CTA tile.
-//   warps 2..9         epilogue (two warps per TMEM lane quadrant, half of the columns each):
-//                      tcgen05.ld 32 lanes x 32 columns (one accumulator ROW per thread) -> fused
-//                      epilogue functor -> swizzled shared-memory staging -> TMA store.  Epilogue INPUTS
-//                      (saved gate values, residual hi/lo pairs) arrive the same way in reverse:
-//                      TMA load into per-warp staging, one chunk ahead.  The TMA unit clips rows >= T
-//                      and columns >= C on stores and zero-fills them on loads, so the epilogue has
-//                      no bounds checks and no global address arithmetic.
+//   warps 2..17        epilogue (four warps per TMEM lane quadrant, a quarter of the columns each; 4 warps
+//                      per scheduler hide the MUFU / conversion latencies of the fused functors):
+//                      tcgen05.ld 32 lanes x 16 columns (one accumulator ROW per thread) -> fused
+//                      epilogue functor -> swizzled shared-memory staging -> TMA store of 32 x 32 chunks.
+//                      Epilogue INPUTS (saved gate values, residual hi/lo pairs) arrive the same way in
+//                      reverse: TMA load into per-warp staging, issued one chunk ahead.  The TMA unit
+//                      clips rows >= T and columns >= C on stores and zero-fills them on loads, so the
+//                      epilogue has no bounds checks and no global address arithmetic.
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA; empty is signalled in both CTAs by a multicast
 // tcgen05.commit) and TMEM full/empty mbarriers (MMA <-> epilogue; the peer's epilogue warps arrive
 // remotely on the leader's tmem_empty barrier).
@@ -37,7 +38,7 @@ namespace cmwg {
 constexpr int TC_BM = 128;                // rows per CTA (the pair covers 256)
 constexpr int TC_BK = 64;                 // 64 x 16-bit = 128 B = one swizzle row
 constexpr int TC_A_BYTES = TC_BM * 128;   // 16 KB
-constexpr int TC_EPI_WARPS = 8;           // 2 per TMEM lane quadrant, each owning half of the tile's columns
+constexpr int TC_EPI_WARPS = 16;          // 4 per TMEM lane quadrant, each owning a quarter of the tile's columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_MAX_WG = 8;              // weight-gradient problems per launch
 constexpr int TC_MAX_OUT = 3;             // output streams of one epilogue
@@ -101,7 +102,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // arrive on the barrier at shared::cluster address `addr` (possibly in the peer CTA)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
@@ -218,6 +219,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // UMMA shared-memory descriptor (sm_100 "version 1"), SWIZZLE_128B
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_enc, uint32_t sbo_enc) {
   uint64_t d = 0;
@@ -258,11 +274,13 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
-__device__ __forceinline__ void stage_store16(uint32_t buf, int lane, const uint32_t (&o)[16]) {
+// half h (0/1) of a 16-bit chunk row: 16 columns = two 16-byte slots (2h, 2h+1)
+__device__ __forceinline__ void stage_store16h(uint32_t buf, int lane, int h, const uint32_t (&o)[8]) {
   const uint32_t base = buf + lane * 64;
   const int sw = (lane >> 1) & 3;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) st_shared_v4(base + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  for (int j = 0; j < 2; ++j)
+    st_shared_v4(base + (((2 * h + j) ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
 }
 __device__ __forceinline__ void stage_load16(uint32_t buf, int lane, uint32_t (&o)[16]) {
   const uint32_t base = buf + lane * 64;
@@ -270,18 +288,20 @@ __device__ __forceinline__ void stage_load16(uint32_t buf, int lane, uint32_t (&
 #pragma unroll
   for (int j = 0; j < 4; ++j) ld_shared_v4(base + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
 }
-__device__ __forceinline__ void stage_store32(uint32_t buf, int lane, const uint32_t (&o)[32]) {
+// half h of an fp32 chunk row: 16 columns = four 16-byte slots (4h .. 4h+3)
+__device__ __forceinline__ void stage_store32h(uint32_t buf, int lane, int h, const uint32_t (&o)[16]) {
   const uint32_t base = buf + lane * 128;
   const int sw = lane & 7;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) st_shared_v4(base + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  for (int j = 0; j < 4; ++j)
+    st_shared_v4(base + (((4 * h + j) ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
 }
 
 template <class Epi>
 struct TcEpiTraits {
   static constexpr int kOutChunk = Epi::kOutF32 ? TC_CHUNK32_BYTES : TC_CHUNK16_BYTES;
   static constexpr int kOutBytes = Epi::kOutBufs * Epi::kOut * kOutChunk;
-  static constexpr int kInBytes = 2 * Epi::kIn * TC_CHUNK16_BYTES;  // inputs: 16-bit, double buffered
+  static constexpr int kInBytes = Epi::kIn * TC_CHUNK16_BYTES;  // inputs: 16-bit, one chunk (re-armed as soon as it is read)
   static constexpr int kWarpBytes = kOutBytes + kInBytes;
 };
 
@@ -308,13 +328,13 @@ struct TcSmem {
   uint64_t* empty;     // [STAGES]
   uint64_t* tmem_full; // [2]
   uint64_t* tmem_empty;// [2]        (leader's is the one in use)
-  uint64_t* in_bar;    // [TC_EPI_WARPS][2] epilogue input loads
+  uint64_t* in_bar;    // [TC_EPI_WARPS] epilogue input loads
   uint32_t* tmem_ptr;
 };
 
 template <int STAGES>
 __device__ __forceinline__ TcSmem tc_carve(uint8_t* raw, int stage_bytes, int epi_warp_bytes) {
-  static_assert((2 * STAGES + 4 + 2 * TC_EPI_WARPS) * 8 + 8 <= TC_BAR_BYTES, "barrier area too small");
+  static_assert((2 * STAGES + 4 + TC_EPI_WARPS) * 8 + 8 <= TC_BAR_BYTES, "barrier area too small");
   TcSmem s;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   s.stages = base;
@@ -325,17 +345,18 @@ __device__ __forceinline__ TcSmem tc_carve(uint8_t* raw, int stage_bytes, int ep
   s.tmem_full = bars + 2 * STAGES;
   s.tmem_empty = bars + 2 * STAGES + 2;
   s.in_bar = bars + 2 * STAGES + 4;
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * TC_EPI_WARPS);
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + TC_EPI_WARPS);
   return s;
 }
 
+// `drain_warps`: epilogue warps per CTA that drain accumulators (arrivals on the leader's tmem_empty per CTA)
 template <int STAGES>
-__device__ __forceinline__ void tc_setup(const TcSmem& s, int warp, int lane, int tmem_cols) {
+__device__ __forceinline__ void tc_setup(const TcSmem& s, int warp, int lane, int tmem_cols, int drain_warps) {
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < STAGES; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], 2 * TC_EPI_WARPS); }
-      for (int i = 0; i < 2 * TC_EPI_WARPS; ++i) mbar_init(&s.in_bar[i], 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&s.tmem_full[i], 1); mbar_init(&s.tmem_empty[i], 2 * drain_warps); }
+      for (int i = 0; i < TC_EPI_WARPS; ++i) mbar_init(&s.in_bar[i], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -378,7 +399,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     for (int i = 0; i < Epi::kOut; ++i) prefetch_tmap(&p.out_map[i]);
     for (int i = 0; i < Epi::kIn; ++i) prefetch_tmap(&p.in_map[i]);
   }
-  tc_setup<STAGES>(s, warp, lane, 2 * BN);
+  constexpr int GW = Epi::kPaired ? BN / 2 : BN;   // epilogue columns of one tile (gate channels when paired)
+  constexpr int NCG = (GW / 32) < 4 ? (GW / 32) : 4;  // column groups = draining warps per TMEM lane quadrant
+  constexpr int NCH = GW / (32 * NCG);             // 32-column chunks per warp per tile
+  tc_setup<STAGES>(s, warp, lane, 2 * BN, 4 * NCG);
   const uint32_t tmem_base = *s.tmem_ptr;
 
   if (warp == 0) {
@@ -433,92 +457,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {
+  } else if ((warp - 2) >> 2 < NCG) {
     const int e = warp - 2;
     const int q = warp & 3;          // TMEM lane quadrant this warp may access (hardware: warp id % 4)
-    const int half = e >> 2;         // which half of the tile's columns this warp drains
-    constexpr int GW = Epi::kPaired ? BN / 2 : BN;  // epilogue columns of one tile (gate channels when paired)
-    constexpr int NCH = (GW / 2) / 32;              // 32-column chunks per warp per tile
+    const int cg = e >> 2;           // column group of this warp
+    constexpr int OUTW = Epi::kOutF32 ? 16 : 8;  // registers per 16-column output fragment
     const uint32_t wbuf = smem_u32(s.epi + e * ET::kWarpBytes);
-    const uint32_t ibuf0 = wbuf + ET::kOutBytes;
-    uint64_t* ibar = s.in_bar + 2 * e;
+    const uint32_t ibuf = wbuf + ET::kOutBytes;
+    uint64_t* ibar = s.in_bar + e;
     const uint32_t tmem_empty_addr = mapa_shared(smem_u32(&s.tmem_empty[0]), 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     int ob = 0;        // output staging buffer in use
-    uint32_t it = 0;   // running chunk counter (input double buffer + phase)
+    uint32_t it = 0;   // running chunk counter (phase of the input barrier)
 
     // coordinates of chunk k of a tile: batch, first row of this warp, first epilogue column
     auto coords = [&](int tile, int k, int& b, int& r0, int& c0) {
       int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
       b = rt / p.tiles_per_batch;
       r0 = (rt % p.tiles_per_batch) * (2 * TC_BM) + rank * TC_BM + q * 32;
-      c0 = nt * GW + half * (GW / 2) + 32 * k;
+      c0 = nt * GW + cg * (GW / NCG) + 32 * k;
     };
-    auto issue_inputs = [&](int tile, int k, uint32_t n) {
+    auto issue_inputs = [&](int tile, int k) {
       if constexpr (Epi::kIn > 0) {
         if (lane == 0) {
           int b, r0, c0;
           coords(tile, k, b, r0, c0);
-          uint32_t buf = ibuf0 + (n & 1) * Epi::kIn * TC_CHUNK16_BYTES;
           fence_proxy_async();
-          mbar_arrive_expect_tx(&ibar[n & 1], Epi::kIn * TC_CHUNK16_BYTES);
+          mbar_arrive_expect_tx(ibar, Epi::kIn * TC_CHUNK16_BYTES);
 #pragma unroll
           for (int i = 0; i < Epi::kIn; ++i)
-            tma_load_3d_local(buf + i * TC_CHUNK16_BYTES, &p.in_map[i], smem_u32(&ibar[n & 1]), epi.in_col(i, c0), r0, b);
+            tma_load_3d_local(ibuf + i * TC_CHUNK16_BYTES, &p.in_map[i], smem_u32(ibar), epi.in_col(i, c0), r0, b);
         }
       }
     };
-    if (pair < p.total_tiles) issue_inputs(pair, 0, 0);
+    if (pair < p.total_tiles) issue_inputs(pair, 0);
 
     for (int tile = pair; tile < p.total_tiles; tile += npairs) {
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + half * (GW / 2);
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + cg * (GW / NCG);
       mbar_wait(&s.tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
       for (int k = 0; k < NCH; ++k, ++it) {
         int b, r0, c0;
         coords(tile, k, b, r0, c0);
-        // epilogue inputs: prefetch the next chunk, wait for this one
+        // epilogue inputs: take this chunk into registers, then re-arm the buffer with the next chunk
         uint32_t in[Epi::kIn > 0 ? Epi::kIn : 1][16];
         if constexpr (Epi::kIn > 0) {
-          if (k + 1 < NCH) issue_inputs(tile, k + 1, it + 1);
-          else if (tile + npairs < p.total_tiles) issue_inputs(tile + npairs, 0, it + 1);
-          mbar_wait(&ibar[it & 1], (it >> 1) & 1);
-          uint32_t buf = ibuf0 + (it & 1) * Epi::kIn * TC_CHUNK16_BYTES;
+          mbar_wait(ibar, it & 1);
 #pragma unroll
-          for (int i = 0; i < Epi::kIn; ++i) stage_load16(buf + i * TC_CHUNK16_BYTES, lane, in[i]);
-        }
-        // accumulators
-        float v[32];
-        tmem_ld32(taddr + 32 * k, v);
-        uint32_t o[Epi::kOut][Epi::kOutF32 ? 32 : 16];
-        if constexpr (Epi::kPaired) {
-          float w[32];
-          tmem_ld32(taddr + GW + 32 * k, w);
-          if (k == NCH - 1) {  // TMEM buffer drained: hand it back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tmem_empty_addr + 8 * acc);
-          }
-          epi.compute(c0, v, w, o);
-        } else {
-          if (k == NCH - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tmem_empty_addr + 8 * acc);
-          }
-          if constexpr (Epi::kIn > 0) epi.compute(c0, v, in, o);
-          else epi.compute(c0, v, o);
+          for (int i = 0; i < Epi::kIn; ++i) stage_load16(ibuf + i * TC_CHUNK16_BYTES, lane, in[i]);
+          __syncwarp();
+          if (k + 1 < NCH) issue_inputs(tile, k + 1);
+          else if (tile + npairs < p.total_tiles) issue_inputs(tile + npairs, 0);
         }
         // staging buffer `ob` must have been read by the TMA store issued Epi::kOutBufs chunks ago
         if (lane == 0) bulk_wait_read<Epi::kOutBufs - 1>();
         __syncwarp();
         const uint32_t obuf = wbuf + ob * Epi::kOut * ET::kOutChunk;
 #pragma unroll
-        for (int i = 0; i < Epi::kOut; ++i) {
-          if constexpr (Epi::kOutF32) stage_store32(obuf + i * ET::kOutChunk, lane, o[i]);
-          else stage_store16(obuf + i * ET::kOutChunk, lane, o[i]);
+        for (int h = 0; h < 2; ++h) {
+          float v[16];
+          uint32_t o[Epi::kOut][OUTW];
+          tmem_ld16(taddr + 32 * k + 16 * h, v);
+          if constexpr (Epi::kPaired) {
+            float w[16];
+            tmem_ld16(taddr + GW + 32 * k + 16 * h, w);
+            if (h == 1 && k == NCH - 1) {  // TMEM buffer drained: hand it back to the MMA issuer
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(tmem_empty_addr + 8 * acc);
+            }
+            epi.compute(c0 + 16 * h, v, w, o);
+          } else {
+            if (h == 1 && k == NCH - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(tmem_empty_addr + 8 * acc);
+            }
+            if constexpr (Epi::kIn > 0) {
+              uint32_t inh[Epi::kIn][8];
+#pragma unroll
+              for (int i = 0; i < Epi::kIn; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) inh[i][j] = in[i][8 * h + j];
+              epi.compute(c0 + 16 * h, v, inh, o);
+            } else {
+              epi.compute(c0 + 16 * h, v, o);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < Epi::kOut; ++i) {
+            if constexpr (Epi::kOutF32) stage_store32h(obuf + i * ET::kOutChunk, lane, h, o[i]);
+            else stage_store16h(obuf + i * ET::kOutChunk, lane, h, o[i]);
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -542,9 +574,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 // The pair computes a 256 (m) x BN (n) tile: each CTA loads its 128 m-columns of A and its BN/2
 // n-columns of B; fp32 partial tiles leave through the TMA store path.
 // ------------------------------------------------------------------------------------------------
-struct WgradEpiShape {  // staging shape of the weight-gradient epilogue (fp32, one stream, double buffered)
+struct WgradEpiShape {  // staging shape of the weight-gradient epilogue (fp32, one stream)
   static constexpr bool kOutF32 = true, kPaired = false;
-  static constexpr int kOut = 1, kIn = 0, kOutBufs = 2;
+  static constexpr int kOut = 1, kIn = 0, kOutBufs = 1;
 };
 
 template <int BN>
@@ -561,7 +593,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nprob; ++i) { prefetch_tmap(&p.a_map[i]); prefetch_tmap(&p.b_map[i]); prefetch_tmap(&p.out_map[i]); }
   }
-  tc_setup<STAGES>(s, warp, lane, 2 * BN);
+  constexpr int NCG = (BN / 32) < 4 ? (BN / 32) : 4;
+  constexpr int NCH = BN / (32 * NCG);
+  tc_setup<STAGES>(s, warp, lane, 2 * BN, 4 * NCG);
   const uint32_t tmem_base = *s.tmem_ptr;
   const int tiles_total = p.tile_begin[p.nprob];
 
@@ -636,11 +670,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else {
+  } else if ((warp - 2) >> 2 < NCG) {
     const int e = warp - 2;
     const int q = warp & 3;
-    const int half = e >> 2;
-    constexpr int NCH = (BN / 2) / 32;
+    const int cg = e >> 2;
     const uint32_t wbuf = smem_u32(s.epi + e * ET::kWarpBytes);
     const uint32_t tmem_empty_addr = mapa_shared(smem_u32(&s.tmem_empty[0]), 0);
     int acc = 0;
@@ -652,30 +685,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       mbar_wait(&s.tmem_full[acc], acc_phase);
       tc_fence_after();
       const int mq = m0 + rank * TC_BM + q * 32;
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + half * (BN / 2);
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + cg * (BN / NCG);
 #pragma unroll 1
       for (int k = 0; k < NCH; ++k) {
-        float v[32];
-        tmem_ld32(taddr + 32 * k, v);
-        if (k == NCH - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tmem_empty_addr + 8 * acc);
-        }
-        uint32_t o[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(v[j]);
-        if (lane == 0) bulk_wait_read<1>();
+        if (lane == 0) bulk_wait_read<WgradEpiShape::kOutBufs - 1>();
         __syncwarp();
         const uint32_t obuf = wbuf + ob * TC_CHUNK32_BYTES;
-        stage_store32(obuf, lane, o);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[16];
+          tmem_ld16(taddr + 32 * k + 16 * h, v);
+          if (h == 1 && k == NCH - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tmem_empty_addr + 8 * acc);
+          }
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(v[j]);
+          stage_store32h(obuf, lane, h, o);
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&p.out_map[pr], obuf, n0 + half * (BN / 2) + 32 * k, mq, split);
+          tma_store_3d(&p.out_map[pr], obuf, n0 + cg * (BN / NCG) + 32 * k, mq, split);
           bulk_commit();
         }
-        ob ^= 1;
+        if (WgradEpiShape::kOutBufs > 1) ob ^= 1;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

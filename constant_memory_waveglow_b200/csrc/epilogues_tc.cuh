@@ -1,6 +1,6 @@
 // Epilogue functors of the tcgen05 engine.  One call covers ONE accumulator row (= one (batch, time)
-// column of the reference's NCL tensors) and 32 consecutive epilogue columns; inputs and outputs are
-// 32-wide register fragments that the engine moves through swizzled shared-memory staging and TMA.
+// column of the reference's NCL tensors) and 16 consecutive epilogue columns; inputs and outputs are
+// register fragments that the engine moves through swizzled shared-memory staging and TMA.
 //
 //   kPaired    the tile's columns [0, BN/2) and [BN/2, BN) are partner pre-activations (tanh / sigmoid)
 //   kOut       output streams (each a slab the engine TMA-stores 32 rows x 32 columns at a time)
@@ -8,6 +8,8 @@
 //   kOutBufs   staging buffers per output stream (2 = the store of chunk i overlaps chunk i+1)
 //   kIn        16-bit input streams, TMA-loaded one chunk ahead
 //   out_col(i, c0) / in_col(i, c0)   channel coordinate of stream i for epilogue column c0
+// Precision / bias switches are warp-uniform branches AROUND the unrolled loops (never per element),
+// so only one variant's instructions are issued.
 #pragma once
 #include "epilogues.cuh"
 
@@ -18,32 +20,32 @@ namespace cmwg {
 template <bool SAVE>
 struct GateTcEpi {
   static constexpr bool kPaired = true, kOutF32 = false;
-  static constexpr int kOut = SAVE ? 3 : 1, kIn = 0, kOutBufs = 2;
+  static constexpr int kOut = SAVE ? 3 : 1, kIn = 0, kOutBufs = 1;
   const float* bias;  // nullptr or [2][Cd]
   int Cd, f16;
   __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
   __device__ __forceinline__ int in_col(int, int c0) const { return c0; }
-  __device__ __forceinline__ void compute(int ch0, const float (&lo)[32], const float (&hi)[32],
-                                          uint32_t (&o)[kOut][16]) const {
+  __device__ __forceinline__ void compute(int ch0, float (&lo)[16], float (&hi)[16], uint32_t (&o)[kOut][8]) const {
+    if (bias) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float a[2], b[2];
+      for (int j = 0; j < 16; ++j) { lo[j] += __ldg(bias + ch0 + j); hi[j] += __ldg(bias + Cd + ch0 + j); }
+    }
+    if (f16) {
+      // MUFU.EX2 + MUFU.RCP forms (~1e-7 abs error): fp16's 11-bit mantissa deserves better than tanh.approx
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        float pt = lo[j + u], ps = hi[j + u];
-        if (bias) { pt += __ldg(bias + ch0 + j + u); ps += __ldg(bias + Cd + ch0 + j + u); }
-        if (f16) {
-          a[u] = tanh_ex2(pt);
-          b[u] = sigmoid_ex2(ps);
-        } else {
-          a[u] = tanh_f<true>(pt);
-          b[u] = sigmoid_f<true>(ps);
-        }
+      for (int j = 0; j < 16; j += 2) {
+        float a0 = tanh_ex2(lo[j]), a1 = tanh_ex2(lo[j + 1]);
+        float b0 = sigmoid_ex2(hi[j]), b1 = sigmoid_ex2(hi[j + 1]);
+        o[0][j >> 1] = pack2(a0 * b0, a1 * b1, 1);
+        if constexpr (SAVE) { o[1][j >> 1] = pack2(a0, a1, 1); o[2][j >> 1] = pack2(b0, b1, 1); }
       }
-      o[0][j >> 1] = pack2(a[0] * b[0], a[1] * b[1], f16);
-      if constexpr (SAVE) {
-        o[1][j >> 1] = pack2(a[0], a[1], f16);
-        o[2][j >> 1] = pack2(b[0], b[1], f16);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        float a0 = tanh_f<true>(lo[j]), a1 = tanh_f<true>(lo[j + 1]);
+        float b0 = sigmoid_f<true>(hi[j]), b1 = sigmoid_f<true>(hi[j + 1]);
+        o[0][j >> 1] = pack2(a0 * b0, a1 * b1, 0);
+        if constexpr (SAVE) { o[1][j >> 1] = pack2(a0, a1, 0); o[2][j >> 1] = pack2(b0, b1, 0); }
       }
     }
   }
@@ -62,57 +64,73 @@ struct SplitTcEpi {
   int f16;
   __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
   __device__ __forceinline__ int in_col(int, int c0) const { return c0; }
-  __device__ __forceinline__ void split(int col0, float (&x)[32], uint32_t (&o)[2][16]) const {
+  template <int F16>
+  __device__ __forceinline__ void split(const float (&x)[16], uint32_t (&o)[2][8]) const {
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float x0 = x[j], x1 = x[j + 1];
-      if (bias) { x0 += __ldg(bias + col0 + j); x1 += __ldg(bias + col0 + j + 1); }
-      uint32_t h = pack2(x0, x1, f16);
+    for (int j = 0; j < 16; j += 2) {
+      uint32_t h = pack2(x[j], x[j + 1], F16);
       float h0, h1;
-      unpack2(h, f16, h0, h1);
+      unpack2(h, F16, h0, h1);
       o[0][j >> 1] = h;
-      o[1][j >> 1] = pack2(x0 - h0, x1 - h1, f16);
+      o[1][j >> 1] = pack2(x[j] - h0, x[j + 1] - h1, F16);
     }
   }
-  __device__ __forceinline__ void compute(int col0, const float (&v)[32], uint32_t (&o)[2][16]) const {
-    float x[32];
+  __device__ __forceinline__ void add_bias(int col0, float (&x)[16]) const {
+    if (bias) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = v[j];
-    split(col0, x, o);
-  }
-  __device__ __forceinline__ void compute(int col0, const float (&v)[32], const uint32_t (&in)[2][16],
-                                          uint32_t (&o)[2][16]) const {
-    float x[32];
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float h0, h1, l0, l1;
-      unpack2(in[0][j >> 1], f16, h0, h1);
-      unpack2(in[1][j >> 1], f16, l0, l1);
-      x[j] = v[j] + (h0 + l0);
-      x[j + 1] = v[j + 1] + (h1 + l1);
+      for (int j = 0; j < 16; ++j) x[j] += __ldg(bias + col0 + j);
     }
-    split(col0, x, o);
+  }
+  __device__ __forceinline__ void compute(int col0, float (&v)[16], uint32_t (&o)[2][8]) const {
+    add_bias(col0, v);
+    if (f16) split<1>(v, o);
+    else split<0>(v, o);
+  }
+  __device__ __forceinline__ void compute(int col0, float (&v)[16], const uint32_t (&in)[2][8],
+                                          uint32_t (&o)[2][8]) const {
+    add_bias(col0, v);
+    if (f16) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        float h0, h1, l0, l1;
+        unpack2(in[0][j >> 1], 1, h0, h1);
+        unpack2(in[1][j >> 1], 1, l0, l1);
+        v[j] += h0 + l0;
+        v[j + 1] += h1 + l1;
+      }
+      split<1>(v, o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        float h0, h1, l0, l1;
+        unpack2(in[0][j >> 1], 0, h0, h1);
+        unpack2(in[1][j >> 1], 0, l0, l1);
+        v[j] += h0 + l0;
+        v[j + 1] += h1 + l1;
+      }
+      split<0>(v, o);
+    }
   }
 };
 
 // ---- gate backward: dpre = dg * d(tanh * sigmoid) ------------------------------------------------
 // inputs: saved tanh / sigmoid values; outputs: the tanh-half and sigmoid-half gradients, columns
-// [0, Cd) and [Cd, 2Cd) of the dpre slab (two tensor maps, one per column window).
+// [0, Cd) and [Cd, 2Cd) of the dpre slab (two tensor maps, one per column window).  bf16 only
+// (training never uses fp16 operands).
 struct GateBwdTcEpi {
   static constexpr bool kPaired = false, kOutF32 = false;
   static constexpr int kOut = 2, kIn = 2, kOutBufs = 1;
-  int Cd, f16;
   __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
   __device__ __forceinline__ int in_col(int, int c0) const { return c0; }
-  __device__ __forceinline__ void compute(int, const float (&v)[32], const uint32_t (&in)[2][16],
-                                          uint32_t (&o)[2][16]) const {
+  __device__ __forceinline__ void compute(int, float (&v)[16], const uint32_t (&in)[2][8], uint32_t (&o)[2][8]) const {
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
+    for (int j = 0; j < 16; j += 2) {
       float a0, a1, b0, b1;
-      unpack2(in[0][j >> 1], f16, a0, a1);
-      unpack2(in[1][j >> 1], f16, b0, b1);
-      o[0][j >> 1] = pack2(v[j] * b0 * (1.f - a0 * a0), v[j + 1] * b1 * (1.f - a1 * a1), f16);
-      o[1][j >> 1] = pack2(v[j] * a0 * b0 * (1.f - b0), v[j + 1] * a1 * b1 * (1.f - b1), f16);
+      unpack2(in[0][j >> 1], 0, a0, a1);
+      unpack2(in[1][j >> 1], 0, b0, b1);
+      float t0 = v[j] * b0, t1 = v[j + 1] * b1;  // dg * sigmoid
+      o[0][j >> 1] = pack2(t0 * (1.f - a0 * a0), t1 * (1.f - a1 * a1), 0);
+      o[1][j >> 1] = pack2(t0 * a0 * (1.f - b0), t1 * a1 * (1.f - b1), 0);
     }
   }
 };
@@ -120,13 +138,17 @@ struct GateBwdTcEpi {
 // ---- plain fp32 store (skip sum, conditioning gradient, self tests) -------------------------------
 struct StoreTcEpi {
   static constexpr bool kPaired = false, kOutF32 = true;
-  static constexpr int kOut = 1, kIn = 0, kOutBufs = 2;
+  static constexpr int kOut = 1, kIn = 0, kOutBufs = 1;
   const float* bias;  // nullptr or [N]
   __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
   __device__ __forceinline__ int in_col(int, int c0) const { return c0; }
-  __device__ __forceinline__ void compute(int col0, const float (&v)[32], uint32_t (&o)[1][32]) const {
+  __device__ __forceinline__ void compute(int col0, float (&v)[16], uint32_t (&o)[1][16]) const {
+    if (bias) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o[0][j] = __float_as_uint(v[j] + (bias ? __ldg(bias + col0 + j) : 0.f));
+      for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + col0 + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[0][j] = __float_as_uint(v[j]);
   }
 };
 

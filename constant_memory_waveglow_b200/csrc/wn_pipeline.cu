@@ -408,7 +408,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
         // N tile (Cd < BN) is clipped instead of spilling into the other half
         io.out[0] = TcStream{dpre_i, 2 * d.Cd, d.Cd, 0};
         io.out[1] = TcStream{dpre_i + d.Cd, 2 * d.Cd, d.Cd, 0};
-        GateBwdTcEpi epi{d.Cd, f16};
+        GateBwdTcEpi epi{};
         CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
       } else {
         GateBwdEpi<OpT> epi;
