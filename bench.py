@@ -32,6 +32,9 @@ FRAMES = 63                      # MelSpec frames of a 16000-sample segment (SUR
 PER_GPU_BATCH = 24
 SIGMA = 0.7
 FWD_GFLOP_PER_SEGMENT = 214.023  # algorithmic, counted on the reference
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE training-shape gate GEMM launch (B=24, saving tanh/sigmoid),
+# from the `ncu --set full` capture summarised in profiles/ (None until captured for the current kernel)
+GATE_TRAFFIC_BYTES_PER_LAUNCH = None
 TRAIN_GFLOP_PER_SEGMENT = 4 * FWD_GFLOP_PER_SEGMENT
 SYNTH_FRAMES = 862               # 10 s at 22.05 kHz -> 220672 samples (model/base.py:47-48)
 
@@ -60,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "25"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -119,11 +122,14 @@ def cpu_oracle_train(batch: int, steps: int, warmup: int):
     return batch / (sum(times) / len(times)), times
 
 
+CPU_SAMPLE_BATCH = 2   # segments per CPU step: ~1.2 s per step on 16 host cores, so K+W steps stay within minutes
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 1
+    batch = CPU_SAMPLE_BATCH
     value, times = cpu_oracle_train(batch, args.steps, args.warmup)
     cores = torch.get_num_threads()
     line = {
@@ -291,14 +297,15 @@ def run_b200(args):
         "config": {"workload": "waveglow_lj_train_fwd+reversible_bwd+adam", "per_gpu_batch": B, "segment": SEGMENT,
                    "n_mels": 80, "channels": 256, "flows": 12, "wn_layers": 8, "precision": args.precision,
                    "l2": "256 MiB flush between timed steps; per-step working set >> 126 MB L2",
-                   "parallelism": f"dp{world}", "loss": float(loss)},
+                   "parallelism": f"dp{world}", "loss": float(loss.detach())},
         "e2e": {"value": value_e2e, "unit": "segments/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + h_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "train_tflops_per_gpu": B * TRAIN_GFLOP_PER_SEGMENT / (ms / args.steps),
         "roofline": {"bound": "tensor", "kernel": "tc_gemm_kernel<gate epilogue> (dilated conv + conditioning GEMM)",
                      "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"],
+                     "frac": achieved / pk["tflops_sustained"], "traffic": GATE_TRAFFIC_BYTES_PER_LAUNCH,
+                     "peak_source": pk["source"],
                      "flops_per_launch": gate_flops, "ms_per_launch": gate_ms, "launches_per_step": gate["launches"],
                      "share_of_gemm_time": gate["ms"] / total_kernel_ms if total_kernel_ms else None,
                      "kernel_classes_ms_per_step": {k: round(v["ms"], 3) for k, v in kern.items()}},
@@ -306,10 +313,11 @@ def run_b200(args):
         "synth": synth,
     }
     if not args.no_cpu_baseline and world == 1:
-        v, times = cpu_oracle_train(1, 1, 1)
+        nb, nsteps = CPU_SAMPLE_BATCH, 8                      # ~10-20 s of CPU work
+        v, times = cpu_oracle_train(nb, nsteps, 1)
         line["cpu_baseline"] = {"value": v, "unit": "segments/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": "oracle port (torch CPU fp32), LJ config, batch 1 x 16000 samples, "
-                                          "1 warm-up + 1 timed forward+loss+backward"}
+                                "sample": f"oracle port (torch CPU fp32), LJ config, {nsteps} timed steps of batch {nb} x "
+                                          f"16000 samples (1 warm-up), forward + loss + backward, {sum(times):.1f} s"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
