@@ -196,6 +196,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_ms = {False: [], True: []}
+
     def timed(nsteps, e2e):
         total_ms = 0.0
         last = None
@@ -213,6 +215,7 @@ def run_b200(args):
             b.record()
             barrier()
             total_ms += a.elapsed_time(b)
+            step_ms[e2e].append(round(a.elapsed_time(b), 3))
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -301,6 +304,7 @@ def run_b200(args):
         "e2e": {"value": value_e2e, "unit": "segments/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + h_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "ms_per_timed_step": {"device_resident": step_ms[False], "e2e": step_ms[True]},
         "train_tflops_per_gpu": B * TRAIN_GFLOP_PER_SEGMENT / (ms / args.steps),
         "roofline": {"bound": "tensor", "kernel": "tc_gemm_kernel<gate epilogue> (dilated conv + conditioning GEMM)",
                      "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",

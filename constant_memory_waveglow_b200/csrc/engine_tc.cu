@@ -121,15 +121,46 @@ int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaS
   return CMWG_OK;
 }
 
+constexpr int TC_PLAN_PAIRS = 74;  // CTA pairs of a B200 (148 SMs); only load balance depends on it
+
+static int wgrad_group_splits(const WgradProblem* probs, int nprob, int bn, int B, int T) {
+  int tiles = 0;
+  for (int i = 0; i < nprob; ++i) tiles += ceil_div(probs[i].M, 2 * TC_BM) * ceil_div(probs[i].N, bn);
+  const int total_units = B * ceil_div(T, TC_BK);
+  int s = tiles > 0 ? TC_PLAN_PAIRS / tiles : 1;
+  if (s < 1) s = 1;
+  if (s > total_units) s = total_units;
+  // whole units per split; drop splits that would be empty
+  const int ups = ceil_div(total_units, s);
+  return ceil_div(total_units, ups);
+}
+
+void tc_wgrad_plan(const WgradProblem* probs, int nprob, int B, int T, int force_splits, int* splits_out) {
+  WgradProblem big[TC_MAX_WG], small[TC_MAX_WG];
+  int nb = 0, ns = 0;
+  for (int i = 0; i < nprob; ++i) {
+    if (probs[i].N >= 256) big[nb++] = probs[i];
+    else small[ns++] = probs[i];
+  }
+  const int total_units = B * ceil_div(T, TC_BK);
+  int fs = force_splits > total_units ? total_units : force_splits;
+  if (fs > 0) fs = ceil_div(total_units, ceil_div(total_units, fs));
+  const int sb = fs > 0 ? fs : wgrad_group_splits(big, nb, 256, B, T);
+  const int ss = fs > 0 ? fs : wgrad_group_splits(small, ns, 128, B, T);
+  for (int i = 0; i < nprob; ++i) splits_out[i] = probs[i].N >= 256 ? sb : ss;
+}
+
 template <int BN>
-static int tc_wgrad_launch_bn(const WgradProblem* probs, int nprob, int B, int T, int Lc, int is_fp16, cudaStream_t st,
-                              int lbo_override, int sbo_override) {
+static int tc_wgrad_launch_bn(const WgradProblem* probs, int nprob, int B, int T, int splits, int is_fp16,
+                              cudaStream_t st, int lbo_override, int sbo_override) {
   TcWgradParams p;
   memset(&p, 0, sizeof(p));
   p.nprob = nprob;
-  p.B = B; p.T = T; p.Lc = Lc;
-  p.chunks_per_batch = ceil_div(T, Lc);
-  p.splits = B * p.chunks_per_batch;
+  p.B = B; p.T = T;
+  p.units_per_batch = ceil_div(T, TC_BK);
+  p.total_units = B * p.units_per_batch;
+  p.splits = splits;
+  p.units_per_split = ceil_div(p.total_units, splits);
   int tiles = 0;
   for (int i = 0; i < nprob; ++i) {
     const WgradProblem& q = probs[i];
@@ -165,19 +196,20 @@ static int tc_wgrad_launch_bn(const WgradProblem* probs, int nprob, int B, int T
   return CMWG_OK;
 }
 
-int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int T, int Lc, int is_fp16, cudaStream_t st,
+int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int T, int is_fp16, cudaStream_t st, int force_splits,
                     int lbo_override, int sbo_override) {
   CMWG_REQUIRE(nprob >= 1 && nprob <= TC_MAX_WG, "tc_wgrad: %d problems (max %d)", nprob, TC_MAX_WG);
-  CMWG_REQUIRE(Lc % TC_BK == 0, "tc_wgrad: chunk length %d not a multiple of %d", Lc, TC_BK);
+  int splits[TC_MAX_WG];
+  tc_wgrad_plan(probs, nprob, B, T, force_splits, splits);
   // group by N tile width
   WgradProblem big[TC_MAX_WG], small[TC_MAX_WG];
-  int nb = 0, ns = 0;
+  int nb = 0, ns = 0, sb = 1, ss = 1;
   for (int i = 0; i < nprob; ++i) {
-    if (probs[i].N >= 256) big[nb++] = probs[i];
-    else small[ns++] = probs[i];
+    if (probs[i].N >= 256) { big[nb++] = probs[i]; sb = splits[i]; }
+    else { small[ns++] = probs[i]; ss = splits[i]; }
   }
-  if (nb) CMWG_PROPAGATE(tc_wgrad_launch_bn<256>(big, nb, B, T, Lc, is_fp16, st, lbo_override, sbo_override));
-  if (ns) CMWG_PROPAGATE(tc_wgrad_launch_bn<128>(small, ns, B, T, Lc, is_fp16, st, lbo_override, sbo_override));
+  if (nb) CMWG_PROPAGATE(tc_wgrad_launch_bn<256>(big, nb, B, T, sb, is_fp16, st, lbo_override, sbo_override));
+  if (ns) CMWG_PROPAGATE(tc_wgrad_launch_bn<128>(small, ns, B, T, ss, is_fp16, st, lbo_override, sbo_override));
   return CMWG_OK;
 }
 
@@ -209,7 +241,6 @@ extern "C" int cmwg_selftest_tc_gemm(const void* a, const void* b, float* d, int
   pr.a = a; pr.lda = M; pr.a_c0 = 0; pr.M = M;
   pr.b = b; pr.ldb = N; pr.b_c0 = 0; pr.N = N;
   pr.shift = 0; pr.partial = d;
-  int Lc = round_up(K, 64);
-  if (variant & 4) return tc_wgrad_launch(&pr, 1, 1, K, Lc, is_fp16, st, 1024 >> 4, 8192 >> 4);
-  return tc_wgrad_launch(&pr, 1, 1, K, Lc, is_fp16, st);
+  if (variant & 4) return tc_wgrad_launch(&pr, 1, 1, K, is_fp16, st, 1, 1024 >> 4, 8192 >> 4);
+  return tc_wgrad_launch(&pr, 1, 1, K, is_fp16, st, 1);
 }

@@ -79,7 +79,9 @@ struct alignas(64) TcWgradParams {
   int M[TC_MAX_WG], N[TC_MAX_WG], shift[TC_MAX_WG], a_c0[TC_MAX_WG], b_c0[TC_MAX_WG];
   int tile_begin[TC_MAX_WG + 1];  // prefix sum of (m_tiles * n_tiles) per problem
   int n_tiles_n[TC_MAX_WG];
-  int B, T, Lc, chunks_per_batch, splits, total_work;
+  // split-K over the flattened (batch, 64-row k-block) sequence: split s covers k-block units
+  // [s * units_per_split, (s+1) * units_per_split) and accumulates ACROSS batch items in TMEM
+  int B, T, units_per_batch, total_units, units_per_split, splits, total_work;
   uint32_t idesc;
   uint32_t desc_lbo, desc_sbo;
 };
@@ -303,6 +305,9 @@ struct TcEpiTraits {
   static constexpr int kOutBytes = Epi::kOutBufs * Epi::kOut * kOutChunk;
   static constexpr int kInBytes = Epi::kIn * TC_CHUNK16_BYTES;  // inputs: 16-bit, one chunk (re-armed as soon as it is read)
   static constexpr int kWarpBytes = kOutBytes + kInBytes;
+  // column groups = draining warps per TMEM lane quadrant (fewer groups = less staging = more operand stages)
+  template <int GW>
+  static constexpr int ncg() { return (GW / 32) < Epi::kColGroups ? (GW / 32) : Epi::kColGroups; }
 };
 
 constexpr int TC_BAR_BYTES = 512;  // mbarriers + TMEM pointer
@@ -310,15 +315,18 @@ constexpr int TC_BAR_BYTES = 512;  // mbarriers + TMEM pointer
 template <int BN, class Epi>
 constexpr int tc_stage_bytes() { return TC_A_BYTES + (BN / 2) * 128; }
 template <int BN, class Epi>
+constexpr int tc_epi_bytes() {
+  return 4 * TcEpiTraits<Epi>::template ncg<(Epi::kPaired ? BN / 2 : BN)>() * TcEpiTraits<Epi>::kWarpBytes;
+}
+template <int BN, class Epi>
 constexpr int tc_num_stages() {
-  int avail = TC_SMEM_LIMIT - 1024 - TC_BAR_BYTES - TC_EPI_WARPS * TcEpiTraits<Epi>::kWarpBytes;
+  int avail = TC_SMEM_LIMIT - 1024 - TC_BAR_BYTES - tc_epi_bytes<BN, Epi>();
   int s = avail / tc_stage_bytes<BN, Epi>();
   return s > 8 ? 8 : s;
 }
 template <int BN, class Epi>
 constexpr size_t tc_smem_bytes() {
-  return (size_t)tc_num_stages<BN, Epi>() * tc_stage_bytes<BN, Epi>() + TC_EPI_WARPS * TcEpiTraits<Epi>::kWarpBytes +
-         TC_BAR_BYTES + 1024;
+  return (size_t)tc_num_stages<BN, Epi>() * tc_stage_bytes<BN, Epi>() + tc_epi_bytes<BN, Epi>() + TC_BAR_BYTES + 1024;
 }
 
 struct TcSmem {
@@ -333,13 +341,13 @@ struct TcSmem {
 };
 
 template <int STAGES>
-__device__ __forceinline__ TcSmem tc_carve(uint8_t* raw, int stage_bytes, int epi_warp_bytes) {
+__device__ __forceinline__ TcSmem tc_carve(uint8_t* raw, int stage_bytes, int epi_bytes) {
   static_assert((2 * STAGES + 4 + TC_EPI_WARPS) * 8 + 8 <= TC_BAR_BYTES, "barrier area too small");
   TcSmem s;
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   s.stages = base;
   s.epi = base + STAGES * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s.epi + TC_EPI_WARPS * epi_warp_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.epi + epi_bytes);
   s.full = bars;
   s.empty = bars + STAGES;
   s.tmem_full = bars + 2 * STAGES;
@@ -388,7 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   constexpr int STAGE_BYTES = tc_stage_bytes<BN, Epi>();
   using ET = TcEpiTraits<Epi>;
   static_assert(STAGES >= 2, "epilogue staging leaves no room for the operand pipeline");
-  const TcSmem s = tc_carve<STAGES>(smem_raw, STAGE_BYTES, ET::kWarpBytes);
+  const TcSmem s = tc_carve<STAGES>(smem_raw, STAGE_BYTES, tc_epi_bytes<BN, Epi>());
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -400,7 +408,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     for (int i = 0; i < Epi::kIn; ++i) prefetch_tmap(&p.in_map[i]);
   }
   constexpr int GW = Epi::kPaired ? BN / 2 : BN;   // epilogue columns of one tile (gate channels when paired)
-  constexpr int NCG = (GW / 32) < 4 ? (GW / 32) : 4;  // column groups = draining warps per TMEM lane quadrant
+  constexpr int NCG = ET::template ncg<GW>();       // column groups = draining warps per TMEM lane quadrant
   constexpr int NCH = GW / (32 * NCG);             // 32-column chunks per warp per tile
   tc_setup<STAGES>(s, warp, lane, 2 * BN, 4 * NCG);
   const uint32_t tmem_base = *s.tmem_ptr;
@@ -576,7 +584,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 // ------------------------------------------------------------------------------------------------
 struct WgradEpiShape {  // staging shape of the weight-gradient epilogue (fp32, one stream)
   static constexpr bool kOutF32 = true, kPaired = false;
-  static constexpr int kOut = 1, kIn = 0, kOutBufs = 1;
+  static constexpr int kOut = 1, kIn = 0, kOutBufs = 1, kColGroups = 4;
 };
 
 template <int BN>
@@ -586,14 +594,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   constexpr int STAGE_BYTES = tc_stage_bytes<BN, WgradEpiShape>();
   using ET = TcEpiTraits<WgradEpiShape>;
   constexpr int BOX_BYTES = 64 * 128;  // {64 channels, 64 time rows} x 16 bit
-  const TcSmem s = tc_carve<STAGES>(smem_raw, STAGE_BYTES, ET::kWarpBytes);
+  const TcSmem s = tc_carve<STAGES>(smem_raw, STAGE_BYTES, tc_epi_bytes<BN, WgradEpiShape>());
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nprob; ++i) { prefetch_tmap(&p.a_map[i]); prefetch_tmap(&p.b_map[i]); prefetch_tmap(&p.out_map[i]); }
   }
-  constexpr int NCG = (BN / 32) < 4 ? (BN / 32) : 4;
+  constexpr int NCG = ET::template ncg<BN>();
   constexpr int NCH = BN / (32 * NCG);
   tc_setup<STAGES>(s, warp, lane, 2 * BN, 4 * NCG);
   const uint32_t tmem_base = *s.tmem_ptr;
@@ -618,22 +626,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       for (int w = pair; w < p.total_work; w += npairs) {
         int pr, m0, n0, split;
         decode(w, pr, m0, n0, split);
-        int b = split / p.chunks_per_batch, tc0 = (split % p.chunks_per_batch) * p.Lc;
-        int nkb = (min(p.Lc, p.T - tc0) + TC_BK - 1) / TC_BK;
+        const int u0 = split * p.units_per_split, u1 = min(u0 + p.units_per_split, p.total_units);
         const int ma = p.a_c0[pr] + m0 + rank * TC_BM;
         const int nb = p.b_c0[pr] + n0 + rank * (BN / 2);
-        for (int kb = 0; kb < nkb; ++kb) {
+        int b = u0 / p.units_per_batch, t = (u0 - b * p.units_per_batch) * TC_BK;
+        for (int u = u0; u < u1; ++u) {
           mbar_wait(&s.empty[stage], phase ^ 1);
           uint32_t sa = smem_u32(s.stages + stage * STAGE_BYTES);
           if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * STAGE_BYTES);
           uint32_t bar = mapa_shared(smem_u32(&s.full[stage]), 0);
-          int t = tc0 + kb * TC_BK;
 #pragma unroll
           for (int j = 0; j < TC_BM / 64; ++j) tma_load_3d(sa + j * BOX_BYTES, &p.a_map[pr], bar, ma + j * 64, t, b);
 #pragma unroll
           for (int j = 0; j < BN / 128; ++j)
             tma_load_3d(sa + TC_A_BYTES + j * BOX_BYTES, &p.b_map[pr], bar, nb + j * 64, t + p.shift[pr], b);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          t += TC_BK;
+          if (t >= p.units_per_batch * TC_BK) { t = 0; ++b; }
         }
       }
     }
@@ -646,8 +655,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
       for (int w = pair; w < p.total_work; w += npairs) {
         int pr, m0, n0, split;
         decode(w, pr, m0, n0, split);
-        int tc0 = (split % p.chunks_per_batch) * p.Lc;
-        int nkb = (min(p.Lc, p.T - tc0) + TC_BK - 1) / TC_BK;
+        const int nkb = min(p.units_per_split, p.total_units - split * p.units_per_split);
         mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         uint32_t d_tmem = tmem_base + acc * BN;
@@ -792,7 +800,11 @@ int tc_gemm_launch(const GemmDesc& d, const TcIo& io, const Epi& epi, cudaStream
   return tc_gemm_launch_bn<128, Epi>(d, io, epi, st);
 }
 
-int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int T, int Lc, int is_fp16, cudaStream_t st,
-                    int lbo_override = -1, int sbo_override = -1);
+// Split-K plan of the weight-gradient launches: problems are grouped by N tile width (>= 256 / < 256) and
+// every group gets as many splits as fit one wave of CTA pairs.  splits_out[i] = splits of problem i
+// (its partial buffer must hold splits_out[i] * M * N floats).  force_splits > 0 overrides the plan.
+void tc_wgrad_plan(const WgradProblem* probs, int nprob, int B, int T, int force_splits, int* splits_out);
+int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int T, int is_fp16, cudaStream_t st,
+                    int force_splits = 0, int lbo_override = -1, int sbo_override = -1);
 
 }  // namespace cmwg

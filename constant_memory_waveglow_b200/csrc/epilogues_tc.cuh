@@ -7,6 +7,8 @@
 //   kOutF32    outputs are fp32 (else 16-bit operands, two per register)
 //   kOutBufs   staging buffers per output stream (2 = the store of chunk i overlaps chunk i+1)
 //   kIn        16-bit input streams, TMA-loaded one chunk ahead
+//   kColGroups epilogue warps per TMEM lane quadrant (4: shortest epilogue; 2: half the staging, more
+//              operand stages -- for GEMMs whose K loop is long enough to hide a longer epilogue)
 //   out_col(i, c0) / in_col(i, c0)   channel coordinate of stream i for epilogue column c0
 // Precision / bias switches are warp-uniform branches AROUND the unrolled loops (never per element),
 // so only one variant's instructions are issued.
@@ -20,7 +22,7 @@ namespace cmwg {
 template <bool SAVE>
 struct GateTcEpi {
   static constexpr bool kPaired = true, kOutF32 = false;
-  static constexpr int kOut = SAVE ? 3 : 1, kIn = 0, kOutBufs = 1;
+  static constexpr int kOut = SAVE ? 3 : 1, kIn = 0, kOutBufs = 1, kColGroups = 4;
   const float* bias;  // nullptr or [2][Cd]
   int Cd, f16;
   __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
@@ -56,10 +58,10 @@ struct GateTcEpi {
 // x = hi + lo with hi = rn16(x), lo = rn16(x - hi) (precision of the pair: 2^-17 relative); hi doubles
 // as the GEMM operand of the next dilated conv.  ADD: out = acc + in_hi + in_lo, the residual add of
 // model/waveglow.py:46 (forward) or the upstream residual gradient (backward), summed in fp32.
-template <bool ADD>
+template <bool ADD, int CG = 4>
 struct SplitTcEpi {
   static constexpr bool kPaired = false, kOutF32 = false;
-  static constexpr int kOut = 2, kIn = ADD ? 2 : 0, kOutBufs = 1;
+  static constexpr int kOut = 2, kIn = ADD ? 2 : 0, kOutBufs = 1, kColGroups = CG;
   const float* bias;
   int f16;
   __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
@@ -119,7 +121,7 @@ struct SplitTcEpi {
 // (training never uses fp16 operands).
 struct GateBwdTcEpi {
   static constexpr bool kPaired = false, kOutF32 = false;
-  static constexpr int kOut = 2, kIn = 2, kOutBufs = 1;
+  static constexpr int kOut = 2, kIn = 2, kOutBufs = 1, kColGroups = 4;
   __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
   __device__ __forceinline__ int in_col(int, int c0) const { return c0; }
   __device__ __forceinline__ void compute(int, float (&v)[16], const uint32_t (&in)[2][8], uint32_t (&o)[2][8]) const {
@@ -138,7 +140,7 @@ struct GateBwdTcEpi {
 // ---- plain fp32 store (skip sum, conditioning gradient, self tests) -------------------------------
 struct StoreTcEpi {
   static constexpr bool kPaired = false, kOutF32 = true;
-  static constexpr int kOut = 1, kIn = 0, kOutBufs = 1;
+  static constexpr int kOut = 1, kIn = 0, kOutBufs = 1, kColGroups = 4;
   const float* bias;  // nullptr or [N]
   __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
   __device__ __forceinline__ int in_col(int, int c0) const { return c0; }

@@ -466,9 +466,14 @@ __global__ void __launch_bounds__(1024) sum_per_batch_kernel(const float* __rest
   __shared__ float red[32];
   int b = blockIdx.x;
   const float* p = a + b * a_bs;
-  float s = 0.f;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) s += p[i];
-  s = block_sum_1024(s, red);
+  // four independent partial sums per thread (fixed order: deterministic) keep 4 loads in flight
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int i = threadIdx.x;
+  for (; i + 3 * 1024 < N; i += 4 * 1024) {
+    s0 += p[i]; s1 += p[i + 1024]; s2 += p[i + 2048]; s3 += p[i + 3072];
+  }
+  for (; i < N; i += 1024) s0 += p[i];
+  float s = block_sum_1024((s0 + s1) + (s2 + s3), red);
   if (threadIdx.x == 0) out[b] = (accumulate ? out[b] : 0.f) + scale * s;
 }
 

@@ -3,6 +3,7 @@
 // fixed-order reductions of block partials.
 #pragma once
 #include "common.cuh"
+#include "epilogues.cuh"
 #include "wn_layout.cuh"
 
 namespace cmwg {
@@ -59,30 +60,46 @@ static __global__ void __launch_bounds__(128) weight_eff_kernel(const WeffTable 
   if (threadIdx.x == 0 && e.inv_norm) e.inv_norm[o] = 1.f / norm;
 }
 
-// weight norm backward: (dw_eff, v, g, 1/||v||) -> (dg, dv); without weight norm dv = dw_eff
-static __global__ void __launch_bounds__(128) weight_norm_bwd_kernel(const float* __restrict__ dw,
-                                                                     const float* __restrict__ v,
-                                                                     const float* __restrict__ g,
-                                                                     const float* __restrict__ inv_norm, int L,
-                                                                     float* __restrict__ dg, float* __restrict__ dv) {
+// weight norm backward for ALL convs of one WN in one launch: (dw_eff, v, g, 1/||v||) -> (dg, dv);
+// without weight norm dv = dw_eff.  One CTA per output channel.
+struct WnBwdEntry {
+  const float* dw;        // effective-weight gradient, natural layout [O][L]
+  const float* v;
+  const float* g;         // nullptr: no weight norm
+  const float* inv_norm;  // [O]
+  float* dg;              // nullptr: not wanted
+  float* dv;
+  int O, L;
+  int row_begin;          // prefix sum of O
+};
+struct WnBwdTable {
+  WnBwdEntry e[3 * CMWG_MAX_DEPTH + 2];
+  int n;
+};
+
+static __global__ void __launch_bounds__(128) weight_norm_bwd_kernel(const __grid_constant__ WnBwdTable tb) {
   __shared__ float red[4];
-  int o = blockIdx.x;
-  const float* dwo = dw + (long long)o * L;
-  if (g == nullptr) {
-    if (dv)
-      for (int l = threadIdx.x; l < L; l += 128) dv[(long long)o * L + l] = dwo[l];
+  int row = blockIdx.x;
+  int ci = 0;
+  while (ci + 1 < tb.n && row >= tb.e[ci + 1].row_begin) ++ci;
+  const WnBwdEntry& e = tb.e[ci];
+  const int o = row - e.row_begin, L = e.L;
+  const float* dwo = e.dw + (long long)o * L;
+  if (e.g == nullptr) {
+    if (e.dv)
+      for (int l = threadIdx.x; l < L; l += 128) e.dv[(long long)o * L + l] = dwo[l];
     return;
   }
-  const float* vo = v + (long long)o * L;
+  const float* vo = e.v + (long long)o * L;
   float dot = 0.f;
   for (int l = threadIdx.x; l < L; l += 128) dot = fmaf(dwo[l], vo[l], dot);
   dot = block_sum_128(dot, red);
-  float inv = inv_norm[o];
-  if (threadIdx.x == 0 && dg) dg[o] = dot * inv;
-  if (dv) {
-    float gs = g[o] * inv;
+  float inv = e.inv_norm[o];
+  if (threadIdx.x == 0 && e.dg) e.dg[o] = dot * inv;
+  if (e.dv) {
+    float gs = e.g[o] * inv;
     float k = dot * inv * inv;
-    for (int l = threadIdx.x; l < L; l += 128) dv[(long long)o * L + l] = gs * (dwo[l] - vo[l] * k);
+    for (int l = threadIdx.x; l < L; l += 128) e.dv[(long long)o * L + l] = gs * (dwo[l] - vo[l] * k);
   }
 }
 
@@ -249,41 +266,82 @@ static __global__ void __launch_bounds__(256) cond_unpack_grad_kernel(const floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// start conv (cin -> Cr, kernel 1): NCL input, slab output            model/waveglow.py:74,99
+// tiny-K 1x1 conv from an NCL tensor to a slab:  out[row][o] = bias[o] + sum_i W[o*so + i*si] * in[b][i][t]
+//   start conv   (model/waveglow.py:74,99):  in = xa (cin channels), W = start weight [Cr][cin]  (so = cin, si = 1)
+//   d(end conv)  (backward of :92,105):      in = d(log_s, t) (2cin channels), W = end weight^T   (so = 1, si = Cs)
+// K = 2..64 is far below a tensor-core tile, and the kernel is bound by the slab write: one thread owns
+// 4 consecutive output channels of one row (16 / 8-byte stores, a warp writes contiguous rows), weights
+// and the input tile sit in shared memory.  Outputs: fp32 slab and / or operand slab, optionally as a
+// (hi, lo) 16-bit pair (x = hi + lo).
 // ------------------------------------------------------------------------------------------------
+constexpr int SMALLK_ROWS = 64;
+
 template <typename OpT>
-static __global__ void __launch_bounds__(256) start_fwd_kernel(const float* __restrict__ x, long long x_bs,
-                                                               const float* __restrict__ ws,
-                                                               const float* __restrict__ bias, int cin, int Cr,
-                                                               int T, int blocks_per_batch,
-                                                               float* __restrict__ h32, OpT* __restrict__ hop,
-                                                               OpT* __restrict__ hlo, int is_fp16) {
+static __global__ void __launch_bounds__(256) smallk_to_slab_kernel(const float* __restrict__ in, long long in_bs,
+                                                                    const float* __restrict__ W, int so, int si,
+                                                                    const float* __restrict__ bias, int K, int C,
+                                                                    int T, int blocks_per_batch,
+                                                                    float* __restrict__ o32, OpT* __restrict__ ohi,
+                                                                    OpT* __restrict__ olo, int is_fp16) {
   extern __shared__ float sm[];
-  float* xs = sm;                          // [cin][32]
-  float* wsm = sm + cin * ROWS_PER_BLOCK;  // [Cr][cin]
-  int b = blockIdx.x / blocks_per_batch;
-  int t0 = (blockIdx.x % blocks_per_batch) * ROWS_PER_BLOCK;
-  for (int idx = threadIdx.x; idx < cin * ROWS_PER_BLOCK; idx += 256) {
-    int i = idx / ROWS_PER_BLOCK, r = idx % ROWS_PER_BLOCK;
+  float* xs = sm;                      // [K][SMALLK_ROWS]
+  float* wsm = sm + K * SMALLK_ROWS;   // [K][C]  (k-major: 4 consecutive outputs are one float4)
+  const int b = blockIdx.x / blocks_per_batch;
+  const int t0 = (blockIdx.x % blocks_per_batch) * SMALLK_ROWS;
+  for (int idx = threadIdx.x; idx < K * SMALLK_ROWS; idx += 256) {
+    int i = idx / SMALLK_ROWS, r = idx % SMALLK_ROWS;
     int t = t0 + r;
-    xs[idx] = (t < T) ? x[b * x_bs + (long long)i * T + t] : 0.f;
+    xs[idx] = (t < T) ? in[b * in_bs + (long long)i * T + t] : 0.f;
   }
-  for (int idx = threadIdx.x; idx < Cr * cin; idx += 256) wsm[idx] = ws[idx];
+  for (int idx = threadIdx.x; idx < K * C; idx += 256) {
+    int i = idx / C, o = idx % C;
+    wsm[idx] = W[(long long)o * so + (long long)i * si];
+  }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < ROWS_PER_BLOCK * Cr; idx += 256) {
-    int r = idx / Cr, o = idx % Cr;
-    int t = t0 + r;
+  const int c4 = C >> 2;
+  for (int idx = threadIdx.x; idx < SMALLK_ROWS * c4; idx += 256) {
+    const int r = idx / c4, o = (idx % c4) * 4;
+    const int t = t0 + r;
     if (t >= T) continue;
-    float acc = bias ? bias[o] : 0.f;
-    for (int i = 0; i < cin; ++i) acc = fmaf(wsm[o * cin + i], xs[i * ROWS_PER_BLOCK + r], acc);
-    long long off = ((long long)b * T + t) * Cr + o;
-    if (h32) h32[off] = acc;
-    if (hop) OpTraits<OpT>::store(hop + off, acc, is_fp16);
-    if (hlo) {  // tc: residual stream as hi + lo
-      float hi = OpTraits<OpT>::load(hop + off, is_fp16);
-      OpTraits<OpT>::store(hlo + off, acc - hi, is_fp16);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (bias) { acc[0] = bias[o]; acc[1] = bias[o + 1]; acc[2] = bias[o + 2]; acc[3] = bias[o + 3]; }
+    for (int i = 0; i < K; ++i) {
+      const float xv = xs[i * SMALLK_ROWS + r];
+      const float4 w = *reinterpret_cast<const float4*>(wsm + i * C + o);
+      acc[0] = fmaf(w.x, xv, acc[0]); acc[1] = fmaf(w.y, xv, acc[1]);
+      acc[2] = fmaf(w.z, xv, acc[2]); acc[3] = fmaf(w.w, xv, acc[3]);
+    }
+    const long long off = ((long long)b * T + t) * C + o;
+    if (o32) *reinterpret_cast<float4*>(o32 + off) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if constexpr (sizeof(OpT) == 4) {
+      if (ohi) *reinterpret_cast<float4*>(ohi + off) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+      if (ohi) {
+        uint32_t h0 = pack2(acc[0], acc[1], is_fp16), h1 = pack2(acc[2], acc[3], is_fp16);
+        *reinterpret_cast<uint2*>(ohi + off) = make_uint2(h0, h1);
+        if (olo) {  // residual stream as hi + lo
+          float f0, f1, f2, f3;
+          unpack2(h0, is_fp16, f0, f1);
+          unpack2(h1, is_fp16, f2, f3);
+          *reinterpret_cast<uint2*>(olo + off) =
+              make_uint2(pack2(acc[0] - f0, acc[1] - f1, is_fp16), pack2(acc[2] - f2, acc[3] - f3, is_fp16));
+        }
+      }
     }
   }
+}
+
+template <typename OpT>
+static int smallk_to_slab(const float* in, long long in_bs, const float* W, int so, int si, const float* bias, int K,
+                          int C, int B, int T, float* o32, OpT* ohi, OpT* olo, int is_fp16, cudaStream_t st) {
+  const int bpb = ceil_div(T, SMALLK_ROWS);
+  size_t smem = (size_t)K * (SMALLK_ROWS + C) * sizeof(float);
+  if (smem > 48 * 1024)
+    CMWG_CHECK_CUDA(cudaFuncSetAttribute(smallk_to_slab_kernel<OpT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  smallk_to_slab_kernel<OpT><<<B * bpb, 256, smem, st>>>(in, in_bs, W, so, si, bias, K, C, T, bpb, o32, ohi, olo, is_fp16);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+  return CMWG_OK;
 }
 
 // start conv backward: dx[:, :cin] += Ws^T dh0 ; block partials of dWs (and dbias)
@@ -345,55 +403,76 @@ static __global__ void __launch_bounds__(256) start_bwd_kernel(const float* __re
 
 // ------------------------------------------------------------------------------------------------
 // end conv (Cs -> 2cin, kernel 1): slab fp32 input, NCL output          model/waveglow.py:92,105
+// Bound by the read of the fp32 skip slab.  One warp owns 32 consecutive time steps: per row every lane
+// loads KV float4 (a fully coalesced row), multiplies with its register-resident weight slice for up
+// to 8 output channels, the partials are summed with xor-shuffles (fixed order: deterministic), and lane
+// r keeps row r's results so that the final NCL stores are 128-byte coalesced.
 // ------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(256) end_fwd_kernel(const float* __restrict__ skip,
+template <int KV>
+static __global__ void __launch_bounds__(128) end_fwd_kernel(const float* __restrict__ skip,
                                                              const float* __restrict__ we,
                                                              const float* __restrict__ bias, int cout, int Cs, int T,
-                                                             int blocks_per_batch, float* __restrict__ lst) {
-  extern __shared__ float sm[];
-  const int LD = Cs + 1;
-  float* sk = sm;  // [32][Cs+1]
-  int b = blockIdx.x / blocks_per_batch;
-  int t0 = (blockIdx.x % blocks_per_batch) * ROWS_PER_BLOCK;
-  for (int idx = threadIdx.x; idx < ROWS_PER_BLOCK * Cs; idx += 256) {
-    int r = idx / Cs, k = idx % Cs;
-    int t = t0 + r;
-    sk[r * LD + k] = (t < T) ? skip[((long long)b * T + t) * Cs + k] : 0.f;
-  }
-  __syncthreads();
-  int r = threadIdx.x & 31, og = threadIdx.x >> 5;
-  int t = t0 + r;
-  for (int oc = og; oc < cout; oc += 8) {
-    float acc = bias ? bias[oc] : 0.f;
-    const float* w = we + (long long)oc * Cs;
-    for (int k = 0; k < Cs; ++k) acc = fmaf(w[k], sk[r * LD + k], acc);
-    if (t < T) lst[((long long)b * cout + oc) * T + t] = acc;
+                                                             int B, float* __restrict__ lst) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = (T + 31) >> 5;
+  const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (gw >= B * wpb) return;
+  const int b = gw / wpb, t0 = (gw % wpb) * 32;
+  const int nrows = min(32, T - t0);
+  const float* base = skip + ((long long)b * T + t0) * Cs;
+  for (int oc0 = 0; oc0 < cout; oc0 += 8) {
+    float4 w[8][KV];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int j = 0; j < KV; ++j) {
+        int k = 4 * lane + 128 * j;
+        w[c][j] = (oc0 + c < cout && k < Cs) ? *reinterpret_cast<const float4*>(we + (long long)(oc0 + c) * Cs + k)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    float mine[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mine[c] = (bias && oc0 + c < cout) ? bias[oc0 + c] : 0.f;
+#pragma unroll 4
+    for (int r = 0; r < nrows; ++r) {
+      float4 sv[KV];
+#pragma unroll
+      for (int j = 0; j < KV; ++j) {
+        int k = 4 * lane + 128 * j;
+        sv[j] = (k < Cs) ? *reinterpret_cast<const float4*>(base + (long long)r * Cs + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float p = 0.f;
+#pragma unroll
+        for (int j = 0; j < KV; ++j) {
+          p = fmaf(w[c][j].x, sv[j].x, p); p = fmaf(w[c][j].y, sv[j].y, p);
+          p = fmaf(w[c][j].z, sv[j].z, p); p = fmaf(w[c][j].w, sv[j].w, p);
+        }
+        p = warp_sum(p);
+        if (lane == r) mine[c] += p;
+      }
+    }
+    if (lane < nrows) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (oc0 + c < cout) lst[((long long)b * cout + oc0 + c) * T + t0 + lane] = mine[c];
+    }
   }
 }
 
-template <typename OpT>
-static __global__ void __launch_bounds__(256) end_bwd_dskip_kernel(const float* __restrict__ dlst,
-                                                                   const float* __restrict__ we, int cout, int Cs,
-                                                                   int T, int blocks_per_batch,
-                                                                   OpT* __restrict__ dskip, int is_fp16) {
-  extern __shared__ float sm[];
-  float* dl = sm;  // [cout][32]
-  int b = blockIdx.x / blocks_per_batch;
-  int t0 = (blockIdx.x % blocks_per_batch) * ROWS_PER_BLOCK;
-  for (int idx = threadIdx.x; idx < cout * ROWS_PER_BLOCK; idx += 256) {
-    int oc = idx / ROWS_PER_BLOCK, r = idx % ROWS_PER_BLOCK;
-    int t = t0 + r;
-    dl[idx] = (t < T) ? dlst[((long long)b * cout + oc) * T + t] : 0.f;
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < ROWS_PER_BLOCK * Cs; idx += 256) {
-    int r = idx / Cs, k = idx % Cs;
-    int t = t0 + r;
-    if (t >= T) continue;
-    float acc = 0.f;
-    for (int oc = 0; oc < cout; ++oc) acc = fmaf(we[(long long)oc * Cs + k], dl[oc * ROWS_PER_BLOCK + r], acc);
-    OpTraits<OpT>::store(dskip + ((long long)b * T + t) * Cs + k, acc, is_fp16);
-  }
+static int end_fwd_launch(const float* skip, const float* we, const float* bias, int cout, int Cs, int B, int T,
+                          float* lst, cudaStream_t st) {
+  const int warps = B * ceil_div(T, 32);
+  const int grid = ceil_div(warps, 4);
+  const int kv = ceil_div(Cs, 128);
+  CMWG_REQUIRE(kv <= 4, "end conv: skip_channels %d > 512 not supported", Cs);
+  if (kv == 1) end_fwd_kernel<1><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, lst);
+  else if (kv == 2) end_fwd_kernel<2><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, lst);
+  else end_fwd_kernel<4><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, lst);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+  return CMWG_OK;
 }
 
 static __global__ void __launch_bounds__(256) end_bwd_dw_kernel(const float* __restrict__ dlst,
@@ -450,13 +529,14 @@ static __global__ void __launch_bounds__(128) reduce_blocks_kernel(const float* 
 // split-K partials [splits][M][N] of several weight-gradient problems -> strided destinations
 struct WgReduceEntry {
   const float* partial;
+  int splits;            // partial tiles to sum
   int M, N, n_valid;     // stored dims, valid columns
   float* out;
   long long sm, sn, off; // out[off + m*sm + n*sn]
 };
 struct WgReduceTable {
   WgReduceEntry e[TC_MAX_WG_REDUCE];
-  int n, splits;
+  int n;
 };
 
 static __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgReduceTable tb) {
@@ -469,7 +549,7 @@ static __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgReduce
     int m = (int)(idx / nv4), n = (int)(idx % nv4) * 4;
     const float* p = e.partial + (long long)m * e.N + n;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < tb.splits; ++j) {  // fixed order: deterministic
+    for (int j = 0; j < e.splits; ++j) {  // fixed order: deterministic
       float4 v = *reinterpret_cast<const float4*>(p + j * stride);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }

@@ -160,7 +160,8 @@ struct BwdLayout {
   size_t dprel[CMWG_MAX_DEPTH];     // tc: per-layer dpre
   size_t partial;    // split-K partials / block partials
   size_t partial_bytes;
-  size_t dweff;      // fp32 scratch for one conv's effective-weight gradient (largest conv)
+  size_t dweff;      // fp32 effective-weight gradients of every conv (consumed by ONE weight-norm backward launch)
+  size_t dweff_layer, dweff_start, dweff_end;  // in floats: per-layer stride, offsets of the start / end conv
   size_t total;
 };
 
@@ -218,6 +219,11 @@ inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
   size_t splits = (size_t)B * ceil_div(T, lc);
   // largest simultaneous partial set: all weight-gradient problems of one layer
   size_t per_layer = (size_t)2 * d.Cd * d.Cr * d.R + (size_t)(d.Cr + d.Cs) * d.Cd + (size_t)2 * d.Cd * d.auxp;
+  // tc engine: at most TC_PLAN_PAIRS (74) splits per problem group, see tc_wgrad_plan
+  if (d.tc) {
+    size_t units = (size_t)B * ceil_div(T, 64);
+    splits = units < 80 ? units : 80;
+  }
   size_t p1 = splits * per_layer * 4;
   // start / end conv and bias-gradient block partials (32-row blocks)
   size_t blocks32 = (size_t)B * ceil_div(T, 32) + 1;
@@ -228,13 +234,14 @@ inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
   size_t p2 = (blocks32 + blocks32 / 64 + 2) * per_block * 4;  // + second-stage scratch
   L->partial_bytes = p1 > p2 ? p1 : p2;
   L->partial = take(L->partial_bytes);
-  // scratch for effective-weight gradients: one layer's dW_o, dW, dV_i side by side
-  size_t big = (size_t)(d.Cr + d.Cs) * d.Cd + (size_t)2 * d.Cd * d.Cr * d.R + (size_t)2 * d.Cd * d.aux;
-  size_t se = (size_t)2 * d.cin * d.Cs;
-  if (se > big) big = se;
-  size_t ss = (size_t)d.Cr * d.cin;
-  if (ss > big) big = ss;
-  L->dweff = take(big * 4 + 4096);
+  // effective-weight gradients: per layer dW_o, dW, dV_i side by side, then the start and end convs
+  size_t per = (size_t)(d.Cr + d.Cs) * d.Cd + (size_t)2 * d.Cd * d.Cr * d.R + (size_t)2 * d.Cd * d.aux;
+  per = align_up(per, 64);
+  L->dweff_layer = per;
+  L->dweff_start = per * d.depth;
+  L->dweff_end = L->dweff_start + align_up((size_t)d.Cr * d.cin, 64);
+  size_t total_f = L->dweff_end + align_up((size_t)2 * d.cin * d.Cs, 64);
+  L->dweff = take(total_f * 4 + 4096);
   L->total = off;
 }
 

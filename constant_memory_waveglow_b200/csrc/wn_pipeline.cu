@@ -156,12 +156,9 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
     float* o32 = (!TC && !save) ? h32 : nullptr;
     OpT* oop = (TC || save) ? hin_op(0) : nullptr;
     OpT* olo = TC ? hlo_op(0) : nullptr;
-    size_t smem = ((size_t)d.cin * ROWS_PER_BLOCK + (size_t)d.Cr * d.cin) * sizeof(float);
-    start_fwd_kernel<OpT><<<B * bpb, 256, smem, st>>>(
-        x, x_bs, reinterpret_cast<const float*>(pk + PL.wStart),
-        d.bias ? reinterpret_cast<const float*>(pk + PL.biasStart) : nullptr, d.cin, d.Cr, T, bpb, o32, oop, olo, f16);
-    CMWG_COUNT_LAUNCH();
-    CMWG_LAUNCH_CHECK();
+    CMWG_PROPAGATE(smallk_to_slab<OpT>(x, x_bs, reinterpret_cast<const float*>(pk + PL.wStart), d.cin, 1,
+                                       d.bias ? reinterpret_cast<const float*>(pk + PL.biasStart) : nullptr, d.cin,
+                                       d.Cr, B, T, o32, oop, olo, f16, st));
   }
 
   for (int i = 0; i < d.depth; ++i) {
@@ -263,14 +260,9 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
   }
   // ---- end conv
   {
-    size_t smem = (size_t)ROWS_PER_BLOCK * (d.Cs + 1) * sizeof(float);
-    if (smem > 48 * 1024)
-      CMWG_CHECK_CUDA(cudaFuncSetAttribute(end_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    end_fwd_kernel<<<B * bpb, 256, smem, st>>>(skip32, reinterpret_cast<const float*>(pk + PL.wEnd),
-                                               d.bias ? reinterpret_cast<const float*>(pk + PL.biasEnd) : nullptr,
-                                               2 * d.cin, d.Cs, T, bpb, lst);
-    CMWG_COUNT_LAUNCH();
-    CMWG_LAUNCH_CHECK();
+    CMWG_PROPAGATE(end_fwd_launch(skip32, reinterpret_cast<const float*>(pk + PL.wEnd),
+                                  d.bias ? reinterpret_cast<const float*>(pk + PL.biasEnd) : nullptr, 2 * d.cin, d.Cs, B,
+                                  T, lst, st));
   }
   return CMWG_OK;
 }
@@ -294,16 +286,26 @@ static int reduce_blocks(const float* partial, int nblocks, int P, float* scratc
   return CMWG_OK;
 }
 
-static int reduce_and_wn_bwd(const float* partial, int nblocks, int O, int Lr, float* scratch, float* dweff,
-                             const cmwg_conv_param& prm, const float* inv_norm, const cmwg_conv_grad& gr,
-                             cudaStream_t st) {
-  if (!gr.g && !gr.v) return CMWG_OK;
-  CMWG_PROPAGATE(reduce_blocks(partial, nblocks, O * Lr, scratch, dweff, st));
-  weight_norm_bwd_kernel<<<O, 128, 0, st>>>(dweff, prm.v, prm.g, inv_norm, Lr, gr.g, gr.v);
-  CMWG_COUNT_LAUNCH();
-  CMWG_LAUNCH_CHECK();
-  return CMWG_OK;
-}
+// deferred weight-norm backward: every conv of the WN appends one entry, one launch at the end
+struct WnBwdQueue {
+  WnBwdTable tb;
+  int rows = 0;
+  WnBwdQueue() { tb.n = 0; }
+  void add(const float* dw, const cmwg_conv_param& prm, const float* inv_norm, const cmwg_conv_grad& gr, int O, int L) {
+    if (!gr.g && !gr.v) return;
+    WnBwdEntry& e = tb.e[tb.n++];
+    e.dw = dw; e.v = prm.v; e.g = prm.g; e.inv_norm = inv_norm; e.dg = gr.g; e.dv = gr.v; e.O = O; e.L = L;
+    e.row_begin = rows;
+    rows += O;
+  }
+  int flush(cudaStream_t st) {
+    if (rows == 0) return CMWG_OK;
+    weight_norm_bwd_kernel<<<rows, 128, 0, st>>>(tb);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+    return CMWG_OK;
+  }
+};
 
 template <typename OpT>
 static int colsum_to(const OpT* a, int ld, int C, long long rows, float* partial, float* out, int f16,
@@ -350,13 +352,12 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   const float* skip32 = reinterpret_cast<const float*>(sv + FL.s_skip);
   const float* wEnd = reinterpret_cast<const float*>(pk + PL.wEnd);
   const float* wStart = reinterpret_cast<const float*>(pk + PL.wStart);
+  WnBwdQueue wq;
 
   // ---- end conv backward: dskip, d end.weight, d end.bias
   {
-    size_t smem = (size_t)cout * ROWS_PER_BLOCK * sizeof(float);
-    end_bwd_dskip_kernel<OpT><<<nblk, 256, smem, st>>>(dlst, wEnd, cout, d.Cs, T, bpb, dskip_op, f16);
-    CMWG_COUNT_LAUNCH();
-    CMWG_LAUNCH_CHECK();
+    CMWG_PROPAGATE(smallk_to_slab<OpT>(dlst, (long long)cout * T, wEnd, 1, d.Cs, nullptr, cout, d.Cs, B, T, nullptr,
+                                       dskip_op, (OpT*)nullptr, f16, st));
     if (gr->end.v || gr->end.bias) {
       size_t smem2 = ((size_t)cout * ROWS_PER_BLOCK + (size_t)ROWS_PER_BLOCK * d.Cs) * sizeof(float);
       float* pw = partial;
@@ -367,15 +368,21 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       CMWG_LAUNCH_CHECK();
       cmwg_conv_grad ge = gr->end;
       ge.g = nullptr;
-      CMWG_PROPAGATE(reduce_and_wn_bwd(pw, nblk, cout, d.Cs, scratch, dweff, prm->end, nullptr, ge, st));
+      cmwg_conv_param pe = prm->end;
+      pe.g = nullptr;  // `end` is never weight-normed (model/waveglow.py:92)
+      if (ge.v) {
+        float* dEnd = dweff + BL.dweff_end;
+        CMWG_PROPAGATE(reduce_blocks(pw, nblk, cout * d.Cs, scratch, dEnd, st));
+        wq.add(dEnd, pe, nullptr, ge, cout, d.Cs);
+      }
       if (gr->end.bias) {
         CMWG_PROPAGATE(reduce_blocks(pb, nblk, cout, scratch, gr->end.bias, st));
       }
     }
   }
 
-  const int Lc = wgrad_chunk_len(B, T);
-  const int splits = B * ceil_div(T, Lc);
+  const int Lc = wgrad_chunk_len(B, T);      // FFMA engine: split-K over (batch, time chunk)
+  const int ff_splits = B * ceil_div(T, Lc);
 
   for (int i = d.depth - 1; i >= 0; --i) {
     const int dil = 1 << i;
@@ -423,22 +430,21 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       WgradProblem pr[TC_MAX_WG];
       WgReduceTable rt;
       int np = 0;
-      float* pcur = partial;
       auto add = [&](const void* a, int lda, int M, const void* b, int ldb, int N, int shift) {
         WgradProblem& q = pr[np];
         q.a = a; q.lda = lda; q.a_c0 = 0; q.M = M; q.b = b; q.ldb = ldb; q.b_c0 = 0; q.N = N; q.shift = shift;
-        q.partial = pcur;
-        pcur += (size_t)splits * M * N;
+        q.partial = nullptr;
         return np++;
       };
-      // destinations live in dweff, laid out as three consecutive natural-layout matrices
-      float* dWo = dweff;
+      // destinations live in this layer's dweff region, three consecutive natural-layout matrices
+      float* dWo = dweff + BL.dweff_layer * (size_t)i;
       float* dW = dWo + (size_t)d.nb(i) * d.Cd;
       float* dV = dW + (size_t)2 * d.Cd * d.Cr * d.R;
       int nr = 0;
       auto red = [&](int pi, float* out, long long sm, long long sn, long long off, int n_valid) {
         WgReduceEntry& e = rt.e[nr++];
-        e.partial = pr[pi].partial; e.M = pr[pi].M; e.N = pr[pi].N; e.n_valid = n_valid;
+        e.partial = nullptr; e.splits = pi;  // problem index for now; resolved once the split plan is known
+        e.M = pr[pi].M; e.N = pr[pi].N; e.n_valid = n_valid;
         e.out = out; e.sm = sm; e.sn = sn; e.off = off;
       };
       const bool want_wo = gr->W_o[i].g || gr->W_o[i].v;
@@ -453,39 +459,40 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
           red(add(dpre_i, 2 * d.Cd, 2 * d.Cd, hin, d.Cr, d.Cr, (s - (d.R - 1) / 2) * dil), dW,
               (long long)d.Cr * d.R, d.R, s, d.Cr);
       if (want_v) red(add(dpre_i, 2 * d.Cd, 2 * d.Cd, ycl, d.auxp, d.auxp, 0), dV, d.aux, 1, 0, d.aux);
-      CMWG_REQUIRE((size_t)((uint8_t*)pcur - (uint8_t*)partial) <= BL.partial_bytes, "wgrad partial buffer overflow");
       if (np) {
+        // split-K plan -> partial buffers
+        int splits[TC_MAX_WG];
+        if (TC) tc_wgrad_plan(pr, np, B, T, 0, splits);
+        else for (int k = 0; k < np; ++k) splits[k] = ff_splits;
+        float* pcur = partial;
+        for (int k = 0; k < np; ++k) {
+          pr[k].partial = pcur;
+          pcur += (size_t)splits[k] * pr[k].M * pr[k].N;
+        }
+        CMWG_REQUIRE((size_t)((uint8_t*)pcur - (uint8_t*)partial) <= BL.partial_bytes, "wgrad partial buffer overflow");
+        for (int k = 0; k < nr; ++k) {
+          int pi = rt.e[k].splits;
+          rt.e[k].partial = pr[pi].partial;
+          rt.e[k].splits = splits[pi];
+        }
         if (TC) {
-          CMWG_PROPAGATE(tc_wgrad_launch(pr, np, B, T, Lc, f16, st));
+          CMWG_PROPAGATE(tc_wgrad_launch(pr, np, B, T, f16, st));
         } else {
           for (int k = 0; k < np; ++k) CMWG_PROPAGATE(ff_wgrad_launch(pr[k], B, T, Lc, st));
         }
-        rt.n = nr; rt.splits = splits;
+        rt.n = nr;
         wgrad_reduce_kernel<<<dim3(num_sms(), nr), 256, 0, st>>>(rt);
         CMWG_COUNT_LAUNCH();
         CMWG_LAUNCH_CHECK();
-        if (want_wo) {
-          weight_norm_bwd_kernel<<<d.nb(i), 128, 0, st>>>(dWo, prm->W_o[i].v, prm->W_o[i].g,
-                                                         reinterpret_cast<const float*>(pk + PL.nWo[i]), d.Cd,
-                                                         gr->W_o[i].g, gr->W_o[i].v);
-          CMWG_COUNT_LAUNCH();
-          CMWG_LAUNCH_CHECK();
-        }
-        if (want_w) {
-          weight_norm_bwd_kernel<<<2 * d.Cd, 128, 0, st>>>(dW, prm->W[i].v, prm->W[i].g,
-                                                          reinterpret_cast<const float*>(pk + PL.nW[i]), d.Cr * d.R,
-                                                          gr->W[i].g, gr->W[i].v);
-          CMWG_COUNT_LAUNCH();
-          CMWG_LAUNCH_CHECK();
-        }
+        if (want_wo)
+          wq.add(dWo, prm->W_o[i], reinterpret_cast<const float*>(pk + PL.nWo[i]), gr->W_o[i], d.nb(i), d.Cd);
+        if (want_w)
+          wq.add(dW, prm->W[i], reinterpret_cast<const float*>(pk + PL.nW[i]), gr->W[i], 2 * d.Cd, d.Cr * d.R);
         if (want_v) {
           size_t ro = (size_t)i * 2 * d.Cd;
-          weight_norm_bwd_kernel<<<2 * d.Cd, 128, 0, st>>>(
-              dV, prm->V.v + ro * d.aux, prm->V.g ? prm->V.g + ro : nullptr,
-              reinterpret_cast<const float*>(pk + PL.nV) + ro, d.aux, gr->V.g ? gr->V.g + ro : nullptr,
-              gr->V.v ? gr->V.v + ro * d.aux : nullptr);
-          CMWG_COUNT_LAUNCH();
-          CMWG_LAUNCH_CHECK();
+          cmwg_conv_param pv{prm->V.g ? prm->V.g + ro : nullptr, prm->V.v + ro * d.aux, nullptr};
+          cmwg_conv_grad gv{gr->V.g ? gr->V.g + ro : nullptr, gr->V.v ? gr->V.v + ro * d.aux : nullptr, nullptr};
+          wq.add(dV, pv, reinterpret_cast<const float*>(pk + PL.nV) + ro, gv, 2 * d.Cd, d.aux);
         }
       }
     }
@@ -530,7 +537,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
         if (!last) {  // the upstream residual gradient (hi, lo) is added in the epilogue
           io.in[0] = op_stream(dhi(i + 1), d.Cr);
           io.in[1] = op_stream(dlo(i + 1), d.Cr);
-          SplitTcEpi<true> epi{nullptr, f16};
+          SplitTcEpi<true, 2> epi{nullptr, f16};  // K = R*2Cd is long: trade epilogue width for operand stages
           CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
         } else {
           SplitTcEpi<false> epi{nullptr, f16};
@@ -577,13 +584,16 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
                                               (d.bias && gr->start.bias) ? pb : nullptr);
     CMWG_COUNT_LAUNCH();
     CMWG_LAUNCH_CHECK();
-    CMWG_PROPAGATE(reduce_and_wn_bwd(pw, nblk, d.Cr, d.cin, scratch, dweff, prm->start,
-                                     reinterpret_cast<const float*>(pk + PL.nStart), gr->start, st));
+    if (gr->start.g || gr->start.v) {
+      float* dStart = dweff + BL.dweff_start;
+      CMWG_PROPAGATE(reduce_blocks(pw, nblk, d.Cr * d.cin, scratch, dStart, st));
+      wq.add(dStart, prm->start, reinterpret_cast<const float*>(pk + PL.nStart), gr->start, d.Cr, d.cin);
+    }
     if (d.bias && gr->start.bias) {
       CMWG_PROPAGATE(reduce_blocks(pb, nblk, d.Cr, scratch, gr->start.bias, st));
     }
   }
-  return CMWG_OK;
+  return wq.flush(st);
 }
 
 }  // namespace cmwg

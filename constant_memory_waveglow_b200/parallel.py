@@ -6,8 +6,11 @@ organised around the structure of the constant-memory backward: flows finish in 
 K-1 ... 0, and each coupling / 1x1-conv Function returns ALL gradients of its flow at once, so the
 natural bucket is "one flow" (~17.9 MB fp32 at the LJ config) plus one bucket for the upsampler.
 
-  * every bucket owns one flat fp32 buffer; the parameters' ``.grad`` tensors are VIEWS into it, so
-    autograd accumulates straight into the communication buffer (no gather / scatter copies);
+  * every bucket owns one flat fp32 buffer; the parameters' ``.grad`` tensors are VIEWS into it.  The
+    fused backward kernels write their gradients DIRECTLY into those views (``grad_buffer``): with
+    ``p.grad is None`` autograd adopts the returned view as ``p.grad`` without a copy or an add kernel
+    (37 parameters x 12 flows would otherwise cost ~450 tiny accumulate launches per step).  Gradients
+    produced by anything else (generic transforms, CPU tests) are copied into the view once;
   * a post-accumulate-grad hook counts arrivals; when a bucket is complete its all-reduce is issued
     immediately with ``async_op=True`` -- NCCL runs it on its own stream over NVLink/NVSwitch while
     the compute stream proceeds with the next flow's recompute + gradient GEMMs;
@@ -22,6 +25,17 @@ from typing import Iterable, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
+
+
+def grad_buffer(p: torch.Tensor) -> torch.Tensor:
+    """Where a fused backward should write the gradient of parameter `p`: a fresh view of the flat
+    communication buffer when `p` belongs to a FlowGradSync and has no gradient yet (autograd then
+    adopts it as ``p.grad`` as is), else a new tensor (ordinary accumulation semantics)."""
+    slot = getattr(p, "_cmwg_grad_slot", None)
+    if slot is not None and p.grad is None:
+        flat, off = slot
+        return flat[off:off + p.numel()].view_as(p)
+    return torch.empty_like(p)
 
 
 def flow_buckets(model) -> List[List[torch.nn.Parameter]]:
@@ -59,13 +73,29 @@ class FlowGradSync:
             self.flat.append(flat)
             off = 0
             for p in params:
-                p.grad = flat[off:off + p.numel()].view_as(p)
+                p._cmwg_grad_slot = (flat, off)
+                p.grad = None
                 off += p.numel()
                 self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
             self._pending.append(len(params))
 
+    @staticmethod
+    def _adopt(param) -> None:
+        """Make `param.grad` the view of its flat-buffer slot (copying once if it was produced elsewhere)."""
+        flat, off = param._cmwg_grad_slot
+        view = flat[off:off + param.numel()].view_as(param)
+        g = param.grad
+        if g is None:
+            view.zero_()
+        elif g.data_ptr() != view.data_ptr() or g.stride() != view.stride():
+            view.copy_(g)
+        else:
+            return
+        param.grad = view
+
     def _make_hook(self, bi: int):
         def hook(param):
+            self._adopt(param)
             self._pending[bi] -= 1
             if self._pending[bi] == 0:
                 self._launch(bi)
@@ -77,16 +107,13 @@ class FlowGradSync:
             self._works.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def zero_grad(self) -> None:
-        """Zero the flat buffers and (re)attach the gradient views; call before every backward."""
+        """Drop all gradients (``p.grad = None``) so that the next backward writes / adopts them in place;
+        call before every backward."""
         self._works.clear()
         self._launch_order.clear()
         for bi, params in enumerate(self.buckets):
-            self.flat[bi].zero_()
-            off = 0
             for p in params:
-                if p.grad is None or p.grad.data_ptr() != self.flat[bi].data_ptr() + off * self.flat[bi].element_size():
-                    p.grad = self.flat[bi][off:off + p.numel()].view_as(p)
-                off += p.numel()
+                p.grad = None
             self._pending[bi] = len(params)
 
     def finish(self) -> None:
@@ -94,9 +121,12 @@ class FlowGradSync:
         for bi, left in enumerate(self._pending):
             if left != 0 and left != len(self.buckets[bi]):
                 raise RuntimeError(f"FlowGradSync: bucket {bi} received only part of its gradients")
-            if left == len(self.buckets[bi]) and self.world > 1:
-                # bucket untouched this step (unused parameters): still reduce so ranks stay in step
-                self._launch(bi)
+            if left == len(self.buckets[bi]):
+                # bucket untouched this step (unused parameters): zero gradients, still reduced so ranks stay in step
+                for p in self.buckets[bi]:
+                    self._adopt(p)
+                if self.world > 1:
+                    self._launch(bi)
         for w in self._works:
             w.wait()
         self._works.clear()
@@ -113,6 +143,10 @@ class FlowGradSync:
         for h in self._handles:
             h.remove()
         self._handles.clear()
+        for params in self.buckets:
+            for p in params:
+                if hasattr(p, "_cmwg_grad_slot"):
+                    del p._cmwg_grad_slot
 
 
 def shard_utterances(n_items: int, rank: Optional[int] = None, world: Optional[int] = None) -> List[int]:

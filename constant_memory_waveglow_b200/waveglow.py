@@ -23,6 +23,7 @@ from . import _lib as L
 from . import ops, precision
 from .base import FlowBase
 from .efficient_modules import AffineCouplingBlock, InvertibleConv1x1, grad_hint, graph_possible
+from .parallel import grad_buffer
 from .utils import add_weight_norms
 
 
@@ -227,9 +228,10 @@ class WN(nn.Module):
         by_param = {}
         for key, mod in self._convs():
             g, v, b = self._gvb(mod)
-            dg = torch.empty_like(g) if g is not None else None
-            dv = torch.empty_like(v)
-            db = torch.empty_like(b) if b is not None else None
+            # gradient destinations: views of the data-parallel communication buffers when available
+            dg = grad_buffer(g) if g is not None else None
+            dv = grad_buffer(v)
+            db = grad_buffer(b) if b is not None else None
             cg = L.ConvGrad(L.ptr(dg), L.ptr(dv), L.ptr(db))
             if isinstance(key, tuple):
                 getattr(grads, key[0])[key[1]] = cg
