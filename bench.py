@@ -272,6 +272,7 @@ def run_b200(args):
         pk = peaks()
         synth = {"value": khz, "unit": "kHz (all GPUs)", "per_gpu_khz": khz / world, "batch_per_gpu": sb,
                  "utterance_samples": SYNTH_FRAMES * LJ["hop_size"], "sigma": 0.6, "ms": t.item(),
+                 "operand_dtype": precision.resolve(True, False),
                  "tflops_per_gpu": samples * 13.3764e6 / (t.item() * 1e-3) / 1e12,
                  "frac_of_bf16_peak": samples * 13.3764e6 / (t.item() * 1e-3) / 1e12 / pk["tflops_sustained"]}
         model.train()
@@ -298,7 +299,8 @@ def run_b200(args):
         "dtype": {"bf16": "bf16", "fp32": "f32", "fp16": "bf16", "auto": "bf16"}[args.precision],
         "data": "synthetic",
         "config": {"workload": "waveglow_lj_train_fwd+reversible_bwd+adam", "per_gpu_batch": B, "segment": SEGMENT,
-                   "n_mels": 80, "channels": 256, "flows": 12, "wn_layers": 8, "precision": args.precision,
+                   "n_mels": 80, "channels": 256, "flows": 12, "wn_layers": 8,
+                   "precision": precision.resolve(True, True),
                    "l2": "256 MiB flush between timed steps; per-step working set >> 126 MB L2",
                    "parallelism": f"dp{world}", "loss": float(loss.detach())},
         "e2e": {"value": value_e2e, "unit": "segments/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + h_host.numel() * 4),
@@ -333,7 +335,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp16", "auto"])
+    ap.add_argument("--precision", default="auto", choices=["bf16", "fp32", "fp16", "auto"],
+                    help="auto = bf16 operands for training steps, fp16 operands for synthesis (fp32 accumulate)")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--synth-batch", type=int, default=4)
     ap.add_argument("--no-synth", action="store_true")

@@ -99,6 +99,7 @@ def test_precision_resolution():
         assert precision.resolve(True, False) == "fp32"
         torch.backends.cudnn.allow_tf32 = True
         assert precision.resolve(True, True) == "bf16"
+        assert precision.resolve(True, False) == "fp16"      # no graph (synthesis): 11-bit mantissa at the same speed
         assert precision.resolve(False, True) == "fp32"
         precision.set_precision("fp16")
         assert precision.resolve(True, False) == "fp16"
