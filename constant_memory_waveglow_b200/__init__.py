@@ -11,8 +11,9 @@ from .loss import WaveGlowLoss
 from .precision import get_precision, set_precision
 from .utils import add_weight_norms, get_instance, remove_weight_norms
 from .waveglow import WN, NonCausalLayer, WaveGlow, fused_gate
+from .wsrglow import WSRGlow
 
 __all__ = ["FlowBase", "Reversible", "AffineCouplingBlock", "InvertibleConv1x1", "AffineCouplingFunc",
            "InvAffineCouplingFunc", "Conv1x1Func", "InvConv1x1Func", "WaveGlowLoss", "WN", "NonCausalLayer",
-           "WaveGlow", "fused_gate", "add_weight_norms", "remove_weight_norms", "get_instance", "set_precision",
+           "WaveGlow", "WSRGlow", "fused_gate", "add_weight_norms", "remove_weight_norms", "get_instance", "set_precision",
            "get_precision"]

@@ -90,6 +90,35 @@ __global__ void __launch_bounds__(128) upsample_bwd_kernel(const float* __restri
   }
 }
 
+// input gradient of the transposed conv: dh[b,c,f] = sum_k w_eff[c,k] dy[b,c,f*stride-pad+k]; one block per (b, c) row
+__global__ void __launch_bounds__(128) upsample_bwd_input_kernel(const float* __restrict__ g,
+                                                                 const float* __restrict__ v,
+                                                                 const float* __restrict__ dy, long long dy_bs,
+                                                                 long long dy_cs, int C, int F, int K, int stride,
+                                                                 int pad, int Tvalid, float* __restrict__ dh) {
+  extern __shared__ float sm[];
+  float* w = sm;  // [K]
+  __shared__ float red[4];
+  int b = blockIdx.x / C, c = blockIdx.x % C;
+  float ss = 0.f;
+  for (int k = threadIdx.x; k < K; k += 128) {
+    float vv = v[(long long)c * K + k];
+    w[k] = vv;
+    ss = fmaf(vv, vv, ss);
+  }
+  ss = block_sum128(ss, red);
+  float scale = g ? g[c] / sqrtf(ss) : 1.f;
+  const float* dyr = dy + b * dy_bs + c * dy_cs;
+  for (int f = threadIdx.x; f < F; f += 128) {
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      int to = f * stride - pad + k;
+      if (to >= 0 && to < Tvalid) acc = fmaf(w[k], dyr[to], acc);
+    }
+    dh[((long long)b * C + c) * F + f] = acc * scale;
+  }
+}
+
 }  // namespace cmwg
 
 using namespace cmwg;
@@ -123,6 +152,18 @@ int cmwg_upsample_bwd(const float* h, const float* g, const float* v, const floa
   if (C == 0) return CMWG_OK;
   upsample_bwd_kernel<<<C, 128, 0, (cudaStream_t)stream>>>(h, g, v, dy, dy_bstride, dy_cstride, B, C, F, K, stride, pad,
                                                            Tvalid, dg, dv, dbias);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+  return CMWG_OK;
+}
+
+int cmwg_upsample_bwd_input(const float* g, const float* v, const float* dy, long long dy_bstride,
+                            long long dy_cstride, int B, int C, int F, int K, int stride, int pad, int Tvalid,
+                            float* dh, void* stream) {
+  CMWG_REQUIRE(v && dy && dh, "cmwg_upsample_bwd_input: null argument");
+  if (B == 0 || C == 0) return CMWG_OK;
+  upsample_bwd_input_kernel<<<B * C, 128, (size_t)K * sizeof(float), (cudaStream_t)stream>>>(
+      g, v, dy, dy_bstride, dy_cstride, C, F, K, stride, pad, Tvalid, dh);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
   return CMWG_OK;

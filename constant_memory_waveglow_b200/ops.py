@@ -188,6 +188,19 @@ def upsample_bwd(h, g, v, dy, stride: int, pad: int, want_bias: bool):
     return dg, dv, db
 
 
+def upsample_bwd_input(g, v, dy, F: int, stride: int, pad: int) -> torch.Tensor:
+    """Gradient w.r.t. the upsampler input h (B, C, F)."""
+    B, Cc, Tv = dy.shape
+    K = v.shape[-1]
+    if dy.stride(2) != 1:
+        dy = dy.contiguous()
+    dh = torch.empty((B, Cc, F), device=dy.device, dtype=torch.float32)
+    L.check(L.load().cmwg_upsample_bwd_input(L.ptr(g), v.data_ptr(), dy.data_ptr(), dy.stride(0), dy.stride(1), B, Cc,
+                                             F, K, stride, pad, Tv, dh.data_ptr(), L.stream_ptr(dy.device)),
+            "upsample_bwd_input")
+    return dh
+
+
 def selftest_tc_gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, variant: int) -> torch.Tensor:
     """16-bit operands through the tcgen05 engine; see cmwg_selftest_tc_gemm."""
     is_fp16 = int(a.dtype == torch.float16)

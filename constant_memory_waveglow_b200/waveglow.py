@@ -300,10 +300,11 @@ class _UpsampleFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         h, g, v = ctx.saved_tensors
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("cmwg_b200: gradient w.r.t. the mel input of the upsampler is not implemented")
+        dh = None
+        if ctx.needs_input_grad[0]:  # trainable conditioning (WSRGlow's embedding tables)
+            dh = ops.upsample_bwd_input(g, v, dy, h.shape[2], ctx.stride, ctx.pad)
         dg, dv, db = ops.upsample_bwd(h, g, v, dy, ctx.stride, ctx.pad, ctx.has_bias)
-        return None, dg, dv, db, None, None
+        return dh, dg, dv, db, None, None
 
 
 class _SqueezeFunction(torch.autograd.Function):

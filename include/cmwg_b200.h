@@ -191,6 +191,11 @@ size_t cmwg_upsample_bwd_workspace(int B, int C, int K);
 int cmwg_upsample_bwd(const float* h, const float* g, const float* v, const float* dy, long long dy_bstride,
                       long long dy_cstride, int B, int C, int F, int K, int stride, int pad, int Tvalid, float* dg,
                       float* dv, float* dbias, void* workspace, void* stream);
+/* Gradient w.r.t. the upsampler INPUT (needed when the conditioning itself is trainable, e.g. the embedding
+ * tables of WSRGlow, model/wsrglow.py:27-31,52-53):  dh[b,c,f] = sum_k w_eff[c,k] dy[b,c,f*stride-pad+k]. */
+int cmwg_upsample_bwd_input(const float* g, const float* v, const float* dy, long long dy_bstride,
+                            long long dy_cstride, int B, int C, int F, int K, int stride, int pad, int Tvalid,
+                            float* dh, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Model glue (model/waveglow.py:153,179; model/loss.py:10-15)

@@ -351,3 +351,70 @@ def random_state(spec: WaveGlowSpec, wn_channels: int, depth: int, seed: int = 0
         else:
             sd[p + "end.weight"] = torch.randn(c, wn_channels, 1, generator=gen, dtype=dtype) * end_std
     return sd
+
+
+# --------------------------------------------------------------------------------------------
+# WSRGlow (model/wsrglow.py:8-56): a WaveGlow whose conditioning is built from the low-rate signal
+# --------------------------------------------------------------------------------------------
+def wsrglow_spec(upsample_rate: int = 2) -> WaveGlowSpec:
+    """``WSRGlow.__init__`` (``model/wsrglow.py:21-26``): WaveGlow(12 flows, n_group 8r, early 4/2,
+    hop 8r, n_mels 8*400 + 51*9 = 3659)."""
+    return WaveGlowSpec(12, 8 * upsample_rate, 4, 2, 8 * upsample_rate, 8 * 400 + 51 * 9)
+
+
+def mu_law_encode(x: Tensor, channels: int = 256) -> Tensor:
+    """torchaudio ``MuLawEncoding(256)`` as used at ``model/wsrglow.py:27-30``:
+    sign(x) log1p(mu |x|) / log1p(mu), mapped to integer codes 0..mu."""
+    mu = torch.tensor(channels - 1.0, dtype=x.dtype)
+    x_mu = torch.sign(x) * torch.log1p(mu * torch.abs(x)) / torch.log1p(mu)
+    return ((x_mu + 1) / 2 * mu + 0.5).to(torch.int64)
+
+
+def wsrglow_cond(sd: State, c: Tensor) -> Tensor:
+    """``WSRGlow._get_cond`` (``model/wsrglow.py:37-50``) on a CLONE of ``c`` (the reference clips in place):
+    mu-law code embedding reshaped to (B, 3200, L/8), 9 STFT magnitudes (n_fft 16, hop 8, hann, reflect
+    pad 4) and 9 x 50 phase-embedding rows -> (B, 3659, L/8)."""
+    c = c.clone().clip_(-1, 1)
+    c_emb = F.embedding(mu_law_encode(c), sd["mu_enc.1.weight"]).view(c.shape[0], -1, 8 * 400).transpose(1, 2)
+    spec = torch.stft(F.pad(c.unsqueeze(1), (4, 4), mode="reflect").squeeze(1), n_fft=16, hop_length=8,
+                      window=sd["window"], center=False, return_complex=True)
+    mag = spec.abs()
+    emb_w = sd["angle_embed.embed.weight"]
+    n_emb = emb_w.shape[0]
+    index = ((spec.angle() / torch.pi + 1) * 0.5 * (n_emb - 1)).long()     # AngleEmbedding.forward, :15-18
+    phase_emb = F.embedding(index, emb_w).permute(0, 1, 3, 2).reshape(spec.shape[0], 50 * 9, -1)
+    return torch.cat([c_emb, mag, phase_emb], dim=1)
+
+
+def wsrglow_forward(sd: State, spec: WaveGlowSpec, x: Tensor, c: Tensor) -> Tuple[Tensor, Tensor]:
+    """``WSRGlow.forward_computation`` (``model/wsrglow.py:52-53``)."""
+    return waveglow_forward(sd, spec, x, wsrglow_cond(sd, c))
+
+
+def wsrglow_reverse(sd: State, spec: WaveGlowSpec, z: Tensor, c: Tensor) -> Tuple[Tensor, Tensor]:
+    """``WSRGlow.reverse_computation`` (``model/wsrglow.py:55-56``)."""
+    return waveglow_reverse(sd, spec, z, wsrglow_cond(sd, c))
+
+
+def wsrglow_train_step(sd: State, spec: WaveGlowSpec, x: Tensor, c: Tensor, sigma: float):
+    """fwd + loss + bwd of WSRGlow; gradients include both embedding tables."""
+    leaf = _leafify(sd)
+    leaf["window"] = sd["window"]
+    z, logdet = wsrglow_forward(leaf, spec, x, c)
+    loss = waveglow_loss(z, logdet, sigma)
+    keys = [k for k, v in leaf.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys], allow_unused=True)
+    return z.detach(), logdet.detach(), loss.detach(), {k: g for k, g in zip(keys, grads) if g is not None}
+
+
+def wsrglow_random_state(upsample_rate: int, wn_channels: int, depth: int, seed: int = 0,
+                         end_std: Optional[float] = None) -> State:
+    """``random_state`` plus WSRGlow's extra entries (``model/wsrglow.py:27-35``): mu-law embedding (256, 400),
+    angle embedding (120, 50) -- nn.Embedding default init N(0, 1) -- and the hann(16) window buffer."""
+    spec = wsrglow_spec(upsample_rate)
+    sd = random_state(spec, wn_channels, depth, seed=seed, end_std=end_std)
+    gen = torch.Generator().manual_seed(seed + 7919)
+    sd["mu_enc.1.weight"] = torch.randn(256, 400, generator=gen)
+    sd["angle_embed.embed.weight"] = torch.randn(120, 50, generator=gen)
+    sd["window"] = torch.hann_window(16)
+    return sd

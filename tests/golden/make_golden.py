@@ -132,6 +132,45 @@ def main():
                 "grads": grads, "x_roundtrip": xr, "logdet_reverse": logdet_r,
                 "infer_z": zs, "infer_audio": audio},
                os.path.join(OUT, "waveglow_tiny.pt"))
+    # ---- 4. WSRGlow 2x (model/wsrglow.py): weights come from the oracle's seeded generator (the state is
+    # ~45 MB, too big for a fixture), the REFERENCE model computes outputs and gradients -------------------
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import flow_oracle as O
+    from model.wsrglow import WSRGlow
+    assert sys.modules["model.wsrglow"].__file__.startswith(REF)
+    gen_args = dict(upsample_rate=2, wn_channels=64, depth=2, seed=5)
+    sdw = O.wsrglow_random_state(**gen_args)
+    wkw = dict(dilation_channels=64, residual_channels=64, skip_channels=64, depth=2, radix=3, bias=False,
+               zero_init=False)
+    set_seed(11)
+    B, T = 2, 2048
+    x = torch.rand(B, T) * 2 - 1
+    c = torch.rand(B, T // 2) * 2.2 - 1.1          # a few samples outside [-1, 1]: exercises the clip
+    m = WSRGlow(upsample_rate=2, memory_efficient=True, **wkw)
+    missing = m.load_state_dict(sdw, strict=True)
+    m.zero_grad()
+    cond = m._get_cond(c.clone()).detach().clone()
+    z, logdet = m(x.clone(), c.clone())
+    loss = WaveGlowLoss(0.7)(z, logdet)
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in m.named_parameters()}
+    # full gradients only for the embeddings, the upsampler, the 1x1 convs and flows 0 / 5 / 11 (minus V.weight_v);
+    # every other tensor is pinned through its norm
+    keep = {n: g for n, g in grads.items()
+            if not n.endswith("V.weight_v") and g.numel() <= 130000 and
+            (not n.startswith("WNs.") or n.split(".")[1] in ("0", "5", "11"))}
+    with torch.no_grad():
+        m2 = WSRGlow(upsample_rate=2, memory_efficient=False, **wkw)
+        m2.load_state_dict(sdw)
+        xr, _ = m2.reverse(z.detach().clone(), c.clone())
+    torch.save({"gen_args": gen_args, "wn_kwargs": wkw, "x": x, "c": c, "sigma": 0.7,
+                "state_keys": list(m.state_dict().keys()),
+                "cond_sum": cond.double().sum(), "cond_abs_sum": cond.double().abs().sum(),
+                "cond_sample": cond[:, ::61, ::7].clone(),
+                "z": z.detach().clone(), "logdet": logdet.detach().clone(), "loss": loss.detach().clone(),
+                "grads": keep, "grad_norms": {n: g.double().norm() for n, g in grads.items()},
+                "x_roundtrip": xr},
+               os.path.join(OUT, "wsrglow_tiny.pt"))
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

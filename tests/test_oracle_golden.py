@@ -109,3 +109,29 @@ def test_random_state_has_reference_keys():
     assert set(sd) == set(fx["state"])
     for k in sd:
         assert sd[k].shape == fx["state"][k].shape, k
+
+
+def test_wsrglow_tiny_against_reference():
+    """WSRGlow 2x (model/wsrglow.py): conditioning front end + flow, outputs and gradients from the
+    unmodified reference; weights are regenerated from the seed the fixture records."""
+    fx = load("wsrglow_tiny.pt")
+    ga = fx["gen_args"]
+    sd = O.wsrglow_random_state(**ga)
+    assert list(sd.keys()) == fx["state_keys"] or set(sd.keys()) == set(fx["state_keys"])
+    spec = O.wsrglow_spec(ga["upsample_rate"])
+    assert spec.n_mels == 3659 and spec.n_group == 16 and spec.upsample_factor == 1 and spec.sub_win == 3
+    cond = O.wsrglow_cond(sd, fx["c"])
+    assert cond.shape == (2, 3659, 128)
+    assert torch.allclose(cond[:, ::61, ::7], fx["cond_sample"], atol=1e-5)
+    assert abs(cond.double().abs().sum().item() - fx["cond_abs_sum"].item()) < 1e-6 * fx["cond_abs_sum"].item()
+    z, logdet, loss, grads = O.wsrglow_train_step(sd, spec, fx["x"], fx["c"], fx["sigma"])
+    assert rel_l2(z, fx["z"]) < 1e-6
+    assert rel_l2(logdet, fx["logdet"]) < 2e-5
+    assert torch.allclose(loss, fx["loss"], rtol=1e-6)
+    for k, g in fx["grads"].items():
+        assert rel_l2(grads[k], g) < 5e-5, k
+    for k, n in fx["grad_norms"].items():
+        assert abs(grads[k].double().norm().item() - n.item()) < 1e-4 * max(n.item(), 1e-12), k
+    xr, _ = O.wsrglow_reverse(sd, spec, fx["z"], fx["c"])
+    assert torch.allclose(xr, fx["x_roundtrip"], atol=2e-6)
+    assert torch.allclose(xr, fx["x"], atol=2e-5)
