@@ -25,7 +25,8 @@ c_float_p = C.POINTER(C.c_float)
 class WnConfig(C.Structure):
     _fields_ = [("in_channels", C.c_int), ("aux_channels", C.c_int), ("dil_channels", C.c_int),
                 ("res_channels", C.c_int), ("skip_channels", C.c_int), ("depth", C.c_int),
-                ("radix", C.c_int), ("has_bias", C.c_int), ("precision", C.c_int)]
+                ("radix", C.c_int), ("has_bias", C.c_int), ("precision", C.c_int),
+                ("height", C.c_int), ("h_dilation", C.c_int * MAX_DEPTH)]
 
 
 class ConvParam(C.Structure):

@@ -4,6 +4,8 @@
 //
 //   D[row][n] = sum_s sum_k A_s[row + shift_s][k] * W[n][koff_s + k]       (ff_gemm_kernel)
 //   D[m][n]   = sum_t  A[t][m] * Bsrc[t + shift][n]                         (ff_wgrad_kernel)
+// Rows are (batch, line, time): a slab is [B][H][T][C] with H = 1 for the 1-D WN of WaveGlow and
+// H = squeezed height for WaveFlow's 2-D WN; a tap shifts time AND line, both zero padded.
 //
 // 128x128 CTA tile, BK = 16, 256 threads, 8x8 register tile per thread (split 4+4 so that the two
 // column groups a thread owns are 64 apart: the gate epilogue needs exactly that pairing),
@@ -22,6 +24,8 @@ struct GemmSeg {
   int K;          // valid channels of this segment
   int shift;      // row (time) shift applied to the A operand
   int koff;       // column offset of this segment inside the weight matrix
+  int shift_h;    // line (height) shift applied to the A operand (2-D WN)
+  int bcast_h;    // the operand has no line dimension ([B][T][C], e.g. the conditioning): same rows for every line
 };
 
 struct GemmDesc {
@@ -32,6 +36,7 @@ struct GemmDesc {
   int N;          // valid output columns
   int n_rows_w;   // rows physically present in w (>= N, used for the TMA map)
   int B, T;
+  int H;          // lines per batch item (0 or 1: plain [B][T] slabs)
   int bn;         // N tile (tc engine)
   int is_fp16;
   int tag;        // CMWG_KCLASS_* for the profiler
@@ -41,7 +46,7 @@ struct FfGemmParams {
   GemmSeg seg[MAX_SEG];
   int nseg;
   const float* w;
-  int ldw, N, B, T, tiles_per_batch;
+  int ldw, N, B, T, H, tiles_per_batch;  // tiles_per_batch: tiles per LINE
 };
 
 __device__ __forceinline__ void ff_mma_tile(const float (*As)[FF_LD], const float (*Bs)[FF_LD], int tx, int ty,
@@ -67,7 +72,8 @@ __global__ void __launch_bounds__(FF_THREADS) ff_gemm_kernel(const FfGemmParams 
   __shared__ __align__(16) float Bs[2][FF_BK][FF_LD];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int b = blockIdx.x / p.tiles_per_batch;
+  const int line = blockIdx.x / p.tiles_per_batch;
+  const int b = line / p.H, h = line - b * p.H;
   const int t0 = (blockIdx.x % p.tiles_per_batch) * FF_BM;
   const int n0 = blockIdx.y * FF_BN;
   const int lr = tid >> 2;         // 0..63 : row inside the half tile
@@ -88,11 +94,14 @@ __global__ void __launch_bounds__(FF_THREADS) ff_gemm_kernel(const FfGemmParams 
     const GemmSeg& sg = p.seg[s];
     const float* ap = reinterpret_cast<const float*>(sg.a);
     int k = kb * FF_BK + kq;
+    const int ha = h + sg.shift_h;
+    const bool hok = sg.bcast_h || (ha >= 0 && ha < p.H);
+    const long long line_a = sg.bcast_h ? (long long)b : (long long)b * p.H + ha;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       int t = t0 + lr + 64 * i + sg.shift;
-      bool ok = (t >= 0) && (t < p.T) && (k < sg.K);
-      ra[i] = ok ? *reinterpret_cast<const float4*>(ap + ((long long)b * p.T + t) * sg.lda + k)
+      bool ok = hok && (t >= 0) && (t < p.T) && (k < sg.K);
+      ra[i] = ok ? *reinterpret_cast<const float4*>(ap + (line_a * p.T + t) * sg.lda + k)
                  : make_float4(0.f, 0.f, 0.f, 0.f);
       int n = n0 + lr + 64 * i;
       bool okb = (n < p.N) && (k < sg.K);
@@ -134,7 +143,7 @@ __global__ void __launch_bounds__(FF_THREADS) ff_gemm_kernel(const FfGemmParams 
     int rl = (ri < 4) ? (ty * 4 + ri) : (64 + ty * 4 + ri - 4);
     int t = t0 + rl;
     if (t >= p.T) continue;
-    long long row = (long long)b * p.T + t;
+    long long row = (long long)line * p.T + t;
     float lo[4] = {acc[ri][0], acc[ri][1], acc[ri][2], acc[ri][3]};
     float hi[4] = {acc[ri][4], acc[ri][5], acc[ri][6], acc[ri][7]};
     if constexpr (PAIRED) {
@@ -156,9 +165,9 @@ int ff_gemm_launch(const GemmDesc& d, const Epi& epi, cudaStream_t st) {
   }
   p.nseg = d.nseg;
   p.w = reinterpret_cast<const float*>(d.w);
-  p.ldw = d.ldw; p.N = d.N; p.B = d.B; p.T = d.T;
+  p.ldw = d.ldw; p.N = d.N; p.B = d.B; p.T = d.T; p.H = d.H > 0 ? d.H : 1;
   p.tiles_per_batch = ceil_div(d.T, FF_BM);
-  dim3 grid(d.B * p.tiles_per_batch, ceil_div(d.N, FF_BN));
+  dim3 grid(d.B * p.H * p.tiles_per_batch, ceil_div(d.N, FF_BN));
   if (grid.x == 0 || grid.y == 0) return CMWG_OK;
   ProfScope prof(st, d.tag);
   ff_gemm_kernel<Epi, PAIRED><<<grid, FF_THREADS, 0, st>>>(p, epi);
@@ -172,12 +181,14 @@ struct WgradProblem {
   const void* a; int lda; int a_c0; int M;   // A[t][a_c0 + m]
   const void* b; int ldb; int b_c0; int N;   // Bsrc[t + shift][b_c0 + n]
   int shift;
+  int shift_h;                               // line shift of the B operand (2-D WN)
+  int bcast_h;                               // B operand has no line dimension ([B][T][C])
   float* partial;                            // [splits][M][N]
 };
 
 struct FfWgradParams {
   WgradProblem pr;
-  int B, T, Lc, chunks_per_batch, n_tiles_n;
+  int B, T, H, Lc, chunks_per_batch, n_tiles_n;  // chunks_per_batch: chunks per LINE
 };
 
 static __global__ void __launch_bounds__(FF_THREADS) ff_wgrad_kernel(const FfWgradParams p) {
@@ -188,7 +199,11 @@ static __global__ void __launch_bounds__(FF_THREADS) ff_wgrad_kernel(const FfWgr
   const int m0 = (blockIdx.x / p.n_tiles_n) * FF_BM;
   const int n0 = (blockIdx.x % p.n_tiles_n) * FF_BN;
   const int split = blockIdx.y;
-  const int b = split / p.chunks_per_batch;
+  const int line = split / p.chunks_per_batch;
+  const int b = line / p.H, h = line - b * p.H;
+  const int hb = h + p.pr.shift_h;
+  const bool hok = p.pr.bcast_h || (hb >= 0 && hb < p.H);
+  const long long line_b = p.pr.bcast_h ? (long long)b : (long long)b * p.H + hb;
   const int tc0 = (split % p.chunks_per_batch) * p.Lc;
   const int tlen = min(p.Lc, p.T - tc0);
   const float* A = reinterpret_cast<const float*>(p.pr.a);
@@ -209,11 +224,11 @@ static __global__ void __launch_bounds__(FF_THREADS) ff_wgrad_kernel(const FfWgr
       int k = kb * FF_BK + lk + 8 * i;
       int t = tc0 + k;
       bool oka = (k < tlen) && (m0 + c4 < p.pr.M);
-      ra[i] = oka ? *reinterpret_cast<const float4*>(A + ((long long)b * p.T + t) * p.pr.lda + p.pr.a_c0 + m0 + c4)
+      ra[i] = oka ? *reinterpret_cast<const float4*>(A + ((long long)line * p.T + t) * p.pr.lda + p.pr.a_c0 + m0 + c4)
                   : make_float4(0.f, 0.f, 0.f, 0.f);
       int tb = t + p.pr.shift;
-      bool okb = (k < tlen) && (tb >= 0) && (tb < p.T) && (n0 + c4 < p.pr.N);
-      rb[i] = okb ? *reinterpret_cast<const float4*>(Bm + ((long long)b * p.T + tb) * p.pr.ldb + p.pr.b_c0 + n0 + c4)
+      bool okb = hok && (k < tlen) && (tb >= 0) && (tb < p.T) && (n0 + c4 < p.pr.N);
+      rb[i] = okb ? *reinterpret_cast<const float4*>(Bm + (line_b * p.T + tb) * p.pr.ldb + p.pr.b_c0 + n0 + c4)
                   : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
@@ -251,15 +266,15 @@ static __global__ void __launch_bounds__(FF_THREADS) ff_wgrad_kernel(const FfWgr
   }
 }
 
-inline int ff_wgrad_launch(const WgradProblem& pr, int B, int T, int Lc, cudaStream_t st) {
+inline int ff_wgrad_launch(const WgradProblem& pr, int B, int H, int T, int Lc, cudaStream_t st) {
   CMWG_REQUIRE(pr.M % 4 == 0 && pr.N % 4 == 0 && pr.lda % 4 == 0 && pr.ldb % 4 == 0 && pr.a_c0 % 4 == 0 &&
                    pr.b_c0 % 4 == 0,
                "ff_wgrad: dims must be multiples of 4");
   FfWgradParams p;
-  p.pr = pr; p.B = B; p.T = T; p.Lc = Lc;
+  p.pr = pr; p.B = B; p.T = T; p.H = H > 0 ? H : 1; p.Lc = Lc;
   p.chunks_per_batch = ceil_div(T, Lc);
   p.n_tiles_n = ceil_div(pr.N, FF_BN);
-  dim3 grid(ceil_div(pr.M, FF_BM) * p.n_tiles_n, B * p.chunks_per_batch);
+  dim3 grid(ceil_div(pr.M, FF_BM) * p.n_tiles_n, B * p.H * p.chunks_per_batch);
   if (grid.x == 0 || grid.y == 0) return CMWG_OK;
   ProfScope prof(st, CMWG_KCLASS_WGRAD);
   ff_wgrad_kernel<<<grid, FF_THREADS, 0, st>>>(p);

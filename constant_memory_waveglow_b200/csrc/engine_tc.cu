@@ -32,17 +32,17 @@ static PFN_encodeTiled get_encode_fn() {
 // ---- tensor-map cache: a training step re-encodes the same few hundred descriptors every step -----
 struct MapKey {
   const void* ptr;
-  int d0, d1, d2, ld, b0, b1, flags;  // dims (d0 innermost), row pitch in elements, box, dtype/swizzle/rank
+  int d0, d1, d2, d3, ld, b0, b1, flags;  // dims (d0 innermost), row pitch in elements, box, dtype/swizzle/rank
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld == o.ld && b0 == o.b0 && b1 == o.b1 &&
-           flags == o.flags;
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && ld == o.ld && b0 == o.b0 &&
+           b1 == o.b1 && flags == o.flags;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
     auto mix = [&](int v) { h ^= (size_t)(unsigned)v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
-    mix(k.d0); mix(k.d1); mix(k.d2); mix(k.ld); mix(k.b0); mix(k.b1); mix(k.flags);
+    mix(k.d0); mix(k.d1); mix(k.d2); mix(k.d3); mix(k.ld); mix(k.b0); mix(k.b1); mix(k.flags);
     return h;
   }
 };
@@ -69,15 +69,17 @@ static int encode_cached(CUtensorMap* m, const MapKey& key, CUtensorMapDataType 
   if (!enc) return CMWG_ERR_CUDA;
   CMWG_REQUIRE((reinterpret_cast<uintptr_t>(key.ptr) & 15) == 0 && ((long long)key.ld * esize) % 16 == 0,
                "tensor map: pointer/row pitch not 16-byte aligned (pitch %d elements)", key.ld);
-  cuuint64_t dims[3] = {(cuuint64_t)key.d0, (cuuint64_t)key.d1, (cuuint64_t)(rank == 3 ? key.d2 : 1)};
-  cuuint64_t strides[2] = {(cuuint64_t)key.ld * esize, (cuuint64_t)key.d1 * key.ld * esize};
-  cuuint32_t box[3] = {(cuuint32_t)key.b0, (cuuint32_t)key.b1, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint64_t dims[4] = {(cuuint64_t)key.d0, (cuuint64_t)key.d1, (cuuint64_t)(rank >= 3 ? key.d2 : 1),
+                        (cuuint64_t)(rank >= 4 ? key.d3 : 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)key.ld * esize, (cuuint64_t)key.d1 * key.ld * esize,
+                           (cuuint64_t)key.d2 * key.d1 * key.ld * esize};
+  cuuint32_t box[4] = {(cuuint32_t)key.b0, (cuuint32_t)key.b1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, dt, rank, const_cast<void*>(key.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(dims %d x %d x %d, box %d x %d, flags %d) failed with CUresult %d", key.d0,
-              key.d1, key.d2, key.b0, key.b1, key.flags, (int)r);
+    set_error("cuTensorMapEncodeTiled(dims %d x %d x %d x %d, box %d x %d, flags %d) failed with CUresult %d", key.d0,
+              key.d1, key.d2, key.d3, key.b0, key.b1, key.flags, (int)r);
     return CMWG_ERR_CUDA;
   }
   std::lock_guard<std::mutex> lk(g_map_mu);
@@ -86,17 +88,17 @@ static int encode_cached(CUtensorMap* m, const MapKey& key, CUtensorMapDataType 
   return CMWG_OK;
 }
 
-int get_slab_map(CUtensorMap* m, const void* ptr, int C, int ld, int T, int B, int box_c, int box_t, int is_fp16,
-                 int kind) {
-  MapKey key{ptr, C, T, B, ld, box_c, box_t, (kind << 4) | (is_fp16 ? 1 : 0) | 2};
+int get_slab_map(CUtensorMap* m, const void* ptr, int C, int ld, int T, int H, int B, int box_c, int box_t,
+                 int is_fp16, int kind) {
+  MapKey key{ptr, C, T, H, B, ld, box_c, box_t, (kind << 4) | (is_fp16 ? 1 : 0) | 2};
   if (kind == TC_MAP_CHUNK32)
-    return encode_cached(m, key, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 3, CU_TENSOR_MAP_SWIZZLE_128B);
-  return encode_cached(m, key, is_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3,
+    return encode_cached(m, key, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 4, CU_TENSOR_MAP_SWIZZLE_128B);
+  return encode_cached(m, key, is_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4,
                        kind == TC_MAP_CHUNK16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 int get_matrix_map(CUtensorMap* m, const void* ptr, int ld, int rows, int box_rows, int is_fp16) {
-  MapKey key{ptr, ld, rows, 1, ld, TC_BK, box_rows, (is_fp16 ? 1 : 0)};
+  MapKey key{ptr, ld, rows, 1, 1, ld, TC_BK, box_rows, (is_fp16 ? 1 : 0)};
   return encode_cached(m, key, is_fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 2,
                        CU_TENSOR_MAP_SWIZZLE_128B);
 }
@@ -123,7 +125,7 @@ int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaS
 
 constexpr int TC_PLAN_PAIRS = 74;  // CTA pairs of a B200 (148 SMs); only load balance depends on it
 
-static int wgrad_group_splits(const WgradProblem* probs, int nprob, int bn, int B, int T) {
+static int wgrad_group_splits(const WgradProblem* probs, int nprob, int bn, int B, int T) {  // B = lines
   int tiles = 0;
   for (int i = 0; i < nprob; ++i) tiles += ceil_div(probs[i].M, 2 * TC_BM) * ceil_div(probs[i].N, bn);
   const int total_units = B * ceil_div(T, TC_BK);
@@ -135,7 +137,8 @@ static int wgrad_group_splits(const WgradProblem* probs, int nprob, int bn, int 
   return ceil_div(total_units, ups);
 }
 
-void tc_wgrad_plan(const WgradProblem* probs, int nprob, int B, int T, int force_splits, int* splits_out) {
+void tc_wgrad_plan(const WgradProblem* probs, int nprob, int B, int H, int T, int force_splits, int* splits_out) {
+  B *= (H > 0 ? H : 1);
   WgradProblem big[TC_MAX_WG], small[TC_MAX_WG];
   int nb = 0, ns = 0;
   for (int i = 0; i < nprob; ++i) {
@@ -151,14 +154,14 @@ void tc_wgrad_plan(const WgradProblem* probs, int nprob, int B, int T, int force
 }
 
 template <int BN>
-static int tc_wgrad_launch_bn(const WgradProblem* probs, int nprob, int B, int T, int splits, int is_fp16,
+static int tc_wgrad_launch_bn(const WgradProblem* probs, int nprob, int B, int H, int T, int splits, int is_fp16,
                               cudaStream_t st, int lbo_override, int sbo_override) {
   TcWgradParams p;
   memset(&p, 0, sizeof(p));
   p.nprob = nprob;
-  p.B = B; p.T = T;
+  p.B = B; p.T = T; p.H = H;
   p.units_per_batch = ceil_div(T, TC_BK);
-  p.total_units = B * p.units_per_batch;
+  p.total_units = B * H * p.units_per_batch;
   p.splits = splits;
   p.units_per_split = ceil_div(p.total_units, splits);
   int tiles = 0;
@@ -166,10 +169,12 @@ static int tc_wgrad_launch_bn(const WgradProblem* probs, int nprob, int B, int T
     const WgradProblem& q = probs[i];
     CMWG_REQUIRE(q.lda % 8 == 0 && q.ldb % 8 == 0 && q.a_c0 % 8 == 0 && q.b_c0 % 8 == 0 && q.N % 4 == 0,
                  "tc_wgrad: leading dimensions must be multiples of 8");
-    CMWG_PROPAGATE(get_slab_map(&p.a_map[i], q.a, q.lda, q.lda, T, B, 64, TC_BK, is_fp16, TC_MAP_OPERAND));
-    CMWG_PROPAGATE(get_slab_map(&p.b_map[i], q.b, q.ldb, q.ldb, T, B, 64, TC_BK, is_fp16, TC_MAP_OPERAND));
-    CMWG_PROPAGATE(get_slab_map(&p.out_map[i], q.partial, q.N, q.N, q.M, p.splits, 32, 32, 0, TC_MAP_CHUNK32));
+    CMWG_PROPAGATE(get_slab_map(&p.a_map[i], q.a, q.lda, q.lda, T, H, B, 64, TC_BK, is_fp16, TC_MAP_OPERAND));
+    CMWG_PROPAGATE(get_slab_map(&p.b_map[i], q.b, q.ldb, q.ldb, T, q.bcast_h ? 1 : H, B, 64, TC_BK, is_fp16,
+                                TC_MAP_OPERAND));
+    CMWG_PROPAGATE(get_slab_map(&p.out_map[i], q.partial, q.N, q.N, q.M, 1, p.splits, 32, 32, 0, TC_MAP_CHUNK32));
     p.M[i] = q.M; p.N[i] = q.N; p.shift[i] = q.shift; p.a_c0[i] = q.a_c0; p.b_c0[i] = q.b_c0;
+    p.shift_h[i] = q.shift_h; p.bcast[i] = q.bcast_h;
     p.n_tiles_n[i] = ceil_div(q.N, BN);
     p.tile_begin[i] = tiles;
     tiles += ceil_div(q.M, 2 * TC_BM) * p.n_tiles_n[i];
@@ -196,11 +201,12 @@ static int tc_wgrad_launch_bn(const WgradProblem* probs, int nprob, int B, int T
   return CMWG_OK;
 }
 
-int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int T, int is_fp16, cudaStream_t st, int force_splits,
-                    int lbo_override, int sbo_override) {
+int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int H, int T, int is_fp16, cudaStream_t st,
+                    int force_splits, int lbo_override, int sbo_override) {
   CMWG_REQUIRE(nprob >= 1 && nprob <= TC_MAX_WG, "tc_wgrad: %d problems (max %d)", nprob, TC_MAX_WG);
+  if (H < 1) H = 1;
   int splits[TC_MAX_WG];
-  tc_wgrad_plan(probs, nprob, B, T, force_splits, splits);
+  tc_wgrad_plan(probs, nprob, B, H, T, force_splits, splits);
   // group by N tile width
   WgradProblem big[TC_MAX_WG], small[TC_MAX_WG];
   int nb = 0, ns = 0, sb = 1, ss = 1;
@@ -208,8 +214,8 @@ int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int T, int is_f
     if (probs[i].N >= 256) { big[nb++] = probs[i]; sb = splits[i]; }
     else { small[ns++] = probs[i]; ss = splits[i]; }
   }
-  if (nb) CMWG_PROPAGATE(tc_wgrad_launch_bn<256>(big, nb, B, T, sb, is_fp16, st, lbo_override, sbo_override));
-  if (ns) CMWG_PROPAGATE(tc_wgrad_launch_bn<128>(small, ns, B, T, ss, is_fp16, st, lbo_override, sbo_override));
+  if (nb) CMWG_PROPAGATE(tc_wgrad_launch_bn<256>(big, nb, B, H, T, sb, is_fp16, st, lbo_override, sbo_override));
+  if (ns) CMWG_PROPAGATE(tc_wgrad_launch_bn<128>(small, ns, B, H, T, ss, is_fp16, st, lbo_override, sbo_override));
   return CMWG_OK;
 }
 
@@ -240,7 +246,7 @@ extern "C" int cmwg_selftest_tc_gemm(const void* a, const void* b, float* d, int
   WgradProblem pr;
   pr.a = a; pr.lda = M; pr.a_c0 = 0; pr.M = M;
   pr.b = b; pr.ldb = N; pr.b_c0 = 0; pr.N = N;
-  pr.shift = 0; pr.partial = d;
-  if (variant & 4) return tc_wgrad_launch(&pr, 1, 1, K, is_fp16, st, 1, 1024 >> 4, 8192 >> 4);
-  return tc_wgrad_launch(&pr, 1, 1, K, is_fp16, st, 1);
+  pr.shift = 0; pr.shift_h = 0; pr.bcast_h = 0; pr.partial = d;
+  if (variant & 4) return tc_wgrad_launch(&pr, 1, 1, 1, K, is_fp16, st, 1, 1024 >> 4, 8192 >> 4);
+  return tc_wgrad_launch(&pr, 1, 1, 1, K, is_fp16, st, 1);
 }

@@ -66,7 +66,9 @@ struct alignas(64) TcGemmParams {
   int seg_nkb[MAX_SEG];
   int seg_shift[MAX_SEG];
   int seg_koff[MAX_SEG];
-  int B, T, tiles_per_batch, n_tiles, total_tiles, N;
+  int seg_shift_h[MAX_SEG];     // line shift of the segment (2-D WN taps)
+  int seg_bcast[MAX_SEG];       // segment has no line dimension: its map has H = 1 and line coordinate 0
+  int B, T, H, tiles_per_batch, n_tiles, total_tiles, N;  // tiles_per_batch: tiles per LINE
   uint32_t idesc;
   uint32_t desc_lbo, desc_sbo;  // >>4 encoded; overridable by the self test
 };
@@ -77,11 +79,12 @@ struct alignas(64) TcWgradParams {
   CUtensorMap out_map[TC_MAX_WG];  // fp32 partials [splits][M][N]
   int nprob;
   int M[TC_MAX_WG], N[TC_MAX_WG], shift[TC_MAX_WG], a_c0[TC_MAX_WG], b_c0[TC_MAX_WG];
+  int shift_h[TC_MAX_WG], bcast[TC_MAX_WG];  // line shift / no-line flag of the B operand
   int tile_begin[TC_MAX_WG + 1];  // prefix sum of (m_tiles * n_tiles) per problem
   int n_tiles_n[TC_MAX_WG];
-  // split-K over the flattened (batch, 64-row k-block) sequence: split s covers k-block units
-  // [s * units_per_split, (s+1) * units_per_split) and accumulates ACROSS batch items in TMEM
-  int B, T, units_per_batch, total_units, units_per_split, splits, total_work;
+  // split-K over the flattened (batch, line, 64-row k-block) sequence: split s covers k-block units
+  // [s * units_per_split, (s+1) * units_per_split) and accumulates ACROSS lines / batch items in TMEM
+  int B, T, H, units_per_batch, total_units, units_per_split, splits, total_work;  // units_per_batch: per LINE
   uint32_t idesc;
   uint32_t desc_lbo, desc_sbo;
 };
@@ -151,6 +154,29 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
           dst),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// slab operand tile: coordinates (channel, time, line, batch)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_local(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                  int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 // CTA-local TMA load (epilogue inputs)
 __device__ __forceinline__ void tma_load_3d_local(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
@@ -419,15 +445,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       uint32_t phase = 0;
       for (int tile = pair; tile < p.total_tiles; tile += npairs) {
         int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
-        int b = rt / p.tiles_per_batch, t0 = (rt % p.tiles_per_batch) * (2 * TC_BM) + rank * TC_BM;
+        int line = rt / p.tiles_per_batch, t0 = (rt % p.tiles_per_batch) * (2 * TC_BM) + rank * TC_BM;
+        int b = line / p.H, h = line - b * p.H;
         int n0 = nt * BN + rank * (BN / 2);
         for (int sg = 0; sg < p.nseg; ++sg) {
+          const int hs = p.seg_bcast[sg] ? 0 : h + p.seg_shift_h[sg];
           for (int kb = 0; kb < p.seg_nkb[sg]; ++kb) {
             mbar_wait(&s.empty[stage], phase ^ 1);
             uint32_t sa = smem_u32(s.stages + stage * STAGE_BYTES);
             if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * STAGE_BYTES);
             uint32_t bar = mapa_shared(smem_u32(&s.full[stage]), 0);
-            tma_load_3d(sa, &p.a_map[sg], bar, kb * TC_BK, t0 + p.seg_shift[sg], b);
+            tma_load_4d(sa, &p.a_map[sg], bar, kb * TC_BK, t0 + p.seg_shift[sg], hs, b);
             tma_load_2d(sa + TC_A_BYTES, &p.b_map, bar, p.seg_koff[sg] + kb * TC_BK, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -479,23 +507,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     int ob = 0;        // output staging buffer in use
     uint32_t it = 0;   // running chunk counter (phase of the input barrier)
 
-    // coordinates of chunk k of a tile: batch, first row of this warp, first epilogue column
-    auto coords = [&](int tile, int k, int& b, int& r0, int& c0) {
+    // coordinates of chunk k of a tile: batch, line, first row of this warp, first epilogue column
+    auto coords = [&](int tile, int k, int& b, int& h, int& r0, int& c0) {
       int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
-      b = rt / p.tiles_per_batch;
+      int line = rt / p.tiles_per_batch;
+      b = line / p.H;
+      h = line - b * p.H;
       r0 = (rt % p.tiles_per_batch) * (2 * TC_BM) + rank * TC_BM + q * 32;
       c0 = nt * GW + cg * (GW / NCG) + 32 * k;
     };
     auto issue_inputs = [&](int tile, int k) {
       if constexpr (Epi::kIn > 0) {
         if (lane == 0) {
-          int b, r0, c0;
-          coords(tile, k, b, r0, c0);
+          int b, h, r0, c0;
+          coords(tile, k, b, h, r0, c0);
           fence_proxy_async();
           mbar_arrive_expect_tx(ibar, Epi::kIn * TC_CHUNK16_BYTES);
 #pragma unroll
           for (int i = 0; i < Epi::kIn; ++i)
-            tma_load_3d_local(ibuf + i * TC_CHUNK16_BYTES, &p.in_map[i], smem_u32(ibar), epi.in_col(i, c0), r0, b);
+            tma_load_4d_local(ibuf + i * TC_CHUNK16_BYTES, &p.in_map[i], smem_u32(ibar), epi.in_col(i, c0), r0, h, b);
         }
       }
     };
@@ -507,8 +537,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       tc_fence_after();
 #pragma unroll 1
       for (int k = 0; k < NCH; ++k, ++it) {
-        int b, r0, c0;
-        coords(tile, k, b, r0, c0);
+        int b, h, r0, c0;
+        coords(tile, k, b, h, r0, c0);
         // epilogue inputs: take this chunk into registers, then re-arm the buffer with the next chunk
         uint32_t in[Epi::kIn > 0 ? Epi::kIn : 1][16];
         if constexpr (Epi::kIn > 0) {
@@ -564,7 +594,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
-          for (int i = 0; i < Epi::kOut; ++i) tma_store_3d(&p.out_map[i], obuf + i * ET::kOutChunk, epi.out_col(i, c0), r0, b);
+          for (int i = 0; i < Epi::kOut; ++i)
+            tma_store_4d(&p.out_map[i], obuf + i * ET::kOutChunk, epi.out_col(i, c0), r0, h, b);
           bulk_commit();
         }
         if (Epi::kOutBufs > 1) ob ^= 1;
@@ -629,20 +660,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
         const int u0 = split * p.units_per_split, u1 = min(u0 + p.units_per_split, p.total_units);
         const int ma = p.a_c0[pr] + m0 + rank * TC_BM;
         const int nb = p.b_c0[pr] + n0 + rank * (BN / 2);
-        int b = u0 / p.units_per_batch, t = (u0 - b * p.units_per_batch) * TC_BK;
+        int line = u0 / p.units_per_batch, t = (u0 - line * p.units_per_batch) * TC_BK;
+        int b = line / p.H, h = line - b * p.H;
+        const int dh = p.shift_h[pr], bc = p.bcast[pr];
         for (int u = u0; u < u1; ++u) {
           mbar_wait(&s.empty[stage], phase ^ 1);
           uint32_t sa = smem_u32(s.stages + stage * STAGE_BYTES);
           if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * STAGE_BYTES);
           uint32_t bar = mapa_shared(smem_u32(&s.full[stage]), 0);
 #pragma unroll
-          for (int j = 0; j < TC_BM / 64; ++j) tma_load_3d(sa + j * BOX_BYTES, &p.a_map[pr], bar, ma + j * 64, t, b);
+          for (int j = 0; j < TC_BM / 64; ++j) tma_load_4d(sa + j * BOX_BYTES, &p.a_map[pr], bar, ma + j * 64, t, h, b);
 #pragma unroll
           for (int j = 0; j < BN / 128; ++j)
-            tma_load_3d(sa + TC_A_BYTES + j * BOX_BYTES, &p.b_map[pr], bar, nb + j * 64, t + p.shift[pr], b);
+            tma_load_4d(sa + TC_A_BYTES + j * BOX_BYTES, &p.b_map[pr], bar, nb + j * 64, t + p.shift[pr],
+                        bc ? 0 : h + dh, b);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           t += TC_BK;
-          if (t >= p.units_per_batch * TC_BK) { t = 0; ++b; }
+          if (t >= p.units_per_batch * TC_BK) {
+            t = 0;
+            if (++h == p.H) { h = 0; ++b; }
+          }
         }
       }
     }
@@ -716,7 +753,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&p.out_map[pr], obuf, n0 + cg * (BN / NCG) + 32 * k, mq, split);
+          tma_store_4d(&p.out_map[pr], obuf, n0 + cg * (BN / NCG) + 32 * k, mq, 0, split);
           bulk_commit();
         }
         if (WgradEpiShape::kOutBufs > 1) ob ^= 1;
@@ -737,10 +774,10 @@ enum TcMapKind {
   TC_MAP_CHUNK16 = 1,   // 16-bit, 64B swizzle, box {32, 32, 1} (epilogue streams)
   TC_MAP_CHUNK32 = 2,   // fp32,   128B swizzle, box {32, 32, 1}
 };
-// cached tensor map over a slab [B][T][ld] of which the first C channels are valid (dims (C, T, B));
-// box (box_c, box_t, 1); zero OOB fill
-int get_slab_map(CUtensorMap* m, const void* ptr, int C, int ld, int T, int B, int box_c, int box_t, int is_fp16,
-                 int kind);
+// cached tensor map over a slab [B][H][T][ld] of which the first C channels are valid (dims (C, T, H, B));
+// box (box_c, box_t, 1, 1); zero OOB fill
+int get_slab_map(CUtensorMap* m, const void* ptr, int C, int ld, int T, int H, int B, int box_c, int box_t,
+                 int is_fp16, int kind);
 // 16-bit tensor map over a matrix [rows][ld]: dims (ld, rows), box (64, box_rows)
 int get_matrix_map(CUtensorMap* m, const void* ptr, int ld, int rows, int box_rows, int is_fp16);
 int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st);
@@ -751,29 +788,32 @@ int tc_gemm_launch_bn(const GemmDesc& d, const TcIo& io, const Epi& epi, cudaStr
   TcGemmParams p;
   memset(&p, 0, sizeof(p));
   p.nseg = d.nseg;
+  const int H = d.H > 0 ? d.H : 1;
   for (int s = 0; s < d.nseg; ++s) {
     CMWG_REQUIRE(d.seg[s].K % TC_BK == 0, "tc_gemm: segment K=%d not a multiple of %d", d.seg[s].K, TC_BK);
-    CMWG_PROPAGATE(get_slab_map(&p.a_map[s], d.seg[s].a, d.seg[s].lda, d.seg[s].lda, d.T, d.B, TC_BK, TC_BM, d.is_fp16,
-                                TC_MAP_OPERAND));
+    CMWG_PROPAGATE(get_slab_map(&p.a_map[s], d.seg[s].a, d.seg[s].lda, d.seg[s].lda, d.T, d.seg[s].bcast_h ? 1 : H, d.B,
+                                TC_BK, TC_BM, d.is_fp16, TC_MAP_OPERAND));
     p.seg_nkb[s] = d.seg[s].K / TC_BK;
     p.seg_shift[s] = d.seg[s].shift;
     p.seg_koff[s] = d.seg[s].koff;
+    p.seg_shift_h[s] = d.seg[s].shift_h;
+    p.seg_bcast[s] = d.seg[s].bcast_h;
   }
   CMWG_PROPAGATE(get_matrix_map(&p.b_map, d.w, d.ldw, d.n_rows_w, BN / 2, d.is_fp16));
   for (int i = 0; i < Epi::kOut; ++i) {
     CMWG_REQUIRE(io.out[i].ptr != nullptr && (io.out[i].is_f32 != 0) == Epi::kOutF32, "tc_gemm: output stream %d mismatch", i);
-    CMWG_PROPAGATE(get_slab_map(&p.out_map[i], io.out[i].ptr, io.out[i].cols, io.out[i].ld, d.T, d.B, 32, 32, d.is_fp16,
+    CMWG_PROPAGATE(get_slab_map(&p.out_map[i], io.out[i].ptr, io.out[i].cols, io.out[i].ld, d.T, H, d.B, 32, 32, d.is_fp16,
                                 Epi::kOutF32 ? TC_MAP_CHUNK32 : TC_MAP_CHUNK16));
   }
   for (int i = 0; i < Epi::kIn; ++i) {
     CMWG_REQUIRE(io.in[i].ptr != nullptr && !io.in[i].is_f32, "tc_gemm: input stream %d mismatch", i);
-    CMWG_PROPAGATE(get_slab_map(&p.in_map[i], io.in[i].ptr, io.in[i].cols, io.in[i].ld, d.T, d.B, 32, 32, d.is_fp16,
+    CMWG_PROPAGATE(get_slab_map(&p.in_map[i], io.in[i].ptr, io.in[i].cols, io.in[i].ld, d.T, H, d.B, 32, 32, d.is_fp16,
                                 TC_MAP_CHUNK16));
   }
-  p.B = d.B; p.T = d.T; p.N = d.N;
+  p.B = d.B; p.T = d.T; p.H = H; p.N = d.N;
   p.tiles_per_batch = ceil_div(d.T, 2 * TC_BM);
   p.n_tiles = ceil_div(d.N, BN);
-  p.total_tiles = d.B * p.tiles_per_batch * p.n_tiles;
+  p.total_tiles = d.B * H * p.tiles_per_batch * p.n_tiles;
   p.idesc = make_idesc(d.is_fp16, 2 * TC_BM, BN, 0, 0);
   p.desc_lbo = lbo_override >= 0 ? (uint32_t)lbo_override : 1u;
   p.desc_sbo = sbo_override >= 0 ? (uint32_t)sbo_override : (1024u >> 4);
@@ -803,8 +843,9 @@ int tc_gemm_launch(const GemmDesc& d, const TcIo& io, const Epi& epi, cudaStream
 // Split-K plan of the weight-gradient launches: problems are grouped by N tile width (>= 256 / < 256) and
 // every group gets as many splits as fit one wave of CTA pairs.  splits_out[i] = splits of problem i
 // (its partial buffer must hold splits_out[i] * M * N floats).  force_splits > 0 overrides the plan.
-void tc_wgrad_plan(const WgradProblem* probs, int nprob, int B, int T, int force_splits, int* splits_out);
-int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int T, int is_fp16, cudaStream_t st,
+// B counts LINES here (batch items x lines per item); H only tells the kernel how lines group into batch items.
+void tc_wgrad_plan(const WgradProblem* probs, int nprob, int B, int H, int T, int force_splits, int* splits_out);
+int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int H, int T, int is_fp16, cudaStream_t st,
                     int force_splits = 0, int lbo_override = -1, int sbo_override = -1);
 
 }  // namespace cmwg

@@ -572,6 +572,22 @@ static __global__ void __launch_bounds__(128) reduce_blocks_stage_kernel(const f
   out[(long long)blockIdx.y * P + p] = s;
 }
 
+// out[b][j] = sum_h in[b][h][j] (fixed order), j in float4 units: per-line conditioning gradient -> (B, T, auxp)
+static __global__ void __launch_bounds__(256) sum_lines_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                               int H, long long n4) {
+  const int b = blockIdx.y;
+  const float4* src = reinterpret_cast<const float4*>(in) + (long long)b * H * n4;
+  float4* dst = reinterpret_cast<float4*>(out) + (long long)b * n4;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n4; j += (long long)gridDim.x * blockDim.x) {
+    float4 s = src[j];
+    for (int h = 1; h < H; ++h) {
+      float4 v = src[(long long)h * n4 + j];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    dst[j] = s;
+  }
+}
+
 // column sums of a slab (bias gradients): block partials over 32 rows
 template <typename OpT>
 static __global__ void __launch_bounds__(256) colsum_partial_kernel(const OpT* __restrict__ a, int ld, int C,

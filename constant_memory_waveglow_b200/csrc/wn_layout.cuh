@@ -14,7 +14,19 @@ constexpr int MAX_SEG = 16;  // K segments of one GEMM: radix taps + conditionin
 constexpr int TC_MAX_WG_REDUCE = 8;  // weight-gradient problems reduced per launch
 
 struct WnDims {
-  int cin, aux, Cd, Cr, Cs, depth, R, bias, prec;
+  int cin, aux, Cd, Cr, Cs, depth, bias, prec;
+  int R;        // taps of W in weight-layout order: radix (1-D) or radix*radix (2-D, tap = kh*radix + kw)
+  int radix;
+  int H;        // lines per batch item (1: 1-D WN)
+  int hdil[CMWG_MAX_DEPTH];
+  // time / line offset of tap s of layer i
+  __host__ __device__ int tap_dt(int i, int s) const {
+    int kw = (H > 1) ? s % radix : s;
+    return (kw - (radix - 1) / 2) * (1 << i);
+  }
+  __host__ __device__ int tap_dh(int i, int s) const {
+    return (H > 1) ? (s / radix - (radix - 1)) * hdil[i] : 0;  // causal in height: rows h-2hd, h-hd, h
+  }
   bool tc;      // tcgen05 engine (16-bit operands) vs FFMA engine (fp32 operands)
   int opsize;   // bytes per operand element
   int kb;       // K granule every GEMM segment is padded to: 64 (tc) / 16 (ff)
@@ -54,8 +66,16 @@ inline int make_dims(const cmwg_wn_config* c, WnDims* d) {
   CMWG_REQUIRE(c->precision == CMWG_PREC_FP32 || c->precision == CMWG_PREC_BF16 || c->precision == CMWG_PREC_FP16,
                "unknown precision %d", c->precision);
   d->cin = c->in_channels; d->aux = c->aux_channels; d->Cd = c->dil_channels; d->Cr = c->res_channels;
-  d->Cs = c->skip_channels; d->depth = c->depth; d->R = c->radix; d->bias = c->has_bias ? 1 : 0;
+  d->Cs = c->skip_channels; d->depth = c->depth; d->radix = c->radix; d->bias = c->has_bias ? 1 : 0;
   d->prec = c->precision;
+  d->H = c->height > 1 ? c->height : 1;
+  d->R = d->H > 1 ? c->radix * c->radix : c->radix;
+  CMWG_REQUIRE(d->H == 1 || c->radix == 3, "2-D WN: radix %d unsupported (3 x 3 only)", c->radix);
+  CMWG_REQUIRE(d->R + 1 <= MAX_SEG, "too many taps");
+  for (int i = 0; i < CMWG_MAX_DEPTH; ++i) {
+    d->hdil[i] = (d->H > 1 && i < c->depth) ? c->h_dilation[i] : 0;
+    CMWG_REQUIRE(d->hdil[i] >= 0 && d->hdil[i] < 4096, "2-D WN: bad height dilation");
+  }
   d->tc = c->precision != CMWG_PREC_FP32;
   if (d->tc && !wn_tc_shapes_ok(*c)) {
     set_error("tensor-core precision requested but WN channels (dil %d, res %d, skip %d) are not multiples of 64",
@@ -160,13 +180,14 @@ struct BwdLayout {
   size_t dprel[CMWG_MAX_DEPTH];     // tc: per-layer dpre
   size_t partial;    // split-K partials / block partials
   size_t partial_bytes;
+  size_t dycl_lines; // [B][H][T][auxp] fp32 per-line conditioning gradient (2-D WN only; summed over lines afterwards)
   size_t dweff;      // fp32 effective-weight gradients of every conv (consumed by ONE weight-norm backward launch)
   size_t dweff_layer, dweff_start, dweff_end;  // in floats: per-layer stride, offsets of the start / end conv
   size_t total;
 };
 
 inline void make_fwd_layout(const WnDims& d, int B, int T, FwdLayout* L) {
-  size_t rows = (size_t)B * T;
+  size_t rows = (size_t)B * d.H * T;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   L->h32 = take(rows * d.Cr * 4);
@@ -201,7 +222,7 @@ inline int wgrad_chunk_len(int B, int T) {
 }
 
 inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
-  size_t rows = (size_t)B * T;
+  size_t rows = (size_t)B * d.H * T;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
   L->dskip_op = take(rows * d.Cs * d.opsize);
@@ -215,18 +236,18 @@ inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
     L->dprel[0] = L->dpre_op;
     for (int i = 1; i < d.depth; ++i) L->dprel[i] = take(rows * 2 * d.Cd * 2);
   }
-  int lc = wgrad_chunk_len(B, T);
-  size_t splits = (size_t)B * ceil_div(T, lc);
+  int lc = wgrad_chunk_len(B * d.H, T);
+  size_t splits = (size_t)B * d.H * ceil_div(T, lc);
   // largest simultaneous partial set: all weight-gradient problems of one layer
   size_t per_layer = (size_t)2 * d.Cd * d.Cr * d.R + (size_t)(d.Cr + d.Cs) * d.Cd + (size_t)2 * d.Cd * d.auxp;
   // tc engine: at most TC_PLAN_PAIRS (74) splits per problem group, see tc_wgrad_plan
   if (d.tc) {
-    size_t units = (size_t)B * ceil_div(T, 64);
+    size_t units = (size_t)B * d.H * ceil_div(T, 64);
     splits = units < 80 ? units : 80;
   }
   size_t p1 = splits * per_layer * 4;
   // start / end conv and bias-gradient block partials (32-row blocks)
-  size_t blocks32 = (size_t)B * ceil_div(T, 32) + 1;
+  size_t blocks32 = (size_t)B * ceil_div(d.H * T, 32) + 1;
   size_t per_block = (size_t)d.Cr * d.cin + d.Cr;
   size_t pe = (size_t)2 * d.cin * d.Cs + 2 * d.cin;
   if (pe > per_block) per_block = pe;
@@ -234,6 +255,7 @@ inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
   size_t p2 = (blocks32 + blocks32 / 64 + 2) * per_block * 4;  // + second-stage scratch
   L->partial_bytes = p1 > p2 ? p1 : p2;
   L->partial = take(L->partial_bytes);
+  L->dycl_lines = d.H > 1 ? take(rows * d.auxp * 4) : 0;
   // effective-weight gradients: per layer dW_o, dW, dV_i side by side, then the start and end convs
   size_t per = (size_t)(d.Cr + d.Cs) * d.Cd + (size_t)2 * d.Cd * d.Cr * d.R + (size_t)2 * d.Cd * d.aux;
   per = align_up(per, 64);

@@ -158,7 +158,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
     OpT* olo = TC ? hlo_op(0) : nullptr;
     CMWG_PROPAGATE(smallk_to_slab<OpT>(x, x_bs, reinterpret_cast<const float*>(pk + PL.wStart), d.cin, 1,
                                        d.bias ? reinterpret_cast<const float*>(pk + PL.biasStart) : nullptr, d.cin,
-                                       d.Cr, B, T, o32, oop, olo, f16, st));
+                                       d.Cr, B, d.H * T, o32, oop, olo, f16, st));
   }
 
   for (int i = 0; i < d.depth; ++i) {
@@ -170,13 +170,14 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
       memset(&g, 0, sizeof(g));
       for (int s = 0; s < d.R; ++s) {
         g.seg[s].a = hin_op(i); g.seg[s].lda = d.Cr; g.seg[s].K = d.Cr;
-        g.seg[s].shift = (s - (d.R - 1) / 2) * dil; g.seg[s].koff = s * d.Crp;
+        g.seg[s].shift = d.tap_dt(i, s); g.seg[s].shift_h = d.tap_dh(i, s); g.seg[s].koff = s * d.Crp;
       }
       g.seg[d.R].a = ycl; g.seg[d.R].lda = d.auxp; g.seg[d.R].K = d.auxp; g.seg[d.R].shift = 0;
       g.seg[d.R].koff = d.R * d.Crp;
+      g.seg[d.R].bcast_h = d.H > 1;  // the conditioning has no height dimension (model/waveflow.py:131)
       g.nseg = d.R + 1;
       g.w = pk + PL.PA[i]; g.ldw = d.KA; g.N = d.npadA; g.n_rows_w = d.npadA;
-      g.B = B; g.T = T; g.bn = d.bn_gate; g.is_fp16 = f16; g.tag = CMWG_KCLASS_GATE;
+      g.B = B; g.T = T; g.H = d.H; g.bn = d.bn_gate; g.is_fp16 = f16; g.tag = CMWG_KCLASS_GATE;
       const float* biasA = d.bias ? reinterpret_cast<const float*>(pk + PL.biasA[i]) : nullptr;
       if constexpr (TC) {
         TcIo io;
@@ -210,7 +211,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
         g.seg[0].a = g_op(i); g.seg[0].lda = d.Cd; g.seg[0].K = d.Cd; g.seg[0].koff = 0;
         g.nseg = 1;
         g.w = pk + PL.PB[i]; g.ldw = d.ldPB; g.N = d.Cr; g.n_rows_w = d.nb(i);
-        g.B = B; g.T = T; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
+        g.B = B; g.T = T; g.H = d.H; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
         TcIo io;
         memset(&io, 0, sizeof(io));
         io.in[0] = op_stream(hin_op(i), d.Cr);
@@ -227,7 +228,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
       g.seg[0].a = g_op(i); g.seg[0].lda = d.Cd; g.seg[0].K = d.Cd; g.seg[0].shift = 0; g.seg[0].koff = 0;
       g.nseg = 1;
       g.w = pk + PL.PB[i]; g.ldw = d.ldPB; g.N = d.nb(i); g.n_rows_w = d.nb(i);
-      g.B = B; g.T = T; g.bn = pick_bn(d.nb(i)); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
+      g.B = B; g.T = T; g.H = d.H; g.bn = pick_bn(d.nb(i)); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
       ResSkipEpi<OpT> epi;
       if (!save) {
         epi.res_src = h32; epi.res_src_op = nullptr; epi.res_dst32 = h32; epi.res_dst_op = nullptr;
@@ -251,7 +252,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
     }
     g.nseg = d.depth;
     g.w = pk + PL.PS; g.ldw = d.ldPS; g.N = d.Cs; g.n_rows_w = d.Cs;
-    g.B = B; g.T = T; g.bn = pick_bn(d.Cs); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
+    g.B = B; g.T = T; g.H = d.H; g.bn = pick_bn(d.Cs); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
     TcIo io;
     memset(&io, 0, sizeof(io));
     io.out[0] = f32_stream(skip32, d.Cs);
@@ -262,7 +263,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
   {
     CMWG_PROPAGATE(end_fwd_launch(skip32, reinterpret_cast<const float*>(pk + PL.wEnd),
                                   d.bias ? reinterpret_cast<const float*>(pk + PL.biasEnd) : nullptr, 2 * d.cin, d.Cs, B,
-                                  T, lst, st));
+                                  d.H * T, lst, st));
   }
   return CMWG_OK;
 }
@@ -334,8 +335,9 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   const uint8_t* pk = cu8(packed);
   const uint8_t* sv = cu8(saved);
   uint8_t* ws = u8(workspace);
-  const long long rows = (long long)B * T;
-  const int bpb = ceil_div(T, ROWS_PER_BLOCK);
+  const int TF = d.H * T;  // flattened (line, time) length of one batch item
+  const long long rows = (long long)B * TF;
+  const int bpb = ceil_div(TF, ROWS_PER_BLOCK);
   const int nblk = B * bpb;
   const int cout = 2 * d.cin;
 
@@ -353,17 +355,19 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   const float* wEnd = reinterpret_cast<const float*>(pk + PL.wEnd);
   const float* wStart = reinterpret_cast<const float*>(pk + PL.wStart);
   WnBwdQueue wq;
+  // 2-D WN: the conditioning is broadcast over lines, so its gradient is computed per line and summed afterwards
+  float* dyl = (dycl && d.H > 1) ? reinterpret_cast<float*>(ws + BL.dycl_lines) : dycl;
 
   // ---- end conv backward: dskip, d end.weight, d end.bias
   {
-    CMWG_PROPAGATE(smallk_to_slab<OpT>(dlst, (long long)cout * T, wEnd, 1, d.Cs, nullptr, cout, d.Cs, B, T, nullptr,
+    CMWG_PROPAGATE(smallk_to_slab<OpT>(dlst, (long long)cout * TF, wEnd, 1, d.Cs, nullptr, cout, d.Cs, B, TF, nullptr,
                                        dskip_op, (OpT*)nullptr, f16, st));
     if (gr->end.v || gr->end.bias) {
       size_t smem2 = ((size_t)cout * ROWS_PER_BLOCK + (size_t)ROWS_PER_BLOCK * d.Cs) * sizeof(float);
       float* pw = partial;
       float* pb = partial + (size_t)nblk * cout * d.Cs;
       float* scratch = pb + (size_t)nblk * cout;
-      end_bwd_dw_kernel<<<nblk, 256, smem2, st>>>(dlst, skip32, cout, d.Cs, T, bpb, pw, gr->end.bias ? pb : nullptr);
+      end_bwd_dw_kernel<<<nblk, 256, smem2, st>>>(dlst, skip32, cout, d.Cs, TF, bpb, pw, gr->end.bias ? pb : nullptr);
       CMWG_COUNT_LAUNCH();
       CMWG_LAUNCH_CHECK();
       cmwg_conv_grad ge = gr->end;
@@ -381,8 +385,8 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     }
   }
 
-  const int Lc = wgrad_chunk_len(B, T);      // FFMA engine: split-K over (batch, time chunk)
-  const int ff_splits = B * ceil_div(T, Lc);
+  const int Lc = wgrad_chunk_len(B * d.H, T);  // FFMA engine: split-K over (batch, line, time chunk)
+  const int ff_splits = B * d.H * ceil_div(T, Lc);
 
   for (int i = d.depth - 1; i >= 0; --i) {
     const int dil = 1 << i;
@@ -405,7 +409,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       ++ns;
       g.nseg = ns;
       g.w = pk + PL.Q1[i]; g.ldw = d.k1(i); g.N = d.Cd; g.n_rows_w = d.Cd;
-      g.B = B; g.T = T; g.bn = pick_bn(d.Cd); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DGATE;
+      g.B = B; g.T = T; g.H = d.H; g.bn = pick_bn(d.Cd); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DGATE;
       if constexpr (TC) {
         TcIo io;
         memset(&io, 0, sizeof(io));
@@ -427,12 +431,13 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     }
     // ---- weight gradients of this layer: W_o (res rows, skip rows), W per tap, V_i
     {
-      WgradProblem pr[TC_MAX_WG];
-      WgReduceTable rt;
+      WgradProblem pr[MAX_SEG + 3];
+      struct RedSpec { int pi; float* out; long long sm, sn, off; int n_valid; } rs[MAX_SEG + 3];
       int np = 0;
-      auto add = [&](const void* a, int lda, int M, const void* b, int ldb, int N, int shift) {
+      auto add = [&](const void* a, int lda, int M, const void* b, int ldb, int N, int shift, int shift_h, int bcast) {
         WgradProblem& q = pr[np];
         q.a = a; q.lda = lda; q.a_c0 = 0; q.M = M; q.b = b; q.ldb = ldb; q.b_c0 = 0; q.N = N; q.shift = shift;
+        q.shift_h = shift_h; q.bcast_h = bcast;
         q.partial = nullptr;
         return np++;
       };
@@ -442,48 +447,53 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       float* dV = dW + (size_t)2 * d.Cd * d.Cr * d.R;
       int nr = 0;
       auto red = [&](int pi, float* out, long long sm, long long sn, long long off, int n_valid) {
-        WgReduceEntry& e = rt.e[nr++];
-        e.partial = nullptr; e.splits = pi;  // problem index for now; resolved once the split plan is known
-        e.M = pr[pi].M; e.N = pr[pi].N; e.n_valid = n_valid;
-        e.out = out; e.sm = sm; e.sn = sn; e.off = off;
+        rs[nr++] = RedSpec{pi, out, sm, sn, off, n_valid};
       };
       const bool want_wo = gr->W_o[i].g || gr->W_o[i].v;
       const bool want_w = gr->W[i].g || gr->W[i].v;
       const bool want_v = gr->V.g || gr->V.v;
       if (want_wo) {
-        if (!last) red(add(dh_next, d.Cr, d.Cr, gsv, d.Cd, d.Cd, 0), dWo, d.Cd, 1, 0, d.Cd);
-        red(add(dskip_op, d.Cs, d.Cs, gsv, d.Cd, d.Cd, 0), dWo, d.Cd, 1, (long long)d.cr_eff(i) * d.Cd, d.Cd);
+        if (!last) red(add(dh_next, d.Cr, d.Cr, gsv, d.Cd, d.Cd, 0, 0, 0), dWo, d.Cd, 1, 0, d.Cd);
+        red(add(dskip_op, d.Cs, d.Cs, gsv, d.Cd, d.Cd, 0, 0, 0), dWo, d.Cd, 1, (long long)d.cr_eff(i) * d.Cd, d.Cd);
       }
       if (want_w)
         for (int s = 0; s < d.R; ++s)
-          red(add(dpre_i, 2 * d.Cd, 2 * d.Cd, hin, d.Cr, d.Cr, (s - (d.R - 1) / 2) * dil), dW,
+          red(add(dpre_i, 2 * d.Cd, 2 * d.Cd, hin, d.Cr, d.Cr, d.tap_dt(i, s), d.tap_dh(i, s), 0), dW,
               (long long)d.Cr * d.R, d.R, s, d.Cr);
-      if (want_v) red(add(dpre_i, 2 * d.Cd, 2 * d.Cd, ycl, d.auxp, d.auxp, 0), dV, d.aux, 1, 0, d.aux);
-      if (np) {
-        // split-K plan -> partial buffers
+      if (want_v)
+        red(add(dpre_i, 2 * d.Cd, 2 * d.Cd, ycl, d.auxp, d.auxp, 0, 0, d.H > 1), dV, d.aux, 1, 0, d.aux);
+      // launch in groups of at most TC_MAX_WG problems (a 3 x 3 conv alone has 9 taps)
+      for (int g0 = 0; g0 < np; g0 += TC_MAX_WG) {
+        const int gn = std::min(TC_MAX_WG, np - g0);
+        WgradProblem* gp = pr + g0;
         int splits[TC_MAX_WG];
-        if (TC) tc_wgrad_plan(pr, np, B, T, 0, splits);
-        else for (int k = 0; k < np; ++k) splits[k] = ff_splits;
+        if (TC) tc_wgrad_plan(gp, gn, B, d.H, T, 0, splits);
+        else for (int k = 0; k < gn; ++k) splits[k] = ff_splits;
         float* pcur = partial;
-        for (int k = 0; k < np; ++k) {
-          pr[k].partial = pcur;
-          pcur += (size_t)splits[k] * pr[k].M * pr[k].N;
+        for (int k = 0; k < gn; ++k) {
+          gp[k].partial = pcur;
+          pcur += (size_t)splits[k] * gp[k].M * gp[k].N;
         }
         CMWG_REQUIRE((size_t)((uint8_t*)pcur - (uint8_t*)partial) <= BL.partial_bytes, "wgrad partial buffer overflow");
-        for (int k = 0; k < nr; ++k) {
-          int pi = rt.e[k].splits;
-          rt.e[k].partial = pr[pi].partial;
-          rt.e[k].splits = splits[pi];
-        }
         if (TC) {
-          CMWG_PROPAGATE(tc_wgrad_launch(pr, np, B, T, f16, st));
+          CMWG_PROPAGATE(tc_wgrad_launch(gp, gn, B, d.H, T, f16, st));
         } else {
-          for (int k = 0; k < np; ++k) CMWG_PROPAGATE(ff_wgrad_launch(pr[k], B, T, Lc, st));
+          for (int k = 0; k < gn; ++k) CMWG_PROPAGATE(ff_wgrad_launch(gp[k], B, d.H, T, Lc, st));
         }
-        rt.n = nr;
-        wgrad_reduce_kernel<<<dim3(num_sms(), nr), 256, 0, st>>>(rt);
+        WgReduceTable rt;
+        rt.n = 0;
+        for (int k = 0; k < nr; ++k) {
+          if (rs[k].pi < g0 || rs[k].pi >= g0 + gn) continue;
+          WgReduceEntry& e = rt.e[rt.n++];
+          const WgradProblem& q = pr[rs[k].pi];
+          e.partial = q.partial; e.splits = splits[rs[k].pi - g0]; e.M = q.M; e.N = q.N; e.n_valid = rs[k].n_valid;
+          e.out = rs[k].out; e.sm = rs[k].sm; e.sn = rs[k].sn; e.off = rs[k].off;
+        }
+        wgrad_reduce_kernel<<<dim3(num_sms(), rt.n), 256, 0, st>>>(rt);
         CMWG_COUNT_LAUNCH();
         CMWG_LAUNCH_CHECK();
+      }
+      if (np) {
         if (want_wo)
           wq.add(dWo, prm->W_o[i], reinterpret_cast<const float*>(pk + PL.nWo[i]), gr->W_o[i], d.nb(i), d.Cd);
         if (want_w)
@@ -514,8 +524,8 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       g.seg[0].a = dpre_i; g.seg[0].lda = 2 * d.Cd; g.seg[0].K = 2 * d.Cd; g.seg[0].shift = 0; g.seg[0].koff = i * d.Cd2p;
       g.nseg = 1;
       g.w = pk + PL.QV[0]; g.ldw = d.ldQV; g.N = d.auxp; g.n_rows_w = d.auxp;
-      g.B = B; g.T = T; g.bn = pick_bn(d.auxp); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DCOND;
-      AccumEpi epi{dycl, d.auxp, d.auxp, last ? 1 : 0};
+      g.B = B; g.T = T; g.H = d.H; g.bn = pick_bn(d.auxp); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DCOND;
+      AccumEpi epi{dyl, d.auxp, d.auxp, last ? 1 : 0};
       CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
     }
     // ---- dx GEMM: dh_i = dh_{i+1} + conv^T(dpre)
@@ -524,11 +534,11 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       memset(&g, 0, sizeof(g));
       for (int s = 0; s < d.R; ++s) {
         g.seg[s].a = dpre_i; g.seg[s].lda = 2 * d.Cd; g.seg[s].K = 2 * d.Cd;
-        g.seg[s].shift = -(s - (d.R - 1) / 2) * dil; g.seg[s].koff = s * d.Cd2p;
+        g.seg[s].shift = -d.tap_dt(i, s); g.seg[s].shift_h = -d.tap_dh(i, s); g.seg[s].koff = s * d.Cd2p;
       }
       g.nseg = d.R;
       g.w = pk + PL.Q2[i]; g.ldw = d.ldQ2; g.N = d.Cr; g.n_rows_w = d.Cr;
-      g.B = B; g.T = T; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DX;
+      g.B = B; g.T = T; g.H = d.H; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DX;
       if constexpr (TC) {
         TcIo io;
         memset(&io, 0, sizeof(io));
@@ -563,13 +573,20 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       }
       g.nseg = d.depth;
       g.w = pk + PL.QV[0]; g.ldw = d.ldQV; g.N = d.auxp; g.n_rows_w = d.auxp;
-      g.B = B; g.T = T; g.bn = pick_bn(d.auxp); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DCOND;
+      g.B = B; g.T = T; g.H = d.H; g.bn = pick_bn(d.auxp); g.is_fp16 = f16; g.tag = CMWG_KCLASS_DCOND;
       TcIo io;
       memset(&io, 0, sizeof(io));
-      io.out[0] = f32_stream(dycl, d.auxp);
+      io.out[0] = f32_stream(dyl, d.auxp);
       StoreTcEpi epi{nullptr};
       CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
     }
+  }
+  if (dycl && d.H > 1) {
+    long long n4 = (long long)T * d.auxp / 4;  // auxp is a multiple of 16
+    dim3 grid((unsigned)std::min<long long>(ceil_div_ll(n4, 256), 4096), B);
+    sum_lines_kernel<<<grid, 256, 0, st>>>(dyl, dycl, d.H, n4);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
   }
 
   // ---- start conv backward
@@ -580,7 +597,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     float* scratch = pb + (size_t)nblk * d.Cr;
     start_bwd_kernel<<<nblk, 256, smem, st>>>(TC ? nullptr : dh32, TC ? reinterpret_cast<const uint16_t*>(dhi(0)) : nullptr,
                                               TC ? reinterpret_cast<const uint16_t*>(dlo(0)) : nullptr, x, x_bs, wStart,
-                                              d.cin, d.Cr, T, bpb, dx, dx_bs, pw,
+                                              d.cin, d.Cr, TF, bpb, dx, dx_bs, pw,
                                               (d.bias && gr->start.bias) ? pb : nullptr);
     CMWG_COUNT_LAUNCH();
     CMWG_LAUNCH_CHECK();

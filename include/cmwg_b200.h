@@ -109,6 +109,13 @@ typedef struct {
   int radix;         /* kernel size of W (odd)                                             */
   int has_bias;      /* bias=True in the reference constructor                             */
   int precision;     /* CMWG_PREC_*                                                        */
+  /* 2-D WN of WaveFlow (model/waveflow.py:14-151).  height <= 1: the 1-D WN above.  height = H > 1: activations
+   * are (B, C, H, T) images, W is a radix x radix Conv2d with dilation (h_dilation[i], 2^i), causal in the
+   * height dimension (top padding 2*h_dilation, :42,57) and 'same' in time; the conditioning has no height
+   * dimension (V(y).unsqueeze(2), :131).  x / lst / dx are then NCL tensors over the FLATTENED (h, t) axis and
+   * the `T` argument of every entry point is the WIDTH of one line. */
+  int height;
+  int h_dilation[CMWG_MAX_DEPTH];
 } cmwg_wn_config;
 
 /* One convolution's parameters.  With weight norm attached: g = weight_g (out,1,1), v = weight_v;
