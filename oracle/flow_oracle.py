@@ -418,3 +418,227 @@ def wsrglow_random_state(upsample_rate: int, wn_channels: int, depth: int, seed:
     sd["angle_embed.embed.weight"] = torch.randn(120, 50, generator=gen)
     sd["window"] = torch.hann_window(16)
     return sd
+
+
+# --------------------------------------------------------------------------------------------
+# WaveFlow (model/waveflow.py:14-265): 2-D WN over the squeezed (height, width) image, row-autoregressive
+# --------------------------------------------------------------------------------------------
+# height dilations per n_group (``model/waveflow.py:81-87``); width dilations are 2**i (``:90-91``)
+WAVEFLOW_H_DILATIONS = {
+    8: [1] * 8,
+    16: [1] * 8,
+    32: [1, 2, 4] * 2 + [1, 2],
+    64: [1, 2, 4, 8, 16, 1, 2, 4],
+    128: [1, 2, 4, 8, 16, 32, 64, 1],
+}
+
+
+class WaveFlowSpec:
+    """Structural hyper-parameters of ``WaveFlow.__init__`` (``model/waveflow.py:154-189``); hop length is
+    fixed at 256 (``:163``)."""
+
+    def __init__(self, flows: int, n_group: int, n_mels: int, use_conv1x1: bool = False):
+        self.flows = flows
+        self.n_group = n_group
+        self.n_mels = n_mels
+        self.use_conv1x1 = use_conv1x1
+        self.hop = 256
+        self.sub_sr = self.hop // n_group
+        self.h_dilations = WAVEFLOW_H_DILATIONS[n_group]
+        self.depth = 8
+
+
+def waveflow_upsample_h(sd: State, spec: WaveFlowSpec, h: Tensor) -> Tensor:
+    """``model/waveflow.py:169-175,263-265``: ReplicationPad1d((0, 1)) -> weight-normed DENSE
+    ConvTranspose1d(n_mels, n_mels, 2*sub_sr+1, stride sub_sr, padding sub_sr//2) -> LeakyReLU(0.4).
+    ``nn.utils.weight_norm`` with dim=0 normalises the (in, out, k) transposed-conv weight per INPUT channel."""
+    w = resolve_weight(sd, "upsampler.1.")
+    hp = F.pad(h, (0, 1), mode="replicate")
+    y = F.conv_transpose1d(hp, w, sd.get("upsampler.1.bias"), stride=spec.sub_sr, padding=spec.sub_sr // 2)
+    return F.leaky_relu(y, 0.4)
+
+
+def wn2d_layer(sd: State, prefix: str, i: int, h_dil: int, x: Tensor, v: Tensor, last: bool):
+    """``NonCausalLayer2D.forward`` (``model/waveflow.py:41-51``): causal padding 2*h_dil rows on top,
+    'same' padding 2**i columns left and right, 3x3 conv with dilation (h_dil, 2**i)."""
+    w = resolve_weight(sd, prefix + f"layers.{i}.W.")
+    radix = w.shape[-1]
+    d = 2 ** i
+    pad = d * (radix - 1) // 2
+    tmp = F.pad(x, [pad, pad, h_dil * (radix - 1), 0])
+    xy = F.conv2d(tmp, w, resolve_bias(sd, prefix + f"layers.{i}.W."), dilation=(h_dil, d)) + v
+    zw, zf = xy.chunk(2, 1)
+    g = fused_gate(zw, zf)
+    ro = F.conv2d(g, resolve_weight(sd, prefix + f"layers.{i}.W_o."), resolve_bias(sd, prefix + f"layers.{i}.W_o."))
+    if last:
+        return None, ro
+    res_ch = x.shape[1]
+    return ro[:, :res_ch] + x, ro[:, res_ch:]
+
+
+def wn2d_forward(sd: State, prefix: str, x: Tensor, y: Tensor, h_dilations: Sequence[int]
+                 ) -> Tuple[Tensor, Tensor]:
+    """``WN2D.forward`` (``model/waveflow.py:128-135``).  x: (B, 1, H, W), y: (B, aux, W) -> (log_s, t)
+    each (B, 1, H, W)."""
+    depth = len(h_dilations)
+    h = F.conv2d(x, resolve_weight(sd, prefix + "start."), resolve_bias(sd, prefix + "start."))
+    v_all = F.conv1d(y, resolve_weight(sd, prefix + "V."), resolve_bias(sd, prefix + "V.")).unsqueeze(2)
+    cum_skip = None
+    for i, v in enumerate(v_all.chunk(depth, 1)):
+        h, skip = wn2d_layer(sd, prefix, i, h_dilations[i], h, v, last=(i == depth - 1))
+        cum_skip = skip if cum_skip is None else cum_skip + skip
+    out = F.conv2d(cum_skip, sd[prefix + "end.weight"], sd.get(prefix + "end.bias"))
+    log_s, t = out.chunk(2, 1)
+    return log_s, t
+
+
+def waveflow_squeeze(x: Tensor, n_group: int) -> Tensor:
+    """``model/waveflow.py:195``: (B, T) -> (B, 1, n_group, T/n_group), image[h, w] = x[w*n_group + h]."""
+    return x.view(x.size(0), 1, -1, n_group).transpose(2, 3).contiguous()
+
+
+def waveflow_unsqueeze(x: Tensor) -> Tensor:
+    """``model/waveflow.py:219,260``."""
+    return x.squeeze(1).transpose(1, 2).contiguous().view(x.size(0), -1)
+
+
+def waveflow_forward(sd: State, spec: WaveFlowSpec, x: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
+    """``WaveFlow.forward_computation`` (``model/waveflow.py:191-219``)."""
+    y = waveflow_upsample_h(sd, spec, h)
+    x = waveflow_squeeze(x, spec.n_group)
+    y = y[..., :x.size(-1)]
+    logdet = 0
+    for k in range(spec.flows):
+        x0 = x[:, :, :1]
+        log_s, t = wn2d_forward(sd, f"WNs.{k}.", x[:, :, :-1], y, spec.h_dilations)
+        xout = x[:, :, 1:] * log_s.exp() + t
+        logdet = logdet + log_s.sum((1, 2, 3))
+        if not spec.use_conv1x1:
+            x = torch.cat((xout.flip(2), x0), 2)
+        else:
+            x, ldw = conv1x1_forward(sd[f"invconv1x1.{k}.weight"], torch.cat((x0, xout), 2).squeeze(1))
+            x = x.unsqueeze(1)
+            logdet = logdet + ldw
+    return waveflow_unsqueeze(x), logdet
+
+
+def wn2d_reverse_step(sd: State, prefix: str, xrow: Tensor, cond: Sequence[Tensor], buffers, h_dilations):
+    """``WN2D.reverse_mode_forward`` (``model/waveflow.py:137-151``) with
+    ``NonCausalLayer2D.reverse_mode_forward`` (``:53-67``): one new row ``xrow`` (B, 1, 1, W) goes through the
+    eight layers; every layer keeps a rolling buffer of its last 2*h_dil+1 input rows (zeros before row 0)."""
+    depth = len(h_dilations)
+    x = F.conv2d(xrow, resolve_weight(sd, prefix + "start."), resolve_bias(sd, prefix + "start."))
+    new_buffers = []
+    cum_skip = None
+    for i in range(depth):
+        hd = h_dilations[i]
+        w = resolve_weight(sd, prefix + f"layers.{i}.W.")
+        radix = w.shape[-1]
+        d = 2 ** i
+        pad = d * (radix - 1) // 2
+        if buffers is None:
+            buf = F.pad(x, [0, 0, hd * (radix - 1), 0])
+        else:
+            buf = torch.cat((buffers[i][:, :, 1:], x), 2)
+        new_buffers.append(buf)
+        xy = F.conv2d(F.pad(buf, [pad, pad]), w, resolve_bias(sd, prefix + f"layers.{i}.W."),
+                      dilation=(hd, d)) + cond[i]
+        zw, zf = xy.chunk(2, 1)
+        g = fused_gate(zw, zf)
+        ro = F.conv2d(g, resolve_weight(sd, prefix + f"layers.{i}.W_o."),
+                      resolve_bias(sd, prefix + f"layers.{i}.W_o."))
+        if i < depth - 1:
+            res_ch = x.shape[1]
+            x, skip = ro[:, :res_ch] + x, ro[:, res_ch:]
+        else:
+            skip = ro
+        cum_skip = skip if cum_skip is None else cum_skip + skip
+    out = F.conv2d(cum_skip, sd[prefix + "end.weight"], sd.get(prefix + "end.bias"))
+    log_s, t = out.chunk(2, 1)
+    return log_s, t, new_buffers
+
+
+def waveflow_reverse(sd: State, spec: WaveFlowSpec, z: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
+    """``WaveFlow.reverse_computation`` (``model/waveflow.py:221-261``): flows in reverse order; inside a flow the
+    rows are generated one after the other, row i from rows < i."""
+    y = waveflow_upsample_h(sd, spec, h)
+    z = waveflow_squeeze(z, spec.n_group)
+    y = y[..., :z.size(-1)]
+    logdet = None
+    for k in range(spec.flows - 1, -1, -1):
+        prefix = f"WNs.{k}."
+        if not spec.use_conv1x1:
+            z = z.flip(2)
+        else:
+            z, ldw = conv1x1_reverse(sd[f"invconv1x1.{k}.weight"], z.squeeze(1))
+            z = z.unsqueeze(1)
+            logdet = ldw.repeat(z.shape[0]) if logdet is None else logdet + ldw
+        cond = F.conv1d(y, resolve_weight(sd, prefix + "V."), resolve_bias(sd, prefix + "V.")
+                        ).unsqueeze(2).chunk(spec.depth, 1)
+        xnew = z[:, :, :1]
+        rows = [xnew]
+        buffers = None
+        for i in range(1, spec.n_group):
+            log_s, t, buffers = wn2d_reverse_step(sd, prefix, xnew, cond, buffers, spec.h_dilations)
+            xnew = (z[:, :, i:i + 1] - t) / log_s.exp()
+            rows.append(xnew)
+            term = -log_s.sum((1, 2, 3))
+            logdet = term if logdet is None else logdet + term
+        z = torch.cat(rows, 2)
+    return waveflow_unsqueeze(z), logdet
+
+
+def waveflow_train_step(sd: State, spec: WaveFlowSpec, x: Tensor, h: Tensor, sigma: float):
+    """fwd + loss + bwd (plain autograd, as the reference trains WaveFlow: ``memory_efficient=false``,
+    ``configs/waveflow_LJ_speech.json:9-10``)."""
+    leaf = _leafify(sd)
+    z, logdet = waveflow_forward(leaf, spec, x, h)
+    loss = waveglow_loss(z, logdet, sigma)
+    keys = [k for k, v in leaf.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys], allow_unused=True)
+    return z.detach(), logdet.detach(), loss.detach(), {k: g for k, g in zip(keys, grads) if g is not None}
+
+
+def waveflow_random_state(spec: WaveFlowSpec, wn_channels: int, seed: int = 0,
+                          end_std: Optional[float] = None, dtype=torch.float32) -> State:
+    """Random-init weights with the reference's WaveFlow key layout (``upsampler.1.*``, ``WNs.k.*`` without the
+    ``.F`` level, 4-D Conv2d weights) and default-init distributions; see ``random_state``."""
+    gen = torch.Generator().manual_seed(seed)
+
+    def uni(shape, fan_in):
+        return (torch.rand(*shape, generator=gen, dtype=dtype) * 2 - 1) / fan_in ** 0.5
+
+    def gv(v):
+        return v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+
+    sd: State = {}
+    K = 2 * spec.sub_sr + 1
+    v = uni((spec.n_mels, spec.n_mels, K), spec.n_mels * K)
+    sd["upsampler.1.bias"] = uni((spec.n_mels,), spec.n_mels * K)
+    sd["upsampler.1.weight_g"] = gv(v)
+    sd["upsampler.1.weight_v"] = v
+    C = wn_channels
+    for k in range(spec.flows):
+        if spec.use_conv1x1:
+            q = torch.linalg.qr(torch.randn(spec.n_group, spec.n_group, generator=gen, dtype=torch.float64))[0]
+            if torch.det(q) < 0:
+                q[:, 0] = -q[:, 0]
+            sd[f"invconv1x1.{k}.weight"] = q.to(dtype).contiguous().unsqueeze(-1)
+    for k in range(spec.flows):
+        p = f"WNs.{k}."
+
+        def put(name, shape, fan_in):
+            vv = uni(shape, fan_in)
+            sd[p + name + ".weight_g"] = gv(vv)
+            sd[p + name + ".weight_v"] = vv
+
+        put("V", (2 * C * spec.depth, spec.n_mels, 1), spec.n_mels)
+        put("start", (C, 1, 1, 1), 1)
+        for i in range(spec.depth):
+            put(f"layers.{i}.W", (2 * C, C, 3, 3), C * 9)
+            put(f"layers.{i}.W_o", (C * (2 if i < spec.depth - 1 else 1), C, 1, 1), C)
+        if end_std is None:
+            sd[p + "end.weight"] = uni((2, C, 1, 1), C)
+        else:
+            sd[p + "end.weight"] = torch.randn(2, C, 1, 1, generator=gen, dtype=dtype) * end_std
+    return sd

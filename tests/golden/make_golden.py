@@ -171,6 +171,34 @@ def main():
                 "grads": keep, "grad_norms": {n: g.double().norm() for n, g in grads.items()},
                 "x_roundtrip": xr},
                os.path.join(OUT, "wsrglow_tiny.pt"))
+    # ---- 5. tiny WaveFlow (model/waveflow.py): forward, loss, plain-autograd backward, row-recurrent reverse ------
+    from model.waveflow import WaveFlow
+    assert sys.modules["model.waveflow"].__file__.startswith(REF)
+    for tag, ng, conv in (("a", 32, False), ("b", 16, True)):
+        set_seed(21 + ng)
+        arch = dict(flows=2, n_group=ng, n_mels=8, use_conv1x1=conv)
+        wkw = dict(dilation_channels=16, residual_channels=16, skip_channels=16, bias=False, zero_init=False)
+        B, frames = 2, 3
+        T = frames * 256
+        m = WaveFlow(memory_efficient=False, **arch, **wkw)
+        sd = cpu_state(m)
+        x = torch.rand(B, T) * 2 - 1
+        h = torch.randn(B, arch["n_mels"], frames)
+        m.zero_grad()
+        z, logdet = m(x.clone(), h)
+        loss = WaveGlowLoss(0.7)(z, logdet)
+        loss.backward()
+        grads = {n: p.grad.clone() for n, p in m.named_parameters()}
+        with torch.no_grad():
+            xr, logdet_r = m.reverse(z.detach().clone(), h)
+            zs = torch.randn(B, T) * 0.6
+            audio, logdet_s = m.reverse_computation(zs.clone(), h)
+            up = m._upsample_h(h).clone()
+        torch.save({"state": sd, "arch": arch, "wn_kwargs": wkw, "x": x, "h": h, "sigma": 0.7,
+                    "upsampled": up, "z": z.detach().clone(), "logdet": logdet.detach().clone(),
+                    "loss": loss.detach().clone(), "grads": grads, "x_roundtrip": xr, "logdet_reverse": logdet_r,
+                    "infer_z": zs, "infer_audio": audio, "infer_logdet": logdet_s},
+                   os.path.join(OUT, f"waveflow_tiny_{tag}.pt"))
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

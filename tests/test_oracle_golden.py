@@ -135,3 +135,57 @@ def test_wsrglow_tiny_against_reference():
     xr, _ = O.wsrglow_reverse(sd, spec, fx["z"], fx["c"])
     assert torch.allclose(xr, fx["x_roundtrip"], atol=2e-6)
     assert torch.allclose(xr, fx["x"], atol=2e-5)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_waveflow_against_reference(tag):
+    """WaveFlow (model/waveflow.py): 2-D WN forward, plain-autograd gradients, row-recurrent reverse."""
+    fx = load(f"waveflow_tiny_{tag}.pt")
+    sd, x, h = fx["state"], fx["x"], fx["h"]
+    spec = O.WaveFlowSpec(**fx["arch"])
+    assert torch.allclose(O.waveflow_upsample_h(sd, spec, h), fx["upsampled"], atol=1e-6, rtol=1e-6)
+    z, logdet, loss, grads = O.waveflow_train_step(sd, spec, x, h, fx["sigma"])
+    assert torch.allclose(z, fx["z"], atol=2e-6, rtol=1e-5)
+    assert torch.allclose(logdet, fx["logdet"], atol=1e-4, rtol=1e-6)
+    assert torch.allclose(loss, fx["loss"], rtol=1e-6)
+    assert set(grads) == set(fx["grads"])
+    for n, g in fx["grads"].items():
+        # d start.weight_v is analytically zero (one input channel: w = g * sign(v)); only rounding noise is left
+        tol = 1e-8 if n.endswith("start.weight_v") else 2e-5 * g.norm().item() + 1e-9
+        assert (grads[n] - g).norm().item() <= tol, n
+    xr, ldr = O.waveflow_reverse(sd, spec, fx["z"], h)
+    assert torch.allclose(xr, fx["x_roundtrip"], atol=2e-6)
+    assert torch.allclose(ldr, fx["logdet_reverse"], atol=1e-4, rtol=1e-6)
+    assert torch.allclose(xr, x, atol=1e-5)
+    audio, lds = O.waveflow_reverse(sd, spec, fx["infer_z"], h)
+    assert torch.allclose(audio, fx["infer_audio"], atol=2e-6, rtol=1e-5)
+    assert torch.allclose(lds, fx["infer_logdet"], atol=1e-4, rtol=1e-6)
+    # the row-recurrent reverse equals running the full-image WN once per generated row (what the CUDA path does)
+    zi = O.waveflow_squeeze(fx["infer_z"], spec.n_group)
+    y = O.waveflow_upsample_h(sd, spec, h)[..., :zi.size(-1)]
+    k = spec.flows - 1
+    if not spec.use_conv1x1:
+        zi = zi.flip(2)
+    else:
+        zi = O.conv1x1_reverse(sd[f"invconv1x1.{k}.weight"], zi.squeeze(1))[0].unsqueeze(1)
+    img = zi.clone()
+    for i in range(1, spec.n_group):
+        ls, t = O.wn2d_forward(sd, f"WNs.{k}.", img[:, :, :i], y, spec.h_dilations)
+        img[:, :, i] = (zi[:, :, i] - t[:, :, i - 1]) / ls[:, :, i - 1].exp()
+    rows = [zi[:, :, :1]]
+    cond = torch.nn.functional.conv1d(y, O.resolve_weight(sd, f"WNs.{k}.V.")).unsqueeze(2).chunk(8, 1)
+    buffers, xnew = None, zi[:, :, :1]
+    for i in range(1, spec.n_group):
+        ls, t, buffers = O.wn2d_reverse_step(sd, f"WNs.{k}.", xnew, cond, buffers, spec.h_dilations)
+        xnew = (zi[:, :, i:i + 1] - t) / ls.exp()
+        rows.append(xnew)
+    assert torch.allclose(img, torch.cat(rows, 2), atol=2e-6, rtol=1e-5)
+
+
+def test_waveflow_random_state_layout():
+    fx = load("waveflow_tiny_b.pt")
+    spec = O.WaveFlowSpec(**fx["arch"])
+    rs = O.waveflow_random_state(spec, 16, seed=3)
+    assert list(sorted(rs)) == list(sorted(fx["state"]))
+    for k, v in fx["state"].items():
+        assert rs[k].shape == v.shape, k

@@ -11,3 +11,6 @@ $NCU --set full --import-source on -k regex:tc_gemm -s 10 -c 8 -f -o gpurun_out/
 # backward GEMMs of the training step: skip the 192 forward + 16 recompute GEMM launches of the last flow
 $NCU --set full --import-source on -k regex:tc_ -s 211 -c 8 -f -o gpurun_out/${TAG}_bwd python tools/profile_step.py train bf16 24 > gpurun_out/${TAG}_bwd.log 2>&1
 ls -la gpurun_out
+# forward GEMMs of the TRAINING step (B=24: the launch bench.py's roofline quotes; gives its DRAM traffic)
+$NCU --set full --import-source on -k regex:tc_gemm -s 10 -c 6 -f -o gpurun_out/${TAG}_trainfwd python tools/profile_step.py train bf16 24 > gpurun_out/${TAG}_trainfwd.log 2>&1
+ls -la gpurun_out
