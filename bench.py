@@ -32,9 +32,11 @@ FRAMES = 63                      # MelSpec frames of a 16000-sample segment (SUR
 PER_GPU_BATCH = 24
 SIGMA = 0.7
 FWD_GFLOP_PER_SEGMENT = 214.023  # algorithmic, counted on the reference
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE training-shape gate GEMM launch (B=24, saving tanh/sigmoid),
-# from the `ncu --set full` capture summarised in profiles/ (None until captured for the current kernel)
-GATE_TRAFFIC_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE training-shape gate GEMM launch (B=24, R=48000 rows, the
+# forward non-saving variant; 37.8 MB read + 1.1 MB written -- the 24.6 MB gate output is still in L2 when the
+# kernel ends), from the `ncu --set full` capture summarised in profiles/r01_v5_ncu_gemm_summary.txt.
+# Algorithmic bytes of the same launch: 48000 x (512 hi + 256 y in, 512 g out) = 61.4 MB.
+GATE_TRAFFIC_BYTES_PER_LAUNCH = 38.9e6
 TRAIN_GFLOP_PER_SEGMENT = 4 * FWD_GFLOP_PER_SEGMENT
 SYNTH_FRAMES = 862               # 10 s at 22.05 kHz -> 220672 samples (model/base.py:47-48)
 

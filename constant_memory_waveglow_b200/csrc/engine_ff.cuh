@@ -37,6 +37,8 @@ struct GemmDesc {
   int n_rows_w;   // rows physically present in w (>= N, used for the TMA map)
   int B, T;
   int H;          // lines per batch item (0 or 1: plain [B][T] slabs)
+  int h0, nh;     // line window: only lines [h0, h0 + nh) of every batch item are computed (nh = 0: all H lines);
+                  // taps still read any line of the slab (row-recurrent inverse of the 2-D WN)
   int bn;         // N tile (tc engine)
   int is_fp16;
   int tag;        // CMWG_KCLASS_* for the profiler
@@ -47,6 +49,7 @@ struct FfGemmParams {
   int nseg;
   const float* w;
   int ldw, N, B, T, H, tiles_per_batch;  // tiles_per_batch: tiles per LINE
+  int h0, nh;                            // line window
 };
 
 __device__ __forceinline__ void ff_mma_tile(const float (*As)[FF_LD], const float (*Bs)[FF_LD], int tx, int ty,
@@ -72,8 +75,9 @@ __global__ void __launch_bounds__(FF_THREADS) ff_gemm_kernel(const FfGemmParams 
   __shared__ __align__(16) float Bs[2][FF_BK][FF_LD];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int line = blockIdx.x / p.tiles_per_batch;
-  const int b = line / p.H, h = line - b * p.H;
+  const int wl = blockIdx.x / p.tiles_per_batch;  // line inside the window
+  const int b = wl / p.nh, h = p.h0 + (wl - b * p.nh);
+  const int line = b * p.H + h;
   const int t0 = (blockIdx.x % p.tiles_per_batch) * FF_BM;
   const int n0 = blockIdx.y * FF_BN;
   const int lr = tid >> 2;         // 0..63 : row inside the half tile
@@ -167,7 +171,10 @@ int ff_gemm_launch(const GemmDesc& d, const Epi& epi, cudaStream_t st) {
   p.w = reinterpret_cast<const float*>(d.w);
   p.ldw = d.ldw; p.N = d.N; p.B = d.B; p.T = d.T; p.H = d.H > 0 ? d.H : 1;
   p.tiles_per_batch = ceil_div(d.T, FF_BM);
-  dim3 grid(d.B * p.H * p.tiles_per_batch, ceil_div(d.N, FF_BN));
+  p.h0 = d.nh > 0 ? d.h0 : 0;
+  p.nh = d.nh > 0 ? d.nh : p.H;
+  CMWG_REQUIRE(p.h0 >= 0 && p.h0 + p.nh <= p.H, "gemm: line window [%d, %d) outside [0, %d)", p.h0, p.h0 + p.nh, p.H);
+  dim3 grid(d.B * p.nh * p.tiles_per_batch, ceil_div(d.N, FF_BN));
   if (grid.x == 0 || grid.y == 0) return CMWG_OK;
   ProfScope prof(st, d.tag);
   ff_gemm_kernel<Epi, PAIRED><<<grid, FF_THREADS, 0, st>>>(p, epi);

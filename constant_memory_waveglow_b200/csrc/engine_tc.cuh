@@ -69,6 +69,7 @@ struct alignas(64) TcGemmParams {
   int seg_shift_h[MAX_SEG];     // line shift of the segment (2-D WN taps)
   int seg_bcast[MAX_SEG];       // segment has no line dimension: its map has H = 1 and line coordinate 0
   int B, T, H, tiles_per_batch, n_tiles, total_tiles, N;  // tiles_per_batch: tiles per LINE
+  int h0, nh;                   // line window [h0, h0 + nh) of every batch item (nh = H: all lines)
   uint32_t idesc;
   uint32_t desc_lbo, desc_sbo;  // >>4 encoded; overridable by the self test
 };
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       for (int tile = pair; tile < p.total_tiles; tile += npairs) {
         int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
         int line = rt / p.tiles_per_batch, t0 = (rt % p.tiles_per_batch) * (2 * TC_BM) + rank * TC_BM;
-        int b = line / p.H, h = line - b * p.H;
+        int b = line / p.nh, h = p.h0 + (line - b * p.nh);
         int n0 = nt * BN + rank * (BN / 2);
         for (int sg = 0; sg < p.nseg; ++sg) {
           const int hs = p.seg_bcast[sg] ? 0 : h + p.seg_shift_h[sg];
@@ -511,8 +512,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     auto coords = [&](int tile, int k, int& b, int& h, int& r0, int& c0) {
       int nt = tile % p.n_tiles, rt = tile / p.n_tiles;
       int line = rt / p.tiles_per_batch;
-      b = line / p.H;
-      h = line - b * p.H;
+      b = line / p.nh;
+      h = p.h0 + (line - b * p.nh);
       r0 = (rt % p.tiles_per_batch) * (2 * TC_BM) + rank * TC_BM + q * 32;
       c0 = nt * GW + cg * (GW / NCG) + 32 * k;
     };
@@ -813,7 +814,10 @@ int tc_gemm_launch_bn(const GemmDesc& d, const TcIo& io, const Epi& epi, cudaStr
   p.B = d.B; p.T = d.T; p.H = H; p.N = d.N;
   p.tiles_per_batch = ceil_div(d.T, 2 * TC_BM);
   p.n_tiles = ceil_div(d.N, BN);
-  p.total_tiles = d.B * H * p.tiles_per_batch * p.n_tiles;
+  p.h0 = d.nh > 0 ? d.h0 : 0;
+  p.nh = d.nh > 0 ? d.nh : H;
+  CMWG_REQUIRE(p.h0 >= 0 && p.h0 + p.nh <= H, "tc_gemm: line window [%d, %d) outside [0, %d)", p.h0, p.h0 + p.nh, H);
+  p.total_tiles = d.B * p.nh * p.tiles_per_batch * p.n_tiles;
   p.idesc = make_idesc(d.is_fp16, 2 * TC_BM, BN, 0, 0);
   p.desc_lbo = lbo_override >= 0 ? (uint32_t)lbo_override : 1u;
   p.desc_sbo = sbo_override >= 0 ? (uint32_t)sbo_override : (1024u >> 4);

@@ -280,18 +280,20 @@ template <typename OpT>
 static __global__ void __launch_bounds__(256) smallk_to_slab_kernel(const float* __restrict__ in, long long in_bs,
                                                                     const float* __restrict__ W, int so, int si,
                                                                     const float* __restrict__ bias, int K, int C,
-                                                                    int T, int blocks_per_batch,
-                                                                    float* __restrict__ o32, OpT* __restrict__ ohi,
-                                                                    OpT* __restrict__ olo, int is_fp16) {
+                                                                    int T, int blocks_per_batch, int t_off,
+                                                                    int t_end, float* __restrict__ o32,
+                                                                    OpT* __restrict__ ohi, OpT* __restrict__ olo,
+                                                                    int is_fp16) {
+  // rows [t_off, t_end) of every batch item are computed; T stays the row count of one item (strides)
   extern __shared__ float sm[];
   float* xs = sm;                      // [K][SMALLK_ROWS]
   float* wsm = sm + K * SMALLK_ROWS;   // [K][C]  (k-major: 4 consecutive outputs are one float4)
   const int b = blockIdx.x / blocks_per_batch;
-  const int t0 = (blockIdx.x % blocks_per_batch) * SMALLK_ROWS;
+  const int t0 = t_off + (blockIdx.x % blocks_per_batch) * SMALLK_ROWS;
   for (int idx = threadIdx.x; idx < K * SMALLK_ROWS; idx += 256) {
     int i = idx / SMALLK_ROWS, r = idx % SMALLK_ROWS;
     int t = t0 + r;
-    xs[idx] = (t < T) ? in[b * in_bs + (long long)i * T + t] : 0.f;
+    xs[idx] = (t < t_end) ? in[b * in_bs + (long long)i * T + t] : 0.f;
   }
   for (int idx = threadIdx.x; idx < K * C; idx += 256) {
     int i = idx / C, o = idx % C;
@@ -302,7 +304,7 @@ static __global__ void __launch_bounds__(256) smallk_to_slab_kernel(const float*
   for (int idx = threadIdx.x; idx < SMALLK_ROWS * c4; idx += 256) {
     const int r = idx / c4, o = (idx % c4) * 4;
     const int t = t0 + r;
-    if (t >= T) continue;
+    if (t >= t_end) continue;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (bias) { acc[0] = bias[o]; acc[1] = bias[o + 1]; acc[2] = bias[o + 2]; acc[3] = bias[o + 3]; }
     for (int i = 0; i < K; ++i) {
@@ -333,12 +335,16 @@ static __global__ void __launch_bounds__(256) smallk_to_slab_kernel(const float*
 
 template <typename OpT>
 static int smallk_to_slab(const float* in, long long in_bs, const float* W, int so, int si, const float* bias, int K,
-                          int C, int B, int T, float* o32, OpT* ohi, OpT* olo, int is_fp16, cudaStream_t st) {
-  const int bpb = ceil_div(T, SMALLK_ROWS);
+                          int C, int B, int T, float* o32, OpT* ohi, OpT* olo, int is_fp16, cudaStream_t st,
+                          int t_off = 0, int t_n = -1) {
+  if (t_n < 0) t_n = T - t_off;
+  const int bpb = ceil_div(t_n, SMALLK_ROWS);
+  if (B * bpb == 0) return CMWG_OK;
   size_t smem = (size_t)K * (SMALLK_ROWS + C) * sizeof(float);
   if (smem > 48 * 1024)
     CMWG_CHECK_CUDA(cudaFuncSetAttribute(smallk_to_slab_kernel<OpT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  smallk_to_slab_kernel<OpT><<<B * bpb, 256, smem, st>>>(in, in_bs, W, so, si, bias, K, C, T, bpb, o32, ohi, olo, is_fp16);
+  smallk_to_slab_kernel<OpT><<<B * bpb, 256, smem, st>>>(in, in_bs, W, so, si, bias, K, C, T, bpb, t_off, t_off + t_n, o32,
+                                                         ohi, olo, is_fp16);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
   return CMWG_OK;
@@ -412,13 +418,14 @@ template <int KV>
 static __global__ void __launch_bounds__(128) end_fwd_kernel(const float* __restrict__ skip,
                                                              const float* __restrict__ we,
                                                              const float* __restrict__ bias, int cout, int Cs, int T,
-                                                             int B, float* __restrict__ lst) {
+                                                             int B, int t_off, int t_n, float* __restrict__ lst) {
+  // rows [t_off, t_off + t_n) of every batch item; T is the row count of one item (strides)
   const int lane = threadIdx.x & 31;
-  const int wpb = (T + 31) >> 5;
+  const int wpb = (t_n + 31) >> 5;
   const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (gw >= B * wpb) return;
-  const int b = gw / wpb, t0 = (gw % wpb) * 32;
-  const int nrows = min(32, T - t0);
+  const int b = gw / wpb, t0 = t_off + (gw % wpb) * 32;
+  const int nrows = min(32, t_off + t_n - t0);
   const float* base = skip + ((long long)b * T + t0) * Cs;
   for (int oc0 = 0; oc0 < cout; oc0 += 8) {
     float4 w[8][KV];
@@ -462,14 +469,16 @@ static __global__ void __launch_bounds__(128) end_fwd_kernel(const float* __rest
 }
 
 static int end_fwd_launch(const float* skip, const float* we, const float* bias, int cout, int Cs, int B, int T,
-                          float* lst, cudaStream_t st) {
-  const int warps = B * ceil_div(T, 32);
+                          float* lst, cudaStream_t st, int t_off = 0, int t_n = -1) {
+  if (t_n < 0) t_n = T - t_off;
+  const int warps = B * ceil_div(t_n, 32);
   const int grid = ceil_div(warps, 4);
+  if (grid == 0) return CMWG_OK;
   const int kv = ceil_div(Cs, 128);
   CMWG_REQUIRE(kv <= 4, "end conv: skip_channels %d > 512 not supported", Cs);
-  if (kv == 1) end_fwd_kernel<1><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, lst);
-  else if (kv == 2) end_fwd_kernel<2><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, lst);
-  else end_fwd_kernel<4><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, lst);
+  if (kv == 1) end_fwd_kernel<1><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, t_off, t_n, lst);
+  else if (kv == 2) end_fwd_kernel<2><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, t_off, t_n, lst);
+  else end_fwd_kernel<4><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, t_off, t_n, lst);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
   return CMWG_OK;
