@@ -73,6 +73,15 @@ SIGNATURES = {
     "cmwg_wn_workspace_bytes": (_SZ, [C.POINTER(WnConfig), _I, _I]),
     "cmwg_wn_saved_bytes": (_SZ, [C.POINTER(WnConfig), _I, _I]),
     "cmwg_wn_forward": (_I, [C.POINTER(WnConfig), _VP, _VP, _LL, _VP, _I, _I, _VP, _VP, _VP, _VP]),
+    "cmwg_wn_line_state_bytes": (_SZ, [C.POINTER(WnConfig), _I, _I]),
+    "cmwg_wn_forward_lines": (_I, [C.POINTER(WnConfig), _VP, _VP, _LL, _VP, _I, _I, _I, _I, _VP, _VP, _VP, _VP]),
+    "cmwg_waveflow_affine": (_I, [_VP, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "cmwg_waveflow_inverse_flow": (_I, [C.POINTER(WnConfig), _VP, _VP, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
+    "cmwg_waveflow_affine_bwd": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "cmwg_upsample_dense_workspace": (_SZ, [_I, _I]),
+    "cmwg_upsample_dense_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, C.c_float, _VP, _VP, _VP]),
+    "cmwg_upsample_dense_bwd": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, C.c_float, _VP, _VP, _VP,
+                                     _VP, _VP]),
     "cmwg_wn_backward": (_I, [C.POINTER(WnConfig), C.POINTER(WnParams), _VP, _VP, _LL, _VP, _I, _I, _VP, _VP,
                               _VP, _VP, _LL, _VP, C.POINTER(WnGrads), _VP]),
     "cmwg_upsample_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP]),

@@ -119,9 +119,21 @@ static int wn_pack_impl(const WnDims& d, const cmwg_wn_params* prm, void* packed
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// Line window of the row-recurrent inverse of the 2-D WN (model/waveflow.py:53-67,137-151,243-258): only lines
+// [h0, h0 + nh) are computed; `state` holds every layer's input slab for ALL lines (the reference's rolling
+// per-layer buffers), so a tap reaching up to line h - 2*h_dilation finds what earlier calls left there.
+struct LineWin {
+  void* state = nullptr;
+  int h0 = 0, nh = 0;  // nh = 0: all lines
+};
+
+static inline size_t line_state_slab_bytes(const WnDims& d, int B, int T) {
+  return align_up((size_t)B * d.H * T * d.Cr * d.opsize, 1024);
+}
+
 template <typename OpT>
 static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, long long x_bs, const void* ycl, int B,
-                           int T, void* workspace, void* saved, float* lst, cudaStream_t st) {
+                           int T, void* workspace, void* saved, float* lst, cudaStream_t st, LineWin lw = LineWin()) {
   using E = EngineSel<OpT>;
   constexpr bool TC = E::kTc;
   const int f16 = d.prec == CMWG_PREC_FP16;
@@ -133,12 +145,19 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
   uint8_t* sv = u8(saved);
   const bool save = saved != nullptr;
   CMWG_REQUIRE(!(save && f16), "fp16 operands are forward/inverse only; training needs bf16 or fp32");
+  CMWG_REQUIRE(!(save && lw.state), "line-window forward keeps no backward state");
+  uint8_t* stt = u8(lw.state);
+  const bool keep = save || stt != nullptr;  // every layer's input slab is kept (per-layer buffers)
+  const size_t st_slab = line_state_slab_bytes(d, B, T);
+  const int t_off = lw.nh > 0 ? lw.h0 * T : 0;             // window over the flattened (line, time) axis
+  const int t_n = lw.nh > 0 ? lw.nh * T : d.H * T;
 
   float* h32 = reinterpret_cast<float*>(ws + FL.h32);
   float* skip32 = save ? reinterpret_cast<float*>(sv + FL.s_skip) : reinterpret_cast<float*>(ws + FL.skip32);
   // operand (16-bit hi half on the tc engine) of layer i's input
   auto hin_op = [&](int i) -> OpT* {
     if (save) return reinterpret_cast<OpT*>(sv + FL.s_hin[i]);
+    if (stt) return reinterpret_cast<OpT*>(stt + (size_t)i * st_slab);
     if (TC) return reinterpret_cast<OpT*>(ws + FL.hi2[i & 1]);
     return reinterpret_cast<OpT*>(ws + FL.hop);  // ff: aliases h32
   };
@@ -153,12 +172,12 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
   // ---- start conv
   {
     // tc: (hi, lo) 16-bit pair; ff inference: h32 only (operand aliases it); ff training: fp32 copy per layer
-    float* o32 = (!TC && !save) ? h32 : nullptr;
-    OpT* oop = (TC || save) ? hin_op(0) : nullptr;
+    float* o32 = (!TC && !keep) ? h32 : nullptr;
+    OpT* oop = (TC || keep) ? hin_op(0) : nullptr;
     OpT* olo = TC ? hlo_op(0) : nullptr;
     CMWG_PROPAGATE(smallk_to_slab<OpT>(x, x_bs, reinterpret_cast<const float*>(pk + PL.wStart), d.cin, 1,
                                        d.bias ? reinterpret_cast<const float*>(pk + PL.biasStart) : nullptr, d.cin,
-                                       d.Cr, B, d.H * T, o32, oop, olo, f16, st));
+                                       d.Cr, B, d.H * T, o32, oop, olo, f16, st, t_off, t_n));
   }
 
   for (int i = 0; i < d.depth; ++i) {
@@ -177,7 +196,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
       g.seg[d.R].bcast_h = d.H > 1;  // the conditioning has no height dimension (model/waveflow.py:131)
       g.nseg = d.R + 1;
       g.w = pk + PL.PA[i]; g.ldw = d.KA; g.N = d.npadA; g.n_rows_w = d.npadA;
-      g.B = B; g.T = T; g.H = d.H; g.bn = d.bn_gate; g.is_fp16 = f16; g.tag = CMWG_KCLASS_GATE;
+      g.B = B; g.T = T; g.H = d.H; g.h0 = lw.h0; g.nh = lw.nh; g.bn = d.bn_gate; g.is_fp16 = f16; g.tag = CMWG_KCLASS_GATE;
       const float* biasA = d.bias ? reinterpret_cast<const float*>(pk + PL.biasA[i]) : nullptr;
       if constexpr (TC) {
         TcIo io;
@@ -211,7 +230,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
         g.seg[0].a = g_op(i); g.seg[0].lda = d.Cd; g.seg[0].K = d.Cd; g.seg[0].koff = 0;
         g.nseg = 1;
         g.w = pk + PL.PB[i]; g.ldw = d.ldPB; g.N = d.Cr; g.n_rows_w = d.nb(i);
-        g.B = B; g.T = T; g.H = d.H; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
+        g.B = B; g.T = T; g.H = d.H; g.h0 = lw.h0; g.nh = lw.nh; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
         TcIo io;
         memset(&io, 0, sizeof(io));
         io.in[0] = op_stream(hin_op(i), d.Cr);
@@ -228,9 +247,9 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
       g.seg[0].a = g_op(i); g.seg[0].lda = d.Cd; g.seg[0].K = d.Cd; g.seg[0].shift = 0; g.seg[0].koff = 0;
       g.nseg = 1;
       g.w = pk + PL.PB[i]; g.ldw = d.ldPB; g.N = d.nb(i); g.n_rows_w = d.nb(i);
-      g.B = B; g.T = T; g.H = d.H; g.bn = pick_bn(d.nb(i)); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
+      g.B = B; g.T = T; g.H = d.H; g.h0 = lw.h0; g.nh = lw.nh; g.bn = pick_bn(d.nb(i)); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
       ResSkipEpi<OpT> epi;
-      if (!save) {
+      if (!keep) {
         epi.res_src = h32; epi.res_src_op = nullptr; epi.res_dst32 = h32; epi.res_dst_op = nullptr;
       } else {
         epi.res_src = nullptr; epi.res_src_op = hin_op(i); epi.res_dst32 = nullptr;
@@ -252,7 +271,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
     }
     g.nseg = d.depth;
     g.w = pk + PL.PS; g.ldw = d.ldPS; g.N = d.Cs; g.n_rows_w = d.Cs;
-    g.B = B; g.T = T; g.H = d.H; g.bn = pick_bn(d.Cs); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
+    g.B = B; g.T = T; g.H = d.H; g.h0 = lw.h0; g.nh = lw.nh; g.bn = pick_bn(d.Cs); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
     TcIo io;
     memset(&io, 0, sizeof(io));
     io.out[0] = f32_stream(skip32, d.Cs);
@@ -263,7 +282,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
   {
     CMWG_PROPAGATE(end_fwd_launch(skip32, reinterpret_cast<const float*>(pk + PL.wEnd),
                                   d.bias ? reinterpret_cast<const float*>(pk + PL.biasEnd) : nullptr, 2 * d.cin, d.Cs, B,
-                                  d.H * T, lst, st));
+                                  d.H * T, lst, st, t_off, t_n));
   }
   return CMWG_OK;
 }
@@ -694,6 +713,53 @@ int cmwg_wn_forward(const cmwg_wn_config* cfg, const void* packed, const float* 
   if (B == 0 || T == 0) return CMWG_OK;
   if (d.tc) return wn_forward_impl<uint16_t>(d, packed, x, x_bstride, ycl, B, T, workspace, saved, lst, (cudaStream_t)stream);
   return wn_forward_impl<float>(d, packed, x, x_bstride, ycl, B, T, workspace, saved, lst, (cudaStream_t)stream);
+}
+
+size_t cmwg_wn_line_state_bytes(const cmwg_wn_config* cfg, int B, int T) {
+  WnDims d;
+  if (make_dims(cfg, &d) != CMWG_OK) return 0;
+  return (size_t)d.depth * line_state_slab_bytes(d, B, T) + 1024;
+}
+
+int cmwg_wn_forward_lines(const cmwg_wn_config* cfg, const void* packed, const float* x, long long x_bstride,
+                          const void* ycl, int B, int T, int line_begin, int line_count, void* workspace, void* state,
+                          float* lst, void* stream) {
+  WnDims d;
+  CMWG_PROPAGATE(make_dims(cfg, &d));
+  CMWG_REQUIRE(packed && x && ycl && workspace && state && lst, "cmwg_wn_forward_lines: null argument");
+  CMWG_REQUIRE(line_begin >= 0 && line_count >= 0 && line_begin + line_count <= d.H,
+               "cmwg_wn_forward_lines: lines [%d, %d) outside [0, %d)", line_begin, line_begin + line_count, d.H);
+  if (B == 0 || T == 0 || line_count == 0) return CMWG_OK;
+  LineWin lw;
+  lw.state = state; lw.h0 = line_begin; lw.nh = line_count;
+  if (d.tc)
+    return wn_forward_impl<uint16_t>(d, packed, x, x_bstride, ycl, B, T, workspace, nullptr, lst, (cudaStream_t)stream, lw);
+  return wn_forward_impl<float>(d, packed, x, x_bstride, ycl, B, T, workspace, nullptr, lst, (cudaStream_t)stream, lw);
+}
+
+int cmwg_waveflow_inverse_flow(const cmwg_wn_config* cfg, const void* packed, const float* z, int in_flip,
+                               const void* ycl, int B, int W, void* workspace, void* state, float* lst, float* x,
+                               void* stream) {
+  WnDims d;
+  CMWG_PROPAGATE(make_dims(cfg, &d));
+  CMWG_REQUIRE(d.H > 1 && d.cin == 1, "cmwg_waveflow_inverse_flow: needs the 2-D WN (height > 1, one input channel)");
+  CMWG_REQUIRE(packed && z && ycl && workspace && state && lst && x, "cmwg_waveflow_inverse_flow: null argument");
+  if (B == 0 || W == 0) return CMWG_OK;
+  const int H = d.H + 1;  // image lines; the WN sees lines 0..H-2
+  cudaStream_t st = (cudaStream_t)stream;
+  // line 0 passes through (xnew = z[:, :, :1], model/waveflow.py:240)
+  CMWG_PROPAGATE(cmwg_waveflow_affine(z, in_flip, nullptr, x, 0, B, H, W, 0, 1, 1, stream));
+  LineWin lw;
+  lw.state = state; lw.nh = 1;
+  for (int i = 1; i < H; ++i) {  // row i from rows < i (:245-258)
+    lw.h0 = i - 1;
+    if (d.tc)
+      CMWG_PROPAGATE(wn_forward_impl<uint16_t>(d, packed, x, (long long)H * W, ycl, B, W, workspace, nullptr, lst, st, lw));
+    else
+      CMWG_PROPAGATE(wn_forward_impl<float>(d, packed, x, (long long)H * W, ycl, B, W, workspace, nullptr, lst, st, lw));
+    CMWG_PROPAGATE(cmwg_waveflow_affine(z, in_flip, lst, x, 0, B, H, W, i, 1, 1, stream));
+  }
+  return CMWG_OK;
 }
 
 int cmwg_wn_backward(const cmwg_wn_config* cfg, const cmwg_wn_params* params, const void* packed, const float* x,

@@ -151,7 +151,7 @@ class WN(nn.Module):
             return mod.weight_g, mod.weight_v, mod.bias
         return None, mod.weight, mod.bias
 
-    def _config(self, prec: str) -> L.WnConfig:
+    def _config(self, prec: str, height: int = 0) -> L.WnConfig:
         return L.WnConfig(self.in_chs, self.aux_chs, self.dil_chs, self.res_chs, self.skp_chs, len(self.layers),
                           self.rdx, int(self.has_bias), L.PREC_NAMES[prec])
 
@@ -172,11 +172,11 @@ class WN(nn.Module):
     def _tc_supported(self) -> bool:
         return bool(L.load().cmwg_wn_tc_supported(C.byref(self._config("fp32"))))
 
-    def _prepare(self, prec: str, device):
+    def _prepare(self, prec: str, device, height: int = 0):
         """(cfg, packed weights, params struct) for `prec`; re-packs only when a parameter changed."""
         params = list(self.parameters())
         L.require_cuda(*params, op="WN")
-        cfg = self._config(prec)
+        cfg = self._config(prec, height)
         key = tuple((p.data_ptr(), p._version) for p in params)
         ent = self._pack_cache.get(prec)
         ps = self._params_struct()
@@ -217,18 +217,13 @@ class WN(nn.Module):
         st.cfg, st.packed, st.params, st.ycl, st.saved, st.B, st.T, st.prec = cfg, packed, ps, ycl, saved, B, T, prec
         return lst, st
 
-    def _cmwg_backward(self, st: _WNState, x: Tensor, dlst: Tensor, dx: Tensor, need_dy: bool):
-        """Accumulates d(xa) into dx[:, :cin]; returns (grads in self.parameters() order, dy or None)."""
-        lib = L.load()
-        x = ops._ncl(x)
-        dlst = dlst.contiguous()
-        dev = x.device
+    def _grads_struct(self):
+        """(cmwg_wn_grads, {id(param): destination tensor}); destinations are views of the data-parallel
+        communication buffers when available."""
         grads = L.WnGrads()
-        out: List[Optional[Tensor]] = []
         by_param = {}
         for key, mod in self._convs():
             g, v, b = self._gvb(mod)
-            # gradient destinations: views of the data-parallel communication buffers when available
             dg = grad_buffer(g) if g is not None else None
             dv = grad_buffer(v)
             db = grad_buffer(b) if b is not None else None
@@ -240,6 +235,15 @@ class WN(nn.Module):
             for p, d in ((g, dg), (v, dv), (b, db)):
                 if p is not None:
                     by_param[id(p)] = d
+        return grads, by_param
+
+    def _cmwg_backward(self, st: _WNState, x: Tensor, dlst: Tensor, dx: Tensor, need_dy: bool):
+        """Accumulates d(xa) into dx[:, :cin]; returns (grads in self.parameters() order, dy or None)."""
+        lib = L.load()
+        x = ops._ncl(x)
+        dlst = dlst.contiguous()
+        dev = x.device
+        grads, by_param = self._grads_struct()
         aux_p = lib.cmwg_wn_aux_padded(C.byref(st.cfg))
         dycl = torch.empty((st.B, st.T, aux_p), device=dev, dtype=torch.float32) if need_dy else None
         ws = torch.empty(int(lib.cmwg_wn_workspace_bytes(C.byref(st.cfg), st.B, st.T)), device=dev, dtype=torch.uint8)
@@ -252,9 +256,7 @@ class WN(nn.Module):
             dy = torch.empty((st.B, self.aux_chs, st.T), device=dev, dtype=torch.float32)
             L.check(lib.cmwg_cond_unpack_grad(C.byref(st.cfg), dycl.data_ptr(), st.B, st.T, dy.data_ptr(),
                                               L.stream_ptr(dev)), "cond_unpack_grad")
-        for p in self.parameters():
-            out.append(by_param[id(p)])
-        return out, dy
+        return [by_param[id(p)] for p in self.parameters()], dy
 
     def forward(self, x, y):
         with grad_hint():

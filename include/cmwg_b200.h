@@ -176,6 +176,18 @@ size_t cmwg_wn_saved_bytes(const cmwg_wn_config* cfg, int B, int T);
 int cmwg_wn_forward(const cmwg_wn_config* cfg, const void* packed, const float* x, long long x_bstride,
                     const void* ycl, int B, int T, void* workspace, void* saved, float* lst, void* stream);
 
+/* Row-recurrent evaluation of the 2-D WN (cfg->height = H > 1), the engine of WaveFlow's inverse
+ * (model/waveflow.py:53-67 NonCausalLayer2D.reverse_mode_forward, :137-151 WN2D.reverse_mode_forward, :243-258 the
+ * per-row loop).  Computes lst for lines [line_begin, line_begin + line_count) only.  `state`
+ * (cmwg_wn_line_state_bytes) keeps every layer's input for ALL lines -- the reference's rolling per-layer
+ * `buffer_list` -- so a tap at line h - k*h_dilation reads what an earlier call left there; lines must therefore be
+ * generated in increasing order, and lines above 0 read as zeros exactly like the reference's F.pad (:57).
+ * x / lst are the same full-height tensors cmwg_wn_forward takes; only the window's lines are read / written. */
+size_t cmwg_wn_line_state_bytes(const cmwg_wn_config* cfg, int B, int T);
+int cmwg_wn_forward_lines(const cmwg_wn_config* cfg, const void* packed, const float* x, long long x_bstride,
+                          const void* ycl, int B, int T, int line_begin, int line_count, void* workspace, void* state,
+                          float* lst, void* stream);
+
 /* Gradient of WN given dlst (B, 2cin, T): the autograd.grad call of
  * model/efficient_modules.py:139-144 / :198-203 for F = WN.
  *   dxa: ACCUMULATED (+=) into dx (NCL, batch stride dx_bstride, first cin channels);
@@ -203,6 +215,46 @@ int cmwg_upsample_bwd(const float* h, const float* g, const float* v, const floa
 int cmwg_upsample_bwd_input(const float* g, const float* v, const float* dy, long long dy_bstride,
                             long long dy_cstride, int B, int C, int F, int K, int stride, int pad, int Tvalid,
                             float* dh, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * WaveFlow glue (model/waveflow.py:154-265).  Images are (B, H, W) fp32 contiguous, H = n_group lines;
+ * lst = (B, 2, (H-1)*W) is the 2-D WN's output for input lines 0..H-2 (log_s, then t).
+ * ------------------------------------------------------------------------------------------- */
+/* With y = cat(x0, xout) in unflipped line order (y[0] = in[0]):
+ *   inverse = 0 (:203-206):  y[j] = in[j] * exp(log_s[j-1]) + t[j-1]
+ *   inverse = 1 (:253):      y[j] = (in[j] - t[j-1]) / exp(log_s[j-1])
+ * for j in [line_begin, line_begin + line_count).  in_flip / out_flip address line H-1-j instead of j: the
+ * height flips of :211 (x = cat(xout.flip(2), x0)) and :230 (z = z.flip(2)).  lst may be NULL when only line 0
+ * is requested. */
+int cmwg_waveflow_affine(const float* in, int in_flip, const float* lst, float* out, int out_flip, int B, int H, int W,
+                         int line_begin, int line_count, int inverse, void* stream);
+/* One flow of WaveFlow's synthesis direction (:237-259): x[0] = z'[0]; for i = 1..H-1: (log_s, t) = WN2D row
+ * i-1 given rows < i (cmwg_wn_forward_lines), x[i] = (z'[i] - t) / exp(log_s), where z' = z read with the height
+ * flip when in_flip != 0.  cfg->height = H-1 (the lines the WN sees); z, x (B, H, W); lst (B, 2, (H-1)*W) is left
+ * filled with every row's (log_s, t) so the caller can form logdet (:255-258); workspace / state as for
+ * cmwg_wn_forward_lines.  The whole row loop is enqueued by this one call (no host round trips). */
+int cmwg_waveflow_inverse_flow(const cmwg_wn_config* cfg, const void* packed, const float* z, int in_flip,
+                               const void* ycl, int B, int W, void* workspace, void* state, float* lst, float* x,
+                               void* stream);
+/* Backward of the inverse = 0 transform (autograd of :203-211): dout is the cotangent of the (optionally flipped)
+ * output image, dlogdet (B floats, may be NULL) the cotangent of log_s.sum((1,2,3)) (:208).  Writes dx (B, H, W):
+ * the direct path only -- the WN backward ACCUMULATES its input gradient into lines 0..H-2 afterwards -- and
+ * dlst (B, 2, (H-1)*W). */
+int cmwg_waveflow_affine_bwd(const float* x, const float* lst, const float* dout, int out_flip, const float* dlogdet,
+                             float* dx, float* dlst, int B, int H, int W, void* stream);
+
+/* Conditioning upsampler (:169-175, 263-265): ReplicationPad1d((0, rpad)) -> DENSE ConvTranspose1d(C, C, K, stride,
+ * pad) with weight norm over dim 0 of the (in, out, K) weight (per INPUT channel; g == NULL: v is the plain
+ * weight) -> LeakyReLU(slope).  h (B, C, F) -> y (B, C, (F+rpad-1)*stride - 2*pad + K).
+ * workspace: cmwg_upsample_dense_workspace(C, K) bytes. */
+size_t cmwg_upsample_dense_workspace(int C, int K);
+int cmwg_upsample_dense_fwd(const float* h, const float* g, const float* v, const float* bias, int B, int C, int F,
+                            int K, int stride, int pad, int rpad, float slope, float* y, void* workspace, void* stream);
+/* y = the forward output (its sign selects the LeakyReLU slope), dy its cotangent (contiguous).
+ * dg (C) / dbias (C) may be NULL; dv (C, C, K). */
+int cmwg_upsample_dense_bwd(const float* h, const float* g, const float* v, const float* y, const float* dy, int B,
+                            int C, int F, int K, int stride, int pad, int rpad, float slope, float* dg, float* dv,
+                            float* dbias, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Model glue (model/waveglow.py:153,179; model/loss.py:10-15)

@@ -1,12 +1,13 @@
 """Drop-in ``model`` package: the import names the reference's train.py / inference.py /
 tests/test_fwd_bwd.py use (reference ``model/__init__.py:1-7``), re-exported from
 constant_memory_waveglow_b200.  Model families outside the hot-path scope of this round
-(WaveFlow, MelGlow, MRWaveGlow, LightModel) raise a clear ImportError on access."""
+(MelGlow, MRWaveGlow, LightModel) raise a clear ImportError on access."""
 from constant_memory_waveglow_b200.base import FlowBase, Reversible
+from constant_memory_waveglow_b200.waveflow import WaveFlow
 from constant_memory_waveglow_b200.waveglow import WaveGlow
 from constant_memory_waveglow_b200.wsrglow import WSRGlow
 
-_NOT_BUILT = ("WaveFlow", "MelGlow", "MRWaveGlow", "LightModel")
+_NOT_BUILT = ("MelGlow", "MRWaveGlow", "LightModel")
 
 
 def __getattr__(name):

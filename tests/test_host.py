@@ -118,3 +118,30 @@ def test_no_product_import_of_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_waveflow_state_dict_layout_matches_reference_fixture(tag):
+    fx = load_golden(f"waveflow_tiny_{tag}.pt")
+    m = cm.WaveFlow(memory_efficient=False, **fx["arch"], **fx["wn_kwargs"])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(fx["state"].keys())
+    for k in sd:
+        assert sd[k].shape == fx["state"][k].shape, k
+    m.load_state_dict(fx["state"])
+    ref_order = list(fx["grads"].keys())
+    assert [n for n, _ in m.named_parameters()] == ref_order
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(fx["x"], fx["h"])
+    import model
+    assert model.WaveFlow is cm.WaveFlow
+
+
+def test_line_state_size_query():
+    import ctypes as C
+    lib = _lib.load()
+    hd = (C.c_int * _lib.MAX_DEPTH)(1, 2, 4, 8, 16, 1, 2, 4)
+    cfg = _lib.WnConfig(1, 80, 64, 64, 64, 8, 3, 0, _lib.PREC_BF16, 63, hd)
+    n = lib.cmwg_wn_line_state_bytes(C.byref(cfg), 2, 100)
+    assert n >= 8 * 2 * 63 * 100 * 64 * 2
+    assert lib.cmwg_upsample_dense_workspace(80, 9) >= (80 * 80 * 9 + 80) * 4
