@@ -162,14 +162,15 @@ static int launch_conv1x1_apply(const float* w, int tr, const float* x, long lon
 // 1x1 conv weight gradient: dm[o][i] = sum_{b,t} dz[b,o,t] x[b,i,t]
 // pass 1: each block reduces a (batch, 512-column) chunk into C*C partials; pass 2: fixed-order sum.
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_COLS = 512;
+// columns per block: 512 up to C = 32, 128 above (shared memory holds 2 * C * (cols + 1) floats)
+static inline int wg_cols(int C) { return C <= 32 ? 512 : 128; }
 constexpr int WG_THREADS = 256;
 
 __global__ void __launch_bounds__(WG_THREADS) conv1x1_wgrad_partial_kernel(const float* __restrict__ dz,
                                                                             long long dz_bs,
                                                                             const float* __restrict__ x,
                                                                             long long x_bs, int C, int T,
-                                                                            int chunks_per_batch,
+                                                                            int chunks_per_batch, int WG_COLS,
                                                                             float* __restrict__ partial) {
   extern __shared__ float sm[];
   const int LD = WG_COLS + 1;
@@ -577,20 +578,21 @@ int cmwg_conv1x1_apply(const float* w, int transpose_w, const float* x, long lon
 }
 
 size_t cmwg_conv1x1_wgrad_workspace(int B, int C, int T) {
-  return (size_t)B * ceil_div(T, WG_COLS) * C * C * sizeof(float);
+  return (size_t)B * ceil_div(T, wg_cols(C)) * C * C * sizeof(float);
 }
 
 int cmwg_conv1x1_wgrad(const float* dz, long long dz_bstride, const float* x, long long x_bstride, int B, int C,
                        int T, float* dm, void* workspace, void* stream) {
-  CMWG_REQUIRE(C >= 1 && C <= 32, "cmwg_conv1x1_wgrad: C=%d out of range [1,32]", C);
+  CMWG_REQUIRE(C >= 1 && C <= 128, "cmwg_conv1x1_wgrad: C=%d out of range [1,128]", C);
   cudaStream_t st = (cudaStream_t)stream;
+  const int WG_COLS = wg_cols(C);
   int chunks = ceil_div(T, WG_COLS);
   int nblocks = B * chunks;
   size_t smem = ((size_t)2 * C * (WG_COLS + 1) + WG_THREADS) * sizeof(float);
   if (smem > 48 * 1024)
     CMWG_CHECK_CUDA(cudaFuncSetAttribute(conv1x1_wgrad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-  conv1x1_wgrad_partial_kernel<<<nblocks, WG_THREADS, smem, st>>>(dz, dz_bstride, x, x_bstride, C, T, chunks,
+  conv1x1_wgrad_partial_kernel<<<nblocks, WG_THREADS, smem, st>>>(dz, dz_bstride, x, x_bstride, C, T, chunks, WG_COLS,
                                                                   (float*)workspace);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();

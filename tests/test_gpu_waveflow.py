@@ -82,8 +82,9 @@ def test_affine_kernels(flip):
     dx_ref, dl_ref = torch.autograd.grad(obj, [xr, lr])
     dx = torch.empty_like(xc)
     dl = torch.empty_like(lc)
-    L.check(L.load().cmwg_waveflow_affine_bwd(xc.data_ptr(), lc.data_ptr(), dout.cuda().data_ptr(), int(flip),
-                                              dld.cuda().data_ptr(), dx.data_ptr(), dl.data_ptr(), B, H, W,
+    doutc, dldc = dout.cuda(), dld.cuda()
+    L.check(L.load().cmwg_waveflow_affine_bwd(xc.data_ptr(), lc.data_ptr(), doutc.data_ptr(), int(flip),
+                                              dldc.data_ptr(), dx.data_ptr(), dl.data_ptr(), B, H, W,
                                               L.stream_ptr(xc.device)), "affine_bwd")
     assert torch.allclose(dx.cpu(), dx_ref, atol=1e-6, rtol=1e-5)
     assert torch.allclose(dl.cpu(), dl_ref, atol=2e-6, rtol=1e-5)
