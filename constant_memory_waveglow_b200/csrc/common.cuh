@@ -59,6 +59,35 @@ struct ProfScope {
   ~ProfScope() { prof_end(st); }
 };
 
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched through launch_pdl() may start -- be scheduled on free
+// SMs, allocate TMEM, initialise barriers, prefetch tensor maps -- while its predecessor in the stream is still
+// running; it must execute pdl_wait() before it touches global memory (the wait returns once the predecessor
+// grid has completed and flushed).  pdl_trigger() at the top of a kernel lets ITS successor start equally early.
+// The short per-line kernels of WaveFlow's row-recurrent inverse and the launch gaps of the synthesis chains are
+// what this buys back.  CMWG_PDL=0 falls back to plain stream-ordered launches.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // kernel launch counter (bench.py reports it as gpu_launches)
 extern unsigned long long g_launch_count;
 #define CMWG_COUNT_LAUNCH() (++::cmwg::g_launch_count)

@@ -110,13 +110,15 @@ int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaS
   cfg.blockDim = dim3(TC_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see common.cuh: both tc kernels pdl_wait()
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   CMWG_CHECK_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
   static const bool dbg_sync = dbg_flag("CMWG_DEBUG_SYNC");
   if (dbg_sync) CMWG_CHECK_CUDA(cudaStreamSynchronize(st));

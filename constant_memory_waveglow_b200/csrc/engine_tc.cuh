@@ -437,8 +437,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   constexpr int GW = Epi::kPaired ? BN / 2 : BN;   // epilogue columns of one tile (gate channels when paired)
   constexpr int NCG = ET::template ncg<GW>();       // column groups = draining warps per TMEM lane quadrant
   constexpr int NCH = GW / (32 * NCG);             // 32-column chunks per warp per tile
+  pdl_trigger();  // the next kernel of the stream may set itself up while this one runs
   tc_setup<STAGES>(s, warp, lane, 2 * BN, 4 * NCG);
   const uint32_t tmem_base = *s.tmem_ptr;
+  pdl_wait();     // everything above touched no global memory; the predecessor's results are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -635,8 +637,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
   }
   constexpr int NCG = ET::template ncg<BN>();
   constexpr int NCH = BN / (32 * NCG);
+  pdl_trigger();
   tc_setup<STAGES>(s, warp, lane, 2 * BN, 4 * NCG);
   const uint32_t tmem_base = *s.tmem_ptr;
+  pdl_wait();
   const int tiles_total = p.tile_begin[p.nprob];
 
   // work item -> (problem, m tile, n tile, split); tiles vary fastest so that one time chunk of the

@@ -5,6 +5,7 @@
 
 #include <math_constants.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -43,6 +44,15 @@ void prof_begin(cudaStream_t st, int cls) {
 void prof_end(cudaStream_t st) {
   if (!g_prof_on || g_prof.empty()) return;
   cudaEventRecord(g_prof.back().b, st);
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* v = getenv("CMWG_PDL");
+    on = (v && v[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
 }
 
 int num_sms() {

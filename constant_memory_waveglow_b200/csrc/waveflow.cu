@@ -17,6 +17,8 @@ namespace cmwg {
 __global__ void __launch_bounds__(256) waveflow_affine_kernel(const float* __restrict__ in, int in_flip,
                                                               const float* __restrict__ lst, float* __restrict__ out,
                                                               int out_flip, int H, int W, int j0, int inverse) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.z, j = j0 + blockIdx.y;
   const int w = blockIdx.x * 256 + threadIdx.x;
   if (w >= W) return;
@@ -186,10 +188,9 @@ int cmwg_waveflow_affine(const float* in, int in_flip, const float* lst, float* 
                "cmwg_waveflow_affine: lines [%d, %d) outside [0, %d)", line_begin, line_begin + line_count, H);
   if (B == 0 || W == 0 || line_count == 0) return CMWG_OK;
   dim3 grid(ceil_div(W, 256), line_count, B);
-  waveflow_affine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, in_flip, lst, out, out_flip, H, W, line_begin,
-                                                                 inverse);
+  CMWG_CHECK_CUDA(launch_pdl(waveflow_affine_kernel, grid, dim3(256), 0, (cudaStream_t)stream, in, in_flip, lst, out,
+                             out_flip, H, W, line_begin, inverse));
   CMWG_COUNT_LAUNCH();
-  CMWG_LAUNCH_CHECK();
   return CMWG_OK;
 }
 

@@ -286,6 +286,8 @@ static __global__ void __launch_bounds__(256) smallk_to_slab_kernel(const float*
                                                                     int is_fp16) {
   // rows [t_off, t_end) of every batch item are computed; T stays the row count of one item (strides)
   extern __shared__ float sm[];
+  pdl_trigger();
+  pdl_wait();
   float* xs = sm;                      // [K][SMALLK_ROWS]
   float* wsm = sm + K * SMALLK_ROWS;   // [K][C]  (k-major: 4 consecutive outputs are one float4)
   const int b = blockIdx.x / blocks_per_batch;
@@ -343,8 +345,8 @@ static int smallk_to_slab(const float* in, long long in_bs, const float* W, int 
   size_t smem = (size_t)K * (SMALLK_ROWS + C) * sizeof(float);
   if (smem > 48 * 1024)
     CMWG_CHECK_CUDA(cudaFuncSetAttribute(smallk_to_slab_kernel<OpT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  smallk_to_slab_kernel<OpT><<<B * bpb, 256, smem, st>>>(in, in_bs, W, so, si, bias, K, C, T, bpb, t_off, t_off + t_n, o32,
-                                                         ohi, olo, is_fp16);
+  CMWG_CHECK_CUDA(launch_pdl(smallk_to_slab_kernel<OpT>, dim3(B * bpb), dim3(256), smem, st, in, in_bs, W, so, si, bias, K,
+                             C, T, bpb, t_off, t_off + t_n, o32, ohi, olo, is_fp16));
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
   return CMWG_OK;
@@ -420,6 +422,8 @@ static __global__ void __launch_bounds__(128) end_fwd_kernel(const float* __rest
                                                              const float* __restrict__ bias, int cout, int Cs, int T,
                                                              int B, int t_off, int t_n, float* __restrict__ lst) {
   // rows [t_off, t_off + t_n) of every batch item; T is the row count of one item (strides)
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = (t_n + 31) >> 5;
   const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -476,9 +480,12 @@ static int end_fwd_launch(const float* skip, const float* we, const float* bias,
   if (grid == 0) return CMWG_OK;
   const int kv = ceil_div(Cs, 128);
   CMWG_REQUIRE(kv <= 4, "end conv: skip_channels %d > 512 not supported", Cs);
-  if (kv == 1) end_fwd_kernel<1><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, t_off, t_n, lst);
-  else if (kv == 2) end_fwd_kernel<2><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, t_off, t_n, lst);
-  else end_fwd_kernel<4><<<grid, 128, 0, st>>>(skip, we, bias, cout, Cs, T, B, t_off, t_n, lst);
+  if (kv == 1)
+    CMWG_CHECK_CUDA(launch_pdl(end_fwd_kernel<1>, dim3(grid), dim3(128), 0, st, skip, we, bias, cout, Cs, T, B, t_off, t_n, lst));
+  else if (kv == 2)
+    CMWG_CHECK_CUDA(launch_pdl(end_fwd_kernel<2>, dim3(grid), dim3(128), 0, st, skip, we, bias, cout, Cs, T, B, t_off, t_n, lst));
+  else
+    CMWG_CHECK_CUDA(launch_pdl(end_fwd_kernel<4>, dim3(grid), dim3(128), 0, st, skip, we, bias, cout, Cs, T, B, t_off, t_n, lst));
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
   return CMWG_OK;

@@ -14,6 +14,7 @@ state-dict keys (``upsampler.1.*``, ``WNs.k.{V,start,layers.i.W,layers.i.W_o}.we
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -317,6 +318,7 @@ class WaveFlow(FlowBase):
             if use_conv1x1:
                 self.invconv1x1.append(InvertibleConv1x1(n_group, memory_efficient=memory_efficient,
                                                          reverse_mode=reverse_mode))
+        self._graphs = {}  # synthesis-direction CUDA graphs, keyed by shapes + weight versions
 
     def _upsample_h(self, h):
         up = self.upsampler[1]
@@ -342,25 +344,60 @@ class WaveFlow(FlowBase):
         z = _SqueezeFunction.apply(img, self.n_group, True)
         return z.view(batch, -1), logdet
 
+    def _reverse_eager(self, z: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
+        y = self._upsample_h(h)
+        batch = z.size(0)
+        img = ops.squeeze(z, self.n_group, False)
+        y = y[..., :img.size(-1)]
+        convs = self.invconv1x1 if hasattr(self, "invconv1x1") else [None] * self.flows
+        logdet = None
+        for wn, invconv in zip(self.WNs[::-1], convs[::-1]):
+            if invconv is not None:
+                img, log_det_w = invconv.reverse(img)
+                logdet = log_det_w.repeat(batch) if logdet is None else logdet + log_det_w
+            img, lst = wn._inverse_flow(img, invconv is None, y)
+            term = ops.sum_per_batch(lst[:, :1], scale=-1.0)
+            logdet = term if logdet is None else logdet + term
+        x = ops.squeeze(img, self.n_group, True)
+        return x.view(batch, -1), logdet
+
+    def _graph_key(self, z: Tensor, h: Tensor):
+        return (tuple(z.shape), tuple(h.shape), z.device.index, precision.get_precision(),
+                torch.backends.cudnn.allow_tf32, tuple((p.data_ptr(), p._version) for p in self.parameters()))
+
     def reverse_computation(self, z: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
         """Synthesis direction (reference ``:221-261``).  Runs without building an autograd graph: the row-recurrent
-        loop is one fused device-side sequence per flow."""
+        loop is one fused device-side sequence per flow (~1200 small launches per flow, launch bound), so from the
+        second call with the same shapes and weights on the whole direction is replayed as ONE CUDA graph
+        (``CMWG_GRAPHS=0`` disables that)."""
         L.require_cuda(z, h, op="WaveFlow.reverse")
         if torch.is_grad_enabled() and (z.requires_grad or h.requires_grad):
             raise NotImplementedError("WaveFlow.reverse_computation is inference-only (no autograd through the row loop)")
         with torch.no_grad():
-            y = self._upsample_h(h)
-            batch = z.size(0)
-            img = ops.squeeze(z.detach().float(), self.n_group, False)
-            y = y[..., :img.size(-1)]
-            convs = self.invconv1x1 if hasattr(self, "invconv1x1") else [None] * self.flows
-            logdet = None
-            for wn, invconv in zip(self.WNs[::-1], convs[::-1]):
-                if invconv is not None:
-                    img, log_det_w = invconv.reverse(img)
-                    logdet = log_det_w.repeat(batch) if logdet is None else logdet + log_det_w
-                img, lst = wn._inverse_flow(img, invconv is None, y)
-                term = ops.sum_per_batch(lst[:, :1], scale=-1.0)
-                logdet = term if logdet is None else logdet + term
-            x = ops.squeeze(img, self.n_group, True)
-        return x.view(batch, -1), logdet
+            z = z.detach().float().contiguous()
+            h = h.detach().float().contiguous()
+            if os.environ.get("CMWG_GRAPHS", "1") == "0" or torch.cuda.is_current_stream_capturing():
+                return self._reverse_eager(z, h)
+            key = self._graph_key(z, h)
+            if key not in self._graphs:
+                # first sight of this (shape, weights) combination: plain launches (this also warms the tensor-map
+                # and weight-pack caches); a repeat is worth a capture
+                self._graphs = {k: v for k, v in self._graphs.items() if v is not None}  # drop stale "seen" marks
+                while len(self._graphs) >= 2:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[key] = None
+                return self._reverse_eager(z, h)
+            if self._graphs[key] is None:
+                sz, sh = z.clone(), h.clone()
+                torch.cuda.synchronize(z.device)
+                graph = torch.cuda.CUDAGraph()
+                _cond_cache.clear()  # conditioning slabs cached from eager calls must be re-packed INSIDE the graph
+                with torch.cuda.graph(graph):
+                    ox, old = self._reverse_eager(sz, sh)
+                _cond_cache.clear()  # ... and slabs living in the graph's private pool must not serve eager calls
+                self._graphs[key] = (graph, sz, sh, ox, old)
+            graph, sz, sh, ox, old = self._graphs[key]
+            sz.copy_(z)
+            sh.copy_(h)
+            graph.replay()
+            return ox.clone(), old.clone()

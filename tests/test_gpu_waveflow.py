@@ -234,3 +234,33 @@ def test_waveflow_lj_shape_against_oracle(prec, conv):
     with torch.no_grad():
         audio = m.infer(h.cuda(), z=zs.cuda())
     assert rel_l2(audio, audio_ref.squeeze()) < max(tol["out"], TOL["fp16"]["out"] if prec != "fp32" else 0)
+
+
+def test_waveflow_synthesis_graph_replay_matches_eager():
+    """Second and later calls with the same shapes/weights replay one CUDA graph; results are bit-identical to the
+    plain launches, new inputs are honoured, and a weight update invalidates the graph."""
+    precision.set_precision("auto")
+    spec = O.WaveFlowSpec(2, 64, 80)
+    sd = O.waveflow_random_state(spec, 64, seed=4)
+    m = cm.WaveFlow(2, 64, 80, False, False, **_wkw(64))
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(0)
+    h = torch.randn(2, 80, 6, generator=g).cuda()
+    z1 = (torch.randn(2, 6 * 256, generator=g) * 0.6).cuda()
+    z2 = (torch.randn(2, 6 * 256, generator=g) * 0.6).cuda()
+    with torch.no_grad():
+        a1, l1 = m.reverse(z1, h)            # plain launches
+        before = L.launch_count()
+        b1, k1 = m.reverse(z1, h)            # capture + replay
+        b2, k2 = m.reverse(z2, h)            # replay with new noise
+        assert torch.equal(a1, b1) and torch.equal(l1, k1)
+        n_after_capture = L.launch_count()
+        c2, _ = m.reverse(z2, h)
+        assert L.launch_count() == n_after_capture  # a replay issues no new launches through the library
+        assert torch.equal(b2, c2) and not torch.equal(b1, b2)
+        assert n_after_capture > before
+        with torch.no_grad():
+            m.WNs[0].end.weight.mul_(0.5)
+        d2, _ = m.reverse(z2, h)             # weights changed: plain launches again, different audio
+        assert not torch.equal(d2, c2)
