@@ -124,6 +124,95 @@ def cpu_oracle_train(batch: int, steps: int, warmup: int):
     return batch / (sum(times) / len(times)), times
 
 
+def cpu_oracle_synth(frames: int):
+    """Oracle port of WaveGlow.infer on `frames` mel frames (one utterance), host cores; returns kHz."""
+    from oracle import flow_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = O.WaveGlowSpec(**LJ)
+    sd = O.random_state(spec, 256, 8, seed=0)
+    g = torch.Generator().manual_seed(0)
+    h = torch.randn(1, LJ["n_mels"], frames, generator=g)
+    z = torch.randn(1, frames * LJ["hop_size"], generator=g) * 0.6
+    with torch.no_grad():
+        O.waveglow_infer(sd, spec, h[..., :8], z[:, :8 * LJ["hop_size"]])   # warm-up
+        t0 = time.perf_counter()
+        O.waveglow_infer(sd, spec, h, z)
+        dt = time.perf_counter() - t0
+    return frames * LJ["hop_size"] / dt / 1e3, dt
+
+
+WAVEFLOW = dict(flows=8, n_group=64, n_mels=80, use_conv1x1=False)       # configs/waveflow_LJ_speech.json:6-15
+WAVEFLOW_WN = dict(dilation_channels=64, residual_channels=64, skip_channels=64, bias=False)
+WAVEFLOW_BATCH = 12                                                       # configs/waveflow_LJ_speech.json:31
+WAVEFLOW_FWD_GFLOP_PER_SEGMENT = 164.502                                  # SURVEY.md section 8d
+
+
+def waveflow_leg(dev, cpu_baseline: bool):
+    """Config 4 (WaveFlow, 64 residual channels, h = 64): training step (forward + loss + plain backward) in
+    segments/s and synthesis of one 10 s utterance in kHz, on one GPU."""
+    import constant_memory_waveglow_b200 as cm
+    torch.manual_seed(0)
+    m = cm.WaveFlow(memory_efficient=False, zero_init=False, **WAVEFLOW, **WAVEFLOW_WN).to(dev).train()
+    loss_fn = cm.WaveGlowLoss(SIGMA)
+    B = WAVEFLOW_BATCH
+    x = torch.rand(B, SEGMENT, device=dev) * 2 - 1
+    h = torch.randn(B, 80, FRAMES, device=dev)
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        z, ld = m(x, h)
+        loss = loss_fn(z, ld)
+        loss.backward()
+        return loss
+
+    def timed(fn, n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    for _ in range(3):
+        step()
+    ms_train = timed(step, 5)
+    m.eval()
+    hs = torch.randn(1, 80, SYNTH_FRAMES, device=dev)
+    zs = torch.randn(1, SYNTH_FRAMES * 256, device=dev) * 0.6
+    with torch.no_grad():
+        for _ in range(2):
+            m.infer(hs, 0.6, z=zs)
+        ms_synth = timed(lambda: m.infer(hs, 0.6, z=zs), 3)
+    out = {"config": {"workload": "waveflow_lj (8 flows, n_group 64, 64 channels)", "train_batch": B, "segment": SEGMENT,
+                      "synth_batch": 1, "utterance_samples": SYNTH_FRAMES * 256},
+           "train_segments_per_s": B / (ms_train * 1e-3), "train_ms_per_step": ms_train,
+           "train_tflops": 3 * B * WAVEFLOW_FWD_GFLOP_PER_SEGMENT / ms_train,
+           "synth_khz": SYNTH_FRAMES * 256 / ms_synth, "synth_ms": ms_synth,
+           "synth_note": "row-recurrent (63 sequential rows x 8 flows), replayed as one CUDA graph"}
+    if cpu_baseline:
+        from oracle import flow_oracle as O
+        spec = O.WaveFlowSpec(8, 64, 80)
+        sd = O.waveflow_random_state(spec, 64, seed=0)
+        g = torch.Generator().manual_seed(0)
+        xc = torch.rand(1, SEGMENT, generator=g) * 2 - 1
+        hc = torch.randn(1, 80, FRAMES, generator=g)
+        O.waveflow_train_step(sd, spec, xc[:, :4096], hc[..., :16], SIGMA)
+        t0 = time.perf_counter()
+        O.waveflow_train_step(sd, spec, xc, hc, SIGMA)
+        t_train = time.perf_counter() - t0
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            O.waveflow_reverse(sd, spec, xc * 0.6, hc)
+            t_syn = time.perf_counter() - t0
+        out["cpu_baseline"] = {"train_segments_per_s": 1.0 / t_train, "synth_khz": SEGMENT / t_syn / 1e3,
+                               "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": f"oracle port, 1 training step of 1 x 16000 samples ({t_train:.1f} s) and the "
+                                         f"row-recurrent reverse of 16000 samples ({t_syn:.1f} s)"}
+    return out
+
+
 CPU_SAMPLE_BATCH = 2   # segments per CPU step: ~1.2 s per step on 16 host cores, so K+W steps stay within minutes
 
 
@@ -320,6 +409,15 @@ def run_b200(args):
         "clocks": clocks,
         "synth": synth,
     }
+    if not args.no_waveflow and world == 1:
+        del model, opt, sync
+        torch.cuda.empty_cache()
+        line["waveflow"] = waveflow_leg(dev, not args.no_cpu_baseline)
+    if not args.no_cpu_baseline and world == 1 and synth is not None:
+        khz, dt = cpu_oracle_synth(86)                        # 1 s of audio, ~1 s of CPU work
+        synth["cpu_baseline"] = {"value": khz, "unit": "kHz", "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": f"oracle port, one utterance of 86 frames = 22016 samples, {dt:.1f} s"}
+        synth["x_cpu_per_gpu"] = synth["per_gpu_khz"] / khz
     if not args.no_cpu_baseline and world == 1:
         nb, nsteps = CPU_SAMPLE_BATCH, 8                      # ~10-20 s of CPU work
         v, times = cpu_oracle_train(nb, nsteps, 1)
@@ -343,6 +441,7 @@ def main():
     ap.add_argument("--synth-batch", type=int, default=4)
     ap.add_argument("--no-synth", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-waveflow", action="store_true", help="skip the WaveFlow (config 4) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
