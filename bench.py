@@ -414,9 +414,9 @@ def run_b200(args):
         torch.cuda.empty_cache()
         line["waveflow"] = waveflow_leg(dev, not args.no_cpu_baseline)
     if not args.no_cpu_baseline and world == 1 and synth is not None:
-        khz, dt = cpu_oracle_synth(86)                        # 1 s of audio, ~1 s of CPU work
+        khz, dt = cpu_oracle_synth(SYNTH_FRAMES)              # the same 10 s utterance, a few seconds of CPU work
         synth["cpu_baseline"] = {"value": khz, "unit": "kHz", "cores": torch.get_num_threads(), "kind": "port",
-                                 "sample": f"oracle port, one utterance of 86 frames = 22016 samples, {dt:.1f} s"}
+                                 "sample": f"oracle port, one utterance of {SYNTH_FRAMES} frames = {SYNTH_FRAMES * 256} samples, {dt:.1f} s"}
         synth["x_cpu_per_gpu"] = synth["per_gpu_khz"] / khz
     if not args.no_cpu_baseline and world == 1:
         nb, nsteps = CPU_SAMPLE_BATCH, 8                      # ~10-20 s of CPU work
