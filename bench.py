@@ -54,53 +54,121 @@ def peaks():
 # clocks sampling
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  NVML is polled in-process from a thread that is
+    started before the warm-up (nvmlInit and an `nvidia-smi` start-up both take driver locks for 100+ ms, which
+    must not land inside a timed step); samples are kept only while `active` is set.  `nvidia-smi -lms` is the
+    fallback when pynvml cannot be used."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    MASKS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self.active = False
+        self.alive = False
         self.proc = None
+        self.nvml = None
+        self.handle = None
+        self.thread = None
+
+    def _open_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        self.nvml, self.handle = pynvml, h
 
     def start(self):
+        """Open the sampler (call before the warm-up); sampling is recorded only between begin() and end()."""
+        try:
+            self._open_nvml()
+            self.alive = True
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "25"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def begin(self):
+        self.active = True
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
+    def end(self):
+        self.active = False
+
+    def _poll_nvml(self):
+        n = self.nvml
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while self.alive:
+            if self.active:
+                try:
+                    mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    try:
+                        bits = int(get_reasons(self.handle))
+                    except Exception:
+                        bits = 0
+                    self.rows.append((mhz, bits))
+                except Exception:
+                    pass
+                time.sleep(0.004)
+            else:
+                time.sleep(0.001)
+
+    def _read_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            parts = [p.strip() for p in r.split(",")]
+        for line in self.proc.stdout:
+            if not self.active:
+                continue
+            parts = [p.strip() for p in line.strip().split(",")]
             if len(parts) < 6:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx = float(parts[1])
+                mhz = float(parts[0])
+                self.max_mhz = float(parts[1])
             except ValueError:
                 continue
-            for n, v in zip(names, parts[2:6]):
+            bits = 0
+            for nme, v in zip(names, parts[2:6]):
                 if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                    bits |= self.MASKS[nme]
+            self.rows.append((mhz, bits))
+
+    def stop(self):
+        self.active = False
+        self.alive = False
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        elif self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        if self.thread is not None and self.nvml is not None:
+            self.thread.join(timeout=1)
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[1]
+        reasons = sorted(k for k, m in self.MASKS.items() if bits & m)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -312,17 +380,25 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), last
 
-    for _ in range(args.warmup):
-        step(x_dev, h_dev)
-    barrier()
-
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()                                    # opened before the warm-up, records only while active
+    for _ in range(args.warmup):
+        step(x_dev, h_dev)
+    for _ in range(min(args.warmup, 2)):                   # warm the pinned-host -> device path of the e2e leg too
+        step(x_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True)).item()
+    barrier()
+
+    import gc
+    gc.collect()
+    gc.disable()                                           # no collector pauses inside a timed step
+    sampler.begin()
     lib.cmwg_reset_launch_count()
     ms, loss = timed(args.steps, e2e=False)
     launches = int(lib.cmwg_launch_count())
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
+    sampler.end()
+    gc.enable()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline leg: device time of every GEMM class over one more step (events on the launching stream)
