@@ -6,8 +6,9 @@
 //
 // One CTA per (batch, frame).  The n_fft real samples are packed as n_fft/2 complex numbers z[n] = x[2n] + i x[2n+1]
 // (window applied, reflected indices resolved while loading), transformed by an in-shared-memory radix-2 FFT of half
-// the length, and split back into the n_fft/2+1 one-sided bins.  A warp per mel band then runs over that band's
-// support [lo, hi) of the triangular filter.
+// the length, and split back into the n_fft/2+1 one-sided bins.  A thread per mel band then runs over that band's
+// support [lo, hi) of the triangular filter.  The real workloads are small (24 x 63 training frames, 863 frames per
+// 10 s utterance), so the kernel is latency bound and a CTA per frame -- the widest decomposition -- is the fast one.
 #include "common.cuh"
 
 namespace cmwg {
@@ -22,32 +23,41 @@ __device__ __forceinline__ int reflect_index(int i, int T) {
 template <int NFFT>
 __global__ void __launch_bounds__(256) melspec_kernel(const float* __restrict__ x, long long x_bstride, int T,
                                                       const float* __restrict__ window,
-                                                      const float* __restrict__ fb, const int* __restrict__ fb_lo,
+                                                      const float* __restrict__ fbt, const int* __restrict__ fb_lo,
                                                       const int* __restrict__ fb_hi, int n_mels, int hop,
                                                       int pad_left, int frames, int power_is_one, float eps,
                                                       int take_log, float* __restrict__ out) {
   constexpr int M = NFFT / 2;  // complex FFT length
   constexpr int LOGM = (M == 64) ? 6 : (M == 128) ? 7 : (M == 256) ? 8 : (M == 512) ? 9 : (M == 1024) ? 10 : 11;
   constexpr int NT = 256;
-  __shared__ float2 z[M];
-  __shared__ float2 tw[M];       // tw[k] = exp(-2 pi i k / NFFT), k < NFFT/2
+  // one pad slot per 16 entries: the bit-reversed scatter (stride M/2) and the strided twiddle reads of the late
+  // stages (stride NFFT >> (s+1)) would otherwise hit a single bank 32 ways
+  constexpr int MP = M + M / 16;
+#define CMWG_PADI(i) ((i) + ((i) >> 4))
+  __shared__ float2 z[MP];
+  __shared__ float2 tw[MP];      // tw[PAD(k)] = exp(-2 pi i k / NFFT), k < NFFT/2
   __shared__ float pw[M + 1];    // |X[k]|^power, k <= NFFT/2
 
   const int b = blockIdx.x / frames, fr = blockIdx.x % frames;
   const float* xb = x + (long long)b * x_bstride;
   const int start = fr * hop - pad_left;
+  int my_lo = 0, my_hi = 0;
+  if (threadIdx.x < n_mels) {
+    my_lo = fb_lo[threadIdx.x];
+    my_hi = fb_hi[threadIdx.x];
+  }
 
   for (int k = threadIdx.x; k < M; k += NT) {
     float s, c;
     sincospif(-2.f * (float)k / (float)NFFT, &s, &c);
-    tw[k] = make_float2(c, s);
+    tw[CMWG_PADI(k)] = make_float2(c, s);
   }
   // bit-reversed scatter of the packed, windowed frame
   for (int n = threadIdx.x; n < M; n += NT) {
     int i0 = reflect_index(start + 2 * n, T), i1 = reflect_index(start + 2 * n + 1, T);
     float a = xb[i0] * window[2 * n], c = xb[i1] * window[2 * n + 1];
     int r = (int)(__brev((unsigned)n) >> (32 - LOGM));
-    z[r] = make_float2(a, c);
+    z[CMWG_PADI(r)] = make_float2(a, c);
   }
   __syncthreads();
   // radix-2 decimation-in-time stages on M points; twiddle exp(-2 pi i pos / (2 half)) = tw[pos * (NFFT / (2 half))]
@@ -58,7 +68,9 @@ __global__ void __launch_bounds__(256) melspec_kernel(const float* __restrict__ 
     for (int j = threadIdx.x; j < M / 2; j += NT) {
       int pos = j & (half - 1);
       int i0 = ((j >> s) << (s + 1)) + pos, i1 = i0 + half;
-      float2 w = tw[pos * tstep];
+      float2 w = tw[CMWG_PADI(pos * tstep)];
+      i0 = CMWG_PADI(i0);
+      i1 = CMWG_PADI(i1);
       float2 u = z[i0], v = z[i1];
       float2 t = make_float2(fmaf(v.x, w.x, -v.y * w.y), fmaf(v.x, w.y, v.y * w.x));
       z[i0] = make_float2(u.x + t.x, u.y + t.y);
@@ -68,10 +80,10 @@ __global__ void __launch_bounds__(256) melspec_kernel(const float* __restrict__ 
   }
   // split: X[k] = (Z[k] + conj Z[M-k]) / 2 - (i/2) exp(-2 pi i k / NFFT) (Z[k] - conj Z[M-k]),  k = 0..M  (Z[M] = Z[0])
   for (int k = threadIdx.x; k <= M; k += NT) {
-    float2 a = z[k & (M - 1)], c = z[(M - k) & (M - 1)];
+    float2 a = z[CMWG_PADI(k & (M - 1))], c = z[CMWG_PADI((M - k) & (M - 1))];
     float er = 0.5f * (a.x + c.x), ei = 0.5f * (a.y - c.y);   // even part
     float dr = 0.5f * (a.x - c.x), di = 0.5f * (a.y + c.y);   // (Z[k] - conj Z[M-k]) / 2
-    float2 w = (k < M) ? tw[k] : make_float2(-1.f, 0.f);
+    float2 w = (k < M) ? tw[CMWG_PADI(k)] : make_float2(-1.f, 0.f);
     // -i * w * d
     float pr = w.x * dr - w.y * di, pi = w.x * di + w.y * dr;
     float xr = er + pi, xi = ei - pr;
@@ -79,17 +91,24 @@ __global__ void __launch_bounds__(256) melspec_kernel(const float* __restrict__ 
     pw[k] = power_is_one ? sqrtf(p) : p;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int m = warp; m < n_mels; m += NT / 32) {
-    int lo = fb_lo[m], hi = fb_hi[m];
-    float acc = 0.f;
-    for (int f = lo + lane; f < hi; f += 32) acc = fmaf(pw[f], fb[(long long)f * n_mels + m], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float v = acc + eps;
-      out[((long long)b * n_mels + m) * frames + fr] = take_log ? logf(v) : v;
+  // a thread per mel band: its [lo, hi) bounds were fetched before the FFT, and the loop's loads are independent of
+  // each other, so the band sums cost one L2 round trip instead of one per band
+  for (int m = threadIdx.x, i = 0; m < n_mels; m += NT, ++i) {
+    int lo = i == 0 ? my_lo : fb_lo[m], hi = i == 0 ? my_hi : fb_hi[m];
+    const float* frow = fbt + (long long)m * (M + 1);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int f = lo;
+    for (; f + 4 <= hi; f += 4) {
+      a0 = fmaf(pw[f], frow[f], a0);
+      a1 = fmaf(pw[f + 1], frow[f + 1], a1);
+      a2 = fmaf(pw[f + 2], frow[f + 2], a2);
+      a3 = fmaf(pw[f + 3], frow[f + 3], a3);
     }
+    for (; f < hi; ++f) a0 = fmaf(pw[f], frow[f], a0);
+    float v = (a0 + a1) + (a2 + a3) + eps;
+    out[((long long)b * n_mels + m) * frames + fr] = take_log ? logf(v) : v;
   }
+#undef CMWG_PADI
 }
 
 }  // namespace cmwg
@@ -103,7 +122,7 @@ extern "C" int cmwg_melspec_frames(int T, int n_fft, int hop) {
 }
 
 extern "C" int cmwg_melspec_fwd(const float* x, long long x_bstride, int B, int T, const float* window,
-                                const float* fb, const int* fb_lo, const int* fb_hi, int n_fft, int hop, int n_mels,
+                                const float* fbt, const int* fb_lo, const int* fb_hi, int n_fft, int hop, int n_mels,
                                 int power_is_one, float eps, int take_log, float* out, void* stream) {
   CMWG_REQUIRE(B >= 0 && T >= 0 && n_mels > 0 && hop > 0, "melspec: bad sizes B=%d T=%d n_mels=%d hop=%d", B, T,
                n_mels, hop);
@@ -116,7 +135,7 @@ extern "C" int cmwg_melspec_fwd(const float* x, long long x_bstride, int B, int 
   dim3 grid((unsigned)(B * frames)), block(256);
 #define CMWG_MEL_CASE(N)                                                                                        \
   case N:                                                                                                       \
-    melspec_kernel<N><<<grid, block, 0, st>>>(x, x_bstride, T, window, fb, fb_lo, fb_hi, n_mels, hop, pad_left, \
+    melspec_kernel<N><<<grid, block, 0, st>>>(x, x_bstride, T, window, fbt, fb_lo, fb_hi, n_mels, hop, pad_left, \
                                               frames, power_is_one, eps, take_log, out);                       \
     break;
   switch (n_fft) {

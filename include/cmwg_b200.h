@@ -217,6 +217,21 @@ int cmwg_upsample_bwd_input(const float* g, const float* v, const float* dy, lon
                             float* dh, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Mel-spectrogram conditioner (model/condition.py:7-19; called at model/lightning.py:54 and inference.py:31):
+ * ReflectionPad1d((n_fft/2 - hop/2, n_fft/2 + hop/2)) -> STFT(n_fft, hop, window, center=False) -> |.|^power ->
+ * mel filterbank -> (+ eps) -> log, fused in one kernel.
+ *   x (B, T) with batch stride x_bstride -> out (B, n_mels, frames), frames = cmwg_melspec_frames(T, n_fft, hop).
+ *   window (n_fft); fbt (n_mels, n_fft/2 + 1) row major = the TRANSPOSE of torchaudio's mel_scale.fb, so a warp
+ *   reads consecutive bins of one band; fb_lo / fb_hi (n_mels) int32: band m is non-zero only on bins
+ *   [fb_lo[m], fb_hi[m]).  n_fft: power of two in [128, 4096].
+ *   power_is_one: 0 -> power 2 (the default), 1 -> magnitude; take_log = 0 returns the mel powers (+ eps).
+ * ------------------------------------------------------------------------------------------- */
+int cmwg_melspec_frames(int T, int n_fft, int hop);
+int cmwg_melspec_fwd(const float* x, long long x_bstride, int B, int T, const float* window, const float* fbt,
+                     const int* fb_lo, const int* fb_hi, int n_fft, int hop, int n_mels, int power_is_one, float eps,
+                     int take_log, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * WaveFlow glue (model/waveflow.py:154-265).  Images are (B, H, W) fp32 contiguous, H = n_group lines;
  * lst = (B, 2, (H-1)*W) is the 2-D WN's output for input lines 0..H-2 (log_s, then t).
  * ------------------------------------------------------------------------------------------- */

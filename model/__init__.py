@@ -6,6 +6,7 @@ from constant_memory_waveglow_b200.base import FlowBase, Reversible
 from constant_memory_waveglow_b200.waveflow import WaveFlow
 from constant_memory_waveglow_b200.waveglow import WaveGlow
 from constant_memory_waveglow_b200.wsrglow import WSRGlow
+from . import condition  # noqa: F401  (reference: `from model import LightModel, condition`, inference.py:10)
 
 _NOT_BUILT = ("MelGlow", "MRWaveGlow", "LightModel")
 
