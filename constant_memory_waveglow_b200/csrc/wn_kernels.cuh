@@ -410,6 +410,180 @@ static __global__ void __launch_bounds__(256) start_bwd_kernel(const float* __re
 }
 
 // ------------------------------------------------------------------------------------------------
+// 256-channel fast paths of the start / end conv backward (the shapes of every shipped config).  Both are one
+// pass over a [rows][256] slab, bound by that read: a warp owns 32 consecutive rows, every lane keeps 8 channels
+// (32-byte loads, a row is one fully coalesced 1 KB / 512 B request), the few "small side" values of a row (x or
+// d(log_s, t): <= 8 per row) are loaded by the lane that owns the row and broadcast with shuffles, and the
+// weight-gradient outer products accumulate in registers.  Warps fold into one partial per CTA in warp order and a
+// CTA's row range is fixed by its index, so results are bitwise reproducible.
+// ------------------------------------------------------------------------------------------------
+constexpr int FAST_ROWS_PER_CTA = 256;  // 8 warps x 32 rows
+
+__device__ __forceinline__ void load_row8(const float* __restrict__ p32, const uint16_t* __restrict__ hi,
+                                          const uint16_t* __restrict__ lo, long long off, float (&v)[8]) {
+  if (p32) {
+    const float4 a = *reinterpret_cast<const float4*>(p32 + off), b = *reinterpret_cast<const float4*>(p32 + off + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    // (hi, lo) bf16 pair: value = hi + lo
+    const uint4 h = *reinterpret_cast<const uint4*>(hi + off), l = *reinterpret_cast<const uint4*>(lo + off);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+      v[2 * j + 1] = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
+    }
+  }
+}
+
+// Sum NACC per-lane accumulators over the 8 warps of a CTA in a fixed tree order (warps 4-7 into 0-3, 2-3 into 0-1,
+// 1 into 0); `buf` holds 4 * NACC * 32 floats laid out [warp][acc][lane] (conflict free).  On return warp 0 has
+// stored the totals to buf[acc * 32 + lane] and the CTA is synchronised.
+template <int NACC>
+__device__ __forceinline__ void cta8_tree_sum(float (&acc)[NACC], float* buf) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int half = 4; half >= 1; half >>= 1) {
+    if (warp >= half && warp < 2 * half) {
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) buf[((warp - half) * NACC + a) * 32 + lane] = acc[a];
+    }
+    __syncthreads();
+    if (warp < half) {
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[a] += buf[(warp * NACC + a) * 32 + lane];
+    }
+    __syncthreads();
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) buf[a * 32 + lane] = acc[a];
+  }
+  __syncthreads();
+}
+
+// start conv backward, Cr == 256:  dx[:, i] += sum_o Ws[o][i] dh0[row][o];  partial dWs[o][i] = sum_row dh0[row][o] x[row][i]
+template <int CIN>
+static __global__ void __launch_bounds__(256) start_bwd256_kernel(const float* __restrict__ dh32,
+                                                                  const uint16_t* __restrict__ dh_hi,
+                                                                  const uint16_t* __restrict__ dh_lo,
+                                                                  const float* __restrict__ x, long long x_bs,
+                                                                  const float* __restrict__ ws, int TF, long long rows,
+                                                                  float* __restrict__ dx, long long dx_bs,
+                                                                  float* __restrict__ partial_w,
+                                                                  float* __restrict__ partial_b) {
+  __shared__ float buf[4 * (8 * CIN + 8) * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // acc[c * CIN + i] = dWs[lane * 8 + c][i] partial, acc[8 * CIN + c] = dbias partial
+  float wreg[8][CIN], acc[8 * CIN + 8];
+#pragma unroll
+  for (int a = 0; a < 8 * CIN + 8; ++a) acc[a] = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) wreg[c][i] = ws[(lane * 8 + c) * CIN + i];
+  const long long g0 = (long long)blockIdx.x * FAST_ROWS_PER_CTA + warp * 32;
+  if (g0 < rows) {
+    const int nrows = (int)min(32LL, rows - g0);
+    const bool valid = lane < nrows;
+    int b = 0, t = 0;
+    if (valid) {
+      b = (int)((g0 + lane) / TF);
+      t = (int)((g0 + lane) - (long long)b * TF);
+    }
+    float xm[CIN], mine[CIN];
+#pragma unroll
+    for (int i = 0; i < CIN; ++i) {
+      xm[i] = valid ? x[b * x_bs + (long long)i * TF + t] : 0.f;
+      mine[i] = 0.f;
+    }
+#pragma unroll 4
+    for (int r = 0; r < nrows; ++r) {
+      float dh[8];
+      load_row8(dh32, dh_hi, dh_lo, (g0 + r) * 256 + lane * 8, dh);
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) {
+        const float xv = __shfl_sync(0xffffffffu, xm[i], r);
+        float p = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          acc[c * CIN + i] = fmaf(dh[c], xv, acc[c * CIN + i]);
+          p = fmaf(wreg[c][i], dh[c], p);
+        }
+        p = warp_sum(p);
+        if (lane == r) mine[i] = p;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[8 * CIN + c] += dh[c];
+    }
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) dx[b * dx_bs + (long long)i * TF + t] += mine[i];
+    }
+  }
+  cta8_tree_sum<8 * CIN + 8>(acc, buf);
+  float* pw = partial_w + (long long)blockIdx.x * 256 * CIN;
+  for (int idx = threadIdx.x; idx < 256 * CIN; idx += 256) {
+    const int o = idx / CIN, i = idx - o * CIN;
+    pw[idx] = buf[((o & 7) * CIN + i) * 32 + (o >> 3)];
+  }
+  if (partial_b)
+    partial_b[(long long)blockIdx.x * 256 + threadIdx.x] = buf[(8 * CIN + (threadIdx.x & 7)) * 32 + (threadIdx.x >> 3)];
+}
+
+// end conv weight gradient, Cs == 256:  partial dWe[oc][k] = sum_row dlst[b][oc][t] skip[row][k];  dbias[oc] = sum dlst
+template <int COUT>
+static __global__ void __launch_bounds__(256) end_bwd_dw256_kernel(const float* __restrict__ dlst,
+                                                                   const float* __restrict__ skip, int TF,
+                                                                   long long rows, float* __restrict__ partial_w,
+                                                                   float* __restrict__ partial_b) {
+  __shared__ float buf[4 * (8 * COUT + COUT) * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // acc[oc * 8 + c] = dWe[oc][lane * 8 + c] partial, acc[8 * COUT + oc] = this lane's share of dbias[oc]
+  float acc[8 * COUT + COUT];
+#pragma unroll
+  for (int a = 0; a < 8 * COUT + COUT; ++a) acc[a] = 0.f;
+  const long long g0 = (long long)blockIdx.x * FAST_ROWS_PER_CTA + warp * 32;
+  if (g0 < rows) {
+    const int nrows = (int)min(32LL, rows - g0);
+    float dl[COUT];
+    if (lane < nrows) {
+      const int b = (int)((g0 + lane) / TF);
+      const int t = (int)((g0 + lane) - (long long)b * TF);
+#pragma unroll
+      for (int oc = 0; oc < COUT; ++oc) dl[oc] = dlst[((long long)b * COUT + oc) * TF + t];
+    } else {
+#pragma unroll
+      for (int oc = 0; oc < COUT; ++oc) dl[oc] = 0.f;
+    }
+#pragma unroll
+    for (int oc = 0; oc < COUT; ++oc) acc[8 * COUT + oc] = dl[oc];
+#pragma unroll 4
+    for (int r = 0; r < nrows; ++r) {
+      float sk[8];
+      load_row8(skip, nullptr, nullptr, (g0 + r) * 256 + lane * 8, sk);
+#pragma unroll
+      for (int oc = 0; oc < COUT; ++oc) {
+        const float v = __shfl_sync(0xffffffffu, dl[oc], r);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[oc * 8 + c] = fmaf(v, sk[c], acc[oc * 8 + c]);
+      }
+    }
+  }
+  cta8_tree_sum<8 * COUT + COUT>(acc, buf);
+  float* pw = partial_w + (long long)blockIdx.x * COUT * 256;
+  for (int idx = threadIdx.x; idx < COUT * 256; idx += 256) {
+    const int oc = idx >> 8, k = idx & 255;
+    pw[idx] = buf[(oc * 8 + (k & 7)) * 32 + (k >> 3)];
+  }
+  if (partial_b && threadIdx.x < COUT * 32) {
+    // one warp per output channel folds the 32 lane shares in shuffle order
+    const float sb = warp_sum(buf[(8 * COUT + warp) * 32 + lane]);
+    if (lane == 0) partial_b[(long long)blockIdx.x * COUT + warp] = sb;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // end conv (Cs -> 2cin, kernel 1): slab fp32 input, NCL output          model/waveglow.py:92,105
 // Bound by the read of the fp32 skip slab.  One warp owns 32 consecutive time steps: per row every lane
 // loads KV float4 (a fully coalesced row), multiplies with its register-resident weight slice for up

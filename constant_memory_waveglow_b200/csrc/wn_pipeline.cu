@@ -386,7 +386,19 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       float* pw = partial;
       float* pb = partial + (size_t)nblk * cout * d.Cs;
       float* scratch = pb + (size_t)nblk * cout;
-      end_bwd_dw_kernel<<<nblk, 256, smem2, st>>>(dlst, skip32, cout, d.Cs, TF, bpb, pw, gr->end.bias ? pb : nullptr);
+      int nblk_e = nblk;  // CTAs whose partials the reductions below fold
+      float* pbe = gr->end.bias ? pb : nullptr;
+      if (d.Cs == 256 && cout <= 8 && cout >= 2 && !(cout & 1)) {
+        nblk_e = (int)ceil_div_ll(rows, FAST_ROWS_PER_CTA);
+        switch (cout) {
+          case 2: end_bwd_dw256_kernel<2><<<nblk_e, 256, 0, st>>>(dlst, skip32, TF, rows, pw, pbe); break;
+          case 4: end_bwd_dw256_kernel<4><<<nblk_e, 256, 0, st>>>(dlst, skip32, TF, rows, pw, pbe); break;
+          case 6: end_bwd_dw256_kernel<6><<<nblk_e, 256, 0, st>>>(dlst, skip32, TF, rows, pw, pbe); break;
+          default: end_bwd_dw256_kernel<8><<<nblk_e, 256, 0, st>>>(dlst, skip32, TF, rows, pw, pbe); break;
+        }
+      } else {
+        end_bwd_dw_kernel<<<nblk, 256, smem2, st>>>(dlst, skip32, cout, d.Cs, TF, bpb, pw, pbe);
+      }
       CMWG_COUNT_LAUNCH();
       CMWG_LAUNCH_CHECK();
       cmwg_conv_grad ge = gr->end;
@@ -395,11 +407,11 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       pe.g = nullptr;  // `end` is never weight-normed (model/waveglow.py:92)
       if (ge.v) {
         float* dEnd = dweff + BL.dweff_end;
-        CMWG_PROPAGATE(reduce_blocks(pw, nblk, cout * d.Cs, scratch, dEnd, st));
+        CMWG_PROPAGATE(reduce_blocks(pw, nblk_e, cout * d.Cs, scratch, dEnd, st));
         wq.add(dEnd, pe, nullptr, ge, cout, d.Cs);
       }
       if (gr->end.bias) {
-        CMWG_PROPAGATE(reduce_blocks(pb, nblk, cout, scratch, gr->end.bias, st));
+        CMWG_PROPAGATE(reduce_blocks(pb, nblk_e, cout, scratch, gr->end.bias, st));
       }
     }
   }
@@ -614,19 +626,32 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     float* pw = partial;
     float* pb = partial + (size_t)nblk * d.Cr * d.cin;
     float* scratch = pb + (size_t)nblk * d.Cr;
-    start_bwd_kernel<<<nblk, 256, smem, st>>>(TC ? nullptr : dh32, TC ? reinterpret_cast<const uint16_t*>(dhi(0)) : nullptr,
-                                              TC ? reinterpret_cast<const uint16_t*>(dlo(0)) : nullptr, x, x_bs, wStart,
-                                              d.cin, d.Cr, TF, bpb, dx, dx_bs, pw,
-                                              (d.bias && gr->start.bias) ? pb : nullptr);
+    const float* a32 = TC ? nullptr : dh32;
+    const uint16_t* ahi = TC ? reinterpret_cast<const uint16_t*>(dhi(0)) : nullptr;
+    const uint16_t* alo = TC ? reinterpret_cast<const uint16_t*>(dlo(0)) : nullptr;
+    float* pbs = (d.bias && gr->start.bias) ? pb : nullptr;
+    int nblk_s = nblk;
+    if (d.Cr == 256 && d.cin >= 1 && d.cin <= 8) {
+      nblk_s = (int)ceil_div_ll(rows, FAST_ROWS_PER_CTA);
+#define CMWG_START_CASE(N) \
+  case N: start_bwd256_kernel<N><<<nblk_s, 256, 0, st>>>(a32, ahi, alo, x, x_bs, wStart, TF, rows, dx, dx_bs, pw, pbs); break;
+      switch (d.cin) {
+        CMWG_START_CASE(1) CMWG_START_CASE(2) CMWG_START_CASE(3) CMWG_START_CASE(4)
+        CMWG_START_CASE(5) CMWG_START_CASE(6) CMWG_START_CASE(7) CMWG_START_CASE(8)
+      }
+#undef CMWG_START_CASE
+    } else {
+      start_bwd_kernel<<<nblk, 256, smem, st>>>(a32, ahi, alo, x, x_bs, wStart, d.cin, d.Cr, TF, bpb, dx, dx_bs, pw, pbs);
+    }
     CMWG_COUNT_LAUNCH();
     CMWG_LAUNCH_CHECK();
     if (gr->start.g || gr->start.v) {
       float* dStart = dweff + BL.dweff_start;
-      CMWG_PROPAGATE(reduce_blocks(pw, nblk, d.Cr * d.cin, scratch, dStart, st));
+      CMWG_PROPAGATE(reduce_blocks(pw, nblk_s, d.Cr * d.cin, scratch, dStart, st));
       wq.add(dStart, prm->start, reinterpret_cast<const float*>(pk + PL.nStart), gr->start, d.Cr, d.cin);
     }
     if (d.bias && gr->start.bias) {
-      CMWG_PROPAGATE(reduce_blocks(pb, nblk, d.Cr, scratch, gr->start.bias, st));
+      CMWG_PROPAGATE(reduce_blocks(pb, nblk_s, d.Cr, scratch, gr->start.bias, st));
     }
   }
   return wq.flush(st);

@@ -89,6 +89,24 @@ def test_coupling_wn_tensor_core_bf16(case, direction):
     run_case("bf16", *case, direction)
 
 
+# 256 channels: the start / end conv backward take their one-pass fast paths (start_bwd256_kernel for in_channels
+# <= 8, end_bwd_dw256_kernel for in_channels <= 4); row counts that are not multiples of 32 make the 32-row warp
+# groups straddle batch items and leave ragged tails
+FAST256 = [(4, 80, 256, 2, 2, 333), (3, 80, 256, 1, 3, 200), (2, 16, 256, 1, 2, 97), (7, 24, 256, 1, 2, 150),
+           (2, 80, 256, 1, 1, 2000)]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", FAST256)
+def test_coupling_wn_256_channel_fast_paths(case, prec):
+    run_case(prec, *case, "forward")
+
+
+def test_wn_256_channel_fast_paths_bias():
+    run_case("fp32", 2, 12, 256, 1, 2, 130, "forward", bias=True)
+    run_case("bf16", 4, 12, 256, 1, 2, 130, "reverse", bias=True)
+
+
 def test_wn_bias_and_radix5_fp32():
     run_case("fp32", 4, 12, 32, 2, 2, 150, "forward", bias=True, radix=5)
     run_case("fp32", 4, 12, 64, 2, 1, 200, "reverse", bias=True)
