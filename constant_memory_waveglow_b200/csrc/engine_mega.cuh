@@ -1,0 +1,384 @@
+// Whole-WN forward as ONE persistent tcgen05 kernel (1-D WN, 16-bit operands).
+//
+// The layer-at-a-time pipeline of wn_pipeline.cu launches 2 GEMMs per layer; every launch boundary is a device-wide
+// barrier that costs a pipeline fill + drain (~8 us measured at the LJ shapes) and rounds the tile count up to whole
+// waves of 74 CTA pairs (384 gate tiles = 5.19 waves -> 6).  Here every GEMM tile of every layer is a TASK in one
+// global, topologically ordered list
+//     for layer i:  G(i, rt, nt)  gate GEMM tiles (dilated conv + conditioning, tanh*sigmoid epilogue)
+//                   R(i, rt)      residual GEMM tiles (W_o[:Cr], epilogue adds the (hi, lo) pair of the layer input)
+//     then          S(rt)         skip GEMM tiles (all layers' W_o[Cr:], K-concatenated)
+// (interleaved: slot u = layer * RT + rt holds G(u, *) and R(u - LAG), so a pair alternates MMA-heavy gate tiles with
+// epilogue-heavy residual tiles and the residual epilogue drains one TMEM buffer while the next gate tile fills the other)
+// and CTA pair p runs tasks p, p + P, p + 2P, ... (P pairs, all co-resident).  Dependencies are per ROW TILE, not per
+// layer: R(i, rt) needs G(i, rt, *); G(i, rt, *) needs R(i-1, rt-1 .. rt+1) (the dilated taps reach at most one
+// 256-row tile away); S(rt) needs G(depth-1, rt, *).  They are tracked by counters in global memory: every epilogue warp
+// adds 1 (release) to its task's counter once its TMA stores have COMPLETED, and the TMA producer (and, for R, the
+// epilogue's input loader) polls (acquire) before it issues loads.  The list is in dependency order and a pair executes
+// its tasks in list order, so the lowest unfinished task is always runnable: no deadlock as long as all pairs are
+// resident (grid <= SM count / 2, one CTA per SM).  A wait that exceeds ~2 s traps instead of hanging the device.
+//
+// Roles, rings, TMEM double buffering and the epilogue functors are those of engine_tc.cuh; the epilogue switches
+// functor per task (warp-uniform), and the residual epilogue works IN PLACE in its staging buffers (inputs are read
+// into registers, outputs overwrite them), which leaves room for 4-5 operand stages.
+#pragma once
+#include "engine_tc.cuh"
+#include "epilogues_tc.cuh"
+
+namespace cmwg {
+
+constexpr int MEGA_D = 8;        // layers
+constexpr int MEGA_BN = 256;     // N tile of every task
+enum { MEGA_G = 0, MEGA_R = 1, MEGA_S = 2, MEGA_NONE = 3 };
+
+struct alignas(64) MegaParams {
+  CUtensorMap hin_op[MEGA_D];   // operand maps (64 ch x 128 rows, 128B swizzle): layer inputs (hi halves)
+  CUtensorMap g_op[MEGA_D];     // operand maps: gate outputs
+  CUtensorMap cond_op;          // operand map: packed conditioning
+  CUtensorMap pa[MEGA_D], pb[MEGA_D], ps;                       // weights (64 x 128-row boxes)
+  CUtensorMap g_c16[MEGA_D], a_c16[MEGA_D], b_c16[MEGA_D];      // 32 x 32 chunk maps: gate outputs (a, b: saved tanh / sigmoid)
+  CUtensorMap hi_c16[MEGA_D], lo_c16[MEGA_D];                   // chunk maps: (hi, lo) pair of every layer's INPUT
+  CUtensorMap skip_c32;                                         // fp32 chunk map: cumulative skip
+  uint32_t* flags;              // [depth][2][RT]: gate-done / residual-done counters (zeroed before the launch)
+  int depth, B, T, tiles_per_batch, RT;
+  int ngt;                      // gate N tiles
+  int taps, kb_h, kb_c, kb_g;   // taps; k-blocks per tap / of the conditioning / of one gate output
+  int Cd, f16;
+  uint32_t idesc, desc_lbo, desc_sbo;
+  int lag;                      // residual tiles trail their gate tiles by `lag` row-tile slots (< RT - 1)
+  int total_tasks;
+  int dbg;                      // timing experiments only (CMWG_MEGA_DBG): 1 no producer waits, 2 no signals, 4 no wait_all
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void mega_wait_flag(const uint32_t* p, uint32_t target) {
+  if (ld_acquire_u32(p) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_u32(p) < target) {
+    __nanosleep(40);
+    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a lost dependency must not hang the device
+  }
+}
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// up to three counters polled with independent relaxed loads (one L2 round trip), then one acquire fence
+__device__ __forceinline__ void mega_wait_flags3(const uint32_t* a, const uint32_t* b, const uint32_t* c, uint32_t target) {
+  const long long t0 = clock64();
+  while (true) {
+    const uint32_t va = ld_relaxed_u32(a), vb = ld_relaxed_u32(b), vc = ld_relaxed_u32(c);
+    if (va >= target && vb >= target && vc >= target) break;
+    __nanosleep(40);
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
+struct MegaTask {
+  int type, layer, rt, nt;
+};
+__device__ __forceinline__ MegaTask mega_decode(const MegaParams& p, int idx) {
+  // slots 0 .. depth*RT + lag - 1, (ngt + 1) positions each: G(u = slot, nt) then R(u = slot - lag); positions whose
+  // task does not exist are MEGA_NONE (skipped by every role alike); the skip tiles follow
+  MegaTask t;
+  const int per_slot = p.ngt + 1;
+  const int slots = p.depth * p.RT + p.lag;
+  t.nt = 0;
+  if (idx >= slots * per_slot) {
+    t.type = MEGA_S; t.layer = p.depth - 1; t.rt = idx - slots * per_slot;
+    return t;
+  }
+  const int sl = idx / per_slot, w = idx - sl * per_slot;
+  const int u = w < p.ngt ? sl : sl - p.lag;
+  t.layer = u >= 0 ? u / p.RT : 0;
+  t.rt = u - t.layer * p.RT;
+  if (w < p.ngt) {
+    t.type = u < p.depth * p.RT ? MEGA_G : MEGA_NONE;
+    t.nt = w;
+  } else {
+    t.type = (u >= 0 && t.layer < p.depth - 1) ? MEGA_R : MEGA_NONE;
+  }
+  return t;
+}
+__device__ __forceinline__ uint32_t* mega_gflag(const MegaParams& p, int layer, int rt) {
+  return p.flags + (size_t)(2 * layer) * p.RT + rt;
+}
+__device__ __forceinline__ uint32_t* mega_rflag(const MegaParams& p, int layer, int rt) {
+  return p.flags + (size_t)(2 * layer + 1) * p.RT + rt;
+}
+
+// Epilogue of ONE task for one warp: GW epilogue columns per tile, four column groups (one per warp of the lane quadrant).
+// kIn > 0: in-place staging -- chunk inputs are TMA-loaded into the buffers the outputs are later stored from; the
+// caller has already issued chunk 0's inputs.  Ends with ALL of this warp's stores complete; then signals `flag`.
+template <class Epi, int GW>
+__device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem_tile, uint64_t* tmem_full, uint32_t full_phase,
+                                                   uint32_t tmem_empty_remote, int q, int cg, int lane, uint32_t wbuf,
+                                                   uint64_t* ibar, uint32_t& it, const CUtensorMap* om0,
+                                                   const CUtensorMap* om1, const CUtensorMap* om2, const CUtensorMap* im0,
+                                                   const CUtensorMap* im1, int b, int r0, int cbase, uint32_t* flag, uint32_t done_cnt, int dbg) {
+  constexpr int NCH = GW / 128;                      // 32-column chunks per warp
+  constexpr int OUTW = Epi::kOutF32 ? 16 : 8;
+  constexpr int OCH = Epi::kOutF32 ? TC_CHUNK32_BYTES : TC_CHUNK16_BYTES;
+  const uint32_t taddr = tmem_tile + ((uint32_t)(q * 32) << 16) + cg * (GW / 4);
+  const CUtensorMap* om[3] = {om0, om1, om2};
+  const CUtensorMap* im[2] = {im0, im1};
+  mbar_wait(tmem_full, full_phase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int k = 0; k < NCH; ++k) {
+    const int c0 = cbase + cg * (GW / 4) + 32 * k;
+    if (k > 0) {  // the previous chunk's stores must have read the staging buffers before they are overwritten
+      if (lane == 0) {
+        bulk_wait_read<0>();
+        if constexpr (Epi::kIn > 0) {
+          fence_proxy_async();
+          mbar_arrive_expect_tx(ibar, Epi::kIn * TC_CHUNK16_BYTES);
+#pragma unroll
+          for (int i = 0; i < Epi::kIn; ++i)
+            tma_load_4d_local(wbuf + i * TC_CHUNK16_BYTES, im[i], smem_u32(ibar), c0, r0, 0, b);
+        }
+      }
+      __syncwarp();
+    }
+    uint32_t in[Epi::kIn > 0 ? Epi::kIn : 1][16];
+    if constexpr (Epi::kIn > 0) {
+      mbar_wait(ibar, it & 1);
+      ++it;
+#pragma unroll
+      for (int i = 0; i < Epi::kIn; ++i) stage_load16(wbuf + i * TC_CHUNK16_BYTES, lane, in[i]);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[16];
+      uint32_t o[Epi::kOut][OUTW];
+      tmem_ld16(taddr + 32 * k + 16 * h, v);
+      if constexpr (Epi::kPaired) {
+        float w[16];
+        tmem_ld16(taddr + GW + 32 * k + 16 * h, w);
+        if (h == 1 && k == NCH - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tmem_empty_remote);
+        }
+        epi.compute(c0 + 16 * h, v, w, o);
+      } else {
+        if (h == 1 && k == NCH - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tmem_empty_remote);
+        }
+        if constexpr (Epi::kIn > 0) {
+          uint32_t inh[Epi::kIn][8];
+#pragma unroll
+          for (int i = 0; i < Epi::kIn; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) inh[i][j] = in[i][8 * h + j];
+          epi.compute(c0 + 16 * h, v, inh, o);
+        } else {
+          epi.compute(c0 + 16 * h, v, o);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < Epi::kOut; ++i) {
+        if constexpr (Epi::kOutF32) stage_store32h(wbuf + i * OCH, lane, h, o[i]);
+        else stage_store16h(wbuf + i * OCH, lane, h, o[i]);
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < Epi::kOut; ++i) tma_store_4d(om[i], wbuf + i * OCH, c0, r0, 0, b);
+      bulk_commit();
+    }
+  }
+  if (lane == 0) {
+    if (dbg & 4) bulk_wait_read<0>();
+    else bulk_wait_all();  // stores COMPLETE (not just read): the staging is free and the results are in global memory
+    if (flag != nullptr && !(dbg & 2)) {
+      // one release per CTA and task instead of one per warp: the warps count in shared memory (acq_rel, so the last
+      // arrival has observed the others' completed stores) and the 16th publishes all of them
+      fence_proxy_async_all();
+      uint32_t old;
+      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(done_cnt) : "memory");
+      if ((old & (TC_EPI_WARPS - 1)) == TC_EPI_WARPS - 1) red_release_add_u32(flag, (uint32_t)TC_EPI_WARPS);
+    }
+  }
+  __syncwarp();
+}
+
+template <bool SAVE>
+constexpr int mega_warp_bytes() { return SAVE ? 3 * TC_CHUNK16_BYTES : 2 * TC_CHUNK16_BYTES; }
+constexpr int MEGA_STAGE_BYTES = TC_A_BYTES + (MEGA_BN / 2) * 128;
+template <bool SAVE>
+constexpr int mega_stages() {
+  return (TC_SMEM_LIMIT - 1024 - TC_BAR_BYTES - TC_EPI_WARPS * mega_warp_bytes<SAVE>()) / MEGA_STAGE_BYTES;
+}
+template <bool SAVE>
+constexpr size_t mega_smem_bytes() {
+  return (size_t)mega_stages<SAVE>() * MEGA_STAGE_BYTES + TC_EPI_WARPS * mega_warp_bytes<SAVE>() + TC_BAR_BYTES + 1024;
+}
+
+template <bool SAVE>
+__global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid_constant__ MegaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int STAGES = mega_stages<SAVE>();
+  constexpr int WB = mega_warp_bytes<SAVE>();
+  static_assert(STAGES >= 3, "staging leaves no room for the operand pipeline");
+  static_assert(2 * TC_CHUNK16_BYTES >= TC_CHUNK32_BYTES, "fp32 chunk must fit the per-warp staging");
+  const TcSmem s = tc_carve<STAGES>(smem_raw, MEGA_STAGE_BYTES, TC_EPI_WARPS * WB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  uint32_t* done_cnt = s.tmem_ptr + 2;  // [4] per-task arrival counters of the epilogue warps (barrier area)
+  static_assert((2 * STAGES + 4 + TC_EPI_WARPS) * 8 + 8 + 4 * 4 + 8 <= TC_BAR_BYTES, "barrier area too small");
+  if (threadIdx.x < 4) done_cnt[threadIdx.x] = 0;
+  pdl_trigger();
+  tc_setup<STAGES>(s, warp, lane, 2 * MEGA_BN, TC_EPI_WARPS);
+  const uint32_t tmem_base = *s.tmem_ptr;
+  pdl_wait();
+  const int Crp = p.kb_h * TC_BK;
+  const uint32_t gtarget = (uint32_t)p.ngt * 2u * TC_EPI_WARPS, rtarget = 2u * TC_EPI_WARPS;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load = [&](const CUtensorMap* am, int ak, int at, int ab, const CUtensorMap* bm, int bk, int bn) {
+        mbar_wait(&s.empty[stage], phase ^ 1);
+        const uint32_t sa = smem_u32(s.stages + stage * MEGA_STAGE_BYTES);
+        if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * MEGA_STAGE_BYTES);
+        const uint32_t bar = mapa_shared(smem_u32(&s.full[stage]), 0);
+        tma_load_4d(sa, am, bar, ak, at, 0, ab);
+        tma_load_2d(sa + TC_A_BYTES, bm, bar, bk, bn);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      for (int task = pair; task < p.total_tasks; task += npairs) {
+        const MegaTask t = mega_decode(p, task);
+        if (t.type == MEGA_NONE) continue;
+        const int b = t.rt / p.tiles_per_batch, tb = t.rt - b * p.tiles_per_batch;
+        const int t0 = tb * (2 * TC_BM) + rank * TC_BM;
+        const int nrow = rank * (MEGA_BN / 2);
+        if (t.type == MEGA_G) {
+          if (t.layer > 0 && !(p.dbg & 1)) {
+            const uint32_t* f1 = mega_rflag(p, t.layer - 1, t.rt);
+            mega_wait_flags3(tb > 0 ? f1 - 1 : f1, f1, tb + 1 < p.tiles_per_batch ? f1 + 1 : f1, rtarget);
+            fence_proxy_async_all();
+          }
+          const int n0 = t.nt * MEGA_BN + nrow;
+          for (int sg = 0; sg < p.taps; ++sg) {
+            const int shift = (sg - (p.taps - 1) / 2) * (1 << t.layer);
+            for (int kb = 0; kb < p.kb_h; ++kb)
+              load(&p.hin_op[t.layer], kb * TC_BK, t0 + shift, b, &p.pa[t.layer], sg * Crp + kb * TC_BK, n0);
+          }
+          for (int kb = 0; kb < p.kb_c; ++kb)
+            load(&p.cond_op, kb * TC_BK, t0, b, &p.pa[t.layer], p.taps * Crp + kb * TC_BK, n0);
+        } else if (t.type == MEGA_R) {
+          if (!(p.dbg & 1)) mega_wait_flag(mega_gflag(p, t.layer, t.rt), gtarget);
+          fence_proxy_async_all();
+          for (int kb = 0; kb < p.kb_g; ++kb) load(&p.g_op[t.layer], kb * TC_BK, t0, b, &p.pb[t.layer], kb * TC_BK, nrow);
+        } else {
+          if (!(p.dbg & 1)) mega_wait_flag(mega_gflag(p, p.depth - 1, t.rt), gtarget);
+          fence_proxy_async_all();
+          for (int j = 0; j < p.depth; ++j)
+            for (int kb = 0; kb < p.kb_g; ++kb)
+              load(&p.g_op[j], kb * TC_BK, t0, b, &p.ps, (j * p.kb_g + kb) * TC_BK, nrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int task = pair; task < p.total_tasks; task += npairs) {
+        const MegaTask t = mega_decode(p, task);
+        if (t.type == MEGA_NONE) continue;
+        const int total_kb = t.type == MEGA_G ? p.taps * p.kb_h + p.kb_c : (t.type == MEGA_R ? p.kb_g : p.depth * p.kb_g);
+        mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * MEGA_BN;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&s.full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(s.stages + stage * MEGA_STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa, p.desc_lbo, p.desc_sbo);
+          const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES, p.desc_lbo, p.desc_sbo);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&s.empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&s.tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int cg = e >> 2;
+    const uint32_t wbuf = smem_u32(s.epi + e * WB);
+    uint64_t* ibar = s.in_bar + e;
+    const uint32_t tmem_empty_addr = mapa_shared(smem_u32(&s.tmem_empty[0]), 0);
+    const GateTcEpi<SAVE> gate_epi{nullptr, p.Cd, p.f16};
+    const SplitTcEpi<true> split_epi{nullptr, p.f16};
+    const StoreTcEpi store_epi{nullptr};
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t it = 0;
+    uint32_t seq = 0;  // tasks done by this pair; warps of a CTA are never more than two tasks apart (TMEM double buffer)
+    for (int task = pair; task < p.total_tasks; task += npairs) {
+      const MegaTask t = mega_decode(p, task);
+      if (t.type == MEGA_NONE) continue;
+      const uint32_t dcnt = smem_u32(done_cnt + (seq++ & 3));
+      const int b = t.rt / p.tiles_per_batch, tb = t.rt - b * p.tiles_per_batch;
+      const int r0 = tb * (2 * TC_BM) + rank * TC_BM + q * 32;
+      const uint32_t tile = tmem_base + acc * MEGA_BN;
+      const uint32_t te = tmem_empty_addr + 8 * acc;
+      if (t.type == MEGA_G) {
+        mega_epilogue_task<GateTcEpi<SAVE>, MEGA_BN / 2>(gate_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf,
+                                                         ibar, it, &p.g_c16[t.layer], &p.a_c16[t.layer], &p.b_c16[t.layer],
+                                                         nullptr, nullptr, b, r0, t.nt * (MEGA_BN / 2),
+                                                         mega_gflag(p, t.layer, t.rt), dcnt, p.dbg);
+      } else if (t.type == MEGA_R) {
+        if (lane == 0) {  // chunk 0 of the layer input's (hi, lo) pair, ahead of the accumulator
+          if (!(p.dbg & 1)) mega_wait_flag(mega_gflag(p, t.layer, t.rt), gtarget);  // implies R(layer-1, rt) is complete
+          fence_proxy_async_all();
+          mbar_arrive_expect_tx(ibar, 2 * TC_CHUNK16_BYTES);
+          const int c0 = cg * (MEGA_BN / 4);
+          tma_load_4d_local(wbuf, &p.hi_c16[t.layer], smem_u32(ibar), c0, r0, 0, b);
+          tma_load_4d_local(wbuf + TC_CHUNK16_BYTES, &p.lo_c16[t.layer], smem_u32(ibar), c0, r0, 0, b);
+        }
+        __syncwarp();
+        mega_epilogue_task<SplitTcEpi<true>, MEGA_BN>(split_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf, ibar,
+                                                      it, &p.hi_c16[t.layer + 1], &p.lo_c16[t.layer + 1], nullptr,
+                                                      &p.hi_c16[t.layer], &p.lo_c16[t.layer], b, r0, 0,
+                                                      mega_rflag(p, t.layer, t.rt), dcnt, p.dbg);
+      } else {
+        mega_epilogue_task<StoreTcEpi, MEGA_BN>(store_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf, ibar, it,
+                                                &p.skip_c32, nullptr, nullptr, nullptr, nullptr, b, r0, 0, nullptr, dcnt, p.dbg);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_teardown(tmem_base, warp, 2 * MEGA_BN);
+}
+
+}  // namespace cmwg

@@ -163,6 +163,7 @@ struct FwdLayout {
   size_t hi2[2];  // ping-pong [rows][Cr] (inference; training keeps hi per layer in `saved`)
   size_t lo2[2];  // ping-pong [rows][Cr]
   size_t gl[CMWG_MAX_DEPTH];  // per-layer gate outputs (inference; the skip GEMM reads all of them at the end)
+  size_t flags;   // [depth][2][row tiles] dependency counters of the single-kernel forward (engine_mega.cuh)
   size_t ws_total;
   // saved (training): per layer
   size_t s_hin[CMWG_MAX_DEPTH], s_g[CMWG_MAX_DEPTH], s_a[CMWG_MAX_DEPTH], s_b[CMWG_MAX_DEPTH];
@@ -198,6 +199,7 @@ inline void make_fwd_layout(const WnDims& d, int B, int T, FwdLayout* L) {
     for (int j = 0; j < 2; ++j) { L->hi2[j] = take(rows * d.Cr * 2); L->lo2[j] = take(rows * d.Cr * 2); }
     for (int i = 0; i < d.depth; ++i) L->gl[i] = take(rows * d.Cd * 2);
   }
+  L->flags = take((size_t)d.depth * 2 * B * d.H * ceil_div(T, 256) * 4);
   L->ws_total = off;
   off = 0;
   for (int i = 0; i < d.depth; ++i) {

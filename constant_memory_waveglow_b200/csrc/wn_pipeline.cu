@@ -14,6 +14,7 @@
 //   dx GEMM     dh_i = dh_{i+1} + sum_tap dpre[row - (tap-c)*2^i] W_tap
 #include "engine_ff.cuh"
 #include "engine_tc.cuh"
+#include "engine_mega.cuh"
 #include "epilogues.cuh"
 #include "epilogues_tc.cuh"
 #include "wn_kernels.cuh"
@@ -131,6 +132,80 @@ static inline size_t line_state_slab_bytes(const WnDims& d, int B, int T) {
   return align_up((size_t)B * d.H * T * d.Cr * d.opsize, 1024);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// single-kernel forward (engine_mega.cuh): every gate / residual / skip GEMM tile of the WN as one task list
+// ------------------------------------------------------------------------------------------------
+static bool mega_enabled() {  // read at every call: tests flip CMWG_MEGA inside one process
+  const char* v = getenv("CMWG_MEGA");
+  return !(v && v[0] == '0');
+}
+
+static inline bool mega_shapes_ok(const WnDims& d, int B, int T) {
+  return d.tc && d.H == 1 && !d.bias && d.depth >= 1 && d.depth <= MEGA_D && d.Cr == 256 && d.Cs == 256 &&
+         d.Cd % 128 == 0 && d.bn_gate == 256 && (((d.radix - 1) / 2) << (d.depth - 1)) <= 2 * TC_BM && d.radix <= 7 &&
+         B >= 1 && T >= 1;
+}
+
+template <bool SAVE>
+static int mega_launch(const MegaParams& p, cudaStream_t st) {
+  auto kern = wn_fwd_mega_kernel<SAVE>;
+  constexpr size_t smem = mega_smem_bytes<SAVE>();
+  static_assert(smem <= TC_SMEM_LIMIT, "shared memory budget exceeded");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CMWG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int pairs = std::min(p.total_tasks, num_sms() / 2);
+  ProfScope prof(st, CMWG_KCLASS_FWDFUSED);
+  void* args[1] = {(void*)&p};
+  CMWG_PROPAGATE(tc_launch_pairs((const void*)kern, smem, pairs, args, st));
+  CMWG_COUNT_LAUNCH();
+  return CMWG_OK;
+}
+
+// hin(i) / hlo(i): (hi, lo) slabs of layer i's input; gop(i), sa(i), sb(i): gate output and saved tanh / sigmoid
+static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLayout& FL, const uint8_t* pk, uint8_t* ws,
+                           const void* ycl, int B, int T, bool save, int f16, void* const* hin, void* const* hlo,
+                           void* const* gop, void* const* sa, void* const* sb, float* skip32, cudaStream_t st) {
+  MegaParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < d.depth; ++i) {
+    CMWG_PROPAGATE(get_slab_map(&p.hin_op[i], hin[i], d.Cr, d.Cr, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
+    CMWG_PROPAGATE(get_slab_map(&p.g_op[i], gop[i], d.Cd, d.Cd, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
+    CMWG_PROPAGATE(get_matrix_map(&p.pa[i], pk + PL.PA[i], d.KA, d.npadA, MEGA_BN / 2, f16));
+    if (i < d.depth - 1) CMWG_PROPAGATE(get_matrix_map(&p.pb[i], pk + PL.PB[i], d.ldPB, d.nb(i), MEGA_BN / 2, f16));
+    CMWG_PROPAGATE(get_slab_map(&p.g_c16[i], gop[i], d.Cd, d.Cd, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+    if (save) {
+      CMWG_PROPAGATE(get_slab_map(&p.a_c16[i], sa[i], d.Cd, d.Cd, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+      CMWG_PROPAGATE(get_slab_map(&p.b_c16[i], sb[i], d.Cd, d.Cd, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+    }
+    CMWG_PROPAGATE(get_slab_map(&p.hi_c16[i], hin[i], d.Cr, d.Cr, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+    CMWG_PROPAGATE(get_slab_map(&p.lo_c16[i], hlo[i], d.Cr, d.Cr, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+  }
+  CMWG_PROPAGATE(get_slab_map(&p.cond_op, ycl, d.auxp, d.auxp, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
+  CMWG_PROPAGATE(get_matrix_map(&p.ps, pk + PL.PS, d.ldPS, d.Cs, MEGA_BN / 2, f16));
+  CMWG_PROPAGATE(get_slab_map(&p.skip_c32, skip32, d.Cs, d.Cs, T, 1, B, 32, 32, f16, TC_MAP_CHUNK32));
+  p.depth = d.depth; p.B = B; p.T = T;
+  p.tiles_per_batch = ceil_div(T, 2 * TC_BM);
+  p.RT = B * p.tiles_per_batch;
+  p.ngt = d.npadA / MEGA_BN;
+  p.taps = d.R; p.kb_h = d.Crp / TC_BK; p.kb_c = d.auxp / TC_BK; p.kb_g = d.Cdp / TC_BK;
+  p.Cd = d.Cd; p.f16 = f16;
+  p.idesc = make_idesc(f16, 2 * TC_BM, MEGA_BN, 0, 0);
+  p.desc_lbo = 1u; p.desc_sbo = 1024u >> 4;
+  // R(u) must come after G(u) and before G(u + RT - 1) (its right-hand neighbour one layer up): lag <= RT - 2
+  static const int lag_env = [] { const char* v = getenv("CMWG_MEGA_LAG"); return v ? atoi(v) : 64; }();
+  p.lag = std::max(0, std::min(lag_env, p.RT - 2));
+  p.total_tasks = (d.depth * p.RT + p.lag) * (p.ngt + 1) + p.RT;
+  static const int dbg_env = [] { const char* v = getenv("CMWG_MEGA_DBG"); return v ? atoi(v) : 0; }();
+  p.dbg = dbg_env;
+  p.flags = reinterpret_cast<uint32_t*>(ws + FL.flags);
+  CMWG_CHECK_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)d.depth * 2 * p.RT * 4, st));
+  return save ? mega_launch<true>(p, st) : mega_launch<false>(p, st);
+}
+
 template <typename OpT>
 static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, long long x_bs, const void* ycl, int B,
                            int T, void* workspace, void* saved, float* lst, cudaStream_t st, LineWin lw = LineWin()) {
@@ -180,7 +255,20 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
                                        d.Cr, B, d.H * T, o32, oop, olo, f16, st, t_off, t_n));
   }
 
-  for (int i = 0; i < d.depth; ++i) {
+  bool fused = false;
+  if constexpr (TC) {
+    if (mega_enabled() && !stt && lw.nh == 0 && mega_shapes_ok(d, B, T)) {
+      void *hin[MEGA_D], *hlo[MEGA_D], *gop[MEGA_D], *sa[MEGA_D], *sb[MEGA_D];
+      for (int i = 0; i < d.depth; ++i) {
+        hin[i] = hin_op(i); hlo[i] = hlo_op(i); gop[i] = g_op(i);
+        sa[i] = save ? sv + FL.s_a[i] : nullptr; sb[i] = save ? sv + FL.s_b[i] : nullptr;
+      }
+      CMWG_PROPAGATE(wn_forward_mega(d, PL, FL, pk, ws, ycl, B, T, save, f16, hin, hlo, gop, sa, sb, skip32, st));
+      fused = true;
+    }
+  }
+
+  for (int i = 0; i < d.depth && !fused; ++i) {
     const int dil = 1 << i;
     const bool last = (i == d.depth - 1);
     // ---- gate GEMM
@@ -261,7 +349,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
       CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
     }
   }
-  if constexpr (TC) {
+  if constexpr (TC) if (!fused) {
     // ---- skip GEMM: cum_skip = sum_i g_i W_skip,i^T as ONE GEMM with the layers concatenated along K
     // (accumulation across layers happens in TMEM; the fp32 result is written once)
     GemmDesc g;

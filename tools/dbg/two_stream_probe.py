@@ -1,4 +1,4 @@
-"""Does running the WN forward as two half-batch chains on two streams beat one full-batch chain (wave quantisation)?"""
+"""Does running the WN forward as sub-batch chains (one stream: L2 residency; two streams: wave quantisation) beat one full-batch chain?"""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -12,17 +12,25 @@ B, T = 24, 2000
 x = torch.randn(B, 8, T, device=dev)
 y = torch.randn(B, 80, T, device=dev)
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+xs = {n: [x[i:i + n].contiguous() for i in range(0, B, n)] for n in (4, 6, 8, 12)}
+ys = {n: [y[i:i + n].contiguous() for i in range(0, B, n)] for n in (4, 6, 8, 12)}
 
 def full(save):
     wn._cmwg_forward(x, y, save=save, prec="bf16")
+
+def chunks(n):
+    def f(save):
+        for a, b in zip(xs[n], ys[n]):
+            wn._cmwg_forward(a, b, save=save, prec="bf16")
+    return f
 
 def halves(save):
     cur = torch.cuda.current_stream()
     s1.wait_stream(cur); s2.wait_stream(cur)
     with torch.cuda.stream(s1):
-        wn._cmwg_forward(x[:12], y[:12], save=save, prec="bf16")
+        wn._cmwg_forward(xs[12][0], ys[12][0], save=save, prec="bf16")
     with torch.cuda.stream(s2):
-        wn._cmwg_forward(x[12:], y[12:], save=save, prec="bf16")
+        wn._cmwg_forward(xs[12][1], ys[12][1], save=save, prec="bf16")
     cur.wait_stream(s1); cur.wait_stream(s2)
 
 def timeit(fn, save, n=20):
@@ -35,4 +43,5 @@ def timeit(fn, save, n=20):
     return a.elapsed_time(b) / n
 
 for save in (False, True):
-    print(f"save={save}: full B=24 {timeit(full, save):.3f} ms   two streams 2 x B=12 {timeit(halves, save):.3f} ms")
+    print(f"save={save}: full B=24 {timeit(full, save):.3f} ms | 2x12 seq {timeit(chunks(12), save):.3f} | 3x8 seq {timeit(chunks(8), save):.3f} | "
+          f"4x6 seq {timeit(chunks(6), save):.3f} | 6x4 seq {timeit(chunks(4), save):.3f} | two streams 2x12 {timeit(halves, save):.3f} ms", flush=True)
