@@ -37,6 +37,8 @@ FWD_GFLOP_PER_SEGMENT = 214.023  # algorithmic, counted on the reference (BASELI
 # kernel ends), from the `ncu --set full` capture summarised in profiles/r01_v5_ncu_gemm_summary.txt.
 # Algorithmic bytes of the same launch: 48000 x (512 hi + 256 y in, 512 g out) = 61.4 MB.
 GATE_TRAFFIC_BYTES_PER_LAUNCH = 38.9e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one wn_fwd_mega_kernel launch at B=24 (ncu --set full, profiles/r01_v9_*)
+FUSED_TRAFFIC_BYTES_PER_LAUNCH = 1143.1e6
 TRAIN_GFLOP_PER_SEGMENT = 4 * FWD_GFLOP_PER_SEGMENT
 SYNTH_FRAMES = 862               # 10 s at 22.05 kHz -> 220672 samples (model/base.py:47-48)
 
@@ -410,7 +412,7 @@ def run_b200(args):
     kn = (C.c_longlong * 8)()
     _lib.check(lib.cmwg_profile_collect(kms, kn), "profile_collect")
     lib.cmwg_profile_enable(0)
-    names = ["gate", "resskip", "dgate", "dx", "dcond", "wgrad"]
+    names = ["gate", "resskip", "dgate", "dx", "dcond", "wgrad", "fwdfused"]
     kern = {n: {"ms": kms[i], "launches": int(kn[i])} for i, n in enumerate(names)}
 
     # ---- synthesis (config 3): sigma 0.6, 10 s utterances, utterance-sharded, no collective
@@ -456,6 +458,14 @@ def run_b200(args):
     rows = B * (SEGMENT // LJ["n_group"])
     gate_flops = 2.0 * rows * 512 * (3 * 256 + 80)          # algorithmic: 80 mel rows, not the padded 128
     gate = kern["gate"]
+    roof_kernel = "tc_gemm_kernel<gate epilogue> (dilated conv + conditioning GEMM)"
+    roof_traffic = GATE_TRAFFIC_BYTES_PER_LAUNCH
+    if kern["fwdfused"]["launches"] > 0:
+        # single-kernel WN forward: per launch all 8 gate GEMMs, 7 residual and 8 skip contractions of one WN
+        gate = kern["fwdfused"]
+        gate_flops = rows * (8 * 2.0 * 512 * (3 * 256 + 80) + 7 * 2.0 * 256 * 256 + 8 * 2.0 * 256 * 256)
+        roof_kernel = "wn_fwd_mega_kernel (all gate / residual / skip GEMM tiles of one WN forward)"
+        roof_traffic = FUSED_TRAFFIC_BYTES_PER_LAUNCH
     gate_ms = gate["ms"] / max(gate["launches"], 1)
     achieved = gate_flops / (gate_ms * 1e-3) / 1e12 if gate_ms > 0 else 0.0
     total_kernel_ms = sum(v["ms"] for v in kern.values())
@@ -475,9 +485,9 @@ def run_b200(args):
         "gpu_launches": launches,
         "ms_per_timed_step": {"device_resident": step_ms[False], "e2e": step_ms[True]},
         "train_tflops_per_gpu": B * TRAIN_GFLOP_PER_SEGMENT / (ms / args.steps),
-        "roofline": {"bound": "tensor", "kernel": "tc_gemm_kernel<gate epilogue> (dilated conv + conditioning GEMM)",
+        "roofline": {"bound": "tensor", "kernel": roof_kernel,
                      "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tflops_sustained"], "traffic": GATE_TRAFFIC_BYTES_PER_LAUNCH,
+                     "frac": achieved / pk["tflops_sustained"], "traffic": roof_traffic,
                      "peak_source": pk["source"],
                      "flops_per_launch": gate_flops, "ms_per_launch": gate_ms, "launches_per_step": gate["launches"],
                      "share_of_gemm_time": gate["ms"] / total_kernel_ms if total_kernel_ms else None,

@@ -46,6 +46,8 @@ struct alignas(64) MegaParams {
   uint32_t idesc, desc_lbo, desc_sbo;
   int lag;                      // residual tiles trail their gate tiles by `lag` row-tile slots (< RT - 1)
   int total_tasks;
+  int lagged;                   // signal a unit's completion one unit later (its stores complete behind the next unit's work)
+  long long* clk;               // nullptr, or [CTAs][18 warps][16] cycle accumulators (CMWG_MEGA_CLK: where the roles wait)
   int dbg;                      // timing experiments only (CMWG_MEGA_DBG): 1 no producer waits, 2 no signals, 4 no wait_all
 };
 
@@ -59,6 +61,24 @@ __device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_complete() {  // all but the N most recent bulk groups of this thread are COMPLETE
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// completion signal of one unit (one TMEM buffer's worth of epilogue) of one warp
+struct MegaSig {
+  uint32_t* flag;     // global dependency counter (nullptr: nothing depends on this unit)
+  uint32_t cnt;       // shared-memory arrival counter of the CTA's epilogue warps for this unit
+};
+// One release per CTA and unit instead of one per warp: the warps count in shared memory (acq_rel, so the last arrival
+// has observed the others' completed stores) and the 16th publishes all of them.
+__device__ __forceinline__ void mega_signal(const MegaSig& sg) {
+  if (sg.flag == nullptr) return;
+  asm volatile("fence.proxy.async;" ::: "memory");
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(sg.cnt) : "memory");
+  if ((old & (TC_EPI_WARPS - 1)) == TC_EPI_WARPS - 1) red_release_add_u32(sg.flag, (uint32_t)TC_EPI_WARPS);
+}
 
 __device__ __forceinline__ void mega_wait_flag(const uint32_t* p, uint32_t target) {
   if (ld_acquire_u32(p) >= target) return;
@@ -75,7 +95,8 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   return v;
 }
 // up to three counters polled with independent relaxed loads (one L2 round trip), then one acquire fence
-__device__ __forceinline__ void mega_wait_flags3(const uint32_t* a, const uint32_t* b, const uint32_t* c, uint32_t target) {
+__device__ __forceinline__ void mega_wait_flags3(const uint32_t* a, const uint32_t* b, const uint32_t* c, uint32_t target,
+                                                 bool fence = true) {
   const long long t0 = clock64();
   while (true) {
     const uint32_t va = ld_relaxed_u32(a), vb = ld_relaxed_u32(b), vc = ld_relaxed_u32(c);
@@ -83,7 +104,7 @@ __device__ __forceinline__ void mega_wait_flags3(const uint32_t* a, const uint32
     __nanosleep(40);
     if (clock64() - t0 > 4000000000ll) __trap();
   }
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  if (fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
 struct MegaTask {
@@ -121,21 +142,25 @@ __device__ __forceinline__ uint32_t* mega_rflag(const MegaParams& p, int layer, 
 
 // Epilogue of ONE task for one warp: GW epilogue columns per tile, four column groups (one per warp of the lane quadrant).
 // kIn > 0: in-place staging -- chunk inputs are TMA-loaded into the buffers the outputs are later stored from; the
-// caller has already issued chunk 0's inputs.  Ends with ALL of this warp's stores complete; then signals `flag`.
+// caller has already issued chunk 0's inputs and made sure the staging buffers are free.  Immediate mode: ends with ALL
+// of this warp's stores complete, then signals `flag`.  Lagged mode (`prev` != nullptr): waits only for the PREVIOUS unit's
+// stores (which completed behind this unit's work), signals that unit and leaves this one pending in `prev`.
 template <class Epi, int GW>
 __device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem_tile, uint64_t* tmem_full, uint32_t full_phase,
                                                    uint32_t tmem_empty_remote, int q, int cg, int lane, uint32_t wbuf,
                                                    uint64_t* ibar, uint32_t& it, const CUtensorMap* om0,
                                                    const CUtensorMap* om1, const CUtensorMap* om2, const CUtensorMap* im0,
-                                                   const CUtensorMap* im1, int b, int r0, int cbase, uint32_t* flag, uint32_t done_cnt, int dbg) {
+                                                   const CUtensorMap* im1, int b, int r0, int cbase, MegaSig sig, MegaSig* prev, int dbg, long long* tt) {
   constexpr int NCH = GW / 128;                      // 32-column chunks per warp
   constexpr int OUTW = Epi::kOutF32 ? 16 : 8;
   constexpr int OCH = Epi::kOutF32 ? TC_CHUNK32_BYTES : TC_CHUNK16_BYTES;
   const uint32_t taddr = tmem_tile + ((uint32_t)(q * 32) << 16) + cg * (GW / 4);
   const CUtensorMap* om[3] = {om0, om1, om2};
   const CUtensorMap* im[2] = {im0, im1};
+  const long long c_a = clock64();
   mbar_wait(tmem_full, full_phase);
   tc_fence_after();
+  const long long c_b = clock64();
 #pragma unroll 1
   for (int k = 0; k < NCH; ++k) {
     const int c0 = cbase + cg * (GW / 4) + 32 * k;
@@ -205,19 +230,23 @@ __device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem
       bulk_commit();
     }
   }
+  const long long c_c = clock64();
   if (lane == 0) {
-    if (dbg & 4) bulk_wait_read<0>();
-    else bulk_wait_all();  // stores COMPLETE (not just read): the staging is free and the results are in global memory
-    if (flag != nullptr && !(dbg & 2)) {
-      // one release per CTA and task instead of one per warp: the warps count in shared memory (acq_rel, so the last
-      // arrival has observed the others' completed stores) and the 16th publishes all of them
-      fence_proxy_async_all();
-      uint32_t old;
-      asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(done_cnt) : "memory");
-      if ((old & (TC_EPI_WARPS - 1)) == TC_EPI_WARPS - 1) red_release_add_u32(flag, (uint32_t)TC_EPI_WARPS);
+    if (dbg & 2) sig.flag = nullptr;
+    if (prev != nullptr) {
+      bulk_wait_complete<NCH>();  // this unit committed NCH groups: everything older is complete
+      mega_signal(*prev);
+      *prev = sig;
+    } else {
+      bulk_wait_all();            // stores COMPLETE (not just read): the results are in global memory
+      mega_signal(sig);
     }
   }
   __syncwarp();
+  tt[0] += c_b - c_a;            // waiting for the accumulator
+  tt[1] += c_c - c_b;            // drain + functor + staging + store issue (+ input waits)
+  tt[2] += clock64() - c_c;      // store completion + signal
+  tt[3] += 1;
 }
 
 template <bool SAVE>
@@ -257,8 +286,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_slot = 0, w_flag = 0;
+      const long long c_start = clock64();
       auto load = [&](const CUtensorMap* am, int ak, int at, int ab, const CUtensorMap* bm, int bk, int bn) {
+        const long long c0 = clock64();
         mbar_wait(&s.empty[stage], phase ^ 1);
+        w_slot += clock64() - c0;
         const uint32_t sa = smem_u32(s.stages + stage * MEGA_STAGE_BYTES);
         if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * MEGA_STAGE_BYTES);
         const uint32_t bar = mapa_shared(smem_u32(&s.full[stage]), 0);
@@ -272,12 +305,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid
         const int b = t.rt / p.tiles_per_batch, tb = t.rt - b * p.tiles_per_batch;
         const int t0 = tb * (2 * TC_BM) + rank * TC_BM;
         const int nrow = rank * (MEGA_BN / 2);
+        const long long cf = clock64();
         if (t.type == MEGA_G) {
           if (t.layer > 0 && !(p.dbg & 1)) {
             const uint32_t* f1 = mega_rflag(p, t.layer - 1, t.rt);
-            mega_wait_flags3(tb > 0 ? f1 - 1 : f1, f1, tb + 1 < p.tiles_per_batch ? f1 + 1 : f1, rtarget);
-            fence_proxy_async_all();
+            mega_wait_flags3(tb > 0 ? f1 - 1 : f1, f1, tb + 1 < p.tiles_per_batch ? f1 + 1 : f1, rtarget, !(p.dbg & 32));
+            if (!(p.dbg & 16)) fence_proxy_async_all();
           }
+          w_flag += clock64() - cf;
           const int n0 = t.nt * MEGA_BN + nrow;
           for (int sg = 0; sg < p.taps; ++sg) {
             const int shift = (sg - (p.taps - 1) / 2) * (1 << t.layer);
@@ -288,15 +323,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid
             load(&p.cond_op, kb * TC_BK, t0, b, &p.pa[t.layer], p.taps * Crp + kb * TC_BK, n0);
         } else if (t.type == MEGA_R) {
           if (!(p.dbg & 1)) mega_wait_flag(mega_gflag(p, t.layer, t.rt), gtarget);
-          fence_proxy_async_all();
+          if (!(p.dbg & 16)) fence_proxy_async_all();
+          w_flag += clock64() - cf;
           for (int kb = 0; kb < p.kb_g; ++kb) load(&p.g_op[t.layer], kb * TC_BK, t0, b, &p.pb[t.layer], kb * TC_BK, nrow);
         } else {
           if (!(p.dbg & 1)) mega_wait_flag(mega_gflag(p, p.depth - 1, t.rt), gtarget);
-          fence_proxy_async_all();
+          if (!(p.dbg & 16)) fence_proxy_async_all();
+          w_flag += clock64() - cf;
           for (int j = 0; j < p.depth; ++j)
             for (int kb = 0; kb < p.kb_g; ++kb)
               load(&p.g_op[j], kb * TC_BK, t0, b, &p.ps, (j * p.kb_g + kb) * TC_BK, nrow);
         }
+      }
+      if (p.clk) {
+        long long* o = p.clk + ((size_t)blockIdx.x * 18 + warp) * 16;
+        o[0] = w_slot; o[1] = w_flag; o[12] = clock64() - c_start;
       }
     }
   } else if (warp == 1) {
@@ -305,16 +346,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long w_empty = 0, w_full = 0;
+      const long long c_start = clock64();
       for (int task = pair; task < p.total_tasks; task += npairs) {
         const MegaTask t = mega_decode(p, task);
         if (t.type == MEGA_NONE) continue;
         const int total_kb = t.type == MEGA_G ? p.taps * p.kb_h + p.kb_c : (t.type == MEGA_R ? p.kb_g : p.depth * p.kb_g);
+        long long c0 = clock64();
         mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        w_empty += clock64() - c0;
         const uint32_t d_tmem = tmem_base + acc * MEGA_BN;
         for (int kb = 0; kb < total_kb; ++kb) {
+          c0 = clock64();
           mbar_wait(&s.full[stage], phase);
           tc_fence_after();
+          w_full += clock64() - c0;
           const uint32_t sa = smem_u32(s.stages + stage * MEGA_STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(sa, p.desc_lbo, p.desc_sbo);
           const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES, p.desc_lbo, p.desc_sbo);
@@ -327,6 +374,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid
         umma_commit(&s.tmem_full[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
+      }
+      if (p.clk) {
+        long long* o = p.clk + ((size_t)blockIdx.x * 18 + warp) * 16;
+        o[0] = w_empty; o[1] = w_full; o[12] = clock64() - c_start;
       }
     }
   } else {
@@ -342,40 +393,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t it = 0;
-    uint32_t seq = 0;  // tasks done by this pair; warps of a CTA are never more than two tasks apart (TMEM double buffer)
+    uint32_t seq = 0;  // units done by this pair; warps of a CTA are never more than two units apart (TMEM double buffer)
+    long long tt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long c_start = clock64();
+    MegaSig pending{nullptr, 0};
+    MegaSig* prev = p.lagged ? &pending : nullptr;
+    bool prev_alt = false;  // the previous unit staged through ONE of the two 2 KB buffers (gate tile without saves)
     for (int task = pair; task < p.total_tasks; task += npairs) {
       const MegaTask t = mega_decode(p, task);
       if (t.type == MEGA_NONE) continue;
-      const uint32_t dcnt = smem_u32(done_cnt + (seq++ & 3));
       const int b = t.rt / p.tiles_per_batch, tb = t.rt - b * p.tiles_per_batch;
       const int r0 = tb * (2 * TC_BM) + rank * TC_BM + q * 32;
       const uint32_t tile = tmem_base + acc * MEGA_BN;
       const uint32_t te = tmem_empty_addr + 8 * acc;
+      const uint32_t dcnt = smem_u32(done_cnt + (seq & 3));
+      const bool alt = !SAVE && t.type == MEGA_G;
+      const uint32_t ubuf = wbuf + (alt ? (seq & 1) * TC_CHUNK16_BYTES : 0);
+      ++seq;
+      if (p.dbg & 8) {  // timing experiment: no epilogue work at all
+        mbar_wait(&s.tmem_full[acc], acc_phase);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(te);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
+      // lagged mode: the previous unit's stores may still be reading its staging (not if both use alternate buffers)
+      if (p.lagged && !(alt && prev_alt)) {
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+      }
+      prev_alt = alt;
       if (t.type == MEGA_G) {
-        mega_epilogue_task<GateTcEpi<SAVE>, MEGA_BN / 2>(gate_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf,
+        mega_epilogue_task<GateTcEpi<SAVE>, MEGA_BN / 2>(gate_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, ubuf,
                                                          ibar, it, &p.g_c16[t.layer], &p.a_c16[t.layer], &p.b_c16[t.layer],
                                                          nullptr, nullptr, b, r0, t.nt * (MEGA_BN / 2),
-                                                         mega_gflag(p, t.layer, t.rt), dcnt, p.dbg);
+                                                         MegaSig{mega_gflag(p, t.layer, t.rt), dcnt}, prev, p.dbg, tt);
       } else if (t.type == MEGA_R) {
         if (lane == 0) {  // chunk 0 of the layer input's (hi, lo) pair, ahead of the accumulator
           if (!(p.dbg & 1)) mega_wait_flag(mega_gflag(p, t.layer, t.rt), gtarget);  // implies R(layer-1, rt) is complete
           fence_proxy_async_all();
           mbar_arrive_expect_tx(ibar, 2 * TC_CHUNK16_BYTES);
           const int c0 = cg * (MEGA_BN / 4);
-          tma_load_4d_local(wbuf, &p.hi_c16[t.layer], smem_u32(ibar), c0, r0, 0, b);
-          tma_load_4d_local(wbuf + TC_CHUNK16_BYTES, &p.lo_c16[t.layer], smem_u32(ibar), c0, r0, 0, b);
+          tma_load_4d_local(ubuf, &p.hi_c16[t.layer], smem_u32(ibar), c0, r0, 0, b);
+          tma_load_4d_local(ubuf + TC_CHUNK16_BYTES, &p.lo_c16[t.layer], smem_u32(ibar), c0, r0, 0, b);
         }
         __syncwarp();
-        mega_epilogue_task<SplitTcEpi<true>, MEGA_BN>(split_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf, ibar,
+        mega_epilogue_task<SplitTcEpi<true>, MEGA_BN>(split_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, ubuf, ibar,
                                                       it, &p.hi_c16[t.layer + 1], &p.lo_c16[t.layer + 1], nullptr,
                                                       &p.hi_c16[t.layer], &p.lo_c16[t.layer], b, r0, 0,
-                                                      mega_rflag(p, t.layer, t.rt), dcnt, p.dbg);
+                                                      MegaSig{mega_rflag(p, t.layer, t.rt), dcnt}, prev, p.dbg, tt + 4);
       } else {
-        mega_epilogue_task<StoreTcEpi, MEGA_BN>(store_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf, ibar, it,
-                                                &p.skip_c32, nullptr, nullptr, nullptr, nullptr, b, r0, 0, nullptr, dcnt, p.dbg);
+        mega_epilogue_task<StoreTcEpi, MEGA_BN>(store_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, ubuf, ibar, it,
+                                                &p.skip_c32, nullptr, nullptr, nullptr, nullptr, b, r0, 0,
+                                                MegaSig{nullptr, dcnt}, prev, p.dbg, tt + 8);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) {  // flush: the last unit's stores, and its signal in lagged mode
+      bulk_wait_all();
+      if (p.lagged) mega_signal(pending);
+      if (p.clk) {
+        long long* o = p.clk + ((size_t)blockIdx.x * 18 + warp) * 16;
+        for (int i = 0; i < 12; ++i) o[i] = tt[i];
+        o[12] = clock64() - c_start;
+      }
     }
   }
   tc_teardown(tmem_base, warp, 2 * MEGA_BN);

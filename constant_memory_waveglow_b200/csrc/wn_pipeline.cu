@@ -136,6 +136,7 @@ static inline size_t line_state_slab_bytes(const WnDims& d, int B, int T) {
 // ------------------------------------------------------------------------------------------------
 // single-kernel forward (engine_mega.cuh): every gate / residual / skip GEMM tile of the WN as one task list
 // ------------------------------------------------------------------------------------------------
+static long long* g_mega_clk = nullptr;
 static bool mega_enabled() {  // read at every call: tests flip CMWG_MEGA inside one process
   const char* v = getenv("CMWG_MEGA");
   return !(v && v[0] == '0');
@@ -201,6 +202,24 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
   p.total_tasks = (d.depth * p.RT + p.lag) * (p.ngt + 1) + p.RT;
   static const int dbg_env = [] { const char* v = getenv("CMWG_MEGA_DBG"); return v ? atoi(v) : 0; }();
   p.dbg = dbg_env;
+  {
+    // lagged completion signals are deadlock-free when no unit can depend, even transitively, on the unit its own pair
+    // ran just before it: every dependency points >= D entries back and a pair's consecutive units are <= 2 * pairs apart
+    const int pairs = std::min(p.total_tasks, num_sms() / 2);
+    const int per_slot = p.ngt + 1;
+    const int D = std::min(per_slot * p.lag + 1, per_slot * (p.RT - 1 - p.lag) - 2);
+    const char* v = getenv("CMWG_MEGA_LAGGED");
+    p.lagged = (D > 2 * pairs + 8 && v && v[0] == '1') ? 1 : 0;  // opt-in: measured slower (0.51 vs 0.476 ms at the LJ shape)
+  }
+  {
+    // CMWG_MEGA_CLK=1: per-role cycle accumulators of the LAST launch, read back with cmwg_mega_clk_read (tools only)
+    const char* v = getenv("CMWG_MEGA_CLK");
+    if (v && v[0] == '1') {
+      if (!g_mega_clk) CMWG_CHECK_CUDA(cudaMalloc(&g_mega_clk, (size_t)256 * 18 * 16 * sizeof(long long)));
+      CMWG_CHECK_CUDA(cudaMemsetAsync(g_mega_clk, 0, (size_t)256 * 18 * 16 * sizeof(long long), st));
+      p.clk = g_mega_clk;
+    }
+  }
   p.flags = reinterpret_cast<uint32_t*>(ws + FL.flags);
   CMWG_CHECK_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)d.depth * 2 * p.RT * 4, st));
   return save ? mega_launch<true>(p, st) : mega_launch<false>(p, st);
@@ -763,6 +782,12 @@ size_t cmwg_wn_packed_bytes(const cmwg_wn_config* cfg) {
   WnDims d;
   if (make_dims(cfg, &d) != CMWG_OK) return 0;
   return make_packed_layout(d).total;
+}
+
+int cmwg_mega_clk_read(long long* host, int n) {
+  if (!cmwg::g_mega_clk) return CMWG_ERR_ARG;
+  cudaError_t e = cudaMemcpy(host, cmwg::g_mega_clk, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
+  return e == cudaSuccess ? CMWG_OK : CMWG_ERR_CUDA;
 }
 
 size_t cmwg_wn_workspace_bytes(const cmwg_wn_config* cfg, int B, int T) {

@@ -1,0 +1,111 @@
+"""Single-kernel WN forward (csrc/engine_mega.cuh: every gate / residual / skip GEMM tile of the WN in one dependency-
+ordered task list) against the layer-at-a-time pipeline (bit for bit) and the fp64 CPU oracle, over the shapes that
+stress its scheduling: one row tile, ragged tiles, fewer tiles than CTA pairs, one layer (no residual tasks), the LJ shape."""
+import os
+
+import pytest
+import torch
+
+import constant_memory_waveglow_b200 as cm
+from constant_memory_waveglow_b200 import precision
+from oracle import flow_oracle as O
+from tests._util import TOL, prefixed, rel_l2, to_double
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _restore():
+    old_p, old_e = precision.get_precision(), os.environ.get("CMWG_MEGA")
+    yield
+    precision.set_precision(old_p)
+    if old_e is None:
+        os.environ.pop("CMWG_MEGA", None)
+    else:
+        os.environ["CMWG_MEGA"] = old_e
+
+
+def _wn(cin, aux, depth, radix=3, seed=0):
+    torch.manual_seed(seed)
+    return cm.WN(cin, aux, dilation_channels=256, residual_channels=256, skip_channels=256, depth=depth, radix=radix,
+                 zero_init=False).cuda()
+
+
+def _both(fn):
+    os.environ["CMWG_MEGA"] = "1"
+    a = fn()
+    os.environ["CMWG_MEGA"] = "0"
+    b = fn()
+    os.environ["CMWG_MEGA"] = "1"
+    return a, b
+
+
+SHAPES = [
+    # cin, aux, depth, B, T
+    (4, 80, 8, 1, 100),     # one row tile: every dependency is the task's own predecessor
+    (4, 80, 8, 2, 300),     # two ragged tiles per item, residual tiles directly behind their gate tiles (lag 0)
+    (3, 20, 1, 2, 700),     # one layer: gate + skip tasks only
+    (4, 80, 2, 3, 1000),
+    (2, 40, 5, 5, 2000),    # 40 row tiles < 74 CTA pairs
+    (4, 80, 8, 24, 2000),   # the LJ training shape: 192 row tiles
+    (4, 80, 8, 2, 27584),   # a 10 s utterance: 108 tiles per item
+]
+
+
+@pytest.mark.parametrize("cin,aux,depth,B,T", SHAPES)
+@pytest.mark.parametrize("prec,save", [("bf16", False), ("bf16", True), ("fp16", False)])
+def test_fused_forward_equals_layered_pipeline(cin, aux, depth, B, T, prec, save):
+    wn = _wn(cin, aux, depth)
+    g = torch.Generator(device="cuda").manual_seed(T + B)
+    x = torch.randn(B, 2 * cin, T, device="cuda", generator=g)
+    y = torch.randn(B, aux, T, device="cuda", generator=g)
+
+    def run():
+        lst, st = wn._cmwg_forward(x, y, save=save, prec=prec)
+        torch.cuda.synchronize()
+        return lst.clone()
+
+    a, b = _both(run)       # (the saved activations are compared through the gradients they produce, below)
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b)
+    assert torch.equal(a, run())         # run to run: same bits (fixed accumulation order, no atomics on data)
+
+
+@pytest.mark.parametrize("cin,aux,depth,B,T", [(4, 80, 8, 2, 300), (3, 20, 1, 2, 700), (4, 80, 4, 2, 1000)])
+def test_fused_forward_against_oracle(cin, aux, depth, B, T):
+    """log_s / t of the WN against the fp64 restatement of model/waveglow.py:98-105, operand-precision tolerance."""
+    wn = _wn(cin, aux, depth, seed=3)
+    torch.manual_seed(5)
+    x = torch.randn(B, 2 * cin, T)
+    y = torch.randn(B, aux, T)
+    sd = to_double({k: v.cpu() for k, v in wn.state_dict().items()})
+    log_s, t = O.wn_forward(sd, "", x[:, :cin].double(), y.double())
+    want = torch.cat([log_s, t], 1)
+    for prec in ("bf16", "fp16"):
+        lst, _ = wn._cmwg_forward(x.cuda(), y.cuda(), save=False, prec=prec)
+        assert rel_l2(lst, want) < TOL[prec]["out"], prec
+
+
+def test_training_step_gradients_equal_layered_pipeline():
+    """Reversible backward through the activations the fused forward saved: every gradient equals the layered
+    pipeline's bit for bit (the backward kernels are the same; their inputs must be)."""
+    torch.manual_seed(0)
+    blk = cm.AffineCouplingBlock(cm.WN, True, in_channels=4, aux_channels=80, zero_init=False, dilation_channels=256,
+                                 residual_channels=256, skip_channels=256, depth=8).cuda()
+    x0 = torch.rand(3, 8, 2000, device="cuda") * 2 - 1
+    y = torch.randn(3, 80, 2000, device="cuda")
+    precision.set_precision("bf16")
+
+    def run():
+        for p in blk.parameters():
+            p.grad = None
+        x = x0.clone().requires_grad_(True)
+        xin = x * 1.0
+        z, log_s = blk(xin, y)
+        (z.square().mean() + log_s.mean()).backward()
+        torch.cuda.synchronize()
+        return [x.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
+
+    ga, gb = _both(run)
+    assert len(ga) == len(gb) and all(torch.equal(a, b) for a, b in zip(ga, gb))
+    assert all(torch.isfinite(a).all() for a in ga)
