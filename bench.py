@@ -128,7 +128,7 @@ class ClockSampler:
                     self.rows.append((mhz, bits))
                 except Exception:
                     pass
-                time.sleep(0.004)
+                time.sleep(0.020)   # NVML queries take a driver lock the launch path shares: keep them sparse
             else:
                 time.sleep(0.001)
 
@@ -412,7 +412,7 @@ def run_b200(args):
     kn = (C.c_longlong * 8)()
     _lib.check(lib.cmwg_profile_collect(kms, kn), "profile_collect")
     lib.cmwg_profile_enable(0)
-    names = ["gate", "resskip", "dgate", "dx", "dcond", "wgrad", "fwdfused"]
+    names = ["gate", "resskip", "dgate", "dx", "dcond", "wgrad", "fwdfused", "bwdfused"]
     kern = {n: {"ms": kms[i], "launches": int(kn[i])} for i, n in enumerate(names)}
 
     # ---- synthesis (config 3): sigma 0.6, 10 s utterances, utterance-sharded, no collective

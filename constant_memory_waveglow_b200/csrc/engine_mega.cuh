@@ -466,4 +466,230 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid
   tc_teardown(tmem_base, warp, 2 * MEGA_BN);
 }
 
+
+// ================================================================================================
+// Backward chain of the WN as one task kernel (same machinery, the reversible backward's dgrad path):
+//     DG(i, rt)  dgate GEMM  dg = [dh_{i+1} | dskip] W_o,  epilogue dpre = dg * d(tanh * sigmoid) from the saved values
+//     DX(i, rt)  dx GEMM     dh_i = dh_{i+1} + sum_tap dpre_i[row - shift] W_tap   (epilogue adds the (hi, lo) pair)
+// for layers depth-1 .. 0.  DG(i, rt) needs DX(i+1, rt); DX(i, rt) needs DG(i, rt-1 .. rt+1).  List: the RT tiles
+// DG(depth-1, *) (they depend on nothing but dskip), then slots u = j * RT + rt (layer i = depth-1-j) holding
+// [DX(u), DG of the layer below for tile u - lag]; pair p takes entry k * P + ((p - k) mod P) in round k (the skew
+// keeps a pair from seeing only one kind of entry: P is even and so is the slot size).  The weight-gradient GEMMs
+// and the conditioning-gradient GEMM run afterwards from the per-layer dpre / dh slabs this kernel leaves behind.
+// ================================================================================================
+enum { MEGA_DG = 0, MEGA_DX = 1 };
+
+struct alignas(64) MegaBwdParams {
+  CUtensorMap dh_op[MEGA_D];      // operand maps: dh_i hi halves (dh_op[i] feeds DG(i-1))
+  CUtensorMap dskip_op;           // operand map: gradient of the cumulative skip
+  CUtensorMap dpre_op[MEGA_D];    // operand maps: dpre_i [rows][2Cd]
+  CUtensorMap q1[MEGA_D], q2[MEGA_D];                       // W_o^T and W^T (per tap) weights
+  CUtensorMap sa_c16[MEGA_D], sb_c16[MEGA_D];               // chunk maps: saved tanh / sigmoid
+  CUtensorMap dpt_c16[MEGA_D], dps_c16[MEGA_D];             // chunk maps: tanh / sigmoid halves of dpre_i
+  CUtensorMap dhi_c16[MEGA_D], dlo_c16[MEGA_D];             // chunk maps: (hi, lo) pair of dh_i
+  uint32_t* flags;                // [depth][2][RT]: DG-done / DX-done counters (zeroed before the launch)
+  int depth, B, T, tiles_per_batch, RT;
+  int taps, kb_r, kb_s, kb_d2;    // taps; k-blocks of dh / dskip / dpre (2Cd)
+  int f16;
+  uint32_t idesc, desc_lbo, desc_sbo;
+  int lag, total_tasks;
+};
+
+__device__ __forceinline__ MegaTask mega_bwd_decode(const MegaBwdParams& p, int idx) {
+  MegaTask t;
+  t.nt = 0;
+  if (idx < p.RT) {
+    t.type = MEGA_DG; t.layer = p.depth - 1; t.rt = idx;
+    return t;
+  }
+  idx -= p.RT;
+  const int sl = idx >> 1, w = idx & 1;
+  const int u = w == 0 ? sl : sl - p.lag;
+  const int j = u >= 0 ? u / p.RT : 0;
+  t.rt = u - j * p.RT;
+  t.layer = p.depth - 1 - j;
+  if (w == 0) {
+    t.type = u < p.depth * p.RT ? MEGA_DX : MEGA_NONE;
+  } else {
+    t.type = (u >= 0 && t.layer >= 1 && j < p.depth) ? MEGA_DG : MEGA_NONE;
+    t.layer -= 1;  // the dgate GEMM of the layer below
+  }
+  return t;
+}
+__device__ __forceinline__ int mega_bwd_entry(int total, int k, int pair, int npairs) {
+  int r = (pair - k) % npairs;
+  if (r < 0) r += npairs;
+  const int e = k * npairs + r;
+  return e < total ? e : -1;
+}
+__device__ __forceinline__ uint32_t* mega_bwd_gflag(const MegaBwdParams& p, int layer, int rt) {
+  return p.flags + (size_t)(2 * layer) * p.RT + rt;
+}
+__device__ __forceinline__ uint32_t* mega_bwd_xflag(const MegaBwdParams& p, int layer, int rt) {
+  return p.flags + (size_t)(2 * layer + 1) * p.RT + rt;
+}
+
+constexpr int MEGA_BWD_WARP_BYTES = 2 * TC_CHUNK16_BYTES;
+constexpr int MEGA_BWD_STAGES = (TC_SMEM_LIMIT - 1024 - TC_BAR_BYTES - TC_EPI_WARPS * MEGA_BWD_WARP_BYTES) / MEGA_STAGE_BYTES;
+constexpr size_t MEGA_BWD_SMEM_BYTES =
+    (size_t)MEGA_BWD_STAGES * MEGA_STAGE_BYTES + TC_EPI_WARPS * MEGA_BWD_WARP_BYTES + TC_BAR_BYTES + 1024;
+
+__global__ void __launch_bounds__(TC_THREADS, 1) wn_bwd_mega_kernel(const __grid_constant__ MegaBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int STAGES = MEGA_BWD_STAGES;
+  constexpr int WB = MEGA_BWD_WARP_BYTES;
+  const TcSmem s = tc_carve<STAGES>(smem_raw, MEGA_STAGE_BYTES, TC_EPI_WARPS * WB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  uint32_t* done_cnt = s.tmem_ptr + 2;
+  static_assert((2 * STAGES + 4 + TC_EPI_WARPS) * 8 + 8 + 4 * 4 + 8 <= TC_BAR_BYTES, "barrier area too small");
+  if (threadIdx.x < 4) done_cnt[threadIdx.x] = 0;
+  pdl_trigger();
+  tc_setup<STAGES>(s, warp, lane, 2 * MEGA_BN, TC_EPI_WARPS);
+  const uint32_t tmem_base = *s.tmem_ptr;
+  pdl_wait();
+  const uint32_t target = 2u * TC_EPI_WARPS;
+  const int rounds = (p.total_tasks + npairs - 1) / npairs;
+  const int Crp = p.kb_r * TC_BK, Cd2p = p.kb_d2 * TC_BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load = [&](const CUtensorMap* am, int ak, int at, int ab, const CUtensorMap* bm, int bk, int bn) {
+        mbar_wait(&s.empty[stage], phase ^ 1);
+        const uint32_t sa = smem_u32(s.stages + stage * MEGA_STAGE_BYTES);
+        if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * MEGA_STAGE_BYTES);
+        const uint32_t bar = mapa_shared(smem_u32(&s.full[stage]), 0);
+        tma_load_4d(sa, am, bar, ak, at, 0, ab);
+        tma_load_2d(sa + TC_A_BYTES, bm, bar, bk, bn);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      for (int k = 0; k < rounds; ++k) {
+        const int task = mega_bwd_entry(p.total_tasks, k, pair, npairs);
+        if (task < 0) continue;
+        const MegaTask t = mega_bwd_decode(p, task);
+        if (t.type == MEGA_NONE) continue;
+        const int b = t.rt / p.tiles_per_batch, tb = t.rt - b * p.tiles_per_batch;
+        const int t0 = tb * (2 * TC_BM) + rank * TC_BM;
+        const int nrow = rank * (MEGA_BN / 2);
+        const bool last = t.layer == p.depth - 1;
+        if (t.type == MEGA_DG) {
+          if (!last) {
+            mega_wait_flag(mega_bwd_xflag(p, t.layer + 1, t.rt), target);
+            fence_proxy_async_all();
+            for (int kb = 0; kb < p.kb_r; ++kb) load(&p.dh_op[t.layer + 1], kb * TC_BK, t0, b, &p.q1[t.layer], kb * TC_BK, nrow);
+          }
+          for (int kb = 0; kb < p.kb_s; ++kb)
+            load(&p.dskip_op, kb * TC_BK, t0, b, &p.q1[t.layer], (last ? 0 : Crp) + kb * TC_BK, nrow);
+        } else {
+          const uint32_t* f1 = mega_bwd_gflag(p, t.layer, t.rt);
+          mega_wait_flags3(tb > 0 ? f1 - 1 : f1, f1, tb + 1 < p.tiles_per_batch ? f1 + 1 : f1, target);
+          fence_proxy_async_all();
+          for (int sg = 0; sg < p.taps; ++sg) {
+            const int shift = -(sg - (p.taps - 1) / 2) * (1 << t.layer);
+            for (int kb = 0; kb < p.kb_d2; ++kb)
+              load(&p.dpre_op[t.layer], kb * TC_BK, t0 + shift, b, &p.q2[t.layer], sg * Cd2p + kb * TC_BK, nrow);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int k = 0; k < rounds; ++k) {
+        const int task = mega_bwd_entry(p.total_tasks, k, pair, npairs);
+        if (task < 0) continue;
+        const MegaTask t = mega_bwd_decode(p, task);
+        if (t.type == MEGA_NONE) continue;
+        const int total_kb = t.type == MEGA_DX ? p.taps * p.kb_d2 : (t.layer == p.depth - 1 ? p.kb_s : p.kb_r + p.kb_s);
+        mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * MEGA_BN;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&s.full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(s.stages + stage * MEGA_STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa, p.desc_lbo, p.desc_sbo);
+          const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES, p.desc_lbo, p.desc_sbo);
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 16; ++kk)
+            umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, p.idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&s.empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&s.tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int cg = e >> 2;
+    const uint32_t wbuf = smem_u32(s.epi + e * WB);
+    uint64_t* ibar = s.in_bar + e;
+    const uint32_t tmem_empty_addr = mapa_shared(smem_u32(&s.tmem_empty[0]), 0);
+    const GateBwdTcEpi gbwd_epi{};
+    const SplitTcEpi<true> add_epi{nullptr, p.f16};
+    const SplitTcEpi<false> first_epi{nullptr, p.f16};
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t it = 0, seq = 0;
+    long long tt[4] = {0, 0, 0, 0};
+    for (int k = 0; k < rounds; ++k) {
+      const int task = mega_bwd_entry(p.total_tasks, k, pair, npairs);
+      if (task < 0) continue;
+      const MegaTask t = mega_bwd_decode(p, task);
+      if (t.type == MEGA_NONE) continue;
+      const int b = t.rt / p.tiles_per_batch, tb = t.rt - b * p.tiles_per_batch;
+      const int r0 = tb * (2 * TC_BM) + rank * TC_BM + q * 32;
+      const uint32_t tile = tmem_base + acc * MEGA_BN;
+      const uint32_t te = tmem_empty_addr + 8 * acc;
+      const uint32_t dcnt = smem_u32(done_cnt + (seq++ & 3));
+      const bool last = t.layer == p.depth - 1;
+      const int c0 = cg * (MEGA_BN / 4);
+      if (t.type == MEGA_DG) {
+        if (lane == 0) {  // chunk 0 of the saved tanh / sigmoid values (written by the forward: always ready)
+          fence_proxy_async_all();
+          mbar_arrive_expect_tx(ibar, 2 * TC_CHUNK16_BYTES);
+          tma_load_4d_local(wbuf, &p.sa_c16[t.layer], smem_u32(ibar), c0, r0, 0, b);
+          tma_load_4d_local(wbuf + TC_CHUNK16_BYTES, &p.sb_c16[t.layer], smem_u32(ibar), c0, r0, 0, b);
+        }
+        __syncwarp();
+        mega_epilogue_task<GateBwdTcEpi, MEGA_BN>(gbwd_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf, ibar, it,
+                                                  &p.dpt_c16[t.layer], &p.dps_c16[t.layer], nullptr, &p.sa_c16[t.layer],
+                                                  &p.sb_c16[t.layer], b, r0, 0,
+                                                  MegaSig{mega_bwd_gflag(p, t.layer, t.rt), dcnt}, nullptr, 0, tt);
+      } else if (!last) {
+        if (lane == 0) {  // chunk 0 of the upstream residual gradient's (hi, lo) pair
+          mega_wait_flag(mega_bwd_xflag(p, t.layer + 1, t.rt), target);
+          fence_proxy_async_all();
+          mbar_arrive_expect_tx(ibar, 2 * TC_CHUNK16_BYTES);
+          tma_load_4d_local(wbuf, &p.dhi_c16[t.layer + 1], smem_u32(ibar), c0, r0, 0, b);
+          tma_load_4d_local(wbuf + TC_CHUNK16_BYTES, &p.dlo_c16[t.layer + 1], smem_u32(ibar), c0, r0, 0, b);
+        }
+        __syncwarp();
+        mega_epilogue_task<SplitTcEpi<true>, MEGA_BN>(add_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf, ibar, it,
+                                                      &p.dhi_c16[t.layer], &p.dlo_c16[t.layer], nullptr,
+                                                      &p.dhi_c16[t.layer + 1], &p.dlo_c16[t.layer + 1], b, r0, 0,
+                                                      MegaSig{mega_bwd_xflag(p, t.layer, t.rt), dcnt}, nullptr, 0, tt);
+      } else {
+        mega_epilogue_task<SplitTcEpi<false>, MEGA_BN>(first_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf, ibar,
+                                                       it, &p.dhi_c16[t.layer], &p.dlo_c16[t.layer], nullptr, nullptr, nullptr,
+                                                       b, r0, 0, MegaSig{mega_bwd_xflag(p, t.layer, t.rt), dcnt}, nullptr, 0,
+                                                       tt);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+  tc_teardown(tmem_base, warp, 2 * MEGA_BN);
+}
+
 }  // namespace cmwg

@@ -178,6 +178,8 @@ struct BwdLayout {
   size_t dh_op;      // [rows][Cr] operand (tc only; ff aliases dh32)
   size_t dpre_op;    // [rows][2Cd] operand
   size_t dhi2[2], dlo2[2];          // tc: (hi, lo) residual-gradient pairs, ping-pong
+  size_t dhi_l[CMWG_MAX_DEPTH];     // tc, single-kernel chain: per-layer hi halves (the weight-gradient GEMMs run afterwards)
+  size_t flags;                     // [depth][2][row tiles] dependency counters of the single-kernel chain
   size_t dprel[CMWG_MAX_DEPTH];     // tc: per-layer dpre
   size_t partial;    // split-K partials / block partials
   size_t partial_bytes;
@@ -237,6 +239,8 @@ inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
     for (int j = 0; j < 2; ++j) { L->dhi2[j] = take(rows * d.Cr * 2); L->dlo2[j] = take(rows * d.Cr * 2); }
     L->dprel[0] = L->dpre_op;
     for (int i = 1; i < d.depth; ++i) L->dprel[i] = take(rows * 2 * d.Cd * 2);
+    for (int i = 0; i < d.depth; ++i) L->dhi_l[i] = take(rows * d.Cr * 2);
+    L->flags = take((size_t)d.depth * 2 * B * d.H * ceil_div(T, 256) * 4);
   }
   int lc = wgrad_chunk_len(B * d.H, T);
   size_t splits = (size_t)B * d.H * ceil_div(T, lc);

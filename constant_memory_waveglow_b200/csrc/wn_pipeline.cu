@@ -225,6 +225,56 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
   return save ? mega_launch<true>(p, st) : mega_launch<false>(p, st);
 }
 
+
+// single-kernel backward chain (engine_mega.cuh): dgate + dx GEMM tiles of all layers as one task list
+static int wn_backward_mega(const WnDims& d, const PackedLayout& PL, const BwdLayout& BL, const uint8_t* pk, uint8_t* ws,
+                            int B, int T, int f16, void* const* dh_hi, void* const* dh_lo, const void* dskip,
+                            void* const* dpre, const void* const* sa, const void* const* sb, cudaStream_t st) {
+  MegaBwdParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < d.depth; ++i) {
+    CMWG_PROPAGATE(get_slab_map(&p.dh_op[i], dh_hi[i], d.Cr, d.Cr, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
+    CMWG_PROPAGATE(get_slab_map(&p.dpre_op[i], dpre[i], 2 * d.Cd, 2 * d.Cd, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
+    CMWG_PROPAGATE(get_matrix_map(&p.q1[i], pk + PL.Q1[i], d.k1(i), d.Cd, MEGA_BN / 2, f16));
+    CMWG_PROPAGATE(get_matrix_map(&p.q2[i], pk + PL.Q2[i], d.ldQ2, d.Cr, MEGA_BN / 2, f16));
+    CMWG_PROPAGATE(get_slab_map(&p.sa_c16[i], sa[i], d.Cd, d.Cd, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+    CMWG_PROPAGATE(get_slab_map(&p.sb_c16[i], sb[i], d.Cd, d.Cd, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+    // two column windows of the dpre slab (each exposes its own Cd channels)
+    CMWG_PROPAGATE(get_slab_map(&p.dpt_c16[i], dpre[i], d.Cd, 2 * d.Cd, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+    CMWG_PROPAGATE(get_slab_map(&p.dps_c16[i], (const uint16_t*)dpre[i] + d.Cd, d.Cd, 2 * d.Cd, T, 1, B, 32, 32, f16,
+                                TC_MAP_CHUNK16));
+    CMWG_PROPAGATE(get_slab_map(&p.dhi_c16[i], dh_hi[i], d.Cr, d.Cr, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+    CMWG_PROPAGATE(get_slab_map(&p.dlo_c16[i], dh_lo[i], d.Cr, d.Cr, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+  }
+  CMWG_PROPAGATE(get_slab_map(&p.dskip_op, dskip, d.Cs, d.Cs, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
+  p.depth = d.depth; p.B = B; p.T = T;
+  p.tiles_per_batch = ceil_div(T, 2 * TC_BM);
+  p.RT = B * p.tiles_per_batch;
+  p.taps = d.R; p.kb_r = d.Crp / TC_BK; p.kb_s = d.Csp / TC_BK; p.kb_d2 = d.Cd2p / TC_BK;
+  p.f16 = f16;
+  p.idesc = make_idesc(f16, 2 * TC_BM, MEGA_BN, 0, 0);
+  p.desc_lbo = 1u; p.desc_sbo = 1024u >> 4;
+  static const int lag_env = [] { const char* v = getenv("CMWG_MEGA_LAG_BWD"); return v ? atoi(v) : 96; }();
+  p.lag = std::max(0, std::min(lag_env, p.RT - 2));
+  p.total_tasks = p.RT + 2 * (d.depth * p.RT + p.lag);
+  p.flags = reinterpret_cast<uint32_t*>(ws + BL.flags);
+  CMWG_CHECK_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)d.depth * 2 * p.RT * 4, st));
+  auto kern = wn_bwd_mega_kernel;
+  constexpr size_t smem = MEGA_BWD_SMEM_BYTES;
+  static_assert(smem <= TC_SMEM_LIMIT, "shared memory budget exceeded");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CMWG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int pairs = std::min(p.total_tasks, num_sms() / 2);
+  ProfScope prof(st, CMWG_KCLASS_BWDFUSED);
+  void* args[1] = {(void*)&p};
+  CMWG_PROPAGATE(tc_launch_pairs((const void*)kern, smem, pairs, args, st));
+  CMWG_COUNT_LAUNCH();
+  return CMWG_OK;
+}
+
 template <typename OpT>
 static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, long long x_bs, const void* ycl, int B,
                            int T, void* workspace, void* saved, float* lst, cudaStream_t st, LineWin lw = LineWin()) {
@@ -473,7 +523,14 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   OpT* dpre_op = reinterpret_cast<OpT*>(ws + BL.dpre_op);
   // tc: per-layer dpre (deferred conditioning-gradient GEMM) and (hi, lo) residual-gradient pairs
   auto dpre_l = [&](int i) -> OpT* { return TC ? reinterpret_cast<OpT*>(ws + BL.dprel[i]) : dpre_op; };
-  auto dhi = [&](int i) -> OpT* { return TC ? reinterpret_cast<OpT*>(ws + BL.dhi2[i & 1]) : dh_op; };
+  // single-kernel chain: dgate + dx tiles of all layers in one launch; the weight-gradient GEMMs follow, so dh keeps
+  // a hi slab per layer
+  const bool fusedb = TC && mega_enabled() && mega_shapes_ok(d, B, T) && d.Cd == 256 && !(getenv("CMWG_MEGA_BWD") && getenv("CMWG_MEGA_BWD")[0] == '0');
+  auto dhi = [&](int i) -> OpT* {
+    if (!TC) return dh_op;
+    if (fusedb) return reinterpret_cast<OpT*>(ws + BL.dhi_l[i < d.depth ? i : d.depth - 1]);
+    return reinterpret_cast<OpT*>(ws + BL.dhi2[i & 1]);
+  };
   auto dlo = [&](int i) -> OpT* { return reinterpret_cast<OpT*>(ws + BL.dlo2[i & 1]); };
   float* partial = reinterpret_cast<float*>(ws + BL.partial);
   float* dweff = reinterpret_cast<float*>(ws + BL.dweff);
@@ -526,6 +583,18 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   const int Lc = wgrad_chunk_len(B * d.H, T);  // FFMA engine: split-K over (batch, line, time chunk)
   const int ff_splits = B * d.H * ceil_div(T, Lc);
 
+  if constexpr (TC) {
+    if (fusedb) {
+      void *hh[MEGA_D], *hl[MEGA_D], *dp[MEGA_D];
+      const void *sa[MEGA_D], *sb[MEGA_D];
+      for (int i = 0; i < d.depth; ++i) {
+        hh[i] = dhi(i); hl[i] = dlo(i); dp[i] = dpre_l(i);
+        sa[i] = sv + FL.s_a[i]; sb[i] = sv + FL.s_b[i];
+      }
+      CMWG_PROPAGATE(wn_backward_mega(d, PL, BL, pk, ws, B, T, f16, hh, hl, dskip_op, dp, sa, sb, st));
+    }
+  }
+
   for (int i = d.depth - 1; i >= 0; --i) {
     const int dil = 1 << i;
     const bool last = (i == d.depth - 1);
@@ -534,7 +603,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     OpT* dpre_i = dpre_l(i);
     const OpT* dh_next = dhi(i + 1);  // operand view of dh_{i+1} (unused for the last layer)
     // ---- dgate GEMM + gate backward epilogue -> dpre
-    {
+    if (!fusedb) {
       GemmDesc g;
       memset(&g, 0, sizeof(g));
       int ns = 0;
@@ -667,7 +736,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       CMWG_PROPAGATE((E::template gemm<false>(g, epi, st)));
     }
     // ---- dx GEMM: dh_i = dh_{i+1} + conv^T(dpre)
-    {
+    if (!fusedb) {
       GemmDesc g;
       memset(&g, 0, sizeof(g));
       for (int s = 0; s < d.R; ++s) {

@@ -299,6 +299,7 @@ int cmwg_sum_per_batch(const float* a, long long a_bstride, int B, int N, float*
 #define CMWG_KCLASS_DCOND 4   /* conditioning gradient GEMM                                */
 #define CMWG_KCLASS_WGRAD 5   /* weight-gradient GEMMs                                     */
 #define CMWG_KCLASS_FWDFUSED 6 /* whole-WN forward task kernel (all gate, residual and skip GEMM tiles of one WN) */
+#define CMWG_KCLASS_BWDFUSED 7 /* dgate + dx GEMM tiles of all layers of one WN backward (task kernel)             */
 #define CMWG_KCLASS_COUNT 8
 /* on != 0: start recording (drops earlier records); on == 0: stop */
 int cmwg_profile_enable(int on);
