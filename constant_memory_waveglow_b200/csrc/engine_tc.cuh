@@ -40,7 +40,8 @@ constexpr int TC_BK = 64;                 // 64 x 16-bit = 128 B = one swizzle r
 constexpr int TC_A_BYTES = TC_BM * 128;   // 16 KB
 constexpr int TC_EPI_WARPS = 16;          // 4 per TMEM lane quadrant, each owning a quarter of the tile's columns
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr int TC_MAX_WG = 8;              // weight-gradient problems per launch
+constexpr int TC_MAX_WG = 48;             // weight-gradient problems per launch (all layers of one WN at once)
+constexpr int TC_WG_GROUP = 8;            // problems per launch of the layer-at-a-time pipeline
 constexpr int TC_MAX_OUT = 3;             // output streams of one epilogue
 constexpr int TC_MAX_IN = 2;              // input streams of one epilogue
 constexpr int TC_SMEM_LIMIT = 232448;     // 227 KB opt-in shared memory per CTA

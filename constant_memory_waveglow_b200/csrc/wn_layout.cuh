@@ -11,7 +11,7 @@
 namespace cmwg {
 
 constexpr int MAX_SEG = 16;  // K segments of one GEMM: radix taps + conditioning / one per layer
-constexpr int TC_MAX_WG_REDUCE = 8;  // weight-gradient problems reduced per launch
+constexpr int TC_MAX_WG_REDUCE = 48;  // weight-gradient problems reduced per launch
 
 struct WnDims {
   int cin, aux, Cd, Cr, Cs, depth, bias, prec;

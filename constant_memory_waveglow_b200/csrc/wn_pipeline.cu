@@ -595,6 +595,48 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     }
   }
 
+  // weight-gradient problems: launched per layer, or -- after the single-kernel chain -- for all layers at once
+  // (63 full-K tiles fill one wave of CTA pairs without any split-K partials)
+  struct RedSpec { int pi; float* out; long long sm, sn, off; int n_valid; };
+  WgradProblem pr[TC_MAX_WG];
+  RedSpec rs[TC_MAX_WG];
+  int np = 0, nr = 0;
+  const bool wg_batched = fusedb && d.depth * (d.R + 3) <= TC_MAX_WG &&
+                          !(getenv("CMWG_WGRAD_BATCH") && getenv("CMWG_WGRAD_BATCH")[0] == '0');
+  auto flush_wgrad = [&](int group) -> int {
+    for (int g0 = 0; g0 < np; g0 += group) {
+      const int gn = std::min(group, np - g0);
+      WgradProblem* gp = pr + g0;
+      int splits[TC_MAX_WG];
+      if (TC) tc_wgrad_plan(gp, gn, B, d.H, T, 0, splits);
+      else for (int k = 0; k < gn; ++k) splits[k] = ff_splits;
+      float* pcur = partial;
+      for (int k = 0; k < gn; ++k) {
+        gp[k].partial = pcur;
+        pcur += (size_t)splits[k] * gp[k].M * gp[k].N;
+      }
+      CMWG_REQUIRE((size_t)((uint8_t*)pcur - (uint8_t*)partial) <= BL.partial_bytes, "wgrad partial buffer overflow");
+      if (TC) {
+        CMWG_PROPAGATE(tc_wgrad_launch(gp, gn, B, d.H, T, f16, st));
+      } else {
+        for (int k = 0; k < gn; ++k) CMWG_PROPAGATE(ff_wgrad_launch(gp[k], B, d.H, T, Lc, st));
+      }
+      WgReduceTable rt;
+      rt.n = 0;
+      for (int k = 0; k < nr; ++k) {
+        if (rs[k].pi < g0 || rs[k].pi >= g0 + gn) continue;
+        WgReduceEntry& e = rt.e[rt.n++];
+        const WgradProblem& q = pr[rs[k].pi];
+        e.partial = q.partial; e.splits = splits[rs[k].pi - g0]; e.M = q.M; e.N = q.N; e.n_valid = rs[k].n_valid;
+        e.out = rs[k].out; e.sm = rs[k].sm; e.sn = rs[k].sn; e.off = rs[k].off;
+      }
+      wgrad_reduce_kernel<<<dim3(num_sms(), rt.n), 256, 0, st>>>(rt);
+      CMWG_COUNT_LAUNCH();
+      CMWG_LAUNCH_CHECK();
+    }
+    return CMWG_OK;
+  };
+
   for (int i = d.depth - 1; i >= 0; --i) {
     const int dil = 1 << i;
     const bool last = (i == d.depth - 1);
@@ -638,9 +680,8 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     }
     // ---- weight gradients of this layer: W_o (res rows, skip rows), W per tap, V_i
     {
-      WgradProblem pr[MAX_SEG + 3];
-      struct RedSpec { int pi; float* out; long long sm, sn, off; int n_valid; } rs[MAX_SEG + 3];
-      int np = 0;
+      if (!wg_batched) { np = 0; nr = 0; }
+      const int np_before = np;
       auto add = [&](const void* a, int lda, int M, const void* b, int ldb, int N, int shift, int shift_h, int bcast) {
         WgradProblem& q = pr[np];
         q.a = a; q.lda = lda; q.a_c0 = 0; q.M = M; q.b = b; q.ldb = ldb; q.b_c0 = 0; q.N = N; q.shift = shift;
@@ -652,7 +693,6 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       float* dWo = dweff + BL.dweff_layer * (size_t)i;
       float* dW = dWo + (size_t)d.nb(i) * d.Cd;
       float* dV = dW + (size_t)2 * d.Cd * d.Cr * d.R;
-      int nr = 0;
       auto red = [&](int pi, float* out, long long sm, long long sn, long long off, int n_valid) {
         rs[nr++] = RedSpec{pi, out, sm, sn, off, n_valid};
       };
@@ -669,38 +709,8 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
               (long long)d.Cr * d.R, d.R, s, d.Cr);
       if (want_v)
         red(add(dpre_i, 2 * d.Cd, 2 * d.Cd, ycl, d.auxp, d.auxp, 0, 0, d.H > 1), dV, d.aux, 1, 0, d.aux);
-      // launch in groups of at most TC_MAX_WG problems (a 3 x 3 conv alone has 9 taps)
-      for (int g0 = 0; g0 < np; g0 += TC_MAX_WG) {
-        const int gn = std::min(TC_MAX_WG, np - g0);
-        WgradProblem* gp = pr + g0;
-        int splits[TC_MAX_WG];
-        if (TC) tc_wgrad_plan(gp, gn, B, d.H, T, 0, splits);
-        else for (int k = 0; k < gn; ++k) splits[k] = ff_splits;
-        float* pcur = partial;
-        for (int k = 0; k < gn; ++k) {
-          gp[k].partial = pcur;
-          pcur += (size_t)splits[k] * gp[k].M * gp[k].N;
-        }
-        CMWG_REQUIRE((size_t)((uint8_t*)pcur - (uint8_t*)partial) <= BL.partial_bytes, "wgrad partial buffer overflow");
-        if (TC) {
-          CMWG_PROPAGATE(tc_wgrad_launch(gp, gn, B, d.H, T, f16, st));
-        } else {
-          for (int k = 0; k < gn; ++k) CMWG_PROPAGATE(ff_wgrad_launch(gp[k], B, d.H, T, Lc, st));
-        }
-        WgReduceTable rt;
-        rt.n = 0;
-        for (int k = 0; k < nr; ++k) {
-          if (rs[k].pi < g0 || rs[k].pi >= g0 + gn) continue;
-          WgReduceEntry& e = rt.e[rt.n++];
-          const WgradProblem& q = pr[rs[k].pi];
-          e.partial = q.partial; e.splits = splits[rs[k].pi - g0]; e.M = q.M; e.N = q.N; e.n_valid = rs[k].n_valid;
-          e.out = rs[k].out; e.sm = rs[k].sm; e.sn = rs[k].sn; e.off = rs[k].off;
-        }
-        wgrad_reduce_kernel<<<dim3(num_sms(), rt.n), 256, 0, st>>>(rt);
-        CMWG_COUNT_LAUNCH();
-        CMWG_LAUNCH_CHECK();
-      }
-      if (np) {
+      if (!wg_batched) CMWG_PROPAGATE(flush_wgrad(TC_WG_GROUP));
+      if (np > np_before) {
         if (want_wo)
           wq.add(dWo, prm->W_o[i], reinterpret_cast<const float*>(pk + PL.nWo[i]), gr->W_o[i], d.nb(i), d.Cd);
         if (want_w)
@@ -768,6 +778,8 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       }
     }
   }
+
+  if (wg_batched) CMWG_PROPAGATE(flush_wgrad(TC_MAX_WG));
 
   if constexpr (TC) {
     // ---- conditioning gradient: dy = sum_i dpre_i V_i as ONE GEMM, layers concatenated along K

@@ -106,6 +106,16 @@ def test_training_step_gradients_equal_layered_pipeline():
         torch.cuda.synchronize()
         return [x.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
 
-    ga, gb = _both(run)
+    os.environ["CMWG_WGRAD_BATCH"] = "0"         # same split-K plan as the layered pipeline: bit for bit
+    try:
+        ga, gb = _both(run)
+    finally:
+        os.environ.pop("CMWG_WGRAD_BATCH", None)
     assert len(ga) == len(gb) and all(torch.equal(a, b) for a, b in zip(ga, gb))
     assert all(torch.isfinite(a).all() for a in ga)
+    # default: the weight-gradient GEMMs of all layers in one launch, full-K tiles instead of split-K partials --
+    # the same products summed in another order
+    gc = run()
+    assert torch.equal(gc[0], ga[0])              # the input gradient does not go through them
+    for a, c in zip(ga[1:], gc[1:]):
+        assert rel_l2(c, a) < 2e-5
