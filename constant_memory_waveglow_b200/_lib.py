@@ -95,6 +95,7 @@ SIGNATURES = {
     "cmwg_sum_per_batch": (_I, [_VP, _LL, _I, _I, _VP, _I, C.c_float, _VP]),
     "cmwg_profile_enable": (_I, [_I]),
     "cmwg_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "cmwg_mega_clk_read": (_I, [C.POINTER(C.c_longlong), _I]),
     "cmwg_selftest_tc_gemm": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
 }
 

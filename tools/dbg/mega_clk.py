@@ -13,7 +13,7 @@ save = len(sys.argv) > 3 and sys.argv[3] == "save"
 x = torch.randn(B, 8, T, device=dev); y = torch.randn(B, 80, T, device=dev)
 for _ in range(3): wn._cmwg_forward(x, y, save=save, prec="bf16")
 torch.cuda.synchronize()
-lib = C.CDLL(_lib.load()._name)
+lib = _lib.load()
 n = 148 * 18 * 16
 buf = (C.c_longlong * n)()
 assert lib.cmwg_mega_clk_read(buf, n) == 0
