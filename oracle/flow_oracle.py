@@ -26,6 +26,7 @@ that the reversible backward performs.
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -642,3 +643,92 @@ def waveflow_random_state(spec: WaveFlowSpec, wn_channels: int, seed: int = 0,
         else:
             sd[p + "end.weight"] = torch.randn(2, C, 1, 1, generator=gen, dtype=dtype) * end_std
     return sd
+
+
+# --------------------------------------------------------------------------------------------
+# MRWaveGlow (model/mr_waveglow.py): Haar-like band split over channels, per-level flows, prior flows
+# --------------------------------------------------------------------------------------------
+@dataclass
+class MRSpec:
+    prior_flows: int
+    n_group: int
+    hop_size: int
+    n_mels: int
+    levels: int = 3
+    flows: int = 4
+    super_resolution: bool = False
+
+    @property
+    def upsample_factor(self) -> int:
+        return self.hop_size // self.n_group
+
+
+def mr_upsample_h(spec: MRSpec, h: Tensor) -> Tensor:
+    """``model/mr_waveglow.py:133-134``: linear interpolation of the mel to the squeezed rate."""
+    return F.interpolate(h, scale_factor=spec.upsample_factor, mode="linear")
+
+
+def _mr_steps(sd: State, conv_prefix: str, wn_prefix: str, n: int, x: Tensor, cond: Tensor, inverse: bool):
+    total = 0
+    for k in (range(n - 1, -1, -1) if inverse else range(n)):
+        w = sd[f"{conv_prefix}{k}.weight"]
+        if inverse:
+            x, log_s = coupling_reverse(sd, f"{wn_prefix}{k}.F.", x, cond)
+            x, ldw = conv1x1_reverse(w, x)
+        else:
+            x, ldw = conv1x1_forward(w, x)
+            x, log_s = coupling_forward(sd, f"{wn_prefix}{k}.F.", x, cond)
+        total = total + ldw + log_s.sum((1, 2))
+    return x, total
+
+
+def mrwaveglow_forward(sd: State, spec: MRSpec, x: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
+    """``MRWaveGlow.forward_computation`` (``model/mr_waveglow.py:60-92``)."""
+    y = mr_upsample_h(spec, h)
+    B = x.size(0)
+    x = x.view(B, -1, spec.n_group).transpose(1, 2)
+    assert x.size(2) <= y.size(2)
+    y = y[..., :x.size(2)]
+    outs, logdet = [], 0
+    for level in range(spec.levels - 1):
+        x0, x1 = x[:, ::2], x[:, 1::2]
+        x_diff, x = x1 - x0, (x0 + x1) * 0.5
+        cond = x if spec.super_resolution else torch.cat([x, y], 1)
+        x_diff, ld = _mr_steps(sd, f"invconv1x1_list.{level}.", f"WNs_list.{level}.", spec.flows, x_diff, cond, False)
+        logdet = logdet + ld
+        outs.append(x_diff)
+    x, ld = _mr_steps(sd, "prior_invconv1x1.", "prior_WNs.", spec.prior_flows, x, y, False)
+    outs.append(x)
+    return torch.cat(outs, 1).transpose(1, 2).contiguous().view(B, -1), logdet + ld
+
+
+def mrwaveglow_reverse(sd: State, spec: MRSpec, z: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
+    """``MRWaveGlow.reverse_computation`` (``model/mr_waveglow.py:94-131``)."""
+    y = mr_upsample_h(spec, h)
+    B = z.size(0)
+    z = z.view(B, -1, spec.n_group).transpose(1, 2)
+    assert z.size(2) <= y.size(2)
+    y = y[..., :z.size(2)]
+    remained = []
+    for _ in range(spec.levels - 1):
+        r, z = z.chunk(2, 1)
+        remained.append(r)
+    z, logdet = _mr_steps(sd, "prior_invconv1x1.", "prior_WNs.", spec.prior_flows, z, y, True)
+    for level in range(spec.levels - 2, -1, -1):
+        z_diff = remained.pop()
+        cond = z if spec.super_resolution else torch.cat([z, y], 1)
+        z_diff, ld = _mr_steps(sd, f"invconv1x1_list.{level}.", f"WNs_list.{level}.", spec.flows, z_diff, cond, True)
+        logdet = logdet + ld
+        z_0, z_1 = z - z_diff * 0.5, z + z_diff * 0.5
+        z = torch.stack([z_0, z_1], 2).view(B, -1, z_0.size(2))
+    return z.transpose(1, 2).contiguous().view(B, -1), logdet
+
+
+def mrwaveglow_train_step(sd: State, spec: MRSpec, x: Tensor, h: Tensor, sigma: float):
+    """One fwd + loss + bwd; returns (z, logdet, loss, grads keyed like the state dict)."""
+    leaf = _leafify(sd)
+    z, logdet = mrwaveglow_forward(leaf, spec, x, h)
+    loss = waveglow_loss(z, logdet, sigma)
+    keys = [k for k, v in leaf.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys], allow_unused=True)
+    return z.detach(), logdet.detach(), loss.detach(), {k: g for k, g in zip(keys, grads) if g is not None}
