@@ -69,6 +69,7 @@ class ClockSampler:
         self.rows = []          # (sm_mhz, reasons bitmask)
         self.max_mhz = None
         self.active = False
+        self.busy = False
         self.alive = False
         self.proc = None
         self.nvml = None
@@ -111,7 +112,12 @@ class ClockSampler:
         self.active = True
 
     def end(self):
+        """Stop recording and wait for a query that is still in flight (on some boxes an NVML query takes tens of
+        milliseconds and holds a driver lock the launch path needs: it must not reach into the next timed leg)."""
         self.active = False
+        t0 = time.time()
+        while self.busy and time.time() - t0 < 1.0:
+            time.sleep(0.001)
 
     def _poll_nvml(self):
         n = self.nvml
@@ -119,6 +125,7 @@ class ClockSampler:
             getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
         while self.alive:
             if self.active:
+                self.busy = True
                 try:
                     mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
                     try:
@@ -128,6 +135,7 @@ class ClockSampler:
                     self.rows.append((mhz, bits))
                 except Exception:
                     pass
+                self.busy = False
                 time.sleep(0.020)   # NVML queries take a driver lock the launch path shares: keep them sparse
             else:
                 time.sleep(0.001)
@@ -343,7 +351,22 @@ def run_b200(args):
     x_dev, h_dev = x_host.to(dev), h_host.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    phase_ms = []
+
     def step(x, h):
+        if os.environ.get("CMWG_BENCH_DEBUG") == "1":
+            t = [time.perf_counter()]
+            sync.zero_grad(); t.append(time.perf_counter())
+            z, logdet = model(x, h); t.append(time.perf_counter())
+            loss = loss_fn(z, logdet); t.append(time.perf_counter())
+            loss.backward(); t.append(time.perf_counter())
+            sync.finish(); t.append(time.perf_counter())
+            opt.step(); t.append(time.perf_counter())
+            ms_ = torch.cuda.memory_stats()
+            phase_ms.append([round((b - a) * 1e3, 1) for a, b in zip(t[:-1], t[1:])] +
+                            [ms_["num_device_alloc"], ms_["num_device_free"], ms_["num_alloc_retries"],
+                             ms_["reserved_bytes.all.current"] >> 20, int(lib.cmwg_debug_counter(0)), int(lib.cmwg_debug_counter(1))])
+            return loss
         sync.zero_grad()
         z, logdet = model(x, h)
         loss = loss_fn(z, logdet)
@@ -358,6 +381,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     step_ms = {False: [], True: []}
+    dbg_host = []
 
     def timed(nsteps, e2e):
         total_ms = 0.0
@@ -367,10 +391,19 @@ def run_b200(args):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
             a.record()
-            if e2e:
-                x = x_host.to(dev, non_blocking=True)
-                h = h_host.to(dev, non_blocking=True)
-                last = step(x, h).item()                   # D2H read of the step's result
+            if e2e and os.environ.get("CMWG_BENCH_DEBUG") == "1":
+                t0 = time.perf_counter()
+                t1 = time.perf_counter()
+                lt = step(x_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True))
+                t2 = time.perf_counter()
+                last = lt.item()
+                t3 = time.perf_counter()
+                dbg_host.append([round((t1 - t0) * 1e3, 2), round((t2 - t1) * 1e3, 2), round((t3 - t2) * 1e3, 2)])
+            elif e2e:
+                # the inputs are temporaries, as in the warm-up: keeping last step's tensors bound while the next ones
+                # are created asks the caching allocator for one more 2 MB segment in the second step, and a cudaMalloc
+                # issued while the device is busy stalled that step's backward by 60-200 ms
+                last = step(x_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True)).item()  # + D2H read
             else:
                 last = step(x_dev, h_dev)
             b.record()
@@ -398,6 +431,14 @@ def run_b200(args):
     lib.cmwg_reset_launch_count()
     ms, loss = timed(args.steps, e2e=False)
     launches = int(lib.cmwg_launch_count())
+    if os.environ.get("CMWG_BENCH_SAMPLE_E2E", "0") != "1":
+        sampler.end()      # clocks are sampled over the device-resident leg (the timed region of `value`): an NVML query
+                           # holds a driver lock, and the e2e leg -- whose host thread cannot run ahead of the device
+                           # because it reads the loss back every step -- showed 60-100 ms stalls with the sampler on
+    # the e2e leg allocates its inputs per step, which shifts where the caching allocator places everything after them:
+    # let it reach its steady state (two alternating layouts) before timing
+    for _ in range(min(args.warmup, 3)):
+        step(x_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True)).item()
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
     sampler.end()
     gc.enable()
@@ -444,6 +485,25 @@ def run_b200(args):
                  "operand_dtype": precision.resolve(True, False),
                  "tflops_per_gpu": samples * 13.3764e6 / (t.item() * 1e-3) / 1e12,
                  "frac_of_bf16_peak": samples * 13.3764e6 / (t.item() * 1e-3) / 1e12 / pk["tflops_sustained"]}
+        # batch sweep of config 3 (10 s utterances, batch 1-64 per GPU): kHz per GPU at each batch size
+        if not args.no_synth_sweep:
+            sweep = {}
+            for sbb in (1, 4, 16, 64):
+                hb = torch.randn(sbb, LJ["n_mels"], SYNTH_FRAMES, device=dev)
+                zb = torch.randn(sbb, SYNTH_FRAMES * LJ["hop_size"], device=dev) * 0.6
+                with torch.no_grad():
+                    model.infer(hb, 0.6, z=zb)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    a.record()
+                    for _ in range(2):
+                        model.infer(hb, 0.6, z=zb)
+                    b.record()
+                    torch.cuda.synchronize()
+                sweep[str(sbb)] = round(sbb * SYNTH_FRAMES * LJ["hop_size"] / (a.elapsed_time(b) / 2 * 1e-3) / 1e3, 1)
+                del hb, zb
+            synth["per_gpu_khz_by_batch"] = sweep
+            torch.cuda.empty_cache()
         model.train()
 
     if rank != 0:
@@ -484,6 +544,7 @@ def run_b200(args):
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "ms_per_timed_step": {"device_resident": step_ms[False], "e2e": step_ms[True]},
+        **({"debug_e2e_host_ms_copy_enqueue_wait": dbg_host, "debug_phase_ms_zero_fwd_loss_bwd_finish_opt": phase_ms[-2 * args.steps - 1:]} if dbg_host else {}),
         "train_tflops_per_gpu": B * TRAIN_GFLOP_PER_SEGMENT / (ms / args.steps),
         "roofline": {"bound": "tensor", "kernel": roof_kernel,
                      "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
@@ -526,6 +587,7 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--synth-batch", type=int, default=4)
     ap.add_argument("--no-synth", action="store_true")
+    ap.add_argument("--no-synth-sweep", action="store_true", help="skip the synthesis batch sweep (1, 4, 16, 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-waveflow", action="store_true", help="skip the WaveFlow (config 4) leg")
     args = ap.parse_args()

@@ -96,6 +96,7 @@ SIGNATURES = {
     "cmwg_profile_enable": (_I, [_I]),
     "cmwg_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "cmwg_mega_clk_read": (_I, [C.POINTER(C.c_longlong), _I]),
+    "cmwg_debug_counter": (C.c_ulonglong, [_I]),
     "cmwg_selftest_tc_gemm": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
 }
 

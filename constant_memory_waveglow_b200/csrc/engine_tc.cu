@@ -47,6 +47,7 @@ struct MapKeyHash {
   }
 };
 static std::mutex g_map_mu;
+static unsigned long long g_map_misses = 0, g_map_clears = 0;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 
 static bool dbg_flag(const char* name) {
@@ -67,6 +68,7 @@ static int encode_cached(CUtensorMap* m, const MapKey& key, CUtensorMapDataType 
   }
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return CMWG_ERR_CUDA;
+  ++g_map_misses;
   CMWG_REQUIRE((reinterpret_cast<uintptr_t>(key.ptr) & 15) == 0 && ((long long)key.ld * esize) % 16 == 0,
                "tensor map: pointer/row pitch not 16-byte aligned (pitch %d elements)", key.ld);
   cuuint64_t dims[4] = {(cuuint64_t)key.d0, (cuuint64_t)key.d1, (cuuint64_t)(rank >= 3 ? key.d2 : 1),
@@ -83,7 +85,9 @@ static int encode_cached(CUtensorMap* m, const MapKey& key, CUtensorMapDataType 
     return CMWG_ERR_CUDA;
   }
   std::lock_guard<std::mutex> lk(g_map_mu);
-  if (g_map_cache.size() > 16384) g_map_cache.clear();
+  // a training step uses ~5000 descriptors; clearing costs one step of re-encoding (~60 ms), so the bound is generous
+  // (2^18 entries ~ 50 MB of host memory) and only reached by workloads whose buffer addresses keep changing
+  if (g_map_cache.size() > (1u << 18)) { g_map_cache.clear(); ++g_map_clears; }
   g_map_cache.emplace(key, *m);
   return CMWG_OK;
 }
@@ -224,6 +228,10 @@ int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int H, int T, i
 }  // namespace cmwg
 
 using namespace cmwg;
+
+extern "C" unsigned long long cmwg_debug_counter(int which) {
+  return which == 0 ? cmwg::g_map_misses : cmwg::g_map_clears;
+}
 
 extern "C" int cmwg_selftest_tc_gemm(const void* a, const void* b, float* d, int M, int N, int K, int is_fp16,
                                      int variant, void* stream) {

@@ -271,7 +271,7 @@ def _coupling_bwd(ctx, out_grad, ls_grad):
     # 1. (re)compute the WN output from the untouched half of the saved OUTPUT (xa == za)
     if recompute:
         if fused:
-            lst, st = F._cmwg_forward(out, y.detach(), save=True, prec=ctx.prec)
+            lst, st = F._cmwg_forward(out, y.detach(), save=True, prec=ctx.prec, transient=True)
         else:
             xa = out[:, :cin].detach().contiguous().requires_grad_(True)
             yy = y.detach().requires_grad_(need_dy)

@@ -191,10 +191,29 @@ class WN(nn.Module):
         self._pack_cache = {prec: (key, buf)}
         return cfg, buf, ps
 
+    # ---- scratch: per (device, stream, purpose) buffers that persist between calls ---------------------------------
+    # The kernels address every slab through TMA descriptors that the library caches by ADDRESS; a fresh torch.empty per
+    # call lands wherever the caching allocator has room, and a step whose workspaces land on new addresses re-encodes a few
+    # thousand descriptors (60-100 ms once measured).  Work on one stream is ordered, so one buffer per stream is safe.
+    _scratch: dict = {}
+    _SCRATCH_MAX = 6 << 30     # larger requests (long-utterance batches) are not kept
+
+    @classmethod
+    def _scratch_buf(cls, nbytes: int, device, purpose: str) -> Tensor:
+        if nbytes > cls._SCRATCH_MAX:
+            return torch.empty(nbytes, device=device, dtype=torch.uint8)
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream, purpose)
+        buf = cls._scratch.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(nbytes, device=device, dtype=torch.uint8)
+            cls._scratch[key] = buf
+        return buf
+
     # ---- fused entry points used by the coupling Functions --------------------------------------
-    def _cmwg_forward(self, x: Tensor, y: Tensor, save: bool, prec: Optional[str] = None):
+    def _cmwg_forward(self, x: Tensor, y: Tensor, save: bool, prec: Optional[str] = None, transient: bool = False):
         """x: (B, >=cin, T) NCL whose first `cin` channels are the WN input.  Returns (lst, state):
-        lst (B, 2cin, T) = [log_s ; t]."""
+        lst (B, 2cin, T) = [log_s ; t].  `transient`: the saved activations are consumed by a `_cmwg_backward` call that
+        follows immediately (the constant-memory recompute), so they may live in the per-stream scratch buffer."""
         L.require_cuda(x, y, op="WN.forward")
         if prec is None:
             prec = precision.resolve(self._tc_supported(), training=save)
@@ -207,9 +226,12 @@ class WN(nn.Module):
         if y.dtype != torch.float32:
             y = y.float()
         ycl = _cond_cache.get(y, cfg)
-        ws = torch.empty(int(lib.cmwg_wn_workspace_bytes(C.byref(cfg), B, T)), device=x.device, dtype=torch.uint8)
-        saved = torch.empty(int(lib.cmwg_wn_saved_bytes(C.byref(cfg), B, T)), device=x.device,
-                            dtype=torch.uint8) if save else None
+        ws = self._scratch_buf(int(lib.cmwg_wn_workspace_bytes(C.byref(cfg), B, T)), x.device, "ws")
+        saved = None
+        if save:
+            nsv = int(lib.cmwg_wn_saved_bytes(C.byref(cfg), B, T))
+            saved = self._scratch_buf(nsv, x.device, "saved") if transient else \
+                torch.empty(nsv, device=x.device, dtype=torch.uint8)
         lst = torch.empty((B, 2 * self.in_chs, T), device=x.device, dtype=torch.float32)
         L.check(lib.cmwg_wn_forward(C.byref(cfg), packed.data_ptr(), x.data_ptr(), ops._bstride(x), ycl.data_ptr(), B, T,
                                     ws.data_ptr(), L.ptr(saved), lst.data_ptr(), L.stream_ptr(x.device)), "wn_forward")
@@ -246,7 +268,7 @@ class WN(nn.Module):
         grads, by_param = self._grads_struct()
         aux_p = lib.cmwg_wn_aux_padded(C.byref(st.cfg))
         dycl = torch.empty((st.B, st.T, aux_p), device=dev, dtype=torch.float32) if need_dy else None
-        ws = torch.empty(int(lib.cmwg_wn_workspace_bytes(C.byref(st.cfg), st.B, st.T)), device=dev, dtype=torch.uint8)
+        ws = self._scratch_buf(int(lib.cmwg_wn_workspace_bytes(C.byref(st.cfg), st.B, st.T)), dev, "ws")
         L.check(lib.cmwg_wn_backward(C.byref(st.cfg), C.byref(st.params), st.packed.data_ptr(), x.data_ptr(),
                                      ops._bstride(x), st.ycl.data_ptr(), st.B, st.T, ws.data_ptr(),
                                      st.saved.data_ptr(), dlst.data_ptr(), dx.data_ptr(), ops._bstride(dx),

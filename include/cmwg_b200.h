@@ -166,6 +166,8 @@ size_t cmwg_wn_packed_bytes(const cmwg_wn_config* cfg);
 int cmwg_wn_pack(const cmwg_wn_config* cfg, const cmwg_wn_params* params, void* packed, void* stream);
 
 size_t cmwg_wn_workspace_bytes(const cmwg_wn_config* cfg, int B, int T);
+/* tools only: 0 = TMA descriptor encodes so far (cache misses), 1 = descriptor cache clears */
+unsigned long long cmwg_debug_counter(int which);
 /* tools only: cycle accumulators [CTA][18 warps][16] of the last single-kernel WN forward launched with CMWG_MEGA_CLK=1 */
 int cmwg_mega_clk_read(long long* host, int n);
 /* bytes of per-layer activations kept between cmwg_wn_forward(save != NULL) and cmwg_wn_backward */
