@@ -129,6 +129,34 @@ int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaS
   return CMWG_OK;
 }
 
+// Task kernels (engine_mega.cuh) spin on counters that OTHER CTAs of the same grid advance: every CTA must be resident.
+// A cooperative launch makes the driver place the whole grid at once (or fail), so two such kernels on different streams
+// cannot each hold part of the machine and wait for the rest.  Cooperative launches do not take the programmatic-
+// dependent-launch attribute; the kernels' griddepcontrol instructions are no-ops then.
+int tc_launch_pairs_coresident(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st) {
+  static const bool off = dbg_flag("CMWG_NO_COOP");
+  if (off) return tc_launch_pairs(kern, smem, pairs, args, st);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  CMWG_CHECK_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+  static const bool dbg_sync = dbg_flag("CMWG_DEBUG_SYNC");
+  if (dbg_sync) CMWG_CHECK_CUDA(cudaStreamSynchronize(st));
+  return CMWG_OK;
+}
+
 constexpr int TC_PLAN_PAIRS = 74;  // CTA pairs of a B200 (148 SMs); only load balance depends on it
 
 static int wgrad_group_splits(const WgradProblem* probs, int nprob, int bn, int B, int T) {  // B = lines

@@ -161,7 +161,7 @@ static int mega_launch(const MegaParams& p, cudaStream_t st) {
   const int pairs = std::min(p.total_tasks, num_sms() / 2);
   ProfScope prof(st, CMWG_KCLASS_FWDFUSED);
   void* args[1] = {(void*)&p};
-  CMWG_PROPAGATE(tc_launch_pairs((const void*)kern, smem, pairs, args, st));
+  CMWG_PROPAGATE(tc_launch_pairs_coresident((const void*)kern, smem, pairs, args, st));
   CMWG_COUNT_LAUNCH();
   return CMWG_OK;
 }
@@ -270,7 +270,7 @@ static int wn_backward_mega(const WnDims& d, const PackedLayout& PL, const BwdLa
   const int pairs = std::min(p.total_tasks, num_sms() / 2);
   ProfScope prof(st, CMWG_KCLASS_BWDFUSED);
   void* args[1] = {(void*)&p};
-  CMWG_PROPAGATE(tc_launch_pairs((const void*)kern, smem, pairs, args, st));
+  CMWG_PROPAGATE(tc_launch_pairs_coresident((const void*)kern, smem, pairs, args, st));
   CMWG_COUNT_LAUNCH();
   return CMWG_OK;
 }

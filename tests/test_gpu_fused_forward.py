@@ -52,6 +52,30 @@ SHAPES = [
 ]
 
 
+def test_fused_forward_radix5_and_two_streams():
+    """Five taps (the halo still reaches one tile at most: 2 * 2^5 = 64 rows), and two streams at once: each stream
+    has its own persistent workspace, so concurrent calls must not disturb each other."""
+    wn = _wn(4, 80, 6, radix=5, seed=2)
+    x = torch.randn(3, 8, 1500, device="cuda")
+    y = torch.randn(3, 80, 1500, device="cuda")
+    a, b = _both(lambda: wn._cmwg_forward(x, y, save=False, prec="bf16")[0].clone())
+    assert torch.equal(a, b)
+
+    wn8 = _wn(4, 80, 8)
+    xs = [torch.randn(6, 8, 2000, device="cuda") for _ in range(2)]
+    ys = [torch.randn(6, 80, 2000, device="cuda") for _ in range(2)]
+    want = [wn8._cmwg_forward(xs[i], ys[i], save=False, prec="bf16")[0].clone() for i in range(2)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [None, None]
+    for rep in range(3):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                got[i] = wn8._cmwg_forward(xs[i], ys[i], save=False, prec="bf16")[0]
+        torch.cuda.synchronize()
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+
+
 @pytest.mark.parametrize("cin,aux,depth,B,T", SHAPES)
 @pytest.mark.parametrize("prec,save", [("bf16", False), ("bf16", True), ("fp16", False)])
 def test_fused_forward_equals_layered_pipeline(cin, aux, depth, B, T, prec, save):
