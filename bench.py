@@ -119,6 +119,23 @@ class ClockSampler:
         while self.busy and time.time() - t0 < 1.0:
             time.sleep(0.001)
 
+    def sample_once(self):
+        """One synchronous sample from the calling thread (used to top up a leg that got fewer than three)."""
+        n = self.nvml
+        if n is None:
+            return
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        try:
+            mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            try:
+                bits = int(get_reasons(self.handle))
+            except Exception:
+                bits = 0
+            self.rows.append((mhz, bits))
+        except Exception:
+            pass
+
     def _poll_nvml(self):
         n = self.nvml
         get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
@@ -136,7 +153,8 @@ class ClockSampler:
                 except Exception:
                     pass
                 self.busy = False
-                time.sleep(0.020)   # NVML queries take a driver lock the launch path shares: keep them sparse
+                time.sleep(0.060)   # a query takes 1 ms on most boxes but 20-40 ms on some, holding a driver lock the
+                                    # launch path needs: a few samples per timed leg are enough for the median   # NVML queries take a driver lock the launch path shares: keep them sparse
             else:
                 time.sleep(0.001)
 
@@ -441,6 +459,14 @@ def run_b200(args):
         step(x_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True)).item()
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
     sampler.end()
+    if rank == 0 and sampler.nvml is not None and len(sampler.rows) < 3:
+        # slow NVML on this box: top the clock samples up under the same load (untimed steps in flight)
+        for _ in range(3):
+            step(x_dev, h_dev)
+        for _ in range(3):
+            sampler.sample_once()
+            time.sleep(0.01)
+        torch.cuda.synchronize()
     gc.enable()
     clocks = sampler.stop() if rank == 0 else None
 
