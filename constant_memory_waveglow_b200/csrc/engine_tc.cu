@@ -130,12 +130,14 @@ int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaS
 }
 
 // Task kernels (engine_mega.cuh) spin on counters that OTHER CTAs of the same grid advance: every CTA must be resident.
-// A cooperative launch makes the driver place the whole grid at once (or fail), so two such kernels on different streams
-// cannot each hold part of the machine and wait for the rest.  Cooperative launches do not take the programmatic-
-// dependent-launch attribute; the kernels' griddepcontrol instructions are no-ops then.
+// On one stream that holds by construction (grid <= SM count / 2 pairs, one CTA per SM, and whatever else runs -- NCCL's
+// kernels -- finishes on its own).  Two task kernels on DIFFERENT streams could each hold part of the machine and wait for
+// the rest; CMWG_COOP=1 launches them cooperatively (the driver places the whole grid at once or not at all; no
+// programmatic dependent launch then).  It is opt-in because Nsight Compute cannot replay cooperative cluster launches
+// (LaunchFailed), and every measurement here goes through it.
 int tc_launch_pairs_coresident(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st) {
-  static const bool off = dbg_flag("CMWG_NO_COOP");
-  if (off) return tc_launch_pairs(kern, smem, pairs, args, st);
+  const char* v = getenv("CMWG_COOP");
+  if (!(v && v[0] == '1')) return tc_launch_pairs(kern, smem, pairs, args, st);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs, 1, 1);

@@ -302,6 +302,41 @@ static __global__ void __launch_bounds__(256) smallk_to_slab_kernel(const float*
     wsm[idx] = W[(long long)o * so + (long long)i * si];
   }
   __syncthreads();
+  if constexpr (sizeof(OpT) == 2) {
+    // 16-bit slabs: 8 channels per thread, one 16-byte store per stream (a quarter warp writes one 128-byte line)
+    if ((C & 7) == 0 && o32 == nullptr && ohi != nullptr) {
+      const int c8 = C >> 3;
+      for (int idx = threadIdx.x; idx < SMALLK_ROWS * c8; idx += 256) {
+        const int r = idx / c8, o = (idx % c8) * 8;
+        const int t = t0 + r;
+        if (t >= t_end) continue;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[o + j] : 0.f;
+        for (int i = 0; i < K; ++i) {
+          const float xv = xs[i * SMALLK_ROWS + r];
+          const float4 w0 = *reinterpret_cast<const float4*>(wsm + i * C + o);
+          const float4 w1 = *reinterpret_cast<const float4*>(wsm + i * C + o + 4);
+          acc[0] = fmaf(w0.x, xv, acc[0]); acc[1] = fmaf(w0.y, xv, acc[1]);
+          acc[2] = fmaf(w0.z, xv, acc[2]); acc[3] = fmaf(w0.w, xv, acc[3]);
+          acc[4] = fmaf(w1.x, xv, acc[4]); acc[5] = fmaf(w1.y, xv, acc[5]);
+          acc[6] = fmaf(w1.z, xv, acc[6]); acc[7] = fmaf(w1.w, xv, acc[7]);
+        }
+        const long long off = ((long long)b * T + t) * C + o;
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h[j] = pack2(acc[2 * j], acc[2 * j + 1], is_fp16);
+          float f0, f1;
+          unpack2(h[j], is_fp16, f0, f1);
+          l[j] = pack2(acc[2 * j] - f0, acc[2 * j + 1] - f1, is_fp16);
+        }
+        *reinterpret_cast<uint4*>(ohi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (olo) *reinterpret_cast<uint4*>(olo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      return;
+    }
+  }
   const int c4 = C >> 2;
   for (int idx = threadIdx.x; idx < SMALLK_ROWS * c4; idx += 256) {
     const int r = idx / c4, o = (idx % c4) * 4;

@@ -68,12 +68,14 @@ def test_fused_forward_radix5_and_two_streams():
     torch.cuda.synchronize()
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]
     got = [None, None]
+    os.environ["CMWG_COOP"] = "1"      # concurrent task kernels: cooperative launches keep each grid whole
     for rep in range(3):
         for i, st in enumerate(streams):
             with torch.cuda.stream(st):
                 got[i] = wn8._cmwg_forward(xs[i], ys[i], save=False, prec="bf16")[0]
         torch.cuda.synchronize()
         assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    os.environ.pop("CMWG_COOP", None)
 
 
 @pytest.mark.parametrize("cin,aux,depth,B,T", SHAPES)
