@@ -732,3 +732,138 @@ def mrwaveglow_train_step(sd: State, spec: MRSpec, x: Tensor, h: Tensor, sigma: 
     keys = [k for k, v in leaf.items() if v.requires_grad]
     grads = torch.autograd.grad(loss, [leaf[k] for k in keys], allow_unused=True)
     return z.detach(), logdet.detach(), loss.detach(), {k: g for k, g in zip(keys, grads) if g is not None}
+
+
+# --------------------------------------------------------------------------------------------
+# MelGlow (model/melglow.py): kernel predictor, location-variable convolution layers, flow wiring
+# --------------------------------------------------------------------------------------------
+@dataclass
+class MelGlowSpec:
+    flows: int
+    n_group: int
+    n_early_every: int
+    n_early_size: int
+    hop_size: int
+    n_mels: int
+    # WN_LVC
+    dilation_channels: int = 48
+    residual_channels: int = 48
+    skip_channels: int = 48
+    depth: int = 7
+    radix: int = 3
+    predict_channels: int = 64
+    predict_layers: int = 3
+
+    @property
+    def upsample_factor(self) -> int:
+        return self.hop_size // self.n_group
+
+
+def _bn_train(sd: State, prefix: str, x: Tensor, eps: float = 1e-5) -> Tensor:
+    """``nn.BatchNorm1d`` in training mode: batch statistics over (batch, time), biased variance."""
+    mean = x.mean((0, 2), keepdim=True)
+    var = x.var((0, 2), unbiased=False, keepdim=True)
+    return (x - mean) / torch.sqrt(var + eps) * sd[prefix + "weight"].view(1, -1, 1) + sd[prefix + "bias"].view(1, -1, 1)
+
+
+def lvc_predictor(sd: State, prefix: str, spec: MelGlowSpec, y: Tensor) -> Tensor:
+    """``Predictor.forward`` (``model/melglow.py:44-49``), BatchNorm in training mode."""
+    g = spec.depth
+    s = torch.tanh(_bn_train(sd, prefix + "start.1.", F.conv1d(y, sd[prefix + "start.0.weight"], sd.get(prefix + "start.0.bias"))))
+    for j in range(spec.predict_layers):
+        b = prefix + f"res_blocks.{j}."
+        u = torch.tanh(_bn_train(sd, b + "1.", F.conv1d(s, sd[b + "0.weight"], sd.get(b + "0.bias"), groups=g)))
+        u = torch.tanh(_bn_train(sd, b + "4.", F.conv1d(u, sd[b + "3.weight"], sd.get(b + "3.bias"), groups=g)))
+        s = u + s
+    return F.conv1d(s, sd[prefix + "end.weight"], sd.get(prefix + "end.bias"), groups=g)
+
+
+def lvc_layer(sd: State, prefix: str, dilation: int, radix: int, x: Tensor, weights: Tensor, last: bool):
+    """``NonCausalLayerLVC.forward`` (``model/melglow.py:74-92``): unfold the padded signal into one window per frame and
+    apply that frame's kernel as a grouped convolution."""
+    batch, steps, cout, cin, _ = weights.shape
+    pad = dilation * (radix - 1) // 2
+    offset = x.shape[2] // steps
+    w = weights.reshape(batch * steps * cout, cin, radix)
+    ux = F.pad(x, (pad, pad)).unfold(2, pad * 2 + offset, offset).transpose(1, 2).contiguous().view(1, -1, pad * 2 + offset)
+    z = F.conv1d(ux, w, dilation=dilation, groups=batch * steps)
+    zw, zv = z.view(batch, steps, cout, -1).transpose(1, 2).contiguous().view(batch, cout, -1).chunk(2, 1)
+    o = F.conv1d(fused_gate(zw, zv), resolve_weight(sd, prefix + "W_o."), resolve_bias(sd, prefix + "W_o."))
+    if last:
+        return None, o
+    cr = x.shape[1]
+    return o[:, :cr] + x, o[:, cr:]
+
+
+def wn_lvc_forward(sd: State, prefix: str, spec: MelGlowSpec, x: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
+    """``WN_LVC.forward`` (``model/melglow.py:147-159``)."""
+    x = F.conv1d(x, resolve_weight(sd, prefix + "start."), resolve_bias(sd, prefix + "start."))
+    wts = lvc_predictor(sd, prefix + "pred.", spec, y)
+    wts = wts.view(wts.shape[0], spec.depth, -1, wts.shape[2]).permute(1, 0, 3, 2).contiguous()
+    cum = 0
+    for i in range(spec.depth):
+        w = wts[i].view(wts.shape[1], wts.shape[2], 2 * spec.dilation_channels, spec.residual_channels, spec.radix)
+        x, skip = lvc_layer(sd, prefix + f"layers.{i}.", 2 ** i, spec.radix, x, w, i == spec.depth - 1)
+        cum = cum + skip
+    out = F.conv1d(cum, sd[prefix + "end.weight"], sd.get(prefix + "end.bias"))
+    return tuple(out.chunk(2, 1))
+
+
+def _lvc_coupling(sd: State, prefix: str, spec: MelGlowSpec, x: Tensor, y: Tensor, inverse: bool):
+    """``AffineCouplingBlock`` around ``WN_LVC`` (``model/efficient_modules.py:77-82,91-96``)."""
+    xa, xb = x.chunk(2, 1)
+    log_s, t = wn_lvc_forward(sd, prefix, spec, xa, y)
+    if inverse:
+        return torch.cat((xa, (xb - t) / log_s.exp()), 1), -log_s
+    return torch.cat((xa, xb * log_s.exp() + t), 1), log_s
+
+
+def melglow_forward(sd: State, spec: MelGlowSpec, x: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
+    """``MelGlow.forward_computation`` (``model/melglow.py:204-232``)."""
+    B = x.size(0)
+    x = x[:, :x.shape[1] // spec.hop_size * spec.hop_size]
+    x = x.view(B, -1, spec.n_group).transpose(1, 2)
+    y = h[..., :x.shape[2] // spec.upsample_factor]
+    outs, logdet = [], 0
+    for k in range(spec.flows):
+        if k % spec.n_early_every == 0 and k:
+            outs.append(x[:, :spec.n_early_size])
+            x = x[:, spec.n_early_size:]
+        x, ldw = conv1x1_forward(sd[f"invconv1x1.{k}.weight"], x)
+        x, log_s = _lvc_coupling(sd, f"WNs.{k}.F.", spec, x, y, False)
+        logdet = logdet + ldw + log_s.sum((1, 2))
+    outs.append(x)
+    return torch.cat([o.transpose(1, 2) for o in outs], 2).reshape(B, -1), logdet
+
+
+def melglow_reverse(sd: State, spec: MelGlowSpec, z: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
+    """``MelGlow.reverse_computation`` (``model/melglow.py:234-258``)."""
+    B = z.size(0)
+    z = z[:, :z.shape[1] // spec.hop_size * spec.hop_size]
+    z = z.view(B, -1, spec.n_group).transpose(1, 2)
+    y = h[..., :z.shape[2] // spec.upsample_factor]
+    sizes, rem = [], spec.n_group
+    for k in range(spec.flows):
+        if k % spec.n_early_every == 0 and k:
+            rem -= spec.n_early_size
+            sizes.append(spec.n_early_size)
+    sizes.append(rem)
+    *remained, z = z.split(sizes, 1)
+    remained = list(remained)
+    logdet = 0
+    for k in range(spec.flows - 1, -1, -1):
+        z, log_s = _lvc_coupling(sd, f"WNs.{k}.F.", spec, z, y, True)
+        z, ldw = conv1x1_reverse(sd[f"invconv1x1.{k}.weight"], z)
+        logdet = logdet + ldw + log_s.sum((1, 2))
+        if k % spec.n_early_every == 0 and k:
+            z = torch.cat((remained.pop(), z), 1)
+    return z.transpose(1, 2).contiguous().view(B, -1), logdet
+
+
+def melglow_train_step(sd: State, spec: MelGlowSpec, x: Tensor, h: Tensor, sigma: float):
+    leaf = _leafify(sd)
+    z, logdet = melglow_forward(leaf, spec, x, h)
+    loss = waveglow_loss(z, logdet, sigma)
+    keys = [k for k, v in leaf.items() if v.requires_grad and "running_" not in k]
+    grads = torch.autograd.grad(loss, [leaf[k] for k in keys], allow_unused=True)
+    return z.detach(), logdet.detach(), loss.detach(), {k: g for k, g in zip(keys, grads) if g is not None}
