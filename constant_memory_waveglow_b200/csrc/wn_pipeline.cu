@@ -200,8 +200,14 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
   static const int lag_env = [] { const char* v = getenv("CMWG_MEGA_LAG"); return v ? atoi(v) : 64; }();
   p.lag = std::max(0, std::min(lag_env, p.RT - 2));
   p.total_tasks = (d.depth * p.RT + p.lag) * (p.ngt + 1) + p.RT;
+  // timing experiments that SKIP synchronisation or epilogue work (wrong results by design) exist only in builds made
+  // with -DCMWG_MEGA_EXPERIMENTS; the shipped library ignores CMWG_MEGA_DBG
+#ifdef CMWG_MEGA_EXPERIMENTS
   static const int dbg_env = [] { const char* v = getenv("CMWG_MEGA_DBG"); return v ? atoi(v) : 0; }();
   p.dbg = dbg_env;
+#else
+  p.dbg = 0;
+#endif
   {
     // lagged completion signals are deadlock-free when no unit can depend, even transitively, on the unit its own pair
     // ran just before it: every dependency points >= D entries back and a pair's consecutive units are <= 2 * pairs apart
