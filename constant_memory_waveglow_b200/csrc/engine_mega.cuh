@@ -18,8 +18,9 @@
 // resident (grid <= SM count / 2, one CTA per SM).  A wait that exceeds ~2 s traps instead of hanging the device.
 //
 // Roles, rings, TMEM double buffering and the epilogue functors are those of engine_tc.cuh; the epilogue switches
-// functor per task (warp-uniform), and the residual epilogue works IN PLACE in its staging buffers (inputs are read
-// into registers, outputs overwrite them), which leaves room for 4-5 operand stages.
+// functor per task (warp-uniform), the residual epilogue works IN PLACE in its staging buffers (inputs are read into
+// registers, outputs overwrite them) and a third output stream waits in registers for the first two stores, so 4 KB of
+// staging per warp suffice and five operand stages fit.
 #pragma once
 #include "engine_tc.cuh"
 #include "epilogues_tc.cuh"
@@ -154,6 +155,8 @@ __device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem
   constexpr int NCH = GW / 128;                      // 32-column chunks per warp
   constexpr int OUTW = Epi::kOutF32 ? 16 : 8;
   constexpr int OCH = Epi::kOutF32 ? TC_CHUNK32_BYTES : TC_CHUNK16_BYTES;
+  constexpr int NST = Epi::kOut < 2 ? Epi::kOut : 2;   // streams staged at once: the staging holds two 2 KB chunks, a third
+                                                       // stream (saved sigmoid) waits in registers for the first stores
   const uint32_t taddr = tmem_tile + ((uint32_t)(q * 32) << 16) + cg * (GW / 4);
   const CUtensorMap* om[3] = {om0, om1, om2};
   const CUtensorMap* im[2] = {im0, im1};
@@ -185,6 +188,7 @@ __device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem
       for (int i = 0; i < Epi::kIn; ++i) stage_load16(wbuf + i * TC_CHUNK16_BYTES, lane, in[i]);
       __syncwarp();
     }
+    uint32_t keep[2][OUTW];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float v[16];
@@ -217,24 +221,40 @@ __device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem
         }
       }
 #pragma unroll
-      for (int i = 0; i < Epi::kOut; ++i) {
+      for (int i = 0; i < NST; ++i) {
         if constexpr (Epi::kOutF32) stage_store32h(wbuf + i * OCH, lane, h, o[i]);
         else stage_store16h(wbuf + i * OCH, lane, h, o[i]);
+      }
+      if constexpr (Epi::kOut > 2) {
+#pragma unroll
+        for (int j = 0; j < OUTW; ++j) keep[h][j] = o[2][j];
       }
     }
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < Epi::kOut; ++i) tma_store_4d(om[i], wbuf + i * OCH, c0, r0, 0, b);
+      for (int i = 0; i < NST; ++i) tma_store_4d(om[i], wbuf + i * OCH, c0, r0, 0, b);
       bulk_commit();
+    }
+    if constexpr (Epi::kOut > 2 && !Epi::kOutF32) {
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+      stage_store16h(wbuf, lane, 0, keep[0]);
+      stage_store16h(wbuf, lane, 1, keep[1]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(om[2], wbuf, c0, r0, 0, b);
+        bulk_commit();
+      }
     }
   }
   const long long c_c = clock64();
   if (lane == 0) {
     if (dbg & 2) sig.flag = nullptr;
     if (prev != nullptr) {
-      bulk_wait_complete<NCH>();  // this unit committed NCH groups: everything older is complete
+      bulk_wait_complete<NCH * (Epi::kOut > 2 ? 2 : 1)>();  // this unit's own groups may be pending, everything older is complete
       mega_signal(*prev);
       *prev = sig;
     } else {
@@ -250,7 +270,7 @@ __device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem
 }
 
 template <bool SAVE>
-constexpr int mega_warp_bytes() { return SAVE ? 3 * TC_CHUNK16_BYTES : 2 * TC_CHUNK16_BYTES; }
+constexpr int mega_warp_bytes() { return 2 * TC_CHUNK16_BYTES; }
 constexpr int MEGA_STAGE_BYTES = TC_A_BYTES + (MEGA_BN / 2) * 128;
 template <bool SAVE>
 constexpr int mega_stages() {
