@@ -1,62 +1,62 @@
-"""Direction-dispatching base classes, mirroring the reference's ``model/base.py`` surface
-(``Reversible`` :7-28, ``FlowBase`` :31-55): same names, methods and argument meaning."""
-from typing import Tuple
+"""Direction dispatch and the flow-model contract: the surface of the reference's ``model/base.py``
+(``Reversible`` :7-28, ``FlowBase`` :31-55) -- same names, methods and argument meaning.
+
+A ``Reversible`` owns two computations, one the inverse of the other; ``reverse_mode=True`` swaps which of them ``forward()``
+runs, so that a flow can be trained in the synthesis direction.  ``FlowBase`` adds the model contract
+``forward(x, h) -> (z, logdet)``, ``reverse(z, h) -> (x, logdet)`` and ``infer(h, sigma) -> audio``.
+"""
+from typing import Callable, Optional, Tuple
 
 import torch
-import torch.nn as nn
-from torch import Tensor
+from torch import Tensor, nn
+
+FlowOut = Tuple[Tensor, Tensor]
 
 
 class Reversible(nn.Module):
-    """A module with a forward and an inverse computation; ``reverse_mode=True`` swaps which one
-    ``forward()`` runs (reference ``model/base.py:20-28``)."""
     _reverse_mode: bool
 
     def __init__(self, reverse_mode, **kwargs) -> None:
         super().__init__(**kwargs)
         self._reverse_mode = reverse_mode
 
-    def forward_computation(self, x: Tensor, *args, **kwargs) -> Tuple[Tensor, Tensor]:
-        raise NotImplementedError
+    # the two directions a subclass provides
+    def forward_computation(self, x: Tensor, *args, **kwargs) -> FlowOut:
+        raise NotImplementedError(f"{type(self).__name__} defines no forward computation")
 
-    def reverse_computation(self, z: Tensor, *args, **kwargs) -> Tuple[Tensor, Tensor]:
-        raise NotImplementedError
+    def reverse_computation(self, z: Tensor, *args, **kwargs) -> FlowOut:
+        raise NotImplementedError(f"{type(self).__name__} defines no reverse computation")
 
-    def forward(self, x: Tensor, *args, **kwargs) -> Tuple[Tensor, Tensor]:
-        fn = self.reverse_computation if self._reverse_mode else self.forward_computation
-        return fn(x, *args, **kwargs)
+    def _direction(self, inverse: bool) -> Callable[..., FlowOut]:
+        """The computation that realises the requested direction under this module's mode (XOR of the two switches)."""
+        return self.reverse_computation if inverse != bool(self._reverse_mode) else self.forward_computation
 
-    def reverse(self, z: Tensor, *args, **kwargs) -> Tuple[Tensor, Tensor]:
-        fn = self.forward_computation if self._reverse_mode else self.reverse_computation
-        return fn(z, *args, **kwargs)
+    def forward(self, x: Tensor, *args, **kwargs) -> FlowOut:
+        return self._direction(False)(x, *args, **kwargs)
+
+    def reverse(self, z: Tensor, *args, **kwargs) -> FlowOut:
+        return self._direction(True)(z, *args, **kwargs)
 
 
 class FlowBase(Reversible):
-    """Flow model contract (reference ``model/base.py:31-55``): ``forward(x, h) -> (z, logdet)``,
-    ``reverse(z, h) -> (x, logdet)``, ``infer(h, sigma) -> audio``."""
-
     def __init__(self, condition_hop_length: int, reverse_mode=False) -> None:
         super().__init__(reverse_mode=reverse_mode)
         self._hop_length = condition_hop_length
 
-    def forward_computation(self, x: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
-        raise NotImplementedError
+    def forward_computation(self, x: Tensor, h: Tensor) -> FlowOut:
+        raise NotImplementedError(f"{type(self).__name__} defines no forward computation")
 
-    def reverse_computation(self, z: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
-        raise NotImplementedError
+    def reverse_computation(self, z: Tensor, h: Tensor) -> FlowOut:
+        raise NotImplementedError(f"{type(self).__name__} defines no reverse computation")
 
     @torch.no_grad()
-    def infer(self, h: Tensor, sigma: float = 1., z: Tensor = None) -> Tensor:
-        """Sample z ~ N(0, sigma^2) of length frames*hop and run the synthesis direction
-        (reference ``model/base.py:42-55``).  ``z`` may be supplied (already scaled) so that parity
-        tests feed the oracle and this path identical noise."""
-        if h.dim() == 2:
-            h = h.unsqueeze(0)
-        batch, _, steps = h.shape
+    def infer(self, h: Tensor, sigma: float = 1., z: Optional[Tensor] = None) -> Tensor:
+        """Synthesis (``model/base.py:42-55``): z ~ N(0, sigma^2) with ``frames * hop`` samples per item, pushed through the
+        direction that maps noise to audio.  ``z`` may be supplied (already scaled) so that parity tests feed the oracle and
+        this path identical noise."""
+        cond = h if h.dim() == 3 else h.unsqueeze(0)
         if z is None:
-            z = h.new_empty((batch, steps * self._hop_length)).normal_(std=sigma)
-        if self._reverse_mode:
-            x, _ = self.forward_computation(z, h)
-        else:
-            x, _ = self.reverse_computation(z, h)
-        return x.squeeze()
+            n_items, frames = cond.shape[0], cond.shape[2]
+            z = cond.new_empty((n_items, frames * self._hop_length)).normal_(std=sigma)
+        audio, _ = self._direction(True)(z, cond)
+        return audio.squeeze()

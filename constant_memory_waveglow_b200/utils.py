@@ -1,29 +1,38 @@
-"""Weight-norm helpers and the reflection factory (reference ``utils.py:5-16``).
+"""Weight-norm helpers and the reflection factory: the names and behaviour of the reference's ``utils.py:5-16``.
 
-``add_weight_norms`` fixes the parameter layout the autograd Functions see (``weight_g`` of shape
-(out,1,1) + ``weight_v``); ``remove_weight_norms`` collapses them back to ``weight`` for inference.
-The kernels never call the wrapped module's forward, so the weight-norm pre-hook costs nothing:
-g*v/||v|| is recomputed on the device by ``cmwg_wn_pack`` once per weight version.
+``add_weight_norms`` / ``remove_weight_norms`` are ``module.apply`` visitors.  They fix the parameter layout the autograd
+Functions see (``weight_g`` of shape (out, 1, 1) + ``weight_v``) and collapse it back to ``weight`` for inference.  The kernels
+never call a wrapped module's forward, so the weight-norm pre-hook costs nothing at run time: g * v / ||v|| is recomputed on
+the device by ``cmwg_wn_pack`` once per weight version.
 """
-import os
+from pathlib import Path
+from typing import Any, Mapping
 
-from torch import nn
+from torch.nn.utils import remove_weight_norm, weight_norm
 
-
-def get_instance(module, config, *args):
-    return getattr(module, config['type'])(*args, **config['args'])
-
-
-def remove_weight_norms(m):
-    if hasattr(m, 'weight_g'):
-        nn.utils.remove_weight_norm(m)
+__all__ = ["get_instance", "add_weight_norms", "remove_weight_norms", "ensure_dir"]
 
 
-def add_weight_norms(m):
-    if hasattr(m, 'weight'):
-        nn.utils.weight_norm(m)
+def get_instance(module: Any, config: Mapping[str, Any], *args):
+    """Build ``module.<config['type']>(*args, **config['args'])`` -- how ``LightModel`` turns the JSON blocks ``arch``,
+    ``conditioner``, ``loss``, ``optimizer`` and ``dataset`` into objects (``model/lightning.py:33-35,42-49``)."""
+    factory = getattr(module, config["type"])
+    return factory(*args, **config["args"])
 
 
-def ensure_dir(path):
-    if not os.path.exists(path):
-        os.makedirs(path)
+def add_weight_norms(m) -> None:
+    """Give every visited module that owns a ``weight`` the (``weight_g``, ``weight_v``) parametrisation over dim 0."""
+    if not hasattr(m, "weight"):
+        return
+    weight_norm(m, name="weight", dim=0)
+
+
+def remove_weight_norms(m) -> None:
+    """Fold (``weight_g``, ``weight_v``) back into a plain ``weight`` where a visited module has them."""
+    if not hasattr(m, "weight_g"):
+        return
+    remove_weight_norm(m, name="weight")
+
+
+def ensure_dir(path) -> None:
+    Path(path).mkdir(parents=True, exist_ok=True)
