@@ -114,7 +114,7 @@ __device__ __forceinline__ void mega_wait_flags3(const uint32_t* a, const uint32
 struct MegaTask {
   int type, layer, rt, nt;
 };
-__device__ __forceinline__ MegaTask mega_decode(const MegaParams& p, int idx) {
+__host__ __device__ __forceinline__ MegaTask mega_decode(const MegaParams& p, int idx) {
   // slots 0 .. depth*RT + lag - 1, (ngt + 1) positions each: G(u = slot, nt) then R(u = slot - lag); positions whose
   // task does not exist are MEGA_NONE (skipped by every role alike); the skip tiles follow
   MegaTask t;
@@ -518,7 +518,7 @@ struct alignas(64) MegaBwdParams {
   int lag, total_tasks;
 };
 
-__device__ __forceinline__ MegaTask mega_bwd_decode(const MegaBwdParams& p, int idx) {
+__host__ __device__ __forceinline__ MegaTask mega_bwd_decode(const MegaBwdParams& p, int idx) {
   MegaTask t;
   t.nt = 0;
   if (idx < p.RT) {

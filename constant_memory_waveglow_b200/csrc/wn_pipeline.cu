@@ -142,6 +142,17 @@ static bool mega_enabled() {  // read at every call: tests flip CMWG_MEGA inside
   return !(v && v[0] == '0');
 }
 
+// residual (forward) / dgate (backward) tiles trail their gate / dx tiles by `lag` row-tile slots; lag <= RT - 2 keeps the
+// list in dependency order (tests/test_host.py::test_task_lists_are_in_dependency_order)
+static inline int mega_fwd_lag(int RT) {
+  static const int lag_env = [] { const char* v = getenv("CMWG_MEGA_LAG"); return v ? atoi(v) : 64; }();
+  return std::max(0, std::min(lag_env, RT - 2));
+}
+static inline int mega_bwd_lag(int RT) {
+  static const int lag_env = [] { const char* v = getenv("CMWG_MEGA_LAG_BWD"); return v ? atoi(v) : 96; }();
+  return std::max(0, std::min(lag_env, RT - 2));
+}
+
 static inline bool mega_shapes_ok(const WnDims& d, int B, int T) {
   return d.tc && d.H == 1 && !d.bias && d.depth >= 1 && d.depth <= MEGA_D && d.Cr == 256 && d.Cs == 256 &&
          d.Cd % 128 == 0 && d.bn_gate == 256 && (((d.radix - 1) / 2) << (d.depth - 1)) <= 2 * TC_BM && d.radix <= 7 &&
@@ -197,8 +208,7 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
   p.idesc = make_idesc(f16, 2 * TC_BM, MEGA_BN, 0, 0);
   p.desc_lbo = 1u; p.desc_sbo = 1024u >> 4;
   // R(u) must come after G(u) and before G(u + RT - 1) (its right-hand neighbour one layer up): lag <= RT - 2
-  static const int lag_env = [] { const char* v = getenv("CMWG_MEGA_LAG"); return v ? atoi(v) : 64; }();
-  p.lag = std::max(0, std::min(lag_env, p.RT - 2));
+  p.lag = mega_fwd_lag(p.RT);
   p.total_tasks = (d.depth * p.RT + p.lag) * (p.ngt + 1) + p.RT;
   // timing experiments that SKIP synchronisation or epilogue work (wrong results by design) exist only in builds made
   // with -DCMWG_MEGA_EXPERIMENTS; the shipped library ignores CMWG_MEGA_DBG
@@ -260,8 +270,7 @@ static int wn_backward_mega(const WnDims& d, const PackedLayout& PL, const BwdLa
   p.f16 = f16;
   p.idesc = make_idesc(f16, 2 * TC_BM, MEGA_BN, 0, 0);
   p.desc_lbo = 1u; p.desc_sbo = 1024u >> 4;
-  static const int lag_env = [] { const char* v = getenv("CMWG_MEGA_LAG_BWD"); return v ? atoi(v) : 96; }();
-  p.lag = std::max(0, std::min(lag_env, p.RT - 2));
+  p.lag = mega_bwd_lag(p.RT);
   p.total_tasks = p.RT + 2 * (d.depth * p.RT + p.lag);
   p.flags = reinterpret_cast<uint32_t*>(ws + BL.flags);
   CMWG_CHECK_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)d.depth * 2 * p.RT * 4, st));
@@ -869,6 +878,37 @@ size_t cmwg_wn_packed_bytes(const cmwg_wn_config* cfg) {
   WnDims d;
   if (make_dims(cfg, &d) != CMWG_OK) return 0;
   return make_packed_layout(d).total;
+}
+
+// host-side listing of the task kernels' lists (the same decode functions the kernels run): entry i -> out[4*i .. 4*i+3] =
+// (type, layer, row tile, N tile); forward types 0 gate / 1 residual / 2 skip / 3 none, backward types 0 dgate / 1 dx / 3 none
+int cmwg_mega_task_list(int backward, int depth, int B, int T, int* out, int cap, int* total, int* lag) {
+  CMWG_REQUIRE(depth >= 1 && depth <= cmwg::MEGA_D && B >= 1 && T >= 1 && out && total && lag, "cmwg_mega_task_list: bad arguments");
+  const int tpb = cmwg::ceil_div(T, 2 * cmwg::TC_BM), RT = B * tpb;
+  if (backward) {
+    cmwg::MegaBwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.depth = depth; p.B = B; p.T = T; p.tiles_per_batch = tpb; p.RT = RT;
+    p.lag = cmwg::mega_bwd_lag(RT);
+    p.total_tasks = RT + 2 * (depth * RT + p.lag);
+    *total = p.total_tasks; *lag = p.lag;
+    for (int i = 0; i < p.total_tasks && i < cap; ++i) {
+      const cmwg::MegaTask t = cmwg::mega_bwd_decode(p, i);
+      out[4 * i] = t.type; out[4 * i + 1] = t.layer; out[4 * i + 2] = t.rt; out[4 * i + 3] = t.nt;
+    }
+  } else {
+    cmwg::MegaParams p;
+    memset(&p, 0, sizeof(p));
+    p.depth = depth; p.B = B; p.T = T; p.tiles_per_batch = tpb; p.RT = RT; p.ngt = 2;
+    p.lag = cmwg::mega_fwd_lag(RT);
+    p.total_tasks = (depth * RT + p.lag) * (p.ngt + 1) + RT;
+    *total = p.total_tasks; *lag = p.lag;
+    for (int i = 0; i < p.total_tasks && i < cap; ++i) {
+      const cmwg::MegaTask t = cmwg::mega_decode(p, i);
+      out[4 * i] = t.type; out[4 * i + 1] = t.layer; out[4 * i + 2] = t.rt; out[4 * i + 3] = t.nt;
+    }
+  }
+  return CMWG_OK;
 }
 
 int cmwg_mega_clk_read(long long* host, int n) {

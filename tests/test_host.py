@@ -145,3 +145,77 @@ def test_line_state_size_query():
     n = lib.cmwg_wn_line_state_bytes(C.byref(cfg), 2, 100)
     assert n >= 8 * 2 * 63 * 100 * 64 * 2
     assert lib.cmwg_upsample_dense_workspace(80, 9) >= (80 * 80 * 9 + 80) * 4
+
+
+# ---- task lists of the single-kernel WN forward / backward chain (csrc/engine_mega.cuh) --------------------------------
+def _task_list(backward, depth, B, T):
+    import ctypes as C
+    lib = _lib.load()
+    cap = 1 << 17
+    out = (C.c_int * (4 * cap))()
+    total, lag = C.c_int(0), C.c_int(0)
+    assert lib.cmwg_mega_task_list(int(backward), depth, B, T, out, cap, C.byref(total), C.byref(lag)) == 0
+    assert total.value <= cap
+    rows = [tuple(out[4 * i:4 * i + 4]) for i in range(total.value)]
+    return rows, lag.value
+
+
+@pytest.mark.parametrize("depth,B,T", [(8, 24, 2000), (8, 1, 100), (8, 2, 300), (1, 2, 700), (3, 5, 2000), (8, 4, 27584),
+                                       (2, 1, 513), (8, 3, 256)])
+def test_task_lists_are_in_dependency_order(depth, B, T):
+    """The kernels' own decode functions, run on the host: every task appears exactly once and AFTER everything it waits
+    for -- the property that makes `pair p runs entries p, p + P, ...` deadlock free (the lowest unfinished entry is always
+    runnable) -- for one row tile, ragged tiles, a single layer, the LJ training shape and a 10 s utterance."""
+    tpb = -(-T // 256)
+    RT = B * tpb
+
+    def neighbours(rt):
+        b, tb = divmod(rt, tpb)
+        return [b * tpb + t for t in (tb - 1, tb, tb + 1) if 0 <= t < tpb]
+
+    # forward: 0 gate G(layer, rt, nt), 1 residual R(layer, rt), 2 skip S(rt)
+    rows, lag = _task_list(False, depth, B, T)
+    assert 0 <= lag <= max(0, RT - 2)
+    pos = {}
+    for i, (typ, layer, rt, nt) in enumerate(rows):
+        if typ == 3:
+            continue
+        key = (typ, layer, rt, nt) if typ == 0 else (typ, layer if typ == 1 else 0, rt, 0)
+        assert key not in pos, key
+        pos[key] = i
+    assert sum(1 for k in pos if k[0] == 0) == depth * RT * 2
+    assert sum(1 for k in pos if k[0] == 1) == (depth - 1) * RT
+    assert sum(1 for k in pos if k[0] == 2) == RT
+    dist = []
+    for (typ, layer, rt, nt), i in pos.items():
+        if typ == 0 and layer > 0:
+            deps = [(1, layer - 1, r, 0) for r in neighbours(rt)]
+        elif typ == 1:
+            deps = [(0, layer, rt, n) for n in (0, 1)]
+        elif typ == 2:
+            deps = [(0, depth - 1, rt, n) for n in (0, 1)]
+        else:
+            deps = []
+        for d in deps:
+            assert d in pos and pos[d] < i, ((typ, layer, rt, nt), d)
+            dist.append(i - pos[d])
+    if (depth, B, T) == (8, 24, 2000):
+        assert lag == 64 and min(dist) >= 190      # 2.6 rounds of 74 pairs between a task and what it waits for
+
+    # backward chain: 0 dgate DG(layer, rt), 1 dx DX(layer, rt)
+    rows, lag = _task_list(True, depth, B, T)
+    assert 0 <= lag <= max(0, RT - 2)
+    pos = {}
+    for i, (typ, layer, rt, _) in enumerate(rows):
+        if typ == 3:
+            continue
+        assert (typ, layer, rt) not in pos
+        pos[(typ, layer, rt)] = i
+    assert len(pos) == 2 * depth * RT
+    for (typ, layer, rt), i in pos.items():
+        if typ == 0:
+            deps = [(1, layer + 1, rt)] if layer < depth - 1 else []
+        else:
+            deps = [(0, layer, r) for r in neighbours(rt)]
+        for d in deps:
+            assert d in pos and pos[d] < i, ((typ, layer, rt), d)
