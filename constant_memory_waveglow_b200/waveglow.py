@@ -200,7 +200,8 @@ class WN(nn.Module):
 
     @classmethod
     def _scratch_buf(cls, nbytes: int, device, purpose: str) -> Tensor:
-        if nbytes > cls._SCRATCH_MAX:
+        if nbytes > cls._SCRATCH_MAX or torch.cuda.is_current_stream_capturing():
+            # too large to keep, or a CUDA graph is being captured (its allocations belong to the graph's private pool)
             return torch.empty(nbytes, device=device, dtype=torch.uint8)
         key = (device.index, torch.cuda.current_stream(device).cuda_stream, purpose)
         buf = cls._scratch.get(key)
