@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid
     const uint32_t tmem_empty_addr = mapa_shared(smem_u32(&s.tmem_empty[0]), 0);
     const GateTcEpi<SAVE> gate_epi{nullptr, p.Cd, p.f16};
     const SplitTcEpi<true> split_epi{nullptr, p.f16};
-    const StoreTcEpi store_epi{nullptr};
+    const StoreTcEpi store_epi{nullptr, nullptr};
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t it = 0;
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_bwd_mega_kernel(const __grid
     const uint32_t wbuf = smem_u32(s.epi + e * WB);
     uint64_t* ibar = s.in_bar + e;
     const uint32_t tmem_empty_addr = mapa_shared(smem_u32(&s.tmem_empty[0]), 0);
-    const GateBwdTcEpi gbwd_epi{};
+    const GateBwdTcEpi gbwd_epi{p.f16};
     const SplitTcEpi<true> add_epi{nullptr, p.f16};
     const SplitTcEpi<false> first_epi{nullptr, p.f16};
     int acc = 0;

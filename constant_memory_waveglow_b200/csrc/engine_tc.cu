@@ -280,7 +280,7 @@ extern "C" int cmwg_selftest_tc_gemm(const void* a, const void* b, float* d, int
     TcIo io;
     memset(&io, 0, sizeof(io));
     io.out[0] = TcStream{d, N, N, 1};
-    StoreTcEpi epi{nullptr};
+    StoreTcEpi epi{nullptr, nullptr};
     return tc_gemm_launch<StoreTcEpi>(g, io, epi, st);
   }
   WgradProblem pr;

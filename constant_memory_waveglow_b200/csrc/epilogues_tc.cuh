@@ -117,23 +117,29 @@ struct SplitTcEpi {
 
 // ---- gate backward: dpre = dg * d(tanh * sigmoid) ------------------------------------------------
 // inputs: saved tanh / sigmoid values; outputs: the tanh-half and sigmoid-half gradients, columns
-// [0, Cd) and [Cd, 2Cd) of the dpre slab (two tensor maps, one per column window).  bf16 only
-// (training never uses fp16 operands).
+// [0, Cd) and [Cd, 2Cd) of the dpre slab (two tensor maps, one per column window).  With fp16 operands
+// the accumulator holds S * dg (gradient scale, wn_kernels.cuh); the functor is linear in it.
 struct GateBwdTcEpi {
   static constexpr bool kPaired = false, kOutF32 = false;
   static constexpr int kOut = 2, kIn = 2, kOutBufs = 1, kColGroups = 4;
+  int f16;
   __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
   __device__ __forceinline__ int in_col(int, int c0) const { return c0; }
-  __device__ __forceinline__ void compute(int, float (&v)[16], const uint32_t (&in)[2][8], uint32_t (&o)[2][8]) const {
+  template <int F16>
+  __device__ __forceinline__ void run(float (&v)[16], const uint32_t (&in)[2][8], uint32_t (&o)[2][8]) const {
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
       float a0, a1, b0, b1;
-      unpack2(in[0][j >> 1], 0, a0, a1);
-      unpack2(in[1][j >> 1], 0, b0, b1);
+      unpack2(in[0][j >> 1], F16, a0, a1);
+      unpack2(in[1][j >> 1], F16, b0, b1);
       float t0 = v[j] * b0, t1 = v[j + 1] * b1;  // dg * sigmoid
-      o[0][j >> 1] = pack2(t0 * (1.f - a0 * a0), t1 * (1.f - a1 * a1), 0);
-      o[1][j >> 1] = pack2(t0 * a0 * (1.f - b0), t1 * a1 * (1.f - b1), 0);
+      o[0][j >> 1] = pack2(t0 * (1.f - a0 * a0), t1 * (1.f - a1 * a1), F16);
+      o[1][j >> 1] = pack2(t0 * a0 * (1.f - b0), t1 * a1 * (1.f - b1), F16);
     }
+  }
+  __device__ __forceinline__ void compute(int, float (&v)[16], const uint32_t (&in)[2][8], uint32_t (&o)[2][8]) const {
+    if (f16) run<1>(v, in, o);
+    else run<0>(v, in, o);
   }
 };
 
@@ -141,10 +147,16 @@ struct GateBwdTcEpi {
 struct StoreTcEpi {
   static constexpr bool kPaired = false, kOutF32 = true;
   static constexpr int kOut = 1, kIn = 0, kOutBufs = 1, kColGroups = 4;
-  const float* bias;  // nullptr or [N]
+  const float* bias;    // nullptr or [N]
+  const float* gscale;  // nullptr, or the gradient-scale triple: the accumulator is multiplied by gscale[2] = 1 / S
   __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
   __device__ __forceinline__ int in_col(int, int c0) const { return c0; }
   __device__ __forceinline__ void compute(int col0, float (&v)[16], uint32_t (&o)[1][16]) const {
+    if (gscale) {
+      const float sc = __ldg(gscale + 2);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= sc;
+    }
     if (bias) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + col0 + j);

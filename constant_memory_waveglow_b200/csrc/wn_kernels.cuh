@@ -283,11 +283,12 @@ static __global__ void __launch_bounds__(256) smallk_to_slab_kernel(const float*
                                                                     int T, int blocks_per_batch, int t_off,
                                                                     int t_end, float* __restrict__ o32,
                                                                     OpT* __restrict__ ohi, OpT* __restrict__ olo,
-                                                                    int is_fp16) {
+                                                                    int is_fp16, const float* __restrict__ gscale) {
   // rows [t_off, t_end) of every batch item are computed; T stays the row count of one item (strides)
   extern __shared__ float sm[];
   pdl_trigger();
   pdl_wait();
+  const float in_scale = gscale ? gscale[1] : 1.f;  // power-of-two gradient scale (fp16 operands), see grad_scale_kernel
   float* xs = sm;                      // [K][SMALLK_ROWS]
   float* wsm = sm + K * SMALLK_ROWS;   // [K][C]  (k-major: 4 consecutive outputs are one float4)
   const int b = blockIdx.x / blocks_per_batch;
@@ -295,7 +296,7 @@ static __global__ void __launch_bounds__(256) smallk_to_slab_kernel(const float*
   for (int idx = threadIdx.x; idx < K * SMALLK_ROWS; idx += 256) {
     int i = idx / SMALLK_ROWS, r = idx % SMALLK_ROWS;
     int t = t0 + r;
-    xs[idx] = (t < t_end) ? in[b * in_bs + (long long)i * T + t] : 0.f;
+    xs[idx] = (t < t_end) ? in[b * in_bs + (long long)i * T + t] * in_scale : 0.f;
   }
   for (int idx = threadIdx.x; idx < K * C; idx += 256) {
     int i = idx / C, o = idx % C;
@@ -373,7 +374,7 @@ static __global__ void __launch_bounds__(256) smallk_to_slab_kernel(const float*
 template <typename OpT>
 static int smallk_to_slab(const float* in, long long in_bs, const float* W, int so, int si, const float* bias, int K,
                           int C, int B, int T, float* o32, OpT* ohi, OpT* olo, int is_fp16, cudaStream_t st,
-                          int t_off = 0, int t_n = -1) {
+                          int t_off = 0, int t_n = -1, const float* gscale = nullptr) {
   if (t_n < 0) t_n = T - t_off;
   const int bpb = ceil_div(t_n, SMALLK_ROWS);
   if (B * bpb == 0) return CMWG_OK;
@@ -381,7 +382,7 @@ static int smallk_to_slab(const float* in, long long in_bs, const float* W, int 
   if (smem > 48 * 1024)
     CMWG_CHECK_CUDA(cudaFuncSetAttribute(smallk_to_slab_kernel<OpT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CMWG_CHECK_CUDA(launch_pdl(smallk_to_slab_kernel<OpT>, dim3(B * bpb), dim3(256), smem, st, in, in_bs, W, so, si, bias, K,
-                             C, T, bpb, t_off, t_off + t_n, o32, ohi, olo, is_fp16));
+                             C, T, bpb, t_off, t_off + t_n, o32, ohi, olo, is_fp16, gscale));
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
   return CMWG_OK;
@@ -395,9 +396,11 @@ static __global__ void __launch_bounds__(256) start_bwd_kernel(const float* __re
                                                                const float* __restrict__ ws, int cin, int Cr, int T,
                                                                int blocks_per_batch, float* __restrict__ dx,
                                                                long long dx_bs, float* __restrict__ partial_w,
-                                                               float* __restrict__ partial_b) {
+                                                               float* __restrict__ partial_b, int is_fp16,
+                                                               const float* __restrict__ gscale) {
   extern __shared__ float sm[];
   const int LD = Cr + 1;
+  const float inv_scale = gscale ? gscale[2] : 1.f;
   float* dhs = sm;                          // [32][Cr+1]
   float* xs = dhs + ROWS_PER_BLOCK * LD;    // [cin][32]
   int b = blockIdx.x / blocks_per_batch;
@@ -408,8 +411,8 @@ static __global__ void __launch_bounds__(256) start_bwd_kernel(const float* __re
     float val = 0.f;
     if (t < T) {
       long long off = ((long long)b * T + t) * Cr + o;
-      // tc engine: dh_0 arrives as a (hi, lo) bf16 pair
-      val = dh0 ? dh0[off] : (op16_to_f32(dh_hi[off], 0) + op16_to_f32(dh_lo[off], 0));
+      // tc engine: dh_0 arrives as a (hi, lo) 16-bit pair, scaled by the gradient scale
+      val = dh0 ? dh0[off] : (op16_to_f32(dh_hi[off], is_fp16) + op16_to_f32(dh_lo[off], is_fp16)) * inv_scale;
     }
     dhs[r * LD + o] = val;
   }
@@ -455,14 +458,26 @@ static __global__ void __launch_bounds__(256) start_bwd_kernel(const float* __re
 constexpr int FAST_ROWS_PER_CTA = 256;  // 8 warps x 32 rows
 
 __device__ __forceinline__ void load_row8(const float* __restrict__ p32, const uint16_t* __restrict__ hi,
-                                          const uint16_t* __restrict__ lo, long long off, float (&v)[8]) {
+                                          const uint16_t* __restrict__ lo, long long off, float (&v)[8],
+                                          int is_fp16 = 0) {
   if (p32) {
     const float4 a = *reinterpret_cast<const float4*>(p32 + off), b = *reinterpret_cast<const float4*>(p32 + off + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
-    // (hi, lo) bf16 pair: value = hi + lo
+    // (hi, lo) 16-bit pair: value = hi + lo
     const uint4 h = *reinterpret_cast<const uint4*>(hi + off), l = *reinterpret_cast<const uint4*>(lo + off);
     const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+    if (is_fp16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float h0, h1, l0, l1;
+        unpack2(hw[j], 1, h0, h1);
+        unpack2(lw[j], 1, l0, l1);
+        v[2 * j] = h0 + l0;
+        v[2 * j + 1] = h1 + l1;
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
@@ -506,8 +521,10 @@ static __global__ void __launch_bounds__(256) start_bwd256_kernel(const float* _
                                                                   const float* __restrict__ ws, int TF, long long rows,
                                                                   float* __restrict__ dx, long long dx_bs,
                                                                   float* __restrict__ partial_w,
-                                                                  float* __restrict__ partial_b) {
+                                                                  float* __restrict__ partial_b, int is_fp16,
+                                                                  const float* __restrict__ gscale) {
   __shared__ float buf[4 * (8 * CIN + 8) * 32];
+  const float inv_scale = gscale ? gscale[2] : 1.f;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // acc[c * CIN + i] = dWs[lane * 8 + c][i] partial, acc[8 * CIN + c] = dbias partial
   float wreg[8][CIN], acc[8 * CIN + 8];
@@ -535,7 +552,9 @@ static __global__ void __launch_bounds__(256) start_bwd256_kernel(const float* _
 #pragma unroll 4
     for (int r = 0; r < nrows; ++r) {
       float dh[8];
-      load_row8(dh32, dh_hi, dh_lo, (g0 + r) * 256 + lane * 8, dh);
+      load_row8(dh32, dh_hi, dh_lo, (g0 + r) * 256 + lane * 8, dh, is_fp16);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dh[c] *= inv_scale;
 #pragma unroll
       for (int i = 0; i < CIN; ++i) {
         const float xv = __shfl_sync(0xffffffffu, xm[i], r);
@@ -739,16 +758,77 @@ static __global__ void __launch_bounds__(256) end_bwd_dw_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// Gradient scaling for fp16 operands.  fp16 carries the same 10 mantissa bits as TF32 (bf16: 7) at bf16's tensor-core rate,
+// but only 5 exponent bits; the backward GEMM chain is LINEAR in the incoming cotangent, so it runs on S * cotangent with S a
+// power of two chosen per call on the device (no host round trip), and every result is multiplied by 1 / S where it leaves
+// the 16-bit slabs (exact: powers of two).  gscale = {bit pattern of max |dlst|, S, 1 / S}.
+//   S = 2^(8 - ceil(log2(max|dlst| * max_k sum_o |W_end[o][k]|)))  =>  |S * dskip| <= 256:
+// 2^8 of headroom below fp16's largest value for the growth of the residual gradient through the layers, and 2^22 of normal
+// range below the largest entry (smaller entries lose precision gradually as fp16 subnormals; they do not matter to any norm).
+// ------------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256) amax_abs_kernel(const float* __restrict__ a, long long n,
+                                                              unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(a[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  // non-negative floats order like their bit patterns; max is order independent, so the result is deterministic
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
+}
+
+static __global__ void __launch_bounds__(256) grad_scale_kernel(float* __restrict__ gscale, const float* __restrict__ w_end,
+                                                                int cout, int Cs) {
+  __shared__ float red[8];
+  float colmax = 0.f;
+  for (int k = threadIdx.x; k < Cs; k += 256) {
+    float s = 0.f;
+    for (int o = 0; o < cout; ++o) s += fabsf(w_end[(long long)o * Cs + k]);
+    colmax = fmaxf(colmax, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) colmax = fmaxf(colmax, __shfl_xor_sync(0xffffffffu, colmax, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = colmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bound = 0.f;
+    for (int i = 0; i < 8; ++i) bound = fmaxf(bound, red[i]);
+    bound *= __uint_as_float(reinterpret_cast<const unsigned int*>(gscale)[0]);
+    float S = 1.f;
+    if (bound > 0.f && bound < 3.0e38f) {
+      int e = 8 - (int)ceilf(log2f(bound));
+      e = max(-60, min(60, e));
+      S = exp2f((float)e);
+    }
+    gscale[1] = S;
+    gscale[2] = 1.f / S;
+  }
+}
+
+// in-place multiply by gscale[idx] (fp32 buffers that leave the scaled domain without passing another kernel)
+static __global__ void __launch_bounds__(256) scale_by_kernel(float* __restrict__ a, long long n4,
+                                                              const float* __restrict__ gscale, int idx) {
+  const float sc = gscale[idx];
+  float4* p = reinterpret_cast<float4*>(a);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = p[i];
+    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    p[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------------
 // out[p] = sum_j partial[j][p], fixed order, fp64 accumulator
 static __global__ void __launch_bounds__(128) reduce_blocks_kernel(const float* __restrict__ partial, int nblocks,
-                                                                   int P, float* __restrict__ out) {
+                                                                   int P, float* __restrict__ out,
+                                                                   const float* __restrict__ gscale) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   double s = 0.0;
   for (int j = 0; j < nblocks; ++j) s += (double)partial[(long long)j * P + p];
-  out[p] = (float)s;
+  out[p] = (float)s * (gscale ? gscale[2] : 1.f);
 }
 
 // split-K partials [splits][M][N] of several weight-gradient problems -> strided destinations
@@ -762,10 +842,12 @@ struct WgReduceEntry {
 struct WgReduceTable {
   WgReduceEntry e[TC_MAX_WG_REDUCE];
   int n;
+  const float* gscale;   // nullptr, or the gradient-scale triple: results are multiplied by gscale[2] = 1 / S
 };
 
 static __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgReduceTable tb) {
   const WgReduceEntry& e = tb.e[blockIdx.y];
+  const float inv_scale = tb.gscale ? tb.gscale[2] : 1.f;
   const int nv4 = (e.n_valid + 3) >> 2;  // stored N is a multiple of 4, so the float4 loads stay in bounds
   long long total = (long long)e.M * nv4;
   const long long stride = (long long)e.M * e.N;
@@ -779,10 +861,10 @@ static __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgReduce
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     float* o = e.out + e.off + m * e.sm + n * e.sn;
-    o[0] = s.x;
-    if (n + 1 < e.n_valid) o[e.sn] = s.y;
-    if (n + 2 < e.n_valid) o[2 * e.sn] = s.z;
-    if (n + 3 < e.n_valid) o[3 * e.sn] = s.w;
+    o[0] = s.x * inv_scale;
+    if (n + 1 < e.n_valid) o[e.sn] = s.y * inv_scale;
+    if (n + 2 < e.n_valid) o[2 * e.sn] = s.z * inv_scale;
+    if (n + 3 < e.n_valid) o[3 * e.sn] = s.w * inv_scale;
   }
 }
 

@@ -186,6 +186,7 @@ struct BwdLayout {
   size_t dycl_lines; // [B][H][T][auxp] fp32 per-line conditioning gradient (2-D WN only; summed over lines afterwards)
   size_t dweff;      // fp32 effective-weight gradients of every conv (consumed by ONE weight-norm backward launch)
   size_t dweff_layer, dweff_start, dweff_end;  // in floats: per-layer stride, offsets of the start / end conv
+  size_t gscale;     // 4 floats: gradient scale of the fp16-operand backward {max|dlst| bits, S, 1/S} (wn_kernels.cuh)
   size_t total;
 };
 
@@ -270,6 +271,7 @@ inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
   L->dweff_end = L->dweff_start + align_up((size_t)d.Cr * d.cin, 64);
   size_t total_f = L->dweff_end + align_up((size_t)2 * d.cin * d.Cs, 64);
   L->dweff = take(total_f * 4 + 4096);
+  L->gscale = take(64);
   L->total = off;
 }
 

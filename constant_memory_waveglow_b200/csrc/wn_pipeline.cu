@@ -303,7 +303,6 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
   uint8_t* ws = u8(workspace);
   uint8_t* sv = u8(saved);
   const bool save = saved != nullptr;
-  CMWG_REQUIRE(!(save && f16), "fp16 operands are forward/inverse only; training needs bf16 or fp32");
   CMWG_REQUIRE(!(save && lw.state), "line-window forward keeps no backward state");
   uint8_t* stt = u8(lw.state);
   const bool keep = save || stt != nullptr;  // every layer's input slab is kept (per-layer buffers)
@@ -447,7 +446,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
     TcIo io;
     memset(&io, 0, sizeof(io));
     io.out[0] = f32_stream(skip32, d.Cs);
-    StoreTcEpi epi{d.bias ? reinterpret_cast<const float*>(pk + PL.biasS) : nullptr};
+    StoreTcEpi epi{d.bias ? reinterpret_cast<const float*>(pk + PL.biasS) : nullptr, nullptr};
     CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
   }
   // ---- end conv
@@ -463,7 +462,8 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
 // backward
 // ------------------------------------------------------------------------------------------------
 // fixed-order reduction of [nblocks][P] block partials into out[P]; `scratch` holds ceil(nblocks/64)*P floats
-static int reduce_blocks(const float* partial, int nblocks, int P, float* scratch, float* out, cudaStream_t st) {
+static int reduce_blocks(const float* partial, int nblocks, int P, float* scratch, float* out, cudaStream_t st,
+                         const float* gscale = nullptr) {
   if (nblocks > 128) {
     int stages = ceil_div(nblocks, 64);
     reduce_blocks_stage_kernel<<<dim3(ceil_div(P, 128), stages), 128, 0, st>>>(partial, nblocks, P, scratch);
@@ -472,7 +472,7 @@ static int reduce_blocks(const float* partial, int nblocks, int P, float* scratc
     partial = scratch;
     nblocks = stages;
   }
-  reduce_blocks_kernel<<<ceil_div(P, 128), 128, 0, st>>>(partial, nblocks, P, out);
+  reduce_blocks_kernel<<<ceil_div(P, 128), 128, 0, st>>>(partial, nblocks, P, out, gscale);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
   return CMWG_OK;
@@ -501,12 +501,12 @@ struct WnBwdQueue {
 
 template <typename OpT>
 static int colsum_to(const OpT* a, int ld, int C, long long rows, float* partial, float* out, int f16,
-                     cudaStream_t st) {
+                     cudaStream_t st, const float* gscale = nullptr) {
   int nblocks = (int)ceil_div_ll(rows, ROWS_PER_BLOCK);
   colsum_partial_kernel<OpT><<<nblocks, 256, 0, st>>>(a, ld, C, rows, partial, f16);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
-  return reduce_blocks(partial, nblocks, C, partial + (size_t)nblocks * C, out, st);
+  return reduce_blocks(partial, nblocks, C, partial + (size_t)nblocks * C, out, st, gscale);
 }
 
 template <typename OpT>
@@ -516,8 +516,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
                             cudaStream_t st) {
   using E = EngineSel<OpT>;
   constexpr bool TC = E::kTc;
-  const int f16 = 0;  // training never uses fp16 operands
-  CMWG_REQUIRE(d.prec != CMWG_PREC_FP16, "fp16 operands are forward/inverse only; training needs bf16 or fp32");
+  const int f16 = d.prec == CMWG_PREC_FP16;
   PackedLayout PL = make_packed_layout(d);
   FwdLayout FL;
   make_fwd_layout(d, B, T, &FL);
@@ -556,10 +555,24 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   // 2-D WN: the conditioning is broadcast over lines, so its gradient is computed per line and summed afterwards
   float* dyl = (dycl && d.H > 1) ? reinterpret_cast<float*>(ws + BL.dycl_lines) : dycl;
 
+  // ---- fp16 operands: the chain below runs on S * dlst, S a power of two chosen here on the device (wn_kernels.cuh)
+  float* gscale = nullptr;
+  if (TC && f16) {
+    gscale = reinterpret_cast<float*>(ws + BL.gscale);
+    CMWG_CHECK_CUDA(cudaMemsetAsync(gscale, 0, 16, st));
+    const long long n = (long long)B * cout * TF;
+    amax_abs_kernel<<<(int)std::min<long long>(ceil_div_ll(n, 256 * 8), 2 * num_sms()), 256, 0, st>>>(
+        dlst, n, reinterpret_cast<unsigned int*>(gscale));
+    CMWG_COUNT_LAUNCH();
+    grad_scale_kernel<<<1, 256, 0, st>>>(gscale, wEnd, cout, d.Cs);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+  }
+
   // ---- end conv backward: dskip, d end.weight, d end.bias
   {
     CMWG_PROPAGATE(smallk_to_slab<OpT>(dlst, (long long)cout * TF, wEnd, 1, d.Cs, nullptr, cout, d.Cs, B, TF, nullptr,
-                                       dskip_op, (OpT*)nullptr, f16, st));
+                                       dskip_op, (OpT*)nullptr, f16, st, 0, -1, gscale));
     if (gr->end.v || gr->end.bias) {
       size_t smem2 = ((size_t)cout * ROWS_PER_BLOCK + (size_t)ROWS_PER_BLOCK * d.Cs) * sizeof(float);
       float* pw = partial;
@@ -638,6 +651,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       }
       WgReduceTable rt;
       rt.n = 0;
+      rt.gscale = gscale;
       for (int k = 0; k < nr; ++k) {
         if (rs[k].pi < g0 || rs[k].pi >= g0 + gn) continue;
         WgReduceEntry& e = rt.e[rt.n++];
@@ -683,7 +697,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
         // N tile (Cd < BN) is clipped instead of spilling into the other half
         io.out[0] = TcStream{dpre_i, 2 * d.Cd, d.Cd, 0};
         io.out[1] = TcStream{dpre_i + d.Cd, 2 * d.Cd, d.Cd, 0};
-        GateBwdTcEpi epi{};
+        GateBwdTcEpi epi{f16};
         CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
       } else {
         GateBwdEpi<OpT> epi;
@@ -741,12 +755,14 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     // ---- bias gradients (bias=True only)
     if (d.bias) {
       // W_i.bias and V.bias[i] both receive the column sums of dpre
-      if (gr->W[i].bias) CMWG_PROPAGATE(colsum_to<OpT>(dpre_i, 2 * d.Cd, 2 * d.Cd, rows, partial, gr->W[i].bias, f16, st));
+      if (gr->W[i].bias)
+        CMWG_PROPAGATE(colsum_to<OpT>(dpre_i, 2 * d.Cd, 2 * d.Cd, rows, partial, gr->W[i].bias, f16, st, gscale));
       if (gr->V.bias)
-        CMWG_PROPAGATE(colsum_to<OpT>(dpre_i, 2 * d.Cd, 2 * d.Cd, rows, partial, gr->V.bias + (size_t)i * 2 * d.Cd, f16, st));
+        CMWG_PROPAGATE(colsum_to<OpT>(dpre_i, 2 * d.Cd, 2 * d.Cd, rows, partial, gr->V.bias + (size_t)i * 2 * d.Cd, f16, st,
+                                      gscale));
       if (gr->W_o[i].bias) {
-        if (!last) CMWG_PROPAGATE(colsum_to<OpT>(dh_next, d.Cr, d.Cr, rows, partial, gr->W_o[i].bias, f16, st));
-        CMWG_PROPAGATE(colsum_to<OpT>(dskip_op, d.Cs, d.Cs, rows, partial, gr->W_o[i].bias + d.cr_eff(i), f16, st));
+        if (!last) CMWG_PROPAGATE(colsum_to<OpT>(dh_next, d.Cr, d.Cr, rows, partial, gr->W_o[i].bias, f16, st, gscale));
+        CMWG_PROPAGATE(colsum_to<OpT>(dskip_op, d.Cs, d.Cs, rows, partial, gr->W_o[i].bias + d.cr_eff(i), f16, st, gscale));
       }
     }
     // ---- conditioning gradient (fp32 engine: accumulate per layer; tc: one deferred GEMM after the loop)
@@ -811,7 +827,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       TcIo io;
       memset(&io, 0, sizeof(io));
       io.out[0] = f32_stream(dyl, d.auxp);
-      StoreTcEpi epi{nullptr};
+      StoreTcEpi epi{nullptr, gscale};
       CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
     }
   }
@@ -837,14 +853,15 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     if (d.Cr == 256 && d.cin >= 1 && d.cin <= 8) {
       nblk_s = (int)ceil_div_ll(rows, FAST_ROWS_PER_CTA);
 #define CMWG_START_CASE(N) \
-  case N: start_bwd256_kernel<N><<<nblk_s, 256, 0, st>>>(a32, ahi, alo, x, x_bs, wStart, TF, rows, dx, dx_bs, pw, pbs); break;
+  case N: start_bwd256_kernel<N><<<nblk_s, 256, 0, st>>>(a32, ahi, alo, x, x_bs, wStart, TF, rows, dx, dx_bs, pw, pbs, f16, gscale); break;
       switch (d.cin) {
         CMWG_START_CASE(1) CMWG_START_CASE(2) CMWG_START_CASE(3) CMWG_START_CASE(4)
         CMWG_START_CASE(5) CMWG_START_CASE(6) CMWG_START_CASE(7) CMWG_START_CASE(8)
       }
 #undef CMWG_START_CASE
     } else {
-      start_bwd_kernel<<<nblk, 256, smem, st>>>(a32, ahi, alo, x, x_bs, wStart, d.cin, d.Cr, TF, bpb, dx, dx_bs, pw, pbs);
+      start_bwd_kernel<<<nblk, 256, smem, st>>>(a32, ahi, alo, x, x_bs, wStart, d.cin, d.Cr, TF, bpb, dx, dx_bs, pw, pbs, f16,
+                                                gscale);
     }
     CMWG_COUNT_LAUNCH();
     CMWG_LAUNCH_CHECK();

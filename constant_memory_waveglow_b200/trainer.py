@@ -353,9 +353,9 @@ class Trainer:
             os.environ.setdefault("MASTER_PORT", "29500")
             dist.init_process_group("nccl" if device.type == "cuda" else "gloo",
                                     **({"device_id": device} if device.type == "cuda" else {}))
-        if self.precision in ("16", "bf16", "16-mixed", "bf16-mixed"):
+        if self.precision in ("16", "16-mixed", "bf16", "bf16-mixed"):
             from . import precision as _p
-            _p.set_precision("bf16")
+            _p.set_precision("fp16" if str(self.precision).startswith("16") else "bf16")
         model.trainer = self
         model.to(device).train()
         opt = model.configure_optimizers()

@@ -79,7 +79,7 @@ def test_fused_forward_radix5_and_two_streams():
 
 
 @pytest.mark.parametrize("cin,aux,depth,B,T", SHAPES)
-@pytest.mark.parametrize("prec,save", [("bf16", False), ("bf16", True), ("fp16", False)])
+@pytest.mark.parametrize("prec,save", [("bf16", False), ("bf16", True), ("fp16", False), ("fp16", True)])
 def test_fused_forward_equals_layered_pipeline(cin, aux, depth, B, T, prec, save):
     wn = _wn(cin, aux, depth)
     g = torch.Generator(device="cuda").manual_seed(T + B)
@@ -112,7 +112,8 @@ def test_fused_forward_against_oracle(cin, aux, depth, B, T):
         assert rel_l2(lst, want) < TOL[prec]["out"], prec
 
 
-def test_training_step_gradients_equal_layered_pipeline():
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_training_step_gradients_equal_layered_pipeline(prec):
     """Reversible backward through the activations the fused forward saved: every gradient equals the layered
     pipeline's bit for bit (the backward kernels are the same; their inputs must be)."""
     torch.manual_seed(0)
@@ -120,7 +121,7 @@ def test_training_step_gradients_equal_layered_pipeline():
                                  residual_channels=256, skip_channels=256, depth=8).cuda()
     x0 = torch.rand(3, 8, 2000, device="cuda") * 2 - 1
     y = torch.randn(3, 80, 2000, device="cuda")
-    precision.set_precision("bf16")
+    precision.set_precision(prec)
 
     def run():
         for p in blk.parameters():

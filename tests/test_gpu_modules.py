@@ -197,7 +197,7 @@ def test_waveglow_against_reference_golden():
         assert torch.allclose(audio2.cpu(), fx["infer_audio"], atol=2e-5)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
 def test_waveglow_128ch_against_oracle(prec):
     """Config 1b of SURVEY 8(d): 12 flows, 128 channels, depth 4, B=2, T=16000, sigma 0.7."""
     precision.set_precision(prec)

@@ -103,7 +103,8 @@ def _wn2d_case(n_group, ch, B, H, W, n_mels, seed):
 
 @pytest.mark.parametrize("prec,n_group,ch,H,W", [("fp32", 32, 16, 9, 45), ("fp32", 64, 8, 63, 20), ("fp32", 16, 64, 5, 300),
                                                  ("bf16", 64, 64, 63, 40), ("bf16", 32, 128, 12, 270),
-                                                 ("fp16", 64, 64, 20, 33)])
+                                                 ("fp16", 64, 64, 20, 33), ("fp16", 64, 64, 63, 40),
+                                                 ("fp16", 32, 128, 12, 270)])
 def test_wn2d_forward_backward(prec, n_group, ch, H, W):
     B, n_mels = 2, 12
     spec, sd, x, y, m = _wn2d_case(n_group, ch, B, H, W, n_mels, seed=H + W)
@@ -117,28 +118,22 @@ def test_wn2d_forward_backward(prec, n_group, ch, H, W):
     gen = torch.Generator().manual_seed(5)
     dls = torch.randn(ls_ref.shape, generator=gen)
     dt = torch.randn(t_ref.shape, generator=gen)
-    xc = x.cuda().requires_grad_(prec != "fp16")
-    yc = y.cuda().requires_grad_(prec != "fp16")
-    if prec == "fp16":
-        with torch.no_grad():
-            ls, t = m(xc, yc)
-    else:
-        ls, t = m(xc, yc)
+    xc = x.cuda().requires_grad_(True)
+    yc = y.cuda().requires_grad_(True)
+    ls, t = m(xc, yc)
     assert ls.shape == ls_ref.shape
     assert rel_l2(ls, ls_ref) < tol["out"] and rel_l2(t, t_ref) < tol["out"]
-    if prec == "fp16":
-        return
     names = [n for n, _ in m.named_parameters()]
     ref = torch.autograd.grad((ls_ref * dls.double()).sum() + (t_ref * dt.double()).sum(),
                               [xd, yd] + [leaf["WNs.0." + n] for n in names])
     ((ls * dls.cuda()).sum() + (t * dt.cuda()).sum()).backward()
-    assert rel_l2(xc.grad, ref[0]) < tol["grad"]
-    assert rel_l2(yc.grad, ref[1]) < tol["grad"]
+    assert rel_l2(xc.grad, ref[0]) < tol["grad_worst"]
+    assert rel_l2(yc.grad, ref[1]) < tol["grad_worst"]
     for (n, p), r in zip(m.named_parameters(), ref[2:]):
         if n == "start.weight_v":  # analytically zero (one input channel): rounding noise only
             assert p.grad.abs().max().item() <= 1e-3 * max(1.0, ref[2 + names.index("start.weight_g")].abs().max().item())
             continue
-        assert rel_l2(p.grad, r) < tol["grad"], n
+        assert rel_l2(p.grad, r) < tol["grad_worst"], n
 
 
 @pytest.mark.parametrize("prec,ch", [("fp32", 16), ("bf16", 64), ("fp16", 64)])
@@ -198,7 +193,7 @@ def test_waveflow_against_reference_fixture(tag):
     assert torch.allclose(m.infer(h, z=fx["infer_z"].cuda()).cpu(), fx["infer_audio"].squeeze(), atol=2e-5, rtol=1e-4)
 
 
-@pytest.mark.parametrize("prec,conv", [("fp32", False), ("bf16", False), ("bf16", True)])
+@pytest.mark.parametrize("prec,conv", [("fp32", False), ("fp16", False), ("fp16", True), ("bf16", False), ("bf16", True)])
 def test_waveflow_lj_shape_against_oracle(prec, conv):
     """n_group 64 / 64 channels (the LJ config's WN shape), 2 flows, short segment, against the fp64 oracle."""
     precision.set_precision(prec)
@@ -223,7 +218,7 @@ def test_waveflow_lj_shape_against_oracle(prec, conv):
         if n.endswith("start.weight_v"):
             continue
         worst = max(worst, rel_l2(p.grad, grads_ref[n]))
-    assert worst < tol["grad"], worst
+    assert worst < tol["grad_worst"], worst
     with torch.no_grad():
         xr, ldr = m.reverse(z.detach(), h.cuda())
     assert rel_l2(xr, x) < tol["roundtrip"]
