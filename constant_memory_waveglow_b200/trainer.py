@@ -295,6 +295,14 @@ class Trainer:
         self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
         self.global_rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        want = max(int(g) if isinstance(g, int) or (isinstance(g, str) and g.isdigit()) else 0 for g in (gpus, devices))
+        if want > 1 and self.world_size == 1:
+            # train.py:51-53,73-78 asks Lightning to spawn one process per GPU; this harness is launched by torchrun
+            # instead, and train.py has already divided the batch by the GPU count
+            import warnings
+            warnings.warn(f"Trainer(gpus/devices={want}) but WORLD_SIZE=1: this process trains on ONE GPU with 1/{want} of the "
+                          f"configured global batch.  Launch with `torchrun --nproc-per-node {want} --master-addr 127.0.0.1 "
+                          f"train.py ...` (or set CUDA_VISIBLE_DEVICES to a single GPU to silence this).", RuntimeWarning)
         self.current_epoch = 0
         self.global_step = 0
         self.optimizers: List[torch.optim.Optimizer] = []

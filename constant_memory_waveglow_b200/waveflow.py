@@ -395,8 +395,11 @@ class WaveFlow(FlowBase):
                 with torch.cuda.graph(graph):
                     ox, old = self._reverse_eager(sz, sh)
                 _cond_cache.clear()  # ... and slabs living in the graph's private pool must not serve eager calls
-                self._graphs[key] = (graph, sz, sh, ox, old)
-            graph, sz, sh, ox, old = self._graphs[key]
+                # the capture baked in the addresses of every WN's packed-weight buffer (allocated by earlier eager calls,
+                # outside the graph's pool): hold them for as long as the graph lives
+                pins = [ent[1] for wn in self.WNs for ent in wn._pack_cache.values()]
+                self._graphs[key] = (graph, sz, sh, ox, old, pins)
+            graph, sz, sh, ox, old, _pins = self._graphs[key]
             sz.copy_(z)
             sh.copy_(h)
             graph.replay()

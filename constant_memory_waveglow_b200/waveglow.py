@@ -72,14 +72,18 @@ class _CondCache:
                auxp, cfg.precision, y.device.index)
         hit = self.entries.get(key)
         if hit is not None:
-            self.entries.move_to_end(key)
-            return hit[1]
+            # the constant-memory ops release a tensor's memory with storage.resize_(0) while the tensor object lives on, so
+            # holding `y` does not pin its address: the entry is valid only while the held tensor still owns the keyed memory
+            st = hit[0].untyped_storage()
+            if st.data_ptr() == key[0] and st.size() > 0:
+                self.entries.move_to_end(key)
+                return hit[1]
+            del self.entries[key]
         B, aux, T = y.shape
         elem = torch.float32 if cfg.precision == L.PREC_FP32 else torch.int16
         ycl = torch.empty((B, T, auxp), device=y.device, dtype=elem)
         L.check(L.load().cmwg_cond_pack(C.byref(cfg), y.data_ptr(), y.stride(0), y.stride(1), y.stride(2), B, T,
                                         ycl.data_ptr(), L.stream_ptr(y.device)), "cond_pack")
-        # holding `y` keeps its storage alive, so the address in the key cannot be recycled
         self.entries[key] = (y, ycl)
         while len(self.entries) > self.capacity:
             self.entries.popitem(last=False)
@@ -188,8 +192,8 @@ class WN(nn.Module):
         buf = ent[1] if (ent is not None and ent[1].numel() == nbytes and ent[1].device == device) else \
             torch.empty(nbytes, device=device, dtype=torch.uint8)
         L.check(L.load().cmwg_wn_pack(C.byref(cfg), C.byref(ps), buf.data_ptr(), L.stream_ptr(device)), "wn_pack")
-        self._pack_cache = {prec: (key, buf)}
-        return cfg, buf, ps
+        self._pack_cache[prec] = (key, buf)   # one entry per precision: captured CUDA graphs and stored-mode states keep
+        return cfg, buf, ps                   # pointing at the buffer of THEIR precision
 
     # ---- scratch: per (device, stream, purpose) buffers that persist between calls ---------------------------------
     # The kernels address every slab through TMA descriptors that the library caches by ADDRESS; a fresh torch.empty per
