@@ -3,11 +3,12 @@
 synthesis kHz/GPU, % of roofline, next to the reference CPU path).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the CPU oracle port of the reference
+    python bench.py --impl reference --steps K --warmup W    # the UNMODIFIED reference (baseline/_ref) on the host cores
 
 A "step" = one constant-memory training step (forward + NLL loss + reversible backward + gradient
 all-reduce + Adam) of the WaveGlow LJ configuration (256 channels, 12 flows, 8 WN layers, 80 mel) on a
-batch of 24 synthetic 16000-sample segments PER GPU (weak scaling).  One JSON line is printed by rank 0.
+batch of 24 synthetic 16000-sample segments PER GPU (weak scaling; the line's `strong` object holds the
+reference's own split, global batch 24 // N per GPU, train.py:51-53).  One JSON line is printed by rank 0.
 """
 from __future__ import annotations
 
@@ -43,6 +44,17 @@ GATE_TRAFFIC_BYTES_PER_LAUNCH = 38.9e6
 FUSED_TRAFFIC_BYTES_PER_LAUNCH = 0.5 * (1143.1e6 + 1759.5e6)
 TRAIN_GFLOP_PER_SEGMENT = 4 * FWD_GFLOP_PER_SEGMENT
 SYNTH_FRAMES = 862               # 10 s at 22.05 kHz -> 220672 samples (model/base.py:47-48)
+GLOBAL_BATCH = 24                # configs/waveglow_LJ_speech.json:31; train.py:51-53 divides it by the GPU count
+WSR_FWD_GFLOP_PER_SEGMENT = 234.978   # WSRGlow-2x, 8192-sample segment
+WSR_SEGMENT, WSR_BATCH = 8192, 12     # configs/wsrglow_vctk_2x.json
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def workload_config(world: int, per_gpu_batch: int):
+    """The `config` object of BOTH arms (the reference arm times a bounded sample of the same workload)."""
+    return {"workload": "waveglow_lj_train_fwd+reversible_bwd+adam", "per_gpu_batch": per_gpu_batch, "segment": SEGMENT,
+            "n_mels": 80, "channels": 256, "flows": 12, "wn_layers": 8,
+            "l2": "256 MiB flush between timed steps; per-step working set >> 126 MB L2", "parallelism": f"dp{world}"}
 
 
 def peaks():
@@ -311,29 +323,198 @@ def waveflow_leg(dev, cpu_baseline: bool):
     return out
 
 
-CPU_SAMPLE_BATCH = 2   # segments per CPU step: ~1.2 s per step on 16 host cores, so K+W steps stay within minutes
+CPU_SAMPLE_BATCH = 2   # segments per CPU step: ~2 s per step on 16 host cores, so K+W steps stay within minutes
+
+
+def import_reference():
+    """The UNMODIFIED reference tree (baseline/_ref, a copy of /root/reference made by __graft_entry__.build()) as the
+    top-level packages `model` / `utils` / `datasets` it expects to be; nothing of this repository is on that path.
+    Only `pytorch_lightning`, which this image does not have, is replaced by an in-memory stub (model/lightning.py:5
+    needs the name at import time; the benchmark never touches Lightning).  Returns the `model` package or None."""
+    if not os.path.exists(os.path.join(REF_DIR, "model", "efficient_modules.py")):
+        return None
+    import types
+    import warnings
+    warnings.filterwarnings("ignore")
+    if "pytorch_lightning" not in sys.modules:
+        try:
+            import importlib.util
+            have = importlib.util.find_spec("pytorch_lightning") is not None and \
+                not os.path.abspath(importlib.util.find_spec("pytorch_lightning").origin).startswith(ROOT)
+        except Exception:
+            have = False
+        if not have:
+            pl = types.ModuleType("pytorch_lightning")
+
+            class _LM(torch.nn.Module):
+                def save_hyperparameters(self, *a, **k):
+                    pass
+
+            pl.LightningModule, pl.Callback, pl.Trainer = _LM, object, object
+            sys.modules["pytorch_lightning"] = pl
+    for name in list(sys.modules):
+        if name in ("model", "utils", "datasets") or name.startswith(("model.", "datasets.")):
+            del sys.modules[name]
+    sys.path[:] = [REF_DIR] + [q for q in sys.path if os.path.abspath(q or ".") != ROOT]
+    import model as ref_model
+    assert os.path.abspath(ref_model.__file__).startswith(REF_DIR), ref_model.__file__
+    return ref_model
+
+
+def ref_waveglow(ref_model, seed=0):
+    torch.manual_seed(seed)
+    m = ref_model.WaveGlow(memory_efficient=True, zero_init=False, **LJ, **LJ_WN)
+    from model.loss import WaveGlowLoss
+    return m, WaveGlowLoss(SIGMA)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = CPU_SAMPLE_BATCH
-    value, times = cpu_oracle_train(batch, args.steps, args.warmup)
+    torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
-    line = {
-        "impl": "reference", "metric": "waveglow_lj_train_segments_per_s", "value": value, "unit": "segments/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "waveglow_lj_train_fwd+reversible_bwd", "per_gpu_batch": PER_GPU_BATCH,
-                   "segment": SEGMENT, "n_mels": 80, "channels": 256, "flows": 12, "wn_layers": 8},
-        "cpu_baseline": {"value": value, "unit": "segments/s", "cores": cores, "kind": "port",
-                         "sample": f"oracle port of the reference (torch CPU fp32, autograd over the naive flow), "
-                                   f"batch {batch} x {SEGMENT} samples per step, forward + loss + backward, no optimizer"},
-        "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line), flush=True)
+    task = args.ref_task
+    ref = import_reference()
+    kind = "reference" if ref is not None else "port"
+    if ref is None:
+        sys.path.insert(0, ROOT)
+    g = torch.Generator().manual_seed(0)
+
+    if task == "train":
+        batch = CPU_SAMPLE_BATCH
+        x = torch.rand(batch, SEGMENT, generator=g) * 2 - 1
+        h = torch.randn(batch, LJ["n_mels"], FRAMES, generator=g)
+        if ref is not None:
+            m, loss_fn = ref_waveglow(ref)
+            m.train()
+            opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+            times = []
+            for i in range(args.warmup + args.steps):
+                t0 = time.perf_counter()
+                opt.zero_grad(set_to_none=True)
+                z, logdet = m(x.clone(), h)
+                loss = loss_fn(z, logdet)
+                loss.backward()
+                opt.step()
+                dt = time.perf_counter() - t0
+                if i >= args.warmup:
+                    times.append(dt)
+            value = batch / (sum(times) / len(times))
+            what = ("baseline/_ref (the unmodified reference): model.WaveGlow(memory_efficient=True) + WaveGlowLoss + "
+                    "torch.optim.Adam on CPU fp32")
+        else:
+            value, times = cpu_oracle_train(batch, args.steps, args.warmup)
+            what = "oracle port of the reference (baseline/_ref missing), autograd over the naive flow, no optimizer"
+        line = {
+            "impl": "reference", "metric": "waveglow_lj_train_segments_per_s", "value": value, "unit": "segments/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus, PER_GPU_BATCH), "sample_batch": batch,
+            "cpu_baseline": {"value": value, "unit": "segments/s", "cores": cores, "kind": kind,
+                             "sample": f"{what}; each step = {batch} of the workload's {PER_GPU_BATCH} segments x {SEGMENT} "
+                                       f"samples: forward + loss + reversible backward + Adam, {sum(times):.1f} s timed"},
+            "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    if task == "synth":      # one 10 s utterance through the reference's inverse (inference.py:50-56 times exactly this)
+        frames = SYNTH_FRAMES
+        h = torch.randn(1, LJ["n_mels"], frames, generator=g)
+        if ref is not None:
+            m, _ = ref_waveglow(ref)
+            import utils as ref_utils
+            m.apply(ref_utils.remove_weight_norms)   # inference.py:17
+            m.eval()
+            with torch.no_grad():
+                m.infer(h[..., :32], 0.6)
+                t0 = time.perf_counter()
+                m.infer(h, 0.6)
+                dt = time.perf_counter() - t0
+            khz = frames * LJ["hop_size"] / dt / 1e3
+        else:
+            khz, dt = cpu_oracle_synth(frames)
+        print(json.dumps({"khz": khz, "seconds": dt, "cores": cores, "kind": kind, "frames": frames}), flush=True)
+        return
+
+    if task == "parity":     # seeded weights / inputs and the reference's own outputs, for the B200 arm to compare with
+        if ref is None:
+            print(json.dumps({"unavailable": "baseline/_ref missing"}), flush=True)
+            return
+        m, loss_fn = ref_waveglow(ref, seed=0)
+        m.train()
+        B = 2
+        x = torch.rand(B, SEGMENT, generator=g) * 2 - 1
+        h = torch.randn(B, LJ["n_mels"], FRAMES, generator=g)
+        zs = torch.randn(B, FRAMES * LJ["hop_size"], generator=g) * 0.6
+        state = {k: v.clone() for k, v in m.state_dict().items()}
+        z, logdet = m(x.clone(), h)
+        loss = loss_fn(z, logdet)
+        loss.backward()
+        grads = {n: p.grad.clone() for n, p in m.named_parameters()}
+        with torch.no_grad():
+            m.eval()
+            audio, _ = m.reverse(zs.clone(), h)
+            xr, _ = m.reverse(z.detach().clone(), h)
+        torch.save({"state": state, "x": x, "h": h, "zs": zs, "z": z.detach(), "logdet": logdet.detach(),
+                    "loss": loss.detach(), "grads": grads, "audio": audio, "ref_roundtrip_rel_l2":
+                    ((xr - x).norm() / x.norm()).item()}, args.out)
+        print(json.dumps({"ok": True, "kind": kind}), flush=True)
+        return
+
+    if task == "wsrglow":    # config 5: one training step and one inverse of a single 8192-sample segment
+        x = torch.rand(1, WSR_SEGMENT, generator=g) * 2 - 1
+        c = torch.rand(1, WSR_SEGMENT // 2, generator=g) * 2 - 1
+        if ref is not None:
+            torch.manual_seed(0)
+            m = ref.WSRGlow(upsample_rate=2, memory_efficient=True, zero_init=False)
+            from model.loss import WaveGlowLoss
+            loss_fn = WaveGlowLoss(1.0)
+            m.train()
+            ts = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                m.zero_grad(set_to_none=True)
+                z, logdet = m(x.clone(), c.clone())
+                loss_fn(z, logdet).backward()
+                ts.append(time.perf_counter() - t0)
+            with torch.no_grad():
+                m.eval()
+                t0 = time.perf_counter()
+                m.reverse(z.detach().clone(), c.clone())
+                t_inv = time.perf_counter() - t0
+            t_train = min(ts)
+        else:
+            from oracle import flow_oracle as O
+            spec = O.wsrglow_spec(2)
+            sd = O.wsrglow_random_state(2, 256, 8, seed=0)
+            t0 = time.perf_counter()
+            z, _, _, _ = O.wsrglow_train_step(sd, spec, x, c, 1.0)
+            t_train = time.perf_counter() - t0
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                O.wsrglow_reverse(sd, spec, z.detach(), c)
+                t_inv = time.perf_counter() - t0
+        print(json.dumps({"train_segments_per_s": 1.0 / t_train, "inverse_khz": WSR_SEGMENT / t_inv / 1e3, "cores": cores,
+                          "kind": kind, "train_seconds": t_train, "inverse_seconds": t_inv}), flush=True)
+        return
+
+
+def reference_subprocess(task: str, extra=(), timeout=600):
+    """Run one reference-arm task in its own interpreter (the reference's `model` / `utils` / `datasets` packages share
+    their names with this repository's drop-in shims, so they never live in one process) and parse its JSON line."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-task", task, *extra]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -362,18 +543,27 @@ def run_b200(args):
     model = cm.WaveGlow(memory_efficient=True, zero_init=False, **LJ, **LJ_WN).to(dev).train()
     loss_fn = cm.WaveGlowLoss(SIGMA)
     sync = FlowGradSync(flow_buckets(model))
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=True)
+    from constant_memory_waveglow_b200.graphs import GraphedTrainStep
+    # the whole step as one CUDA graph per batch shape (constant_memory_waveglow_b200/graphs.py): same kernels, same order,
+    # one launch; --no-graph times the eager step (Python issuing every launch through autograd)
+    gstep = None if args.no_graph else GraphedTrainStep(model, lambda x_, h_: loss_fn(*model(x_, h_)), opt, sync)
 
     B = args.batch
     g = torch.Generator().manual_seed(1234 + rank)
     x_host = (torch.rand(B, SEGMENT, generator=g) * 2 - 1).pin_memory()
     h_host = torch.randn(B, LJ["n_mels"], FRAMES, generator=g).pin_memory()
     x_dev, h_dev = x_host.to(dev), h_host.to(dev)
+    Bs = max(1, GLOBAL_BATCH // world)                     # the reference's split (train.py:51-53)
+    xs_dev, hs_dev = x_dev[:Bs].clone(), h_dev[:Bs].clone()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     phase_ms = []
 
-    def step(x, h):
+    def step(x, h, eager=False):
+        if gstep is not None and not eager:
+            return gstep(x, h)
+        x, h = x.to(dev, non_blocking=True), h.to(dev, non_blocking=True)
         if os.environ.get("CMWG_BENCH_DEBUG") == "1":
             t = [time.perf_counter()]
             sync.zero_grad(); t.append(time.perf_counter())
@@ -414,7 +604,7 @@ def run_b200(args):
             if e2e and os.environ.get("CMWG_BENCH_DEBUG") == "1":
                 t0 = time.perf_counter()
                 t1 = time.perf_counter()
-                lt = step(x_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True))
+                lt = step(x_host, h_host)
                 t2 = time.perf_counter()
                 last = lt.item()
                 t3 = time.perf_counter()
@@ -423,7 +613,7 @@ def run_b200(args):
                 # the inputs are temporaries, as in the warm-up: keeping last step's tensors bound while the next ones
                 # are created asks the caching allocator for one more 2 MB segment in the second step, and a cudaMalloc
                 # issued while the device is busy stalled that step's backward by 60-200 ms
-                last = step(x_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True)).item()  # + D2H read
+                last = step(x_host, h_host).item()  # H2D from pinned memory inside step(), + D2H read of the loss
             else:
                 last = step(x_dev, h_dev)
             b.record()
@@ -441,7 +631,7 @@ def run_b200(args):
     for _ in range(args.warmup):
         step(x_dev, h_dev)
     for _ in range(min(args.warmup, 2)):                   # warm the pinned-host -> device path of the e2e leg too
-        step(x_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True)).item()
+        step(x_host, h_host).item()
     barrier()
 
     import gc
@@ -451,6 +641,8 @@ def run_b200(args):
     lib.cmwg_reset_launch_count()
     ms, loss = timed(args.steps, e2e=False)
     launches = int(lib.cmwg_launch_count())
+    if gstep is not None:
+        launches = gstep.launches_per_step * args.steps    # counted while the step was captured; every replay runs them all
     if os.environ.get("CMWG_BENCH_SAMPLE_E2E", "0") != "1":
         sampler.end()      # clocks are sampled over the device-resident leg (the timed region of `value`): an NVML query
                            # holds a driver lock, and the e2e leg -- whose host thread cannot run ahead of the device
@@ -458,13 +650,13 @@ def run_b200(args):
     # the e2e leg allocates its inputs per step, which shifts where the caching allocator places everything after them:
     # let it reach its steady state (two alternating layouts) before timing
     for _ in range(min(args.warmup, 3)):
-        step(x_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True)).item()
+        step(x_host, h_host).item()
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
     sampler.end()
     if rank == 0 and sampler.nvml is not None and len(sampler.rows) < 3:
         # slow NVML on this box: top the clock samples up under the same load (untimed steps in flight)
         for _ in range(3):
-            step(x_dev, h_dev)
+            step(x_dev, h_dev, eager=True)
         for _ in range(3):
             sampler.sample_once()
             time.sleep(0.01)
@@ -472,10 +664,32 @@ def run_b200(args):
     gc.enable()
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- reference-semantics split: global batch 24 divided over the GPUs (24 // N segments per GPU), same timing rules
+    strong = None
+    if world > 1 and not args.no_strong:
+        for _ in range(args.warmup):
+            step(xs_dev, hs_dev)
+        barrier()
+        tot = 0.0
+        for _ in range(args.steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record()
+            step(xs_dev, hs_dev)
+            b.record()
+            barrier()
+            tot += a.elapsed_time(b)
+        t = torch.tensor([tot], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"value": world * Bs * args.steps / (t.item() * 1e-3), "unit": "segments/s", "scaling": "strong",
+                  "global_batch": world * Bs, "per_gpu_batch": Bs, "ms_per_step": t.item() / args.steps,
+                  "note": "train.py:51-53 semantics: batch_size //= gpus; row tiles per GPU = per_gpu_batch * 8 for 74 CTA pairs"}
+
     # ---- roofline leg: device time of every GEMM class over one more step (events on the launching stream)
     import ctypes as C
     lib.cmwg_profile_enable(1)
-    step(x_dev, h_dev)
+    step(x_dev, h_dev, eager=True)                         # eager: the per-class CUDA events sit between the launches
     torch.cuda.synchronize()
     kms = (C.c_double * 8)()
     kn = (C.c_longlong * 8)()
@@ -489,30 +703,61 @@ def run_b200(args):
     if not args.no_synth:
         model.eval()
         sb = args.synth_batch
-        hs = torch.randn(sb, LJ["n_mels"], SYNTH_FRAMES, device=dev)
+        hs_host = torch.randn(sb, LJ["n_mels"], SYNTH_FRAMES).pin_memory()
+        audio_host = torch.empty(sb, SYNTH_FRAMES * LJ["hop_size"]).pin_memory()
+        hs = hs_host.to(dev)
         zs = torch.randn(sb, SYNTH_FRAMES * LJ["hop_size"], device=dev) * 0.6
-        with torch.no_grad():
-            for _ in range(2):
-                model.infer(hs, 0.6, z=zs)
-            reps = 3
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            a.record()
-            for _ in range(reps):
-                audio = model.infer(hs, 0.6, z=zs)
-            b.record()
-            barrier()
-        t = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
         samples = sb * SYNTH_FRAMES * LJ["hop_size"]
-        khz = world * samples / (t.item() * 1e-3) / 1e3
         pk = peaks()
-        synth = {"value": khz, "unit": "kHz (all GPUs)", "per_gpu_khz": khz / world, "batch_per_gpu": sb,
-                 "utterance_samples": SYNTH_FRAMES * LJ["hop_size"], "sigma": 0.6, "ms": t.item(),
+
+        def timed_synth(fn, reps=3):
+            with torch.no_grad():
+                for _ in range(2):
+                    fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                a.record()
+                for _ in range(reps):
+                    fn()
+                b.record()
+                barrier()
+            t = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+
+        ms_dev = timed_synth(lambda: model.infer(hs, 0.6, z=zs))
+
+        def synth_e2e():
+            # the call a user makes (inference.py:50-56): mel from pinned host memory, noise drawn on the device by infer(),
+            # audio back to the host
+            audio_host.copy_(model.infer(hs_host.to(dev, non_blocking=True), 0.6).view(sb, -1), non_blocking=True)
+
+        ms_e2e_s = timed_synth(synth_e2e)
+        # roofline of the synthesis path's dominant kernel: the non-saving forward task kernel, 12 launches per call
+        lib.cmwg_profile_enable(1)
+        with torch.no_grad():
+            model.infer(hs, 0.6, z=zs)
+        torch.cuda.synchronize()
+        sms, sn = (C.c_double * 8)(), (C.c_longlong * 8)()
+        _lib.check(lib.cmwg_profile_collect(sms, sn), "profile_collect")
+        lib.cmwg_profile_enable(0)
+        srows = sb * SYNTH_FRAMES * LJ["hop_size"] // LJ["n_group"]
+        sflops = srows * (8 * 2.0 * 512 * (3 * 256 + 80) + 7 * 2.0 * 256 * 256 + 8 * 2.0 * 256 * 256)
+        s_ms = sms[6] / max(int(sn[6]), 1)
+        s_ach = sflops / (s_ms * 1e-3) / 1e12 if s_ms > 0 else 0.0
+        khz = world * samples / (ms_dev * 1e-3) / 1e3
+        synth = {"metric": "waveglow_lj_synth_khz", "value": khz, "unit": "kHz (all GPUs)", "per_gpu_khz": khz / world,
+                 "batch_per_gpu": sb, "utterance_samples": SYNTH_FRAMES * LJ["hop_size"], "sigma": 0.6, "ms": ms_dev,
                  "operand_dtype": precision.resolve(True, False),
-                 "tflops_per_gpu": samples * 13.3764e6 / (t.item() * 1e-3) / 1e12,
-                 "frac_of_bf16_peak": samples * 13.3764e6 / (t.item() * 1e-3) / 1e12 / pk["tflops_sustained"]}
+                 "e2e": {"value": world * samples / (ms_e2e_s * 1e-3) / 1e3, "unit": "kHz (all GPUs)", "ms": ms_e2e_s,
+                         "h2d_bytes_per_step": int(hs_host.numel() * 4), "d2h_bytes_per_step": int(audio_host.numel() * 4)},
+                 "tflops_per_gpu": samples * 13.3764e6 / (ms_dev * 1e-3) / 1e12,
+                 "frac_of_bf16_peak": samples * 13.3764e6 / (ms_dev * 1e-3) / 1e12 / pk["tflops_sustained"],
+                 "roofline": {"bound": "tensor", "kernel": "wn_fwd_mega_kernel<no saves>", "achieved": s_ach,
+                              "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": s_ach / pk["tflops_sustained"],
+                              "flops_per_launch": sflops, "ms_per_launch": s_ms, "launches_per_call": int(sn[6]),
+                              "traffic": None}}
         # batch sweep of config 3 (10 s utterances, batch 1-64 per GPU): kHz per GPU at each batch size
         if not args.no_synth_sweep:
             sweep = {}
@@ -557,20 +802,22 @@ def run_b200(args):
     gate_ms = gate["ms"] / max(gate["launches"], 1)
     achieved = gate_flops / (gate_ms * 1e-3) / 1e12 if gate_ms > 0 else 0.0
     total_kernel_ms = sum(v["ms"] for v in kern.values())
+    mode = precision.resolve(True, True)
     line = {
         "metric": "waveglow_lj_train_segments_per_s", "value": value, "unit": "segments/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": {"bf16": "bf16", "fp32": "f32", "fp16": "bf16", "auto": "bf16"}[args.precision],
+        "dtype": {"bf16": "bf16", "fp32": "f32", "fp16": "fp16"}[mode],
+        "operand_precision": {"fp16": "fp16 operands (10 mantissa bits = TF32's), fp32 accumulate in TMEM, power-of-two "
+                                      "gradient scale chosen on the device", "bf16": "bf16 operands, fp32 accumulate",
+                              "fp32": "fp32 FFMA engine"}[mode],
         "data": "synthetic",
-        "config": {"workload": "waveglow_lj_train_fwd+reversible_bwd+adam", "per_gpu_batch": B, "segment": SEGMENT,
-                   "n_mels": 80, "channels": 256, "flows": 12, "wn_layers": 8,
-                   "precision": precision.resolve(True, True),
-                   "l2": "256 MiB flush between timed steps; per-step working set >> 126 MB L2",
-                   "parallelism": f"dp{world}", "loss": float(loss.detach())},
+        "config": workload_config(world, B), "loss": float(loss.detach()),
         "e2e": {"value": value_e2e, "unit": "segments/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + h_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "launch_mode": "eager (one Python-issued launch per kernel)" if gstep is None else
+                       f"one CUDA graph per step ({gstep.launches_per_step} kernels of libcmwg_b200.so per replay, + optimizer / torch glue)",
         "ms_per_timed_step": {"device_resident": step_ms[False], "e2e": step_ms[True]},
         **({"debug_e2e_host_ms_copy_enqueue_wait": dbg_host, "debug_phase_ms_zero_fwd_loss_bwd_finish_opt": phase_ms[-2 * args.steps - 1:]} if dbg_host else {}),
         "train_tflops_per_gpu": B * TRAIN_GFLOP_PER_SEGMENT / (ms / args.steps),
@@ -584,24 +831,164 @@ def run_b200(args):
         "clocks": clocks,
         "synth": synth,
     }
+    if strong is not None:
+        line["strong"] = strong
+    want_cpu = not args.no_cpu_baseline and world == 1
+    # ---- parity of THIS arm's precision mode against the unmodified reference on the same weights and inputs
+    if want_cpu and not args.no_parity:
+        line["parity"] = parity_leg(model, loss_fn, dev, args)
+    del opt, sync, gstep
+    if not args.no_wsrglow and world == 1:
+        del model
+        model = None
+        torch.cuda.empty_cache()
+        line["wsrglow"] = wsrglow_leg(dev, flush, want_cpu)
     if not args.no_waveflow and world == 1:
-        del model, opt, sync
+        model = None
         torch.cuda.empty_cache()
         line["waveflow"] = waveflow_leg(dev, not args.no_cpu_baseline)
-    if not args.no_cpu_baseline and world == 1 and synth is not None:
-        khz, dt = cpu_oracle_synth(SYNTH_FRAMES)              # the same 10 s utterance, a few seconds of CPU work
-        synth["cpu_baseline"] = {"value": khz, "unit": "kHz", "cores": torch.get_num_threads(), "kind": "port",
-                                 "sample": f"oracle port, one utterance of {SYNTH_FRAMES} frames = {SYNTH_FRAMES * 256} samples, {dt:.1f} s"}
-        synth["x_cpu_per_gpu"] = synth["per_gpu_khz"] / khz
-    if not args.no_cpu_baseline and world == 1:
-        nb, nsteps = CPU_SAMPLE_BATCH, 8                      # ~10-20 s of CPU work
-        v, times = cpu_oracle_train(nb, nsteps, 1)
-        line["cpu_baseline"] = {"value": v, "unit": "segments/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"oracle port (torch CPU fp32), LJ config, {nsteps} timed steps of batch {nb} x "
-                                          f"16000 samples (1 warm-up), forward + loss + backward, {sum(times):.1f} s"}
+    if want_cpu and synth is not None:
+        r = reference_subprocess("synth")                     # the same 10 s utterance, a few seconds of CPU work
+        if "khz" in r:
+            synth["cpu_baseline"] = {"value": r["khz"], "unit": "kHz", "cores": r["cores"], "kind": r["kind"],
+                                     "sample": f"one utterance of {SYNTH_FRAMES} frames = {SYNTH_FRAMES * 256} samples through "
+                                               f"the reference's infer() after remove_weight_norms, {r['seconds']:.1f} s"}
+            synth["x_cpu_per_gpu"] = synth["per_gpu_khz"] / r["khz"]
+        else:
+            synth["cpu_baseline"] = r
+    if want_cpu:
+        r = reference_subprocess("train", ["--steps", "6", "--warmup", "1"])   # ~15-25 s of CPU work
+        line["cpu_baseline"] = r.get("cpu_baseline", r)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_leg(model, loss_fn, dev, args):
+    """z / log-det / loss / every parameter gradient / synthesis audio / round trip of the CUDA path in the precision mode
+    being benchmarked, against the UNMODIFIED reference (baseline/_ref, CPU fp32) on the same random-init weights and inputs
+    (LJ config, 2 segments): the reference process writes its state dict and results, this one loads the state dict."""
+    from constant_memory_waveglow_b200 import precision
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    r = reference_subprocess("parity", ["--out", args.out])
+    if not r.get("ok"):
+        return {"unavailable": r}
+    fx = torch.load(args.out, map_location="cpu", weights_only=False)
+    os.remove(args.out)
+    keep = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model.load_state_dict(fx["state"])
+    model.train()
+    for p_ in model.parameters():
+        p_.grad = None
+
+    def rel(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
+
+    z, logdet = model(fx["x"].to(dev), fx["h"].to(dev))
+    loss = loss_fn(z, logdet)
+    loss.backward()
+    num = den = 0.0
+    worst = ("", 0.0)
+    for n, p_ in model.named_parameters():
+        gr = fx["grads"][n].double()
+        e2 = (p_.grad.double().cpu() - gr).pow(2).sum().item()
+        d2 = gr.pow(2).sum().item()
+        num += e2
+        den += d2
+        e = (e2 / max(d2, 1e-300)) ** 0.5
+        if e > worst[1]:
+            worst = (n, e)
+    with torch.no_grad():
+        model.eval()
+        xr, _ = model.reverse(z.detach().clone(), fx["h"].to(dev))
+        audio, _ = model.reverse(fx["zs"].to(dev), fx["h"].to(dev))
+    out = {"against": "baseline/_ref (unmodified reference, CPU fp32), LJ config, 2 x 16000 samples, same state dict",
+           "mode": precision.resolve(True, True), "z_rel_l2": rel(z, fx["z"]), "logdet_rel_l2": rel(logdet, fx["logdet"]),
+           "loss_rel": abs(loss.item() - fx["loss"].item()) / abs(fx["loss"].item()),
+           "grad_rel_l2_aggregate": (num / max(den, 1e-300)) ** 0.5,
+           "grad_rel_l2_worst": {"tensor": worst[0], "rel_l2": worst[1]},
+           "audio_rel_l2": rel(audio, fx["audio"]), "roundtrip_rel_l2": rel(xr, fx["x"]),
+           "reference_roundtrip_rel_l2": fx["ref_roundtrip_rel_l2"],
+           "tolerance": "north_star: rel-L2 <= 1e-3 (tensor-core operands), <= 1e-5 (fp32)"}
+    model.load_state_dict(keep)
+    model.train()
+    for p_ in model.parameters():
+        p_.grad = None
+    return out
+
+
+def wsrglow_leg(dev, flush, cpu_baseline: bool):
+    """Config 5 (WSRGlow 2x super-resolution, VCTK shape: 12 segments of 8192 samples, 4096-sample low-rate input,
+    configs/wsrglow_vctk_2x.json): training step (forward + loss + reversible backward + Adam) and the inverse."""
+    import constant_memory_waveglow_b200 as cm
+    from constant_memory_waveglow_b200 import _lib, precision
+    lib = _lib.load()
+    torch.manual_seed(0)
+    m = cm.WSRGlow(upsample_rate=2, memory_efficient=True, zero_init=False).to(dev).train()
+    loss_fn = cm.WaveGlowLoss(1.0)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True)
+    B = WSR_BATCH
+    x = torch.rand(B, WSR_SEGMENT, device=dev) * 2 - 1
+    c = torch.rand(B, WSR_SEGMENT // 2, device=dev) * 2 - 1
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        z, logdet = m(x.clone(), c.clone())
+        loss = loss_fn(z, logdet)
+        loss.backward()
+        opt.step()
+        return z
+
+    def timed(fn, n):
+        tot = 0.0
+        for _ in range(n):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / n
+
+    for _ in range(3):
+        z = step()
+    lib.cmwg_reset_launch_count()
+    ms_train = timed(step, 3)
+    launches = int(lib.cmwg_launch_count()) // 3
+    z = z.detach()
+    m.eval()
+    with torch.no_grad():
+        for _ in range(2):
+            m.reverse(z.clone(), c.clone())
+        ms_inv = timed(lambda: m.reverse(z.clone(), c.clone()), 3)
+    pk = peaks()
+    tf_train = 4 * B * WSR_FWD_GFLOP_PER_SEGMENT / ms_train
+    tf_inv = B * WSR_FWD_GFLOP_PER_SEGMENT / ms_inv
+    out = {"config": {"workload": "wsrglow_2x_vctk (12 flows, n_group 16, 256 channels, 8 WN layers, 3659 conditioning rows)",
+                      "batch": B, "segment": WSR_SEGMENT, "low_rate_samples": WSR_SEGMENT // 2},
+           "operand_dtype": precision.resolve(True, True),
+           "train_segments_per_s": B / (ms_train * 1e-3), "train_ms_per_step": ms_train, "gpu_launches_per_step": launches,
+           "train_tflops": tf_train, "train_frac_of_peak": tf_train / pk["tflops_sustained"],
+           "inverse_khz": B * WSR_SEGMENT / ms_inv, "inverse_ms": ms_inv, "inverse_tflops": tf_inv,
+           "inverse_frac_of_peak": tf_inv / pk["tflops_sustained"],
+           "flops": "234.978 GFLOP per 8192-sample segment forward (SURVEY 8d), training = 4x"}
+    del m, opt
+    torch.cuda.empty_cache()
+    if cpu_baseline:
+        r = reference_subprocess("wsrglow")
+        if "train_segments_per_s" in r:
+            out["cpu_baseline"] = {"train_segments_per_s": r["train_segments_per_s"], "inverse_khz": r["inverse_khz"],
+                                   "cores": r["cores"], "kind": r["kind"],
+                                   "sample": f"one 8192-sample segment: forward + loss + reversible backward "
+                                             f"({r['train_seconds']:.1f} s) and the inverse ({r['inverse_seconds']:.1f} s)"}
+            out["train_x_cpu"] = out["train_segments_per_s"] / r["train_segments_per_s"]
+            out["inverse_x_cpu"] = out["inverse_khz"] / r["inverse_khz"]
+        else:
+            out["cpu_baseline"] = r
+    return out
 
 
 def main():
@@ -611,7 +998,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="auto", choices=["bf16", "fp32", "fp16", "auto"],
-                    help="auto = bf16 operands for training steps, fp16 operands for synthesis (fp32 accumulate)")
+                    help="auto = fp16 operands (TF32's mantissa) with fp32 accumulation, gradients scaled on the device")
+    ap.add_argument("--ref-task", default="train", choices=["train", "synth", "parity", "wsrglow"],
+                    help="--impl reference only: which bounded sample of the reference to time")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ref_parity.pt"))
+    ap.add_argument("--no-graph", action="store_true", help="eager training step instead of one CUDA graph per step")
+    ap.add_argument("--no-strong", action="store_true", help="skip the reference-semantics (24 // N per GPU) leg at N > 1")
+    ap.add_argument("--no-wsrglow", action="store_true", help="skip the WSRGlow (config 5) leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity check against baseline/_ref")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--synth-batch", type=int, default=4)
     ap.add_argument("--no-synth", action="store_true")

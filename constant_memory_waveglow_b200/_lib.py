@@ -86,6 +86,7 @@ SIGNATURES = {
                               _VP, _VP, _LL, _VP, C.POINTER(WnGrads), _VP]),
     "cmwg_melspec_frames": (_I, [_I, _I, _I]),
     "cmwg_melspec_fwd": (_I, [_VP, _LL, _I, _I, _VP, _VP, _VP, _VP, _I, _I, _I, _I, C.c_float, _I, _VP, _VP]),
+    "cmwg_wsrglow_cond": (_I, [_VP, _I, _I, _VP, _I, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, _VP]),
     "cmwg_upsample_fwd": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, _VP]),
     "cmwg_upsample_bwd_workspace": (_SZ, [_I, _I, _I]),
     "cmwg_upsample_bwd": (_I, [_VP, _VP, _VP, _VP, _LL, _LL, _I, _I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]),

@@ -144,5 +144,21 @@ template <bool FAST> __device__ __forceinline__ float sigmoid_f(float x) {
 // whose 11-bit mantissa would otherwise be wasted on the gate approximation
 __device__ __forceinline__ float tanh_ex2(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 __device__ __forceinline__ float sigmoid_ex2(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// tanh(x), sigmoid(y) and their product with ONE reciprocal:  E1 = e^(2x), E2 = e^(-y), r = 1 / ((E1 + 1)(1 + E2));
+//   tanh = (E1 - 1)(1 + E2) r,  sigmoid = (E1 + 1) r,  tanh * sigmoid = (E1 - 1) r.
+// x is clamped above at 15 (tanh = 1 to fp32 precision beyond 9.1) and y below at -30 so that the product stays finite.
+template <bool WANT_AB>
+__device__ __forceinline__ void gate_ex2(float x, float y, float& a, float& b, float& g) {
+  float e1, e2, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(x, 15.f) * 2.885390082f));   // 2 log2(e)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaxf(y, -30.f) * -1.442695041f));
+  const float p = e1 + 1.f, q = 1.f + e2, m = e1 - 1.f;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p * q));
+  g = m * r;
+  if (WANT_AB) {
+    b = p * r;
+    a = m * q * r;
+  }
+}
 
 }  // namespace cmwg

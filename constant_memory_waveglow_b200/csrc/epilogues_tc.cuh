@@ -33,12 +33,15 @@ struct GateTcEpi {
       for (int j = 0; j < 16; ++j) { lo[j] += __ldg(bias + ch0 + j); hi[j] += __ldg(bias + Cd + ch0 + j); }
     }
     if (f16) {
-      // MUFU.EX2 + MUFU.RCP forms (~1e-7 abs error): fp16's 11-bit mantissa deserves better than tanh.approx
+      // fp16's 11-bit mantissa deserves better than tanh.approx (2^-11 relative error): exact-to-1e-7 forms on
+      // MUFU.EX2 / MUFU.RCP, three MUFU operations per gate value (the MUFU pipe runs 16 lanes per clock per SM, a
+      // quarter of an epilogue's budget at four) -- see gate_ex2()
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
-        float a0 = tanh_ex2(lo[j]), a1 = tanh_ex2(lo[j + 1]);
-        float b0 = sigmoid_ex2(hi[j]), b1 = sigmoid_ex2(hi[j + 1]);
-        o[0][j >> 1] = pack2(a0 * b0, a1 * b1, 1);
+        float a0, b0, g0, a1, b1, g1;
+        gate_ex2<SAVE>(lo[j], hi[j], a0, b0, g0);
+        gate_ex2<SAVE>(lo[j + 1], hi[j + 1], a1, b1, g1);
+        o[0][j >> 1] = pack2(g0, g1, 1);
         if constexpr (SAVE) { o[1][j >> 1] = pack2(a0, a1, 1); o[2][j >> 1] = pack2(b0, b1, 1); }
       }
     } else {

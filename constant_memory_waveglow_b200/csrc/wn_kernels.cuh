@@ -761,47 +761,64 @@ static __global__ void __launch_bounds__(256) end_bwd_dw_kernel(const float* __r
 // Gradient scaling for fp16 operands.  fp16 carries the same 10 mantissa bits as TF32 (bf16: 7) at bf16's tensor-core rate,
 // but only 5 exponent bits; the backward GEMM chain is LINEAR in the incoming cotangent, so it runs on S * cotangent with S a
 // power of two chosen per call on the device (no host round trip), and every result is multiplied by 1 / S where it leaves
-// the 16-bit slabs (exact: powers of two).  gscale = {bit pattern of max |dlst|, S, 1 / S}.
+// the 16-bit slabs (exact: powers of two).  gscale = {max |dlst|, S, 1 / S}.
 //   S = 2^(8 - ceil(log2(max|dlst| * max_k sum_o |W_end[o][k]|)))  =>  |S * dskip| <= 256:
 // 2^8 of headroom below fp16's largest value for the growth of the residual gradient through the layers, and 2^22 of normal
 // range below the largest entry (smaller entries lose precision gradually as fp16 subnormals; they do not matter to any norm).
 // ------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(256) amax_abs_kernel(const float* __restrict__ a, long long n,
-                                                              unsigned int* __restrict__ out_bits) {
+static __global__ void __launch_bounds__(1024) grad_scale_kernel(float* __restrict__ gscale, const float* __restrict__ dlst,
+                                                                 long long n, const float* __restrict__ w_end, int cout,
+                                                                 int Cs) {
+  // one CTA: dlst is B * 2cin * T floats (1.5 MB at the LJ training shape), a few microseconds of one SM's bandwidth, and a
+  // single launch replaces memset + grid-wide atomic max + finalise.  max() is order independent: deterministic.
+  __shared__ float red[32];
   float m = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(a[i]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  // non-negative floats order like their bit patterns; max is order independent, so the result is deterministic
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
-}
-
-static __global__ void __launch_bounds__(256) grad_scale_kernel(float* __restrict__ gscale, const float* __restrict__ w_end,
-                                                                int cout, int Cs) {
-  __shared__ float red[8];
+  const long long n4 = n >> 2;
+  const float4* a4 = reinterpret_cast<const float4*>(dlst);
+  for (long long i = threadIdx.x; i < n4; i += 1024) {
+    const float4 v = a4[i];
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  for (long long i = (n4 << 2) + threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(dlst[i]));
   float colmax = 0.f;
-  for (int k = threadIdx.x; k < Cs; k += 256) {
+  for (int k = threadIdx.x; k < Cs; k += 1024) {
     float s = 0.f;
     for (int o = 0; o < cout; ++o) s += fabsf(w_end[(long long)o * Cs + k]);
     colmax = fmaxf(colmax, s);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) colmax = fmaxf(colmax, __shfl_xor_sync(0xffffffffu, colmax, o));
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    colmax = fmaxf(colmax, __shfl_xor_sync(0xffffffffu, colmax, o));
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    m = v;
+  }
+  __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = colmax;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float bound = 0.f;
-    for (int i = 0; i < 8; ++i) bound = fmaxf(bound, red[i]);
-    bound *= __uint_as_float(reinterpret_cast<const unsigned int*>(gscale)[0]);
-    float S = 1.f;
-    if (bound > 0.f && bound < 3.0e38f) {
-      int e = 8 - (int)ceilf(log2f(bound));
-      e = max(-60, min(60, e));
-      S = exp2f((float)e);
+  if (threadIdx.x < 32) {
+    float v = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) {
+      const float bound = v * m;
+      float S = 1.f;
+      if (bound > 0.f && bound < 3.0e38f) {
+        int e = 8 - (int)ceilf(log2f(bound));
+        e = max(-60, min(60, e));
+        S = exp2f((float)e);
+      }
+      gscale[0] = m;
+      gscale[1] = S;
+      gscale[2] = 1.f / S;
     }
-    gscale[1] = S;
-    gscale[2] = 1.f / S;
   }
 }
 

@@ -464,7 +464,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
 // fixed-order reduction of [nblocks][P] block partials into out[P]; `scratch` holds ceil(nblocks/64)*P floats
 static int reduce_blocks(const float* partial, int nblocks, int P, float* scratch, float* out, cudaStream_t st,
                          const float* gscale = nullptr) {
-  if (nblocks > 128) {
+  if (nblocks > 512) {
     int stages = ceil_div(nblocks, 64);
     reduce_blocks_stage_kernel<<<dim3(ceil_div(P, 128), stages), 128, 0, st>>>(partial, nblocks, P, scratch);
     CMWG_COUNT_LAUNCH();
@@ -559,12 +559,8 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   float* gscale = nullptr;
   if (TC && f16) {
     gscale = reinterpret_cast<float*>(ws + BL.gscale);
-    CMWG_CHECK_CUDA(cudaMemsetAsync(gscale, 0, 16, st));
-    const long long n = (long long)B * cout * TF;
-    amax_abs_kernel<<<(int)std::min<long long>(ceil_div_ll(n, 256 * 8), 2 * num_sms()), 256, 0, st>>>(
-        dlst, n, reinterpret_cast<unsigned int*>(gscale));
-    CMWG_COUNT_LAUNCH();
-    grad_scale_kernel<<<1, 256, 0, st>>>(gscale, wEnd, cout, d.Cs);
+    CMWG_REQUIRE((reinterpret_cast<uintptr_t>(dlst) & 15) == 0, "cmwg_wn_backward: dlst must be 16-byte aligned");
+    grad_scale_kernel<<<1, 1024, 0, st>>>(gscale, dlst, (long long)B * cout * TF, wEnd, cout, d.Cs);
     CMWG_COUNT_LAUNCH();
     CMWG_LAUNCH_CHECK();
   }

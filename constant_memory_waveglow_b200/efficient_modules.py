@@ -128,7 +128,11 @@ def _conv1x1_bwd(ctx, z_grad, log_det_grad, restore: bool):
         dm = ops.conv1x1_wgrad(z_grad, x)
         if log_det_grad is None:
             log_det_grad = torch.zeros((), device=z.device)
-        dw = ops.conv1x1_dw_finalize(dm, winv, log_det_grad, T, inverse).reshape(weight.shape)
+        # written straight into the parameter's slot of its data-parallel gradient bucket when there is one (parallel.py):
+        # autograd then adopts the view as .grad without a copy kernel
+        from .parallel import grad_buffer
+        dw = grad_buffer(weight)
+        ops.conv1x1_dw_finalize(dm, winv, log_det_grad, T, inverse, out=dw.view(dm.shape))
     return dx, dw
 
 

@@ -72,10 +72,10 @@ def conv1x1_wgrad(dz: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
 
 
 def conv1x1_dw_finalize(dm: torch.Tensor, winv: torch.Tensor, dlogdet: torch.Tensor, T: int,
-                        inverse_mode: bool) -> torch.Tensor:
+                        inverse_mode: bool, out: torch.Tensor = None) -> torch.Tensor:
     c = dm.shape[0]
     dlogdet = dlogdet.detach().reshape(()).float().contiguous()
-    dw = torch.empty_like(dm)
+    dw = out if out is not None else torch.empty_like(dm)
     L.check(L.load().cmwg_conv1x1_dw_finalize(dm.data_ptr(), winv.data_ptr(), dlogdet.data_ptr(), c, T,
                                               int(inverse_mode), dw.data_ptr(), L.stream_ptr(dm.device)),
             "conv1x1_dw_finalize")
@@ -173,15 +173,19 @@ def upsample_fwd(h, g, v, bias, stride: int, pad: int) -> torch.Tensor:
     return y
 
 
-def upsample_bwd(h, g, v, dy, stride: int, pad: int, want_bias: bool):
+def upsample_bwd(h, g, v, dy, stride: int, pad: int, want_bias: bool, out=None):
+    """`out` = (dg, dv, db) destination tensors (e.g. views of the data-parallel gradient buckets) or None."""
     h = h.contiguous().float()
     B, Cc, F = h.shape
     K = v.shape[-1]
     if dy.stride(2) != 1:
         dy = dy.contiguous()
-    dg = torch.empty_like(g) if g is not None else None
-    dv = torch.empty_like(v)
-    db = torch.empty((Cc,), device=h.device, dtype=torch.float32) if want_bias else None
+    if out is not None:
+        dg, dv, db = out
+    else:
+        dg = torch.empty_like(g) if g is not None else None
+        dv = torch.empty_like(v)
+        db = torch.empty((Cc,), device=h.device, dtype=torch.float32) if want_bias else None
     L.check(L.load().cmwg_upsample_bwd(h.data_ptr(), L.ptr(g), v.data_ptr(), dy.data_ptr(), dy.stride(0), dy.stride(1),
                                        B, Cc, F, K, stride, pad, dy.shape[2], L.ptr(dg), dv.data_ptr(), L.ptr(db), 0,
                                        L.stream_ptr(h.device)), "upsample_bwd")

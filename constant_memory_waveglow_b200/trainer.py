@@ -384,6 +384,21 @@ class Trainer:
         if rest:
             buckets.append(rest)
         sync = FlowGradSync(buckets)
+        # CMWG_TRAIN_GRAPH=1: the whole step (forward, loss, reversible backward, all-reduces, optimizer) replayed as one CUDA
+        # graph per batch shape (graphs.py); needs capturable optimizers and a training_step without host round trips
+        graphed = None
+        if os.environ.get("CMWG_TRAIN_GRAPH", "0") == "1" and device.type == "cuda" and len(self.optimizers) == 1:
+            from .graphs import GraphedTrainStep
+            o = self.optimizers[0]
+            if not o.state:                                  # fresh optimizer: its step counters can live on the device
+                for g_ in o.param_groups:
+                    if "capturable" in g_:
+                        g_["capturable"] = True
+            if all(g_.get("capturable", False) for g_ in o.param_groups):
+                # training_step's self.log(...) calls store device tensors in self.logged_metrics; captured once, those are the
+                # graph's static outputs and every replay refreshes them in place
+                graphed = GraphedTrainStep(model, lambda batch_: model.training_step(batch_, 0), o, sync,
+                                           clip_grad_norm=self.gradient_clip_val or None)
 
         loader = model.train_dataloader()
         sampler = None
@@ -414,14 +429,17 @@ class Trainer:
                 for batch_idx, batch in enumerate(DevicePrefetcher(loader, device)):
                     if batch_idx >= nb:
                         break
-                    sync.zero_grad()
-                    loss = model.training_step(batch, batch_idx)
-                    loss.backward()
-                    sync.finish()
-                    if self.gradient_clip_val:
-                        torch.nn.utils.clip_grad_norm_(trainable, self.gradient_clip_val)
-                    for o in self.optimizers:
-                        o.step()
+                    if graphed is not None:
+                        loss = graphed(batch)
+                    else:
+                        sync.zero_grad()
+                        loss = model.training_step(batch, batch_idx)
+                        loss.backward()
+                        sync.finish()
+                        if self.gradient_clip_val:
+                            torch.nn.utils.clip_grad_norm_(trainable, self.gradient_clip_val)
+                        for o in self.optimizers:
+                            o.step()
                     self.global_step += 1
                     for cb in self.callbacks:
                         cb.on_train_batch_end(self, model, loss, batch, batch_idx)

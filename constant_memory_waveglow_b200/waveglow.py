@@ -322,6 +322,7 @@ class _UpsampleFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, g, v, bias, stride, pad):
         ctx.save_for_backward(h, g, v)
+        ctx.params = (g, v, bias)
         ctx.stride, ctx.pad, ctx.has_bias = stride, pad, bias is not None
         return ops.upsample_fwd(h.detach(), None if g is None else g.detach(), v.detach(),
                                 None if bias is None else bias.detach(), stride, pad)
@@ -332,7 +333,9 @@ class _UpsampleFunction(torch.autograd.Function):
         dh = None
         if ctx.needs_input_grad[0]:  # trainable conditioning (WSRGlow's embedding tables)
             dh = ops.upsample_bwd_input(g, v, dy, h.shape[2], ctx.stride, ctx.pad)
-        dg, dv, db = ops.upsample_bwd(h, g, v, dy, ctx.stride, ctx.pad, ctx.has_bias)
+        pg, pv, pb = ctx.params
+        out = (grad_buffer(pg) if pg is not None else None, grad_buffer(pv), grad_buffer(pb) if pb is not None else None)
+        dg, dv, db = ops.upsample_bwd(h, g, v, dy, ctx.stride, ctx.pad, ctx.has_bias, out=out)
         return dh, dg, dv, db, None, None
 
 

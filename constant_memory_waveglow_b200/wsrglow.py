@@ -5,18 +5,61 @@
 embedding (3200 rows), 9 STFT magnitudes and 9 x 50 phase-embedding rows, at one conditioning column per
 squeezed time step (upsample factor 1).  The flow itself -- 1x1 convs, couplings, the WN stack whose ``V``
 conv is now 3659 -> 2*Cd*depth and dominates the FLOPs (78 %) -- runs on the same libcmwg_b200.so kernels as
-WaveGlow; the conditioning front end is a handful of index / elementwise torch ops (no cuFFT: the 16-point
-STFT is written out as a windowed DFT so that it stays a plain elementwise + reduction computation).
+WaveGlow; the conditioning front end is ONE kernel, ``cmwg_wsrglow_cond`` (csrc/wsrglow_cond.cu: clip, mu-law codes, table
+gathers, the 16-point windowed DFT, phase codes, written straight into the (B, 3659, F) layout), whose backward scatters the
+cotangent into the two embedding tables.  ``_get_cond_torch`` keeps the op-by-op form the kernel is tested against.
 """
 from __future__ import annotations
 
 import math
 
+import ctypes as C
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib as L
 from .waveglow import WaveGlow
+
+
+class _CondFunction(torch.autograd.Function):
+    """cmwg_wsrglow_cond with the gradient of the two embedding tables (the signal itself gets none: its path goes through
+    integer codes, as in the reference)."""
+
+    @staticmethod
+    def forward(ctx, c, emb, aemb, window):
+        L.require_cuda(c, emb, aemb, op="WSRGlow._get_cond")
+        if c.dim() != 2 or c.dtype != torch.float32 or not c.is_contiguous():
+            raise RuntimeError("WSRGlow: the low-rate signal must be a contiguous fp32 (B, T) tensor")
+        B, Tc = c.shape
+        E, P = emb.shape[1], aemb.shape[1]
+        nf = Tc // 8
+        need = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        out = torch.empty((B, 8 * E + 9 + 9 * P, nf), device=c.device, dtype=torch.float32)
+        codes = torch.empty((B, Tc), device=c.device, dtype=torch.int32) if need else None
+        phase = torch.empty((B, 9, nf), device=c.device, dtype=torch.int32) if need else None
+        L.check(L.load().cmwg_wsrglow_cond(c.data_ptr(), B, Tc, emb.detach().contiguous().data_ptr(), E, emb.shape[0],
+                                           aemb.detach().contiguous().data_ptr(), P, aemb.shape[0],
+                                           window.contiguous().data_ptr(), out.data_ptr(), L.ptr(codes), L.ptr(phase),
+                                           L.stream_ptr(c.device)), "wsrglow_cond")
+        ctx.mark_dirty(c)                      # clipped in place, like the reference's c.clip_(-1, 1)
+        ctx.save_for_backward(codes, phase)
+        ctx.dims = (B, nf, E, P, emb.shape[0], aemb.shape[0])
+        return out, c
+
+    @staticmethod
+    def backward(ctx, dout, _dc):
+        codes, phase = ctx.saved_tensors
+        B, nf, E, P, n_codes, n_phase = ctx.dims
+        d_emb = d_aemb = None
+        if ctx.needs_input_grad[1]:
+            src = dout[:, :8 * E].reshape(B, 8, E, nf).permute(0, 3, 1, 2).reshape(-1, E)       # sample 8f + j <- row j*E + e
+            d_emb = torch.zeros((n_codes, E), device=dout.device, dtype=dout.dtype).index_add_(0, codes.flatten().long(), src)
+        if ctx.needs_input_grad[2]:
+            src = dout[:, 8 * E + 9:].reshape(B, 9, P, nf).permute(0, 1, 3, 2).reshape(-1, P)
+            d_aemb = torch.zeros((n_phase, P), device=dout.device, dtype=dout.dtype).index_add_(0, phase.flatten().long(), src)
+        return None, d_emb, d_aemb, None
 
 
 class AngleEmbedding(nn.Module):
@@ -79,6 +122,13 @@ class WSRGlow(WaveGlow):
         return re, im
 
     def _get_cond(self, c):
+        if not c.is_cuda:
+            raise RuntimeError("cmwg_b200 WSRGlow: expected CUDA tensors; this package has no CPU implementation")
+        cond, _ = _CondFunction.apply(c, self.mu_enc[1].weight, self.angle_embed.embed.weight, self.window)
+        return cond
+
+    def _get_cond_torch(self, c):
+        """The same computation op by op (test reference for the kernel; not on the product path)."""
         c = c.clip_(-1, 1)
         c_emb = self.mu_enc(c).view(c.shape[0], -1, 8 * 400).transpose(1, 2)
         re, im = self._stft(c)

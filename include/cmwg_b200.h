@@ -37,7 +37,8 @@ extern "C" {
 /* precision of the WN GEMM operands (accumulation, flow state, coupling and log-det are fp32) */
 #define CMWG_PREC_FP32 0 /* exact: CUDA-core FFMA engine                                   */
 #define CMWG_PREC_BF16 1 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM       */
-#define CMWG_PREC_FP16 2 /* tcgen05 kind::f16, fp16 operands (forward/inverse only)         */
+#define CMWG_PREC_FP16 2 /* tcgen05 kind::f16, fp16 operands (TF32's mantissa); the backward     */
+                         /* runs on a power-of-two multiple of the cotangent chosen on the device */
 
 const char* cmwg_last_error(void);
 int cmwg_version(void);
@@ -237,6 +238,18 @@ int cmwg_melspec_frames(int T, int n_fft, int hop);
 int cmwg_melspec_fwd(const float* x, long long x_bstride, int B, int T, const float* window, const float* fbt,
                      const int* fb_lo, const int* fb_hi, int n_fft, int hop, int n_mels, int power_is_one, float eps,
                      int take_log, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * WSRGlow conditioning front end (model/wsrglow.py:37-50, `_get_cond`), one kernel:
+ *   c (B, Tc) fp32 low-rate signal, CLIPPED TO [-1, 1] IN PLACE like the reference's c.clip_(-1, 1) (:38);
+ *   out (B, 8E + 9 + 9P, Tc/8) fp32 NCL = cat(mu-law code embedding rows (emb: n_codes x E, :39), the 9 magnitudes of
+ *   STFT(reflect_pad(c, 4), n_fft 16, hop 8, window, center=False) (:40-47), phase-code embedding rows (aemb: n_phase x P,
+ *   index ((angle/pi + 1) * 0.5 * (n_phase - 1)) truncated, :15-17,48-49)).  window: 16 floats.
+ *   codes (B, Tc) / phase_codes (B, 9, Tc/8) int32: the table indices used (NULL: not wanted); the backward pass scatters
+ *   the cotangent into the two tables with them.
+ * ------------------------------------------------------------------------------------------- */
+int cmwg_wsrglow_cond(float* c, int B, int Tc, const float* emb, int E, int n_codes, const float* aemb, int P, int n_phase,
+                      const float* window, float* out, int* codes, int* phase_codes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * WaveFlow glue (model/waveflow.py:154-265).  Images are (B, H, W) fp32 contiguous, H = n_group lines;

@@ -26,6 +26,25 @@ def build(fx, efficient=True):
     return m.cuda().train(), sd
 
 
+def test_conditioning_kernel_matches_op_by_op_form():
+    """cmwg_wsrglow_cond against the same computation written as torch ops, at the VCTK shape (4096 low-rate samples) and at a
+    ragged frame count; the input is clipped in place by both."""
+    torch.manual_seed(0)
+    m = cm.WSRGlow(upsample_rate=2, memory_efficient=True, dilation_channels=64, residual_channels=64, skip_channels=64,
+                   depth=1).cuda()
+    for B, Tc in ((3, 4096), (2, 8 * 37)):
+        c = (torch.rand(B, Tc, device="cuda") * 2.4 - 1.2)
+        c1, c2 = c.clone(), c.clone()
+        with torch.no_grad():
+            got = m._get_cond(c1)
+            want = m._get_cond_torch(c2)
+        assert got.shape == want.shape == (B, 3659, Tc // 8)
+        assert torch.equal(c1, c2) and c1.abs().max() <= 1.0            # clipped in place
+        bad = ((got - want).abs() > 1e-5).float().mean().item()         # a code flips where a sample sits on a bin edge
+        assert bad < 1e-3, bad
+        assert torch.allclose(got[:, 3200:3209], want[:, 3200:3209], atol=2e-6)
+
+
 def test_conditioning_front_end_matches_reference():
     fx = load_golden("wsrglow_tiny.pt")
     m, sd = build(fx)

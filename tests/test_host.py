@@ -98,12 +98,14 @@ def test_precision_resolution():
         torch.backends.cudnn.allow_tf32 = False
         assert precision.resolve(True, False) == "fp32"
         torch.backends.cudnn.allow_tf32 = True
-        assert precision.resolve(True, True) == "bf16"
-        assert precision.resolve(True, False) == "fp16"      # no graph (synthesis): 11-bit mantissa at the same speed
+        assert precision.resolve(True, True) == "fp16"       # training: fp16 operands + device-side gradient scale
+        assert precision.resolve(True, False) == "fp16"      # synthesis: TF32's mantissa at bf16's tensor-core rate
         assert precision.resolve(False, True) == "fp32"
+        precision.set_precision("bf16")
+        assert precision.resolve(True, True) == "bf16" and precision.resolve(True, False) == "bf16"   # opt-in only
         precision.set_precision("fp16")
         assert precision.resolve(True, False) == "fp16"
-        assert precision.resolve(True, True) == "bf16"
+        assert precision.resolve(True, True) == "fp16"
         with pytest.raises(ValueError):
             precision.set_precision("int8")
     finally:
