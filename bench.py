@@ -560,6 +560,11 @@ def run_b200(args):
 
     phase_ms = []
 
+    def trace(msg):
+        if os.environ.get("CMWG_BENCH_TRACE") == "1":
+            torch.cuda.synchronize()
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     def step(x, h, eager=False):
         if gstep is not None and not eager:
             return gstep(x, h)
@@ -637,6 +642,7 @@ def run_b200(args):
     import gc
     gc.collect()
     gc.disable()                                           # no collector pauses inside a timed step
+    trace("warm-up done")
     sampler.begin()
     lib.cmwg_reset_launch_count()
     ms, loss = timed(args.steps, e2e=False)
@@ -651,7 +657,9 @@ def run_b200(args):
     # let it reach its steady state (two alternating layouts) before timing
     for _ in range(min(args.warmup, 3)):
         step(x_host, h_host).item()
+    trace("device-resident leg done")
     ms_e2e, loss_e2e = timed(args.steps, e2e=True)
+    trace("e2e leg done")
     sampler.end()
     if rank == 0 and sampler.nvml is not None and len(sampler.rows) < 3:
         # slow NVML on this box: top the clock samples up under the same load (untimed steps in flight)
@@ -686,6 +694,7 @@ def run_b200(args):
                   "global_batch": world * Bs, "per_gpu_batch": Bs, "ms_per_step": t.item() / args.steps,
                   "note": "train.py:51-53 semantics: batch_size //= gpus; row tiles per GPU = per_gpu_batch * 8 for 74 CTA pairs"}
 
+    trace("strong leg done")
     # ---- roofline leg: device time of every GEMM class over one more step (events on the launching stream)
     import ctypes as C
     lib.cmwg_profile_enable(1)
@@ -698,6 +707,7 @@ def run_b200(args):
     names = ["gate", "resskip", "dgate", "dx", "dcond", "wgrad", "fwdfused", "bwdfused"]
     kern = {n: {"ms": kms[i], "launches": int(kn[i])} for i, n in enumerate(names)}
 
+    trace("roofline leg done")
     # ---- synthesis (config 3): sigma 0.6, 10 s utterances, utterance-sharded, no collective
     synth = None
     if not args.no_synth:

@@ -10,7 +10,7 @@ from .efficient_modules import (AffineCouplingBlock, AffineCouplingFunc, Conv1x1
 from .loss import WaveGlowLoss
 from .precision import get_precision, set_precision
 from .utils import add_weight_norms, get_instance, remove_weight_norms
-from .waveglow import WN, NonCausalLayer, WaveGlow, fused_gate
+from .waveglow import WN, NonCausalLayer, WaveGlow, fused_gate, invalidate_packs
 from .waveflow import WN2D, NonCausalLayer2D, WaveFlow
 from .wsrglow import WSRGlow
 from .mr_waveglow import MRWaveGlow
@@ -19,4 +19,4 @@ from .melglow import MelGlow, WN_LVC
 __all__ = ["FlowBase", "Reversible", "AffineCouplingBlock", "InvertibleConv1x1", "AffineCouplingFunc",
            "InvAffineCouplingFunc", "Conv1x1Func", "InvConv1x1Func", "WaveGlowLoss", "WN", "NonCausalLayer",
            "WaveGlow", "WSRGlow", "MRWaveGlow", "MelGlow", "WN_LVC", "WaveFlow", "WN2D", "NonCausalLayer2D", "fused_gate", "add_weight_norms", "remove_weight_norms", "get_instance", "set_precision",
-           "get_precision"]
+           "get_precision", "invalidate_packs"]

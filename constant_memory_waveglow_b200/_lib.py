@@ -62,6 +62,8 @@ SIGNATURES = {
     "cmwg_conv1x1_wgrad_workspace": (_SZ, [_I, _I, _I]),
     "cmwg_conv1x1_wgrad": (_I, [_VP, _LL, _VP, _LL, _I, _I, _I, _VP, _VP, _VP]),
     "cmwg_conv1x1_dw_finalize": (_I, [_VP, _VP, _VP, _I, _I, _I, _VP, _VP]),
+    "cmwg_conv1x1_backward_workspace": (_SZ, [_I, _I, _I]),
+    "cmwg_conv1x1_backward": (_I, [_VP, _VP, _I, _VP, _LL, _VP, _LL, _VP, _I, _I, _I, _VP, _LL, _VP, _LL, _VP, _VP, _VP]),
     "cmwg_coupling_apply": (_I, [_VP, _LL, _VP, _VP, _LL, _VP, _I, _I, _I, _I, _VP]),
     "cmwg_coupling_bwd": (_I, [_VP, _LL, _VP, _VP, _LL, _VP, _LL, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "cmwg_wn_tc_supported": (_I, [C.POINTER(WnConfig)]),
@@ -94,6 +96,7 @@ SIGNATURES = {
     "cmwg_squeeze": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "cmwg_nll_loss": (_I, [_VP, _VP, _I, _I, C.c_float, _I, _VP, _VP, _VP, _VP]),
     "cmwg_sum_per_batch": (_I, [_VP, _LL, _I, _I, _VP, _I, C.c_float, _VP]),
+    "cmwg_logdet_accumulate": (_I, [_VP, _LL, _I, _I, _VP, _VP, _VP, _VP]),
     "cmwg_profile_enable": (_I, [_I]),
     "cmwg_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "cmwg_mega_clk_read": (_I, [C.POINTER(C.c_longlong), _I]),

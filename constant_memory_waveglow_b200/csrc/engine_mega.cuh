@@ -28,6 +28,13 @@
 namespace cmwg {
 
 constexpr int MEGA_D = 8;        // layers
+// Warp 18 is a SECOND TMA producer.  One thread issuing both operand loads of every k-block spends ~590 cycles per k-block
+// on its own instruction stream (barrier wait, expect_tx, two UTMALDG, task decode, dependency polling: measured with
+// CMWG_MEGA_CLK), MORE than the 512 cycles the tensor pipe needs for the k-block -- the MMA issuer waited 27 % of the kernel
+// on operands.  The weight (B) tiles depend on nothing, so a second thread streams them: it walks the same task list and
+// waits only for free ring slots, while warp 0 keeps the activation (A) tiles and the dependency counters.
+constexpr int MEGA_THREADS = TC_THREADS + 32;
+constexpr int MEGA_BWARP = TC_THREADS / 32;   // index of the weight-producer warp
 constexpr int MEGA_BN = 256;     // N tile of every task
 enum { MEGA_G = 0, MEGA_R = 1, MEGA_S = 2, MEGA_NONE = 3 };
 
@@ -50,6 +57,7 @@ struct alignas(64) MegaParams {
   int lagged;                   // signal a unit's completion one unit later (its stores complete behind the next unit's work)
   long long* clk;               // nullptr, or [CTAs][18 warps][16] cycle accumulators (CMWG_MEGA_CLK: where the roles wait)
   int dbg;                      // timing experiments only (CMWG_MEGA_DBG): 1 no producer waits, 2 no signals, 4 no wait_all
+  int dual;                     // 1: warp MEGA_BWARP issues the weight tiles (default), 0: warp 0 issues both operands
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -285,7 +293,7 @@ constexpr size_t mega_smem_bytes() {
 }
 
 template <bool SAVE>
-__global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid_constant__ MegaParams p) {
+__global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __grid_constant__ MegaParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int STAGES = mega_stages<SAVE>();
   constexpr int WB = mega_warp_bytes<SAVE>();
@@ -311,15 +319,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid
       uint32_t phase = 0;
       long long w_slot = 0, w_flag = 0;
       const long long c_start = clock64();
+      const uint32_t full0 = mapa_shared(smem_u32(&s.full[0]), 0);
+      const bool both = p.dual == 0;
       auto load = [&](const CUtensorMap* am, int ak, int at, int ab, const CUtensorMap* bm, int bk, int bn) {
-        const long long c0 = clock64();
-        mbar_wait(&s.empty[stage], phase ^ 1);
-        w_slot += clock64() - c0;
+        if (p.clk) {
+          const long long c0 = clock64();
+          mbar_wait(&s.empty[stage], phase ^ 1);
+          w_slot += clock64() - c0;
+        } else {
+          mbar_wait(&s.empty[stage], phase ^ 1);
+        }
         const uint32_t sa = smem_u32(s.stages + stage * MEGA_STAGE_BYTES);
         if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * MEGA_STAGE_BYTES);
-        const uint32_t bar = mapa_shared(smem_u32(&s.full[stage]), 0);
+        const uint32_t bar = full0 + 8 * stage;
         tma_load_4d(sa, am, bar, ak, at, 0, ab);
-        tma_load_2d(sa + TC_A_BYTES, bm, bar, bk, bn);
+        if (both) tma_load_2d(sa + TC_A_BYTES, bm, bar, bk, bn);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       };
       for (int task = pair; task < p.total_tasks; task += npairs) {
@@ -361,6 +375,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_fwd_mega_kernel(const __grid
       if (p.clk) {
         long long* o = p.clk + ((size_t)blockIdx.x * 18 + warp) * 16;
         o[0] = w_slot; o[1] = w_flag; o[12] = clock64() - c_start;
+      }
+    }
+  } else if (warp == MEGA_BWARP) {
+    if (lane == 0 && p.dual) {
+      // weight tiles of the same task sequence: no dependencies, only free ring slots
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full0 = mapa_shared(smem_u32(&s.full[0]), 0);
+      auto loadb = [&](const CUtensorMap* bm, int bk, int bn) {
+        mbar_wait(&s.empty[stage], phase ^ 1);
+        tma_load_2d(smem_u32(s.stages + stage * MEGA_STAGE_BYTES) + TC_A_BYTES, bm, full0 + 8 * stage, bk, bn);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      for (int task = pair; task < p.total_tasks; task += npairs) {
+        const MegaTask t = mega_decode(p, task);
+        if (t.type == MEGA_NONE) continue;
+        const int nrow = rank * (MEGA_BN / 2);
+        if (t.type == MEGA_G) {
+          const int n0 = t.nt * MEGA_BN + nrow;
+          const int nkb = p.taps * p.kb_h + p.kb_c;
+          for (int kb = 0; kb < nkb; ++kb) loadb(&p.pa[t.layer], kb * TC_BK, n0);
+        } else if (t.type == MEGA_R) {
+          for (int kb = 0; kb < p.kb_g; ++kb) loadb(&p.pb[t.layer], kb * TC_BK, nrow);
+        } else {
+          for (int kb = 0; kb < p.depth * p.kb_g; ++kb) loadb(&p.ps, kb * TC_BK, nrow);
+        }
       }
     }
   } else if (warp == 1) {
@@ -516,6 +556,7 @@ struct alignas(64) MegaBwdParams {
   int f16;
   uint32_t idesc, desc_lbo, desc_sbo;
   int lag, total_tasks;
+  int dual;                       // see MegaParams::dual
 };
 
 __host__ __device__ __forceinline__ MegaTask mega_bwd_decode(const MegaBwdParams& p, int idx) {
@@ -557,7 +598,7 @@ constexpr int MEGA_BWD_STAGES = (TC_SMEM_LIMIT - 1024 - TC_BAR_BYTES - TC_EPI_WA
 constexpr size_t MEGA_BWD_SMEM_BYTES =
     (size_t)MEGA_BWD_STAGES * MEGA_STAGE_BYTES + TC_EPI_WARPS * MEGA_BWD_WARP_BYTES + TC_BAR_BYTES + 1024;
 
-__global__ void __launch_bounds__(TC_THREADS, 1) wn_bwd_mega_kernel(const __grid_constant__ MegaBwdParams p) {
+__global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __grid_constant__ MegaBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int STAGES = MEGA_BWD_STAGES;
   constexpr int WB = MEGA_BWD_WARP_BYTES;
@@ -580,13 +621,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_bwd_mega_kernel(const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t full0 = mapa_shared(smem_u32(&s.full[0]), 0);
+      const bool both = p.dual == 0;
       auto load = [&](const CUtensorMap* am, int ak, int at, int ab, const CUtensorMap* bm, int bk, int bn) {
         mbar_wait(&s.empty[stage], phase ^ 1);
         const uint32_t sa = smem_u32(s.stages + stage * MEGA_STAGE_BYTES);
         if (rank == 0) mbar_arrive_expect_tx(&s.full[stage], 2 * MEGA_STAGE_BYTES);
-        const uint32_t bar = mapa_shared(smem_u32(&s.full[stage]), 0);
+        const uint32_t bar = full0 + 8 * stage;
         tma_load_4d(sa, am, bar, ak, at, 0, ab);
-        tma_load_2d(sa + TC_A_BYTES, bm, bar, bk, bn);
+        if (both) tma_load_2d(sa + TC_A_BYTES, bm, bar, bk, bn);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       };
       for (int k = 0; k < rounds; ++k) {
@@ -615,6 +658,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wn_bwd_mega_kernel(const __grid
             for (int kb = 0; kb < p.kb_d2; ++kb)
               load(&p.dpre_op[t.layer], kb * TC_BK, t0 + shift, b, &p.q2[t.layer], sg * Cd2p + kb * TC_BK, nrow);
           }
+        }
+      }
+    }
+  } else if (warp == MEGA_BWARP) {
+    if (lane == 0 && p.dual) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t full0 = mapa_shared(smem_u32(&s.full[0]), 0);
+      auto loadb = [&](const CUtensorMap* bm, int bk, int bn) {
+        mbar_wait(&s.empty[stage], phase ^ 1);
+        tma_load_2d(smem_u32(s.stages + stage * MEGA_STAGE_BYTES) + TC_A_BYTES, bm, full0 + 8 * stage, bk, bn);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      for (int k = 0; k < rounds; ++k) {
+        const int task = mega_bwd_entry(p.total_tasks, k, pair, npairs);
+        if (task < 0) continue;
+        const MegaTask t = mega_bwd_decode(p, task);
+        if (t.type == MEGA_NONE) continue;
+        const int nrow = rank * (MEGA_BN / 2);
+        if (t.type == MEGA_DG) {
+          const int nkb = (t.layer == p.depth - 1) ? p.kb_s : p.kb_r + p.kb_s;
+          for (int kb = 0; kb < nkb; ++kb) loadb(&p.q1[t.layer], kb * TC_BK, nrow);
+        } else {
+          for (int kb = 0; kb < p.taps * p.kb_d2; ++kb) loadb(&p.q2[t.layer], kb * TC_BK, nrow);
         }
       }
     }

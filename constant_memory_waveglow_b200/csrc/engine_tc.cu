@@ -107,11 +107,11 @@ int get_matrix_map(CUtensorMap* m, const void* ptr, int ld, int rows, int box_ro
                        CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st) {
+int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st, int threads) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs, 1, 1);
-  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -135,13 +135,13 @@ int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaS
 // the rest; CMWG_COOP=1 launches them cooperatively (the driver places the whole grid at once or not at all; no
 // programmatic dependent launch then).  It is opt-in because Nsight Compute cannot replay cooperative cluster launches
 // (LaunchFailed), and every measurement here goes through it.
-int tc_launch_pairs_coresident(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st) {
+int tc_launch_pairs_coresident(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st, int threads) {
   const char* v = getenv("CMWG_COOP");
-  if (!(v && v[0] == '1')) return tc_launch_pairs(kern, smem, pairs, args, st);
+  if (!(v && v[0] == '1')) return tc_launch_pairs(kern, smem, pairs, args, st, threads);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs, 1, 1);
-  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];

@@ -786,8 +786,9 @@ int get_slab_map(CUtensorMap* m, const void* ptr, int C, int ld, int T, int H, i
                  int is_fp16, int kind);
 // 16-bit tensor map over a matrix [rows][ld]: dims (ld, rows), box (64, box_rows)
 int get_matrix_map(CUtensorMap* m, const void* ptr, int ld, int rows, int box_rows, int is_fp16);
-int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st);
-int tc_launch_pairs_coresident(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st);
+int tc_launch_pairs(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st, int threads = TC_THREADS);
+int tc_launch_pairs_coresident(const void* kern, size_t smem, int pairs, void** args, cudaStream_t st,
+                               int threads = TC_THREADS);
 
 template <int BN, class Epi>
 int tc_gemm_launch_bn(const GemmDesc& d, const TcIo& io, const Epi& epi, cudaStream_t st, int lbo_override = -1,

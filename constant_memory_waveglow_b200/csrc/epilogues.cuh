@@ -14,10 +14,10 @@ namespace cmwg {
 // two floats -> one packed 16-bit pair with a single cvt.rn.{bf16x2,f16x2}.f32
 __device__ __forceinline__ uint32_t pack2(float lo, float hi, int f16) {
   if (f16) {
-    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-    __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
+    // one F2FP.SATFINITE.F16.F32.PACK_AB: round to nearest even, +-65504 instead of inf beyond fp16's range
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
   }
   __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&b);

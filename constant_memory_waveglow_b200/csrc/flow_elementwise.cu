@@ -266,6 +266,129 @@ __global__ void conv1x1_dw_finalize_kernel(const float* __restrict__ dm, const f
 }
 
 // ------------------------------------------------------------------------------------------------
+// Whole backward of the invertible 1x1 conv in two launches (C <= 8):
+//   pass 1, one sweep over (out, dout):  in = Minv out  (the freed input, re-materialised: efficient_modules.py:236,268),
+//           din = Mt dout (:239,273), block partials of dm[o][i] = sum dout[o] in[i] (:240-241,274-275);
+//   pass 2, one CTA: fixed-order sum of the block partials + the dW formula of conv1x1_dw_finalize_kernel.
+// One thread owns 4 consecutive time steps of one batch item with every channel in registers; the C*C outer-product
+// accumulators stay in registers across the grid-stride loop and are folded once per CTA (shuffles, then warp order).
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) conv1x1_bwd_fused_kernel(const float* __restrict__ minv, const float* __restrict__ w,
+                                                                int transpose_w, const float* __restrict__ out, long long out_bs,
+                                                                const float* __restrict__ dout, long long dout_bs,
+                                                                float* __restrict__ restored, long long r_bs,
+                                                                float* __restrict__ din, long long din_bs, int T, int nv,
+                                                                long long total, float* __restrict__ partial) {
+  __shared__ float m1[C * C], m2[C * C];
+  __shared__ float red[8][C * C];
+  for (int i = threadIdx.x; i < C * C; i += 256) {
+    const int o = i / C, k = i % C;
+    m1[i] = minv[i];
+    m2[i] = transpose_w ? w[k * C + o] : w[i];
+  }
+  __syncthreads();
+  float acc[C * C];
+#pragma unroll
+  for (int i = 0; i < C * C; ++i) acc[i] = 0.f;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int b = (int)(idx / nv), t = (int)(idx % nv) * 4;
+    float zv[C][4], gv[C][4], xv[C][4];
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+      const float4 a = *reinterpret_cast<const float4*>(out + b * out_bs + (long long)i * T + t);
+      const float4 g = *reinterpret_cast<const float4*>(dout + b * dout_bs + (long long)i * T + t);
+      zv[i][0] = a.x; zv[i][1] = a.y; zv[i][2] = a.z; zv[i][3] = a.w;
+      gv[i][0] = g.x; gv[i][1] = g.y; gv[i][2] = g.z; gv[i][3] = g.w;
+    }
+#pragma unroll
+    for (int o = 0; o < C; ++o) {
+      float x4[4] = {0.f, 0.f, 0.f, 0.f}, d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < C; ++i) {
+        const float a = m1[o * C + i], bq = m2[o * C + i];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { x4[v] = fmaf(a, zv[i][v], x4[v]); d4[v] = fmaf(bq, gv[i][v], d4[v]); }
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) xv[o][v] = x4[v];
+      if (restored) *reinterpret_cast<float4*>(restored + b * r_bs + (long long)o * T + t) = make_float4(x4[0], x4[1], x4[2], x4[3]);
+      *reinterpret_cast<float4*>(din + b * din_bs + (long long)o * T + t) = make_float4(d4[0], d4[1], d4[2], d4[3]);
+    }
+    if (partial) {
+#pragma unroll
+      for (int o = 0; o < C; ++o)
+#pragma unroll
+        for (int i = 0; i < C; ++i)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[o * C + i] = fmaf(gv[o][v], xv[i][v], acc[o * C + i]);
+    }
+  }
+  if (!partial) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < C * C; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += 256) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) sacc += red[wq][i];
+    partial[(long long)blockIdx.x * C * C + i] = sacc;
+  }
+}
+
+// pass 2: dm = sum_j partial[j] (fixed order, fp64), then dW as in conv1x1_dw_finalize_kernel
+__global__ void __launch_bounds__(64) conv1x1_dw_from_partials_kernel(const float* __restrict__ partial, int nblocks,
+                                                                      const float* __restrict__ winv,
+                                                                      const float* __restrict__ dlogdet, int c, int T,
+                                                                      int inverse_mode, float* __restrict__ dw) {
+  __shared__ float dm[64], tmp[64];
+  const int n = c * c;
+  const float scale = (dlogdet ? *dlogdet : 0.f) * (float)T;
+  for (int p = threadIdx.x; p < n; p += 64) {
+    double sacc = 0.0;
+    for (int j = 0; j < nblocks; ++j) sacc += (double)partial[(long long)j * n + p];
+    dm[p] = (float)sacc;
+  }
+  __syncthreads();
+  if (!inverse_mode) {
+    for (int p = threadIdx.x; p < n; p += 64) {
+      const int o = p / c, i = p % c;
+      dw[p] = dm[p] + winv[i * c + o] * scale;
+    }
+    return;
+  }
+  for (int p = threadIdx.x; p < n; p += 64) {
+    const int o = p / c, i = p % c;
+    float sacc = 0.f;
+    for (int k = 0; k < c; ++k) sacc = fmaf(winv[k * c + o], dm[k * c + i], sacc);
+    tmp[p] = sacc;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < n; p += 64) {
+    const int o = p / c, i = p % c;
+    float sacc = 0.f;
+    for (int k = 0; k < c; ++k) sacc = fmaf(tmp[o * c + k], winv[i * c + k], sacc);
+    dw[p] = -sacc - winv[i * c + o] * scale;
+  }
+}
+
+template <int C>
+static int launch_conv1x1_bwd_fused(const float* minv, const float* w, int tr, const float* out, long long out_bs,
+                                    const float* dout, long long dout_bs, float* restored, long long r_bs, float* din,
+                                    long long din_bs, int B, int T, float* partial, int blocks, cudaStream_t st) {
+  const int nv = T / 4;
+  conv1x1_bwd_fused_kernel<C><<<blocks, 256, 0, st>>>(minv, w, tr, out, out_bs, dout, dout_bs, restored, r_bs, din, din_bs, T,
+                                                       nv, (long long)B * nv, partial);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+  return CMWG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // tiny LU (Gauss-Jordan with partial pivoting, fp64 internally): inverse + log det, c <= 64
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) small_inverse_logdet_kernel(const float* __restrict__ w, int c,
@@ -488,6 +611,23 @@ __global__ void __launch_bounds__(1024) sum_per_batch_kernel(const float* __rest
   if (threadIdx.x == 0) out[b] = (accumulate ? out[b] : 0.f) + scale * s;
 }
 
+// logdet += log_det_W + log_s.sum((1, 2))  (model/waveglow.py:175,199) in one launch: out[b] = prev[b] + *ldw + sum a[b, :]
+__global__ void __launch_bounds__(1024) logdet_accumulate_kernel(const float* __restrict__ a, long long a_bs, int N,
+                                                                 const float* __restrict__ prev,
+                                                                 const float* __restrict__ ldw, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* p = a + b * a_bs;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int i = threadIdx.x;
+  for (; i + 3 * 1024 < N; i += 4 * 1024) {
+    s0 += p[i]; s1 += p[i + 1024]; s2 += p[i + 2048]; s3 += p[i + 3072];
+  }
+  for (; i < N; i += 1024) s0 += p[i];
+  const float s = block_sum_1024((s0 + s1) + (s2 + s3), red);
+  if (threadIdx.x == 0) out[b] = ((prev ? prev[b] : 0.f) + (ldw ? *ldw : 0.f)) + s;
+}
+
 __global__ void __launch_bounds__(1024) nll_rows_kernel(const float* __restrict__ z, int T, float* __restrict__ rows) {
   __shared__ float red[32];
   int b = blockIdx.x;
@@ -623,6 +763,64 @@ int cmwg_conv1x1_dw_finalize(const float* dm, const float* w_inv, const float* d
   return CMWG_OK;
 }
 
+static inline int conv1x1_bwd_blocks(int B, int T) {
+  return (int)std::min<long long>(ceil_div_ll((long long)B * (T / 4), 256), (long long)num_sms() * 2);
+}
+
+size_t cmwg_conv1x1_backward_workspace(int B, int C, int T) {
+  const size_t fused = (size_t)std::max(conv1x1_bwd_blocks(B, T), 1) * C * C * sizeof(float);
+  return std::max(fused, cmwg_conv1x1_wgrad_workspace(B, C, T)) + (size_t)C * C * sizeof(float) + 256;
+}
+
+int cmwg_conv1x1_backward(const float* w, const float* w_inv, int inverse_mode, const float* out, long long out_bstride,
+                          const float* dout, long long dout_bstride, const float* dlogdet, int B, int C, int T,
+                          float* restored, long long restored_bstride, float* din, long long din_bstride, float* dw,
+                          void* workspace, void* stream) {
+  CMWG_REQUIRE(w && w_inv && out && dout && din, "cmwg_conv1x1_backward: null argument");
+  CMWG_REQUIRE(C >= 1 && C <= 64, "cmwg_conv1x1_backward: C=%d out of range [1,64]", C);
+  CMWG_REQUIRE(!dw || workspace, "cmwg_conv1x1_backward: the weight gradient needs a workspace");
+  if (B == 0 || T == 0) return CMWG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // forward was out = M in with M = W (inverse_mode 0) or W^-1 (1):  in = M^-1 out,  din = M^T dout
+  const float* m_restore = inverse_mode ? w : w_inv;
+  const float* m_din = inverse_mode ? w_inv : w;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool fusable = C <= 8 && (C % 2 == 0) && T % 4 == 0 && out_bstride % 4 == 0 && dout_bstride % 4 == 0 &&
+                       din_bstride % 4 == 0 && (!restored || restored_bstride % 4 == 0) && al16(out) && al16(dout) &&
+                       al16(din) && (!restored || al16(restored));
+  if (fusable) {
+    const int blocks = conv1x1_bwd_blocks(B, T);
+    float* partial = dw ? reinterpret_cast<float*>(workspace) : nullptr;
+    int rc;
+    switch (C) {
+      case 2: rc = launch_conv1x1_bwd_fused<2>(m_restore, m_din, 1, out, out_bstride, dout, dout_bstride, restored, restored_bstride, din, din_bstride, B, T, partial, blocks, st); break;
+      case 4: rc = launch_conv1x1_bwd_fused<4>(m_restore, m_din, 1, out, out_bstride, dout, dout_bstride, restored, restored_bstride, din, din_bstride, B, T, partial, blocks, st); break;
+      case 6: rc = launch_conv1x1_bwd_fused<6>(m_restore, m_din, 1, out, out_bstride, dout, dout_bstride, restored, restored_bstride, din, din_bstride, B, T, partial, blocks, st); break;
+      default: rc = launch_conv1x1_bwd_fused<8>(m_restore, m_din, 1, out, out_bstride, dout, dout_bstride, restored, restored_bstride, din, din_bstride, B, T, partial, blocks, st); break;
+    }
+    CMWG_PROPAGATE(rc);
+    if (dw) {
+      conv1x1_dw_from_partials_kernel<<<1, 64, 0, st>>>(partial, blocks, w_inv, dlogdet, C, T, inverse_mode, dw);
+      CMWG_COUNT_LAUNCH();
+      CMWG_LAUNCH_CHECK();
+    }
+    return CMWG_OK;
+  }
+  // general shapes: the separate kernels, same arithmetic
+  float* scratch_in = restored;
+  CMWG_REQUIRE(restored || !dw, "cmwg_conv1x1_backward: general shapes need `restored` to form the weight gradient");
+  if (restored) CMWG_PROPAGATE(cmwg_conv1x1_apply(m_restore, 0, out, out_bstride, restored, restored_bstride, B, C, T, stream));
+  CMWG_PROPAGATE(cmwg_conv1x1_apply(m_din, 1, dout, dout_bstride, din, din_bstride, B, C, T, stream));
+  if (dw) {
+    float* dm = reinterpret_cast<float*>(workspace);
+    void* ws2 = reinterpret_cast<uint8_t*>(workspace) + align_up((size_t)C * C * sizeof(float), 256);
+    CMWG_PROPAGATE(cmwg_conv1x1_wgrad(dout, dout_bstride, scratch_in, restored_bstride, B, C, T, dm, ws2, stream));
+    CMWG_REQUIRE(dlogdet, "cmwg_conv1x1_backward: dlogdet missing");
+    CMWG_PROPAGATE(cmwg_conv1x1_dw_finalize(dm, w_inv, dlogdet, C, T, inverse_mode, dw, stream));
+  }
+  return CMWG_OK;
+}
+
 int cmwg_coupling_apply(const float* x, long long x_bstride, const float* lst, float* z, long long z_bstride,
                         float* neg_log_s, int B, int cin, int T, int inverse, void* stream) {
   if (B == 0 || T == 0 || cin == 0) return CMWG_OK;
@@ -672,6 +870,16 @@ int cmwg_sum_per_batch(const float* a, long long a_bstride, int B, int N, float*
                        void* stream) {
   if (B == 0) return CMWG_OK;
   sum_per_batch_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(a, a_bstride, N, out, accumulate, scale);
+  CMWG_COUNT_LAUNCH();
+  CMWG_LAUNCH_CHECK();
+  return CMWG_OK;
+}
+
+int cmwg_logdet_accumulate(const float* a, long long a_bstride, int B, int N, const float* prev, const float* log_det_w,
+                           float* out, void* stream) {
+  CMWG_REQUIRE(a && out, "cmwg_logdet_accumulate: null argument");
+  if (B == 0) return CMWG_OK;
+  logdet_accumulate_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(a, a_bstride, N, prev, log_det_w, out);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
   return CMWG_OK;

@@ -62,8 +62,18 @@ static __global__ void __launch_bounds__(128) weight_eff_kernel(const WeffTable 
 
 // weight norm backward for ALL convs of one WN in one launch: (dw_eff, v, g, 1/||v||) -> (dg, dv);
 // without weight norm dv = dw_eff.  One CTA per output channel.
+// A row of the effective-weight gradient may also be GATHERED from the full-K tiles the batched weight-gradient launch
+// leaves behind (one tile per tap / per W_o row block, see wn_pipeline.cu): source j covers rows [row0, row0 + M) of the
+// conv and writes tile element (m, n) to position col0 + n * sn of row row0 + m.  That folds the split-K "reduce" pass (a
+// pure re-layout when there is a single split) into this kernel.
+struct WnBwdSrc {
+  const float* tile;   // [M][ld] fp32
+  int M, ld, n_valid;  // rows, row pitch, valid columns
+  int row0, col0, sn;  // destination row offset, column offset, column stride
+};
+constexpr int WN_BWD_MAX_SRC = 4;
 struct WnBwdEntry {
-  const float* dw;        // effective-weight gradient, natural layout [O][L]
+  const float* dw;        // effective-weight gradient, natural layout [O][L] (used when nsrc == 0)
   const float* v;
   const float* g;         // nullptr: no weight norm
   const float* inv_norm;  // [O]
@@ -71,20 +81,38 @@ struct WnBwdEntry {
   float* dv;
   int O, L;
   int row_begin;          // prefix sum of O
+  int nsrc;
+  WnBwdSrc src[WN_BWD_MAX_SRC];
 };
 struct WnBwdTable {
   WnBwdEntry e[3 * CMWG_MAX_DEPTH + 2];
   int n;
+  const float* gscale;    // nullptr, or the gradient-scale triple: gathered tiles are multiplied by gscale[2] = 1 / S
 };
+
+constexpr int WN_BWD_MAX_L = 7 * 256;   // longest conv row gathered through shared memory (radix 7 x 256 channels)
 
 static __global__ void __launch_bounds__(128) weight_norm_bwd_kernel(const __grid_constant__ WnBwdTable tb) {
   __shared__ float red[4];
+  __shared__ float rowbuf[WN_BWD_MAX_L];
   int row = blockIdx.x;
   int ci = 0;
   while (ci + 1 < tb.n && row >= tb.e[ci + 1].row_begin) ++ci;
   const WnBwdEntry& e = tb.e[ci];
   const int o = row - e.row_begin, L = e.L;
   const float* dwo = e.dw + (long long)o * L;
+  if (e.nsrc > 0) {
+    const float inv_scale = tb.gscale ? tb.gscale[2] : 1.f;
+    for (int j = 0; j < e.nsrc; ++j) {
+      const WnBwdSrc& sj = e.src[j];
+      const int m = o - sj.row0;
+      if (m < 0 || m >= sj.M) continue;
+      const float* t = sj.tile + (long long)m * sj.ld;
+      for (int n = threadIdx.x; n < sj.n_valid; n += 128) rowbuf[sj.col0 + n * sj.sn] = t[n] * inv_scale;
+    }
+    __syncthreads();
+    dwo = rowbuf;
+  }
   if (e.g == nullptr) {
     if (e.dv)
       for (int l = threadIdx.x; l < L; l += 128) e.dv[(long long)o * L + l] = dwo[l];

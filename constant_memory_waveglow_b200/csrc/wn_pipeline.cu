@@ -153,6 +153,11 @@ static inline int mega_bwd_lag(int RT) {
   return std::max(0, std::min(lag_env, RT - 2));
 }
 
+static inline int mega_dual() {  // CMWG_MEGA_DUAL=0: one TMA producer thread for both operands (the round-1 arrangement)
+  static const int v = [] { const char* e = getenv("CMWG_MEGA_DUAL"); return (e && e[0] == '0') ? 0 : 1; }();
+  return v;
+}
+
 static inline bool mega_shapes_ok(const WnDims& d, int B, int T) {
   return d.tc && d.H == 1 && !d.bias && d.depth >= 1 && d.depth <= MEGA_D && d.Cr == 256 && d.Cs == 256 &&
          d.Cd % 128 == 0 && d.bn_gate == 256 && (((d.radix - 1) / 2) << (d.depth - 1)) <= 2 * TC_BM && d.radix <= 7 &&
@@ -172,7 +177,7 @@ static int mega_launch(const MegaParams& p, cudaStream_t st) {
   const int pairs = std::min(p.total_tasks, num_sms() / 2);
   ProfScope prof(st, CMWG_KCLASS_FWDFUSED);
   void* args[1] = {(void*)&p};
-  CMWG_PROPAGATE(tc_launch_pairs_coresident((const void*)kern, smem, pairs, args, st));
+  CMWG_PROPAGATE(tc_launch_pairs_coresident((const void*)kern, smem, pairs, args, st, MEGA_THREADS));
   CMWG_COUNT_LAUNCH();
   return CMWG_OK;
 }
@@ -209,6 +214,7 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
   p.desc_lbo = 1u; p.desc_sbo = 1024u >> 4;
   // R(u) must come after G(u) and before G(u + RT - 1) (its right-hand neighbour one layer up): lag <= RT - 2
   p.lag = mega_fwd_lag(p.RT);
+  p.dual = mega_dual();
   p.total_tasks = (d.depth * p.RT + p.lag) * (p.ngt + 1) + p.RT;
   // timing experiments that SKIP synchronisation or epilogue work (wrong results by design) exist only in builds made
   // with -DCMWG_MEGA_EXPERIMENTS; the shipped library ignores CMWG_MEGA_DBG
@@ -271,6 +277,7 @@ static int wn_backward_mega(const WnDims& d, const PackedLayout& PL, const BwdLa
   p.idesc = make_idesc(f16, 2 * TC_BM, MEGA_BN, 0, 0);
   p.desc_lbo = 1u; p.desc_sbo = 1024u >> 4;
   p.lag = mega_bwd_lag(p.RT);
+  p.dual = mega_dual();
   p.total_tasks = p.RT + 2 * (d.depth * p.RT + p.lag);
   p.flags = reinterpret_cast<uint32_t*>(ws + BL.flags);
   CMWG_CHECK_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)d.depth * 2 * p.RT * 4, st));
@@ -285,7 +292,7 @@ static int wn_backward_mega(const WnDims& d, const PackedLayout& PL, const BwdLa
   const int pairs = std::min(p.total_tasks, num_sms() / 2);
   ProfScope prof(st, CMWG_KCLASS_BWDFUSED);
   void* args[1] = {(void*)&p};
-  CMWG_PROPAGATE(tc_launch_pairs_coresident((const void*)kern, smem, pairs, args, st));
+  CMWG_PROPAGATE(tc_launch_pairs_coresident((const void*)kern, smem, pairs, args, st, MEGA_THREADS));
   CMWG_COUNT_LAUNCH();
   return CMWG_OK;
 }
@@ -488,9 +495,24 @@ struct WnBwdQueue {
     WnBwdEntry& e = tb.e[tb.n++];
     e.dw = dw; e.v = prm.v; e.g = prm.g; e.inv_norm = inv_norm; e.dg = gr.g; e.dv = gr.v; e.O = O; e.L = L;
     e.row_begin = rows;
+    e.nsrc = 0;
     rows += O;
   }
-  int flush(cudaStream_t st) {
+  // gather `dw` from a full-K weight-gradient tile instead of a materialised matrix (see WnBwdSrc); false: no room / no entry
+  bool add_source(const float* dw, const float* tile, int M, int ld, int n_valid, long long sm, long long sn, long long off) {
+    for (int i = 0; i < tb.n; ++i) {
+      WnBwdEntry& e = tb.e[i];
+      if (e.dw != dw) continue;
+      if (e.nsrc >= WN_BWD_MAX_SRC || sm != e.L || e.L > WN_BWD_MAX_L) return false;
+      WnBwdSrc& sj = e.src[e.nsrc++];
+      sj.tile = tile; sj.M = M; sj.ld = ld; sj.n_valid = n_valid;
+      sj.row0 = (int)(off / e.L); sj.col0 = (int)(off % e.L); sj.sn = (int)sn;
+      return true;
+    }
+    return false;
+  }
+  int flush(cudaStream_t st, const float* gscale = nullptr) {
+    tb.gscale = gscale;
     if (rows == 0) return CMWG_OK;
     weight_norm_bwd_kernel<<<rows, 128, 0, st>>>(tb);
     CMWG_COUNT_LAUNCH();
@@ -622,11 +644,15 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   // weight-gradient problems: launched per layer, or -- after the single-kernel chain -- for all layers at once
   // (63 full-K tiles fill one wave of CTA pairs without any split-K partials)
   struct RedSpec { int pi; float* out; long long sm, sn, off; int n_valid; };
+  struct GatherSpec { float* out; const float* tile; int M, N, n_valid; long long sm, sn, off; };
   WgradProblem pr[TC_MAX_WG];
   RedSpec rs[TC_MAX_WG];
-  int np = 0, nr = 0;
+  GatherSpec gather[TC_MAX_WG];
+  int np = 0, nr = 0, ngather = 0;
+  bool pending_gather = false;
   const bool wg_batched = fusedb && d.depth * (d.R + 3) <= TC_MAX_WG &&
                           !(getenv("CMWG_WGRAD_BATCH") && getenv("CMWG_WGRAD_BATCH")[0] == '0');
+  const bool deferred_gather = wg_batched && !(getenv("CMWG_WGRAD_GATHER") && getenv("CMWG_WGRAD_GATHER")[0] == '0');
   auto flush_wgrad = [&](int group) -> int {
     for (int g0 = 0; g0 < np; g0 += group) {
       const int gn = std::min(group, np - g0);
@@ -644,6 +670,21 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
         CMWG_PROPAGATE(tc_wgrad_launch(gp, gn, B, d.H, T, f16, st));
       } else {
         for (int k = 0; k < gn; ++k) CMWG_PROPAGATE(ff_wgrad_launch(gp[k], B, d.H, T, Lc, st));
+      }
+      if (deferred_gather) {
+        // single split per problem: the "reduction" would be a re-layout only -- the weight-norm backward gathers the
+        // tiles itself (WnBwdSrc); anything it cannot take falls through to the reduce kernel below
+        bool all = true;
+        for (int k = 0; k < gn; ++k) all = all && splits[k] == 1;
+        if (all) {
+          pending_gather = true;
+          for (int k = 0; k < nr; ++k) {
+            if (rs[k].pi < g0 || rs[k].pi >= g0 + gn) continue;
+            const WgradProblem& q = pr[rs[k].pi];
+            gather[ngather++] = GatherSpec{rs[k].out, q.partial, q.M, q.N, rs[k].n_valid, rs[k].sm, rs[k].sn, rs[k].off};
+          }
+          continue;
+        }
       }
       WgReduceTable rt;
       rt.n = 0;
@@ -807,6 +848,24 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   }
 
   if (wg_batched) CMWG_PROPAGATE(flush_wgrad(TC_MAX_WG));
+  if (pending_gather) {
+    // every destination matrix has its weight-norm entry by now: attach the tiles; leftovers go through one reduce launch
+    WgReduceTable rt;
+    rt.n = 0;
+    rt.gscale = gscale;
+    for (int k = 0; k < ngather; ++k) {
+      const GatherSpec& gs = gather[k];
+      if (wq.add_source(gs.out, gs.tile, gs.M, gs.N, gs.n_valid, gs.sm, gs.sn, gs.off)) continue;
+      WgReduceEntry& e = rt.e[rt.n++];
+      e.partial = gs.tile; e.splits = 1; e.M = gs.M; e.N = gs.N; e.n_valid = gs.n_valid;
+      e.out = gs.out; e.sm = gs.sm; e.sn = gs.sn; e.off = gs.off;
+    }
+    if (rt.n > 0) {
+      wgrad_reduce_kernel<<<dim3(num_sms(), rt.n), 256, 0, st>>>(rt);
+      CMWG_COUNT_LAUNCH();
+      CMWG_LAUNCH_CHECK();
+    }
+  }
 
   if constexpr (TC) {
     // ---- conditioning gradient: dy = sum_i dpre_i V_i as ONE GEMM, layers concatenated along K
@@ -870,7 +929,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       CMWG_PROPAGATE(reduce_blocks(pb, nblk_s, d.Cr, scratch, gr->start.bias, st));
     }
   }
-  return wq.flush(st);
+  return wq.flush(st, gscale);
 }
 
 }  // namespace cmwg

@@ -108,31 +108,31 @@ def _conv1x1_fwd(ctx, x, weight, inverse: bool):
     z = ops.conv1x1_apply(winv if inverse else w2, xd)
     log_det_w = (-logdet if inverse else logdet) * T
     ctx.inverse = inverse
-    ctx.save_for_backward(xd, weight, z)
+    ctx.save_for_backward(xd, weight, z, winv)
     return z, log_det_w
 
 
 def _conv1x1_bwd(ctx, z_grad, log_det_grad, restore: bool):
-    x, weight, z = ctx.saved_tensors
+    x, weight, z, winv = ctx.saved_tensors          # winv: W^-1 from the forward pass (the weight has not changed since)
     inverse = ctx.inverse
-    T = z.shape[-1]
     w2 = weight.detach().reshape(weight.shape[0], weight.shape[1]).float().contiguous()
-    winv, _ = ops.small_inverse_logdet(w2)
-    if restore:
-        # forward was z = M x with M = W (or W^-1): x = M^-1 z back into the freed storage
-        _write_restored(x, lambda out: ops.conv1x1_apply(w2 if inverse else winv, z, out=out))
     z_grad = z_grad.contiguous() if z_grad is not None else torch.zeros_like(z)
-    dx = ops.conv1x1_apply(winv if inverse else w2, z_grad, transpose=True)
     dw = None
     if ctx.needs_input_grad[1]:
-        dm = ops.conv1x1_wgrad(z_grad, x)
-        if log_det_grad is None:
-            log_det_grad = torch.zeros((), device=z.device)
         # written straight into the parameter's slot of its data-parallel gradient bucket when there is one (parallel.py):
         # autograd then adopts the view as .grad without a copy kernel
         from .parallel import grad_buffer
         dw = grad_buffer(weight)
-        ops.conv1x1_dw_finalize(dm, winv, log_det_grad, T, inverse, out=dw.view(dm.shape))
+    # forward was z = M x with M = W (or W^-1): x = M^-1 z goes back into the freed storage (restore) or into a scratch
+    # tensor (stored mode: only the weight gradient needs it); dx = M^T dz and dW come from the same sweep
+    direct = restore and x.is_contiguous()
+    if restore:
+        _restore_storage(x)
+    dst = x if direct else (torch.empty(z.shape, device=z.device) if (restore or dw is not None) else None)
+    dx = ops.conv1x1_backward(w2, winv, inverse, z, z_grad, log_det_grad, dst,
+                              None if dw is None else dw.view(w2.shape))
+    if restore and not direct:
+        x.data.copy_(dst)
     return dx, dw
 
 

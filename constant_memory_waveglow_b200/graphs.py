@@ -56,7 +56,7 @@ class GraphedTrainStep:
         return loss
 
     def _capture(self, key, inputs):
-        from .waveglow import _cond_cache
+        from .waveglow import _cond_cache, invalidate_packs
         static_in = tuple(torch.empty(t.shape, dtype=t.dtype, device=self._device) for t in inputs)
         for s, t in zip(static_in, inputs):
             s.copy_(t, non_blocking=True)
@@ -90,6 +90,7 @@ class GraphedTrainStep:
         del p_keep, s_keep
         torch.cuda.synchronize(self._device)
         _cond_cache.clear()                  # conditioning slabs cached by eager calls must be re-packed INSIDE the graph
+        invalidate_packs()                   # ... and so must the weight packs: the optimizer step is inside the graph too
         lib = L.load()
         before = int(lib.cmwg_launch_count())
         graph = torch.cuda.CUDAGraph()

@@ -82,6 +82,26 @@ def conv1x1_dw_finalize(dm: torch.Tensor, winv: torch.Tensor, dlogdet: torch.Ten
     return dw
 
 
+def conv1x1_backward(w: torch.Tensor, winv: torch.Tensor, inverse: bool, out: torch.Tensor, dout: torch.Tensor,
+                     dlogdet, restored, dw_out):
+    """Restore the forward call's input into `restored` (contiguous (B, C, T) or None), return din; `dw_out` (C x C view
+    or None) receives the weight gradient.  One fused sweep + one finalise launch for even C <= 8."""
+    out, dout = _ncl(out), _ncl(dout)
+    B, Cc, T = out.shape
+    lib = L.load()
+    din = torch.empty((B, Cc, T), device=out.device, dtype=torch.float32)
+    ws = None
+    if dw_out is not None:
+        ws = torch.empty(int(lib.cmwg_conv1x1_backward_workspace(B, Cc, T)), device=out.device, dtype=torch.uint8)
+        if dlogdet is not None:
+            dlogdet = dlogdet.detach().reshape(()).float().contiguous()
+    L.check(lib.cmwg_conv1x1_backward(w.data_ptr(), winv.data_ptr(), int(inverse), out.data_ptr(), _bstride(out),
+                                      dout.data_ptr(), _bstride(dout), L.ptr(dlogdet) if dw_out is not None else 0, B, Cc, T,
+                                      L.ptr(restored), Cc * T, din.data_ptr(), Cc * T, L.ptr(dw_out), L.ptr(ws),
+                                      L.stream_ptr(out.device)), "conv1x1_backward")
+    return din
+
+
 # ---------------------------------------------------------------------------------------------
 # affine coupling
 # ---------------------------------------------------------------------------------------------
@@ -142,6 +162,21 @@ def sum_per_batch(a: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     out = torch.empty((B,), device=a.device, dtype=torch.float32)
     L.check(L.load().cmwg_sum_per_batch(a.data_ptr(), a.stride(0) if B > 1 else N, B, N, out.data_ptr(), 0,
                                         float(scale), L.stream_ptr(a.device)), "sum_per_batch")
+    return out
+
+
+def logdet_accumulate(log_s: torch.Tensor, prev, log_det_w) -> torch.Tensor:
+    """prev (B,) or None  +  log_det_w (0-dim) or None  +  log_s.sum((1, 2)), one launch."""
+    a = _ncl(log_s)
+    B = a.shape[0]
+    N = a[0].numel()
+    out = torch.empty((B,), device=a.device, dtype=torch.float32)
+    if log_det_w is not None:
+        log_det_w = log_det_w.detach().reshape(()).float().contiguous()
+    if prev is not None:
+        prev = prev.detach().float().contiguous()
+    L.check(L.load().cmwg_logdet_accumulate(a.data_ptr(), a.stride(0) if B > 1 else N, B, N, L.ptr(prev), L.ptr(log_det_w),
+                                            out.data_ptr(), L.stream_ptr(a.device)), "logdet_accumulate")
     return out
 
 

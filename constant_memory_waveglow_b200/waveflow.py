@@ -27,7 +27,7 @@ from . import ops, precision
 from .base import FlowBase
 from .efficient_modules import InvertibleConv1x1, grad_hint, graph_possible
 from .utils import add_weight_norms
-from .waveglow import WN, _cond_cache, _SqueezeFunction, _WNState, fused_gate
+from .waveglow import WN, _cond_cache, _SqueezeFunction, _WNState, fused_gate, pack_generation
 
 
 class NonCausalLayer2D(nn.Module):
@@ -363,7 +363,8 @@ class WaveFlow(FlowBase):
 
     def _graph_key(self, z: Tensor, h: Tensor):
         return (tuple(z.shape), tuple(h.shape), z.device.index, precision.get_precision(),
-                torch.backends.cudnn.allow_tf32, tuple((p.data_ptr(), p._version) for p in self.parameters()))
+                torch.backends.cudnn.allow_tf32, pack_generation(),
+                tuple((p.data_ptr(), p._version) for p in self.parameters()))
 
     def reverse_computation(self, z: Tensor, h: Tensor) -> Tuple[Tensor, Tensor]:
         """Synthesis direction (reference ``:221-261``).  Runs without building an autograd graph: the row-recurrent

@@ -96,6 +96,33 @@ class _CondCache:
 _cond_cache = _CondCache()
 
 
+# ---------------------------------------------------------------------------------------------
+# Weight-pack invalidation.  A pack (effective weights after weight norm, re-laid-out as GEMM operands) is keyed on
+# (address, version counter) of every parameter -- but in-place updates that bypass the version counter exist and are
+# common: torch's FUSED optimizers (`Adam(..., fused=True)` leaves `p._version` untouched), `p.data.copy_(...)`, EMA
+# swaps.  So the key also carries a process-wide generation number that every optimizer step bumps (a global
+# optimizer-step post hook), that `load_state_dict` / `.to()` / `.cuda()` bump through the module hooks below, and that
+# user code which edits `.data` directly can bump with `invalidate_packs()`.
+# ---------------------------------------------------------------------------------------------
+_pack_generation = [0]
+
+
+def invalidate_packs() -> None:
+    """Force every WN to re-pack its weights at its next call (and WaveFlow to drop its captured synthesis graphs)."""
+    _pack_generation[0] += 1
+
+
+def pack_generation() -> int:
+    return _pack_generation[0]
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post
+    _reg_post(lambda _opt, _args, _kwargs: invalidate_packs())
+except Exception:  # pragma: no cover  (very old torch: fall back to the version counters alone)
+    pass
+
+
 class _WNState:
     """What one fused WN forward leaves behind for its backward."""
     __slots__ = ("cfg", "packed", "params", "ycl", "saved", "B", "T", "prec")
@@ -181,7 +208,7 @@ class WN(nn.Module):
         params = list(self.parameters())
         L.require_cuda(*params, op="WN")
         cfg = self._config(prec, height)
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (_pack_generation[0],) + tuple((p.data_ptr(), p._version) for p in params)
         ent = self._pack_cache.get(prec)
         ps = self._params_struct()
         if ent is not None and ent[0] == key and ent[1].device == device:
@@ -194,6 +221,14 @@ class WN(nn.Module):
         L.check(L.load().cmwg_wn_pack(C.byref(cfg), C.byref(ps), buf.data_ptr(), L.stream_ptr(device)), "wn_pack")
         self._pack_cache[prec] = (key, buf)   # one entry per precision: captured CUDA graphs and stored-mode states keep
         return cfg, buf, ps                   # pointing at the buffer of THEIR precision
+
+    def _apply(self, fn, *args, **kwargs):          # .to() / .cuda() / .float(): parameters are replaced or rewritten
+        invalidate_packs()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):   # load_state_dict copies into .data without a version bump guarantee
+        invalidate_packs()
+        return super()._load_from_state_dict(*args, **kwargs)
 
     # ---- scratch: per (device, stream, purpose) buffers that persist between calls ---------------------------------
     # The kernels address every slab through TMA descriptors that the library caches by ADDRESS; a fresh torch.empty per
@@ -363,6 +398,29 @@ class _SumPerBatch(torch.autograd.Function):
         return g.view(-1, 1, 1).expand(ctx.shape)
 
 
+class _LogdetAccumulate(torch.autograd.Function):
+    """``logdet + log_det_W + log_s.sum((1, 2))`` of ``model/waveglow.py:175,199`` as one kernel (three launches as torch ops)."""
+
+    @staticmethod
+    def forward(ctx, prev, log_det_w, log_s):
+        ctx.shape = log_s.shape
+        ctx.has_prev = prev is not None
+        return ops.logdet_accumulate(log_s.detach(), prev, log_det_w)
+
+    @staticmethod
+    def backward(ctx, g):
+        # every flow of the chain receives the SAME cotangent tensor: its batch sum (the cotangent of the 0-dim log_det_W)
+        # is formed once and handed down the chain with it
+        gs = getattr(g, "_cmwg_batch_sum", None)
+        if gs is None:
+            gs = g.sum()
+            try:
+                g._cmwg_batch_sum = gs
+            except Exception:  # pragma: no cover
+                pass
+        return (g if ctx.has_prev else None), (gs if ctx.needs_input_grad[1] else None), g.view(-1, 1, 1).expand(ctx.shape)
+
+
 class WaveGlow(FlowBase):
     """Reference ``model/waveglow.py:108-212``: upsampler, squeeze, ``flows`` x (invertible 1x1 conv ->
     affine coupling with WN), early outputs every ``n_early_every`` flows."""
@@ -419,8 +477,7 @@ class WaveGlow(FlowBase):
                     x = x.clone()  # the efficient ops consume (free) their input
             x, log_det_w = invconv(x)
             x, log_s = coup(x, y)
-            term = log_det_w + _SumPerBatch.apply(log_s)
-            logdet = term if logdet is None else logdet + term
+            logdet = _LogdetAccumulate.apply(logdet, log_det_w, log_s)
         early.append(x)
         z = _SqueezeFunction.apply(torch.cat(early, 1), self.n_group, True)
         return z.view(batch, -1), logdet
@@ -441,8 +498,7 @@ class WaveGlow(FlowBase):
         for k in range(len(self.WNs) - 1, -1, -1):
             z, log_s = self.WNs[k].reverse(z, y)
             z, log_det_w = self.invconv1x1[k].reverse(z)
-            term = log_det_w + _SumPerBatch.apply(log_s)
-            logdet = term if logdet is None else logdet + term
+            logdet = _LogdetAccumulate.apply(logdet, log_det_w, log_s)
             if k % self.n_early_every == 0 and k:
                 z = torch.cat((parts.pop(), z), 1)
         x = _SqueezeFunction.apply(z, self.n_group, True)

@@ -74,6 +74,20 @@ int cmwg_conv1x1_wgrad(const float* dz, long long dz_bstride, const float* x, lo
 int cmwg_conv1x1_dw_finalize(const float* dm, const float* w_inv, const float* dlogdet, int c, int T,
                              int inverse_mode, float* dw, void* stream);
 
+/* The whole of Conv1x1Func.backward / InvConv1x1Func.backward (model/efficient_modules.py:229-244, 262-279) in two launches
+ * for even C <= 8 (any other shape runs the separate entry points above, same arithmetic).  With M = W (inverse_mode 0) or
+ * W^-1 (1) the forward call was out = M in:
+ *   restored (B, C, T; may be NULL) <- in = M^-1 out       the freed input, re-materialised
+ *   din      (B, C, T)             <- M^T dout
+ *   dw       (C, C; may be NULL)   <- dm + W^-T dlogdet T   resp.  -W^-T dm W^-T - W^-T dlogdet T,  dm = sum dout in^T
+ * w_inv = W^-1 as cmwg_small_inverse_logdet returned it in the forward pass; dlogdet: one device float (NULL = 0);
+ * workspace: cmwg_conv1x1_backward_workspace(B, C, T) bytes (only needed with dw). */
+size_t cmwg_conv1x1_backward_workspace(int B, int C, int T);
+int cmwg_conv1x1_backward(const float* w, const float* w_inv, int inverse_mode, const float* out, long long out_bstride,
+                          const float* dout, long long dout_bstride, const float* dlogdet, int B, int C, int T,
+                          float* restored, long long restored_bstride, float* din, long long din_bstride, float* dw,
+                          void* workspace, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Affine coupling  (model/efficient_modules.py:57-212)
  * `lst` is the WN output, NCL (B, 2*cin, T): channels [0,cin) = log_s, [cin,2cin) = t.
@@ -305,6 +319,12 @@ int cmwg_nll_loss(const float* z, const float* logdet, int B, int T, float sigma
 /* per-batch sum over (channel, time) of an NCL tensor: the log_s.sum((1,2)) of model/waveglow.py:175 */
 int cmwg_sum_per_batch(const float* a, long long a_bstride, int B, int N, float* out, int accumulate, float scale,
                        void* stream);
+
+/* One flow's log-det bookkeeping, `logdet = logdet + log_det_W + log_s.sum((1, 2))` (model/waveglow.py:175,199), in one
+ * launch: out[b] = prev[b] + *log_det_w + sum over (channel, time) of a[b];  prev (B floats) and log_det_w (one device
+ * float) may be NULL (= 0); out may alias prev.  Deterministic. */
+int cmwg_logdet_accumulate(const float* a, long long a_bstride, int B, int N, const float* prev, const float* log_det_w,
+                           float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-kernel-class device timing (CUDA events recorded on the launching stream around each GEMM

