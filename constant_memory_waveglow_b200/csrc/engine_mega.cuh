@@ -58,6 +58,12 @@ struct alignas(64) MegaParams {
   long long* clk;               // nullptr, or [CTAs][18 warps][16] cycle accumulators (CMWG_MEGA_CLK: where the roles wait)
   int dbg;                      // timing experiments only (CMWG_MEGA_DBG): 1 no producer waits, 2 no signals, 4 no wait_all
   int dual;                     // 1: warp MEGA_BWARP issues the weight tiles (default), 0: warp 0 issues both operands
+  // `end` conv fused into the skip tiles' epilogue (model/waveglow.py:92,105): lst[b][o][t] = sum_c w_end[o][c] * cum_skip[b][t][c].
+  // lst == nullptr: off (the fp32 skip slab is written and a separate kernel reads it back).
+  float* lst;                   // (B, cout, T) fp32 NCL
+  const float* w_end;           // [MEGA_END_MAXC][Cs] fp32, rows >= cout zero
+  int cout;
+  int store_skip;               // also keep the fp32 cumulative skip slab (training: the `end` weight gradient reads it)
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -92,12 +98,21 @@ __device__ __forceinline__ void mega_signal(const MegaSig& sg) {
   if ((old & (TC_EPI_WARPS - 1)) == TC_EPI_WARPS - 1) red_release_add_u32(sg.flag, (uint32_t)TC_EPI_WARPS);
 }
 
+// ~20 s at 1.9 GHz.  A wait this long means a lost dependency (a bug) -- or that part of this grid is not resident because
+// another kernel holds its SMs for that long; a collective that waits for a peer rank is the one legitimate case, and it is
+// given time: the kernel reports which CTA gave up before it traps.
+constexpr long long MEGA_WAIT_LIMIT = 40000000000ll;
+__device__ __noinline__ void mega_timeout(const uint32_t* p, uint32_t target) {
+  printf("cmwg_b200 task kernel: CTA %d waited > %lld cycles for dependency counter %p (value %u, needs %u); trapping\n",
+         (int)blockIdx.x, MEGA_WAIT_LIMIT, (const void*)p, *(volatile const uint32_t*)p, target);
+  __trap();
+}
 __device__ __forceinline__ void mega_wait_flag(const uint32_t* p, uint32_t target) {
   if (ld_acquire_u32(p) >= target) return;
   const long long t0 = clock64();
   while (ld_acquire_u32(p) < target) {
     __nanosleep(40);
-    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a lost dependency must not hang the device
+    if (clock64() - t0 > MEGA_WAIT_LIMIT) mega_timeout(p, target);  // a lost dependency must not hang the device
   }
 }
 
@@ -114,7 +129,7 @@ __device__ __forceinline__ void mega_wait_flags3(const uint32_t* a, const uint32
     const uint32_t va = ld_relaxed_u32(a), vb = ld_relaxed_u32(b), vc = ld_relaxed_u32(c);
     if (va >= target && vb >= target && vc >= target) break;
     __nanosleep(40);
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if (clock64() - t0 > MEGA_WAIT_LIMIT) mega_timeout(b, target);
   }
   if (fence) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
@@ -162,7 +177,7 @@ __device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem
                                                    uint32_t tmem_empty_remote, int q, int cg, int lane, uint32_t wbuf,
                                                    uint64_t* ibar, uint32_t& it, const CUtensorMap* om0,
                                                    const CUtensorMap* om1, const CUtensorMap* om2, const CUtensorMap* im0,
-                                                   const CUtensorMap* im1, int b, int r0, int cbase, MegaSig sig, MegaSig* prev, int dbg, long long* tt) {
+                                                   const CUtensorMap* im1, int b, int r0, int cbase, MegaSig sig, MegaSig* prev, int dbg, uint32_t* tt) {
   constexpr int NCH = GW / 128;                      // 32-column chunks per warp
   constexpr int OUTW = Epi::kOutF32 ? 16 : 8;
   constexpr int OCH = Epi::kOutF32 ? TC_CHUNK32_BYTES : TC_CHUNK16_BYTES;
@@ -171,10 +186,10 @@ __device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem
   const uint32_t taddr = tmem_tile + ((uint32_t)(q * 32) << 16) + cg * (GW / 4);
   const CUtensorMap* om[3] = {om0, om1, om2};
   const CUtensorMap* im[2] = {im0, im1};
-  const long long c_a = clock64();
+  const uint32_t c_a = (uint32_t)clock();
   mbar_wait(tmem_full, full_phase);
   tc_fence_after();
-  const long long c_b = clock64();
+  const uint32_t c_b = (uint32_t)clock();
 #pragma unroll 1
   for (int k = 0; k < NCH; ++k) {
     const int c0 = cbase + cg * (GW / 4) + 32 * k;
@@ -261,7 +276,7 @@ __device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem
       }
     }
   }
-  const long long c_c = clock64();
+  const uint32_t c_c = (uint32_t)clock();
   if (lane == 0) {
     if (dbg & 2) sig.flag = nullptr;
     if (prev != nullptr) {
@@ -276,8 +291,87 @@ __device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem
   __syncwarp();
   tt[0] += c_b - c_a;            // waiting for the accumulator
   tt[1] += c_c - c_b;            // drain + functor + staging + store issue (+ input waits)
-  tt[2] += clock64() - c_c;      // store completion + signal
+  tt[2] += (uint32_t)clock() - c_c;  // store completion + signal
   tt[3] += 1;
+}
+
+constexpr int MEGA_END_MAXC = 16;   // output channels of the fused `end` conv (2 * in_channels; every shipped config has <= 8)
+
+// Skip tile with the `end` 1x1 conv in its epilogue.  A warp owns 32 rows x 64 of the tile's 256 skip channels: it folds its
+// columns into NC partial outputs per row (weights are warp-uniform loads, L1 resident), the four warps of a TMEM lane quadrant
+// meet through their staging buffers and a 128-thread named barrier, and the first of them writes the (B, cout, T) rows --
+// 32 consecutive time steps per output channel, one coalesced 128-byte store each.
+template <int NC>
+__device__ __noinline__ void mega_end_task(const MegaParams& p, uint32_t tmem_tile, uint64_t* tmem_full, uint32_t full_phase,
+                                              uint32_t tmem_empty_remote, int q, int cg, int lane, uint8_t* epi_base, int WB,
+                                              int b, int r0) {
+  const uint32_t taddr = tmem_tile + ((uint32_t)(q * 32) << 16) + cg * (MEGA_BN / 4);
+  const int e = cg * 4 + q;
+  const uint32_t wbuf = smem_u32(epi_base + e * WB);
+  float acc[NC];
+#pragma unroll
+  for (int o = 0; o < NC; ++o) acc[o] = 0.f;
+  mbar_wait(tmem_full, full_phase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int k = 0; k < 2; ++k) {
+    const int c0 = cg * (MEGA_BN / 4) + 32 * k;
+    if (p.store_skip && k > 0) {
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[16];
+      tmem_ld16(taddr + 32 * k + 16 * h, v);
+      if (h == 1 && k == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_remote);
+      }
+      const float* w = p.w_end + c0 + 16 * h;
+#pragma unroll
+      for (int o = 0; o < NC; ++o) {
+        float a = acc[o];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a = fmaf(v[j], __ldg(w + o * MEGA_BN + j), a);
+        acc[o] = a;
+      }
+      if (p.store_skip) {
+        uint32_t ov[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) ov[j] = __float_as_uint(v[j]);
+        stage_store32h(wbuf, lane, h, ov);
+      }
+    }
+    if (p.store_skip) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&p.skip_c32, wbuf, c0, r0, 0, b);
+        bulk_commit();
+      }
+    }
+  }
+  if (p.store_skip) {   // the staging doubles as the exchange buffer: the last store must have read it
+    if (lane == 0) bulk_wait_read<0>();
+    __syncwarp();
+  }
+  float* part = reinterpret_cast<float*>(epi_base + e * WB);
+#pragma unroll
+  for (int o = 0; o < NC; ++o) part[o * 32 + lane] = acc[o];
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+  if (cg == 0) {
+    const int t = r0 + lane;
+#pragma unroll
+    for (int o = 0; o < NC; ++o) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) sacc += reinterpret_cast<const float*>(epi_base + (g * 4 + q) * WB)[o * 32 + lane];
+      if (o < p.cout && t < p.T) p.lst[((long long)b * p.cout + o) * p.T + t] = sacc;
+    }
+  }
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");   // the partials have been read: staging may be reused
 }
 
 template <bool SAVE>
@@ -457,8 +551,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
     uint32_t acc_phase = 0;
     uint32_t it = 0;
     uint32_t seq = 0;  // units done by this pair; warps of a CTA are never more than two units apart (TMEM double buffer)
-    long long tt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const long long c_start = clock64();
+    uint32_t tt[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // 32-bit cycle counters: a launch is far below 2^32 cycles
+    const uint32_t c_start = (uint32_t)clock();
     MegaSig pending{nullptr, 0};
     MegaSig* prev = p.lagged ? &pending : nullptr;
     bool prev_alt = false;  // the previous unit staged through ONE of the two 2 KB buffers (gate tile without saves)
@@ -508,6 +602,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
                                                       it, &p.hi_c16[t.layer + 1], &p.lo_c16[t.layer + 1], nullptr,
                                                       &p.hi_c16[t.layer], &p.lo_c16[t.layer], b, r0, 0,
                                                       MegaSig{mega_rflag(p, t.layer, t.rt), dcnt}, prev, p.dbg, tt + 4);
+      } else if (p.lst != nullptr) {
+        if (p.lagged) {   // staging is about to be used as plain memory: no store may still be reading it
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+        }
+        if (p.cout <= 8) mega_end_task<8>(p, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, s.epi, WB, b, r0);
+        else mega_end_task<MEGA_END_MAXC>(p, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, s.epi, WB, b, r0);
       } else {
         mega_epilogue_task<StoreTcEpi, MEGA_BN>(store_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, ubuf, ibar, it,
                                                 &p.skip_c32, nullptr, nullptr, nullptr, nullptr, b, r0, 0,
@@ -522,7 +623,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
       if (p.clk) {
         long long* o = p.clk + ((size_t)blockIdx.x * 18 + warp) * 16;
         for (int i = 0; i < 12; ++i) o[i] = tt[i];
-        o[12] = clock64() - c_start;
+        o[12] = (uint32_t)clock() - c_start;
       }
     }
   }
@@ -730,7 +831,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t it = 0, seq = 0;
-    long long tt[4] = {0, 0, 0, 0};
+    uint32_t tt[4] = {0, 0, 0, 0};
     for (int k = 0; k < rounds; ++k) {
       const int task = mega_bwd_entry(p.total_tasks, k, pair, npairs);
       if (task < 0) continue;

@@ -335,6 +335,47 @@ static __global__ void __launch_bounds__(256) smallk_to_slab_kernel(const float*
     // 16-bit slabs: 8 channels per thread, one 16-byte store per stream (a quarter warp writes one 128-byte line)
     if ((C & 7) == 0 && o32 == nullptr && ohi != nullptr) {
       const int c8 = C >> 3;
+      if (K <= 8 && (256 % c8) == 0) {
+        // the shapes of every shipped config (start conv: K = in_channels <= 8, d(end conv): K = 2 in_channels <= 8, 256
+        // channels): a thread keeps its 8 x K weights in registers and walks the rows of its channel group
+        const int o = (threadIdx.x % c8) * 8;
+        float wr[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) wr[i][j] = i < K ? wsm[i * C + o + j] : 0.f;
+        float bv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bv[j] = bias ? bias[o + j] : 0.f;
+        const int rstep = 256 / c8;
+        for (int r = threadIdx.x / c8; r < SMALLK_ROWS; r += rstep) {
+          const int t = t0 + r;
+          if (t >= t_end) break;
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = bv[j];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < K) {
+              const float xv = xs[i * SMALLK_ROWS + r];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = fmaf(wr[i][j], xv, acc[j]);
+            }
+          }
+          const long long off = ((long long)b * T + t) * C + o;
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            h[j] = pack2(acc[2 * j], acc[2 * j + 1], is_fp16);
+            float f0, f1;
+            unpack2(h[j], is_fp16, f0, f1);
+            l[j] = pack2(acc[2 * j] - f0, acc[2 * j + 1] - f1, is_fp16);
+          }
+          *reinterpret_cast<uint4*>(ohi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+          if (olo) *reinterpret_cast<uint4*>(olo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        return;
+      }
       for (int idx = threadIdx.x; idx < SMALLK_ROWS * c8; idx += 256) {
         const int r = idx / c8, o = (idx % c8) * 8;
         const int t = t0 + r;

@@ -126,7 +126,7 @@ inline PackedLayout make_packed_layout(const WnDims& d) {
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   L.wV = take((size_t)2 * d.Cd * d.depth * d.aux * 4);
   L.wStart = take((size_t)d.Cr * d.cin * 4);
-  L.wEnd = take((size_t)2 * d.cin * d.Cs * 4);
+  L.wEnd = take((size_t)(2 * d.cin > 16 ? 2 * d.cin : 16) * d.Cs * 4);  // >= 16 rows, tail zero (fused end conv epilogue)
   L.nV = take((size_t)2 * d.Cd * d.depth * 4);
   L.nStart = take((size_t)d.Cr * 4);
   L.biasStart = take((size_t)d.Cr * 4);

@@ -70,6 +70,8 @@ static int wn_pack_impl(const WnDims& d, const cmwg_wn_params* prm, void* packed
     add(prm->W_o[i], L.wWo[i], L.nWo[i], d.nb(i), d.Cd);
   }
   tb.n = n;
+  if (2 * d.cin < 16)   // zero rows behind the `end` weights: the fused epilogue of the task kernel reads 8 or 16 rows
+    CMWG_CHECK_CUDA(cudaMemsetAsync(base + L.wEnd + (size_t)2 * d.cin * d.Cs * 4, 0, (size_t)(16 - 2 * d.cin) * d.Cs * 4, st));
   weight_eff_kernel<<<rows, 128, 0, st>>>(tb);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
@@ -183,9 +185,14 @@ static int mega_launch(const MegaParams& p, cudaStream_t st) {
 }
 
 // hin(i) / hlo(i): (hi, lo) slabs of layer i's input; gop(i), sa(i), sb(i): gate output and saved tanh / sigmoid
+static inline bool mega_end_fused(const WnDims& d) {  // CMWG_MEGA_END=0: separate end conv kernel (read at every call: tests flip it)
+  const char* e = getenv("CMWG_MEGA_END");
+  return !(e && e[0] == '0') && 2 * d.cin <= MEGA_END_MAXC && !d.bias && d.Cs == MEGA_BN;
+}
+
 static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLayout& FL, const uint8_t* pk, uint8_t* ws,
                            const void* ycl, int B, int T, bool save, int f16, void* const* hin, void* const* hlo,
-                           void* const* gop, void* const* sa, void* const* sb, float* skip32, cudaStream_t st) {
+                           void* const* gop, void* const* sa, void* const* sb, float* skip32, float* lst, cudaStream_t st) {
   MegaParams p;
   memset(&p, 0, sizeof(p));
   for (int i = 0; i < d.depth; ++i) {
@@ -215,6 +222,12 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
   // R(u) must come after G(u) and before G(u + RT - 1) (its right-hand neighbour one layer up): lag <= RT - 2
   p.lag = mega_fwd_lag(p.RT);
   p.dual = mega_dual();
+  if (mega_end_fused(d)) {
+    p.lst = lst;
+    p.w_end = reinterpret_cast<const float*>(pk + PL.wEnd);
+    p.cout = 2 * d.cin;
+    p.store_skip = save ? 1 : 0;
+  }
   p.total_tasks = (d.depth * p.RT + p.lag) * (p.ngt + 1) + p.RT;
   // timing experiments that SKIP synchronisation or epilogue work (wrong results by design) exist only in builds made
   // with -DCMWG_MEGA_EXPERIMENTS; the shipped library ignores CMWG_MEGA_DBG
@@ -353,7 +366,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
         hin[i] = hin_op(i); hlo[i] = hlo_op(i); gop[i] = g_op(i);
         sa[i] = save ? sv + FL.s_a[i] : nullptr; sb[i] = save ? sv + FL.s_b[i] : nullptr;
       }
-      CMWG_PROPAGATE(wn_forward_mega(d, PL, FL, pk, ws, ycl, B, T, save, f16, hin, hlo, gop, sa, sb, skip32, st));
+      CMWG_PROPAGATE(wn_forward_mega(d, PL, FL, pk, ws, ycl, B, T, save, f16, hin, hlo, gop, sa, sb, skip32, lst, st));
       fused = true;
     }
   }
@@ -456,8 +469,8 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
     StoreTcEpi epi{d.bias ? reinterpret_cast<const float*>(pk + PL.biasS) : nullptr, nullptr};
     CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
   }
-  // ---- end conv
-  {
+  // ---- end conv (the task kernel has it in the epilogue of its skip tiles)
+  if (!(fused && mega_end_fused(d))) {
     CMWG_PROPAGATE(end_fwd_launch(skip32, reinterpret_cast<const float*>(pk + PL.wEnd),
                                   d.bias ? reinterpret_cast<const float*>(pk + PL.biasEnd) : nullptr, 2 * d.cin, d.Cs, B,
                                   d.H * T, lst, st, t_off, t_n));

@@ -221,9 +221,11 @@ def upsample_bwd(h, g, v, dy, stride: int, pad: int, want_bias: bool, out=None):
         dg = torch.empty_like(g) if g is not None else None
         dv = torch.empty_like(v)
         db = torch.empty((Cc,), device=h.device, dtype=torch.float32) if want_bias else None
-    L.check(L.load().cmwg_upsample_bwd(h.data_ptr(), L.ptr(g), v.data_ptr(), dy.data_ptr(), dy.stride(0), dy.stride(1),
-                                       B, Cc, F, K, stride, pad, dy.shape[2], L.ptr(dg), dv.data_ptr(), L.ptr(db), 0,
-                                       L.stream_ptr(h.device)), "upsample_bwd")
+    lib = L.load()
+    ws = torch.empty(max(int(lib.cmwg_upsample_bwd_workspace(B, Cc, K)), 4), device=h.device, dtype=torch.uint8)
+    L.check(lib.cmwg_upsample_bwd(h.data_ptr(), L.ptr(g), v.data_ptr(), dy.data_ptr(), dy.stride(0), dy.stride(1),
+                                  B, Cc, F, K, stride, pad, dy.shape[2], L.ptr(dg), dv.data_ptr(), L.ptr(db), ws.data_ptr(),
+                                  L.stream_ptr(h.device)), "upsample_bwd")
     return dg, dv, db
 
 

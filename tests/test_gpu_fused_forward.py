@@ -32,12 +32,46 @@ def _wn(cin, aux, depth, radix=3, seed=0):
 
 
 def _both(fn):
+    """(task kernel, layered pipeline).  The bit-for-bit comparisons keep the `end` conv in its own kernel on both sides
+    (CMWG_MEGA_END=0): fused into the skip tiles' epilogue it sums the same products in another order
+    (test_fused_end_conv_matches_separate_kernel)."""
+    os.environ["CMWG_MEGA_END"] = "0"
     os.environ["CMWG_MEGA"] = "1"
-    a = fn()
-    os.environ["CMWG_MEGA"] = "0"
-    b = fn()
-    os.environ["CMWG_MEGA"] = "1"
+    try:
+        a = fn()
+        os.environ["CMWG_MEGA"] = "0"
+        b = fn()
+    finally:
+        os.environ["CMWG_MEGA"] = "1"
+        os.environ.pop("CMWG_MEGA_END", None)
     return a, b
+
+
+@pytest.mark.parametrize("cin,aux,depth,B,T", [(4, 80, 8, 2, 300), (2, 80, 8, 3, 2000), (3, 20, 1, 2, 700), (4, 80, 8, 24, 2000),
+                                               (8, 80, 2, 1, 1000)])
+@pytest.mark.parametrize("save", [False, True])
+def test_fused_end_conv_matches_separate_kernel(cin, aux, depth, B, T, save):
+    """`end` 1x1 conv in the epilogue of the skip tiles (default) against the separate kernel reading the fp32 skip slab: the
+    same fp32 products, summed in a different order; ragged last tiles, 2 .. 16 output channels, with and without saves."""
+    wn = _wn(cin, aux, depth, seed=11)
+    g = torch.Generator(device="cuda").manual_seed(B * T)
+    x = torch.randn(B, 2 * cin, T, device="cuda", generator=g)
+    y = torch.randn(B, aux, T, device="cuda", generator=g)
+
+    def run():
+        lst, st = wn._cmwg_forward(x, y, save=save, prec="fp16")
+        torch.cuda.synchronize()
+        return lst.clone()
+
+    fused = run()
+    os.environ["CMWG_MEGA_END"] = "0"
+    try:
+        sep = run()
+    finally:
+        os.environ.pop("CMWG_MEGA_END", None)
+    assert torch.isfinite(fused).all()
+    assert rel_l2(fused, sep) < 2e-6, rel_l2(fused, sep)
+    assert torch.equal(fused, run())          # deterministic
 
 
 SHAPES = [
@@ -94,7 +128,9 @@ def test_fused_forward_equals_layered_pipeline(cin, aux, depth, B, T, prec, save
     a, b = _both(run)       # (the saved activations are compared through the gradients they produce, below)
     assert torch.isfinite(a).all()
     assert torch.equal(a, b)
-    assert torch.equal(a, run())         # run to run: same bits (fixed accumulation order, no atomics on data)
+    c = run()                            # default arrangement (`end` conv in the skip tiles' epilogue)
+    assert torch.equal(c, run())         # run to run: same bits (fixed accumulation order, no atomics on data)
+    assert rel_l2(c, a) < 2e-6
 
 
 @pytest.mark.parametrize("cin,aux,depth,B,T", [(4, 80, 8, 2, 300), (3, 20, 1, 2, 700), (4, 80, 4, 2, 1000)])
@@ -143,6 +179,10 @@ def test_training_step_gradients_equal_layered_pipeline(prec):
     # default: the weight-gradient GEMMs of all layers in one launch, full-K tiles instead of split-K partials --
     # the same products summed in another order
     gc = run()
-    assert torch.equal(gc[0], ga[0])              # the input gradient does not go through them
-    for a, c in zip(ga[1:], gc[1:]):
-        assert rel_l2(c, a) < 2e-5
+    # ... and the `end` conv sits in the skip tiles' epilogue (its fp32 products summed in another order: log_s / t move by
+    # ~1e-7, which flips a few 16-bit roundings of the gradient slabs downstream), so every gradient agrees to well below
+    # the operand precision rather than bit for bit
+    for a, c in zip(ga, gc):
+        assert rel_l2(c, a) < (1e-4 if prec == "fp16" else 5e-4), rel_l2(c, a)
+    gd = run()
+    assert all(torch.equal(c, d) for c, d in zip(gc, gd))      # the default arrangement is deterministic too
