@@ -237,15 +237,10 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
 #else
   p.dbg = 0;
 #endif
-  {
-    // lagged completion signals are deadlock-free when no unit can depend, even transitively, on the unit its own pair
-    // ran just before it: every dependency points >= D entries back and a pair's consecutive units are <= 2 * pairs apart
-    const int pairs = std::min(p.total_tasks, num_sms() / 2);
-    const int per_slot = p.ngt + 1;
-    const int D = std::min(per_slot * p.lag + 1, per_slot * (p.RT - 1 - p.lag) - 2);
-    const char* v = getenv("CMWG_MEGA_LAGGED");
-    p.lagged = (D > 2 * pairs + 8 && v && v[0] == '1') ? 1 : 0;  // opt-in: measured slower (0.51 vs 0.476 ms at the LJ shape)
-  }
+  // "lagged" completion signals (a unit's stores complete behind the next unit's work, its dependency counter is released one
+  // unit later) were measured slower in round 1 (0.51 vs 0.476 ms at the LJ shape: consumers wait longer than the epilogue
+  // warps save) and are not maintained with the scout / fused-epilogue arrangement: always immediate.
+  p.lagged = 0;
   {
     // CMWG_MEGA_CLK=1: per-role cycle accumulators of the LAST launch, read back with cmwg_mega_clk_read (tools only)
     const char* v = getenv("CMWG_MEGA_CLK");
