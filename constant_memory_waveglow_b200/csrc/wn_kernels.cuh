@@ -71,7 +71,7 @@ struct WnBwdSrc {
   int M, ld, n_valid;  // rows, row pitch, valid columns
   int row0, col0, sn;  // destination row offset, column offset, column stride
 };
-constexpr int WN_BWD_MAX_SRC = 4;
+constexpr int WN_BWD_MAX_SRC = 8;   // radix <= 7 taps of W, or the two row blocks of W_o
 struct WnBwdEntry {
   const float* dw;        // effective-weight gradient, natural layout [O][L] (used when nsrc == 0)
   const float* v;
@@ -830,64 +830,63 @@ static __global__ void __launch_bounds__(256) end_bwd_dw_kernel(const float* __r
 // Gradient scaling for fp16 operands.  fp16 carries the same 10 mantissa bits as TF32 (bf16: 7) at bf16's tensor-core rate,
 // but only 5 exponent bits; the backward GEMM chain is LINEAR in the incoming cotangent, so it runs on S * cotangent with S a
 // power of two chosen per call on the device (no host round trip), and every result is multiplied by 1 / S where it leaves
-// the 16-bit slabs (exact: powers of two).  gscale = {max |dlst|, S, 1 / S}.
+// the 16-bit slabs (exact: powers of two).  gscale = {max |dlst| (bit pattern), S, 1 / S, arrival counter}.
 //   S = 2^(8 - ceil(log2(max|dlst| * max_k sum_o |W_end[o][k]|)))  =>  |S * dskip| <= 256:
 // 2^8 of headroom below fp16's largest value for the growth of the residual gradient through the layers, and 2^22 of normal
 // range below the largest entry (smaller entries lose precision gradually as fp16 subnormals; they do not matter to any norm).
 // ------------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(1024) grad_scale_kernel(float* __restrict__ gscale, const float* __restrict__ dlst,
-                                                                 long long n, const float* __restrict__ w_end, int cout,
-                                                                 int Cs) {
-  // one CTA: dlst is B * 2cin * T floats (1.5 MB at the LJ training shape), a few microseconds of one SM's bandwidth, and a
-  // single launch replaces memset + grid-wide atomic max + finalise.  max() is order independent: deterministic.
-  __shared__ float red[32];
+static __global__ void __launch_bounds__(256) grad_scale_kernel(float* __restrict__ gscale, const float* __restrict__ dlst,
+                                                                long long n, const float* __restrict__ w_end, int cout,
+                                                                int Cs) {
+  // gscale[0] (bit pattern of the running max) and gscale[3] (arrival counter) are zeroed by the caller.  Every CTA folds its
+  // slice of dlst into the max (order independent: deterministic); the last CTA to arrive forms the bound and the scale.
+  __shared__ float red[8];
+  __shared__ bool last;
   float m = 0.f;
   const long long n4 = n >> 2;
   const float4* a4 = reinterpret_cast<const float4*>(dlst);
-  for (long long i = threadIdx.x; i < n4; i += 1024) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     const float4 v = a4[i];
     m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
   }
-  for (long long i = (n4 << 2) + threadIdx.x; i < n; i += 1024) m = fmaxf(m, fabsf(dlst[i]));
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += 256) m = fmaxf(m, fabsf(dlst[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    if (m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(gscale), __float_as_uint(m));  // non-negative floats order like their bits
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned int*>(gscale) + 3, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
   float colmax = 0.f;
-  for (int k = threadIdx.x; k < Cs; k += 1024) {
+  for (int k = threadIdx.x; k < Cs; k += 256) {
     float s = 0.f;
     for (int o = 0; o < cout; ++o) s += fabsf(w_end[(long long)o * Cs + k]);
     colmax = fmaxf(colmax, s);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    colmax = fmaxf(colmax, __shfl_xor_sync(0xffffffffu, colmax, o));
-  }
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = red[threadIdx.x];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    m = v;
-  }
+  for (int o = 16; o > 0; o >>= 1) colmax = fmaxf(colmax, __shfl_xor_sync(0xffffffffu, colmax, o));
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = colmax;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = red[threadIdx.x];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (threadIdx.x == 0) {
-      const float bound = v * m;
-      float S = 1.f;
-      if (bound > 0.f && bound < 3.0e38f) {
-        int e = 8 - (int)ceilf(log2f(bound));
-        e = max(-60, min(60, e));
-        S = exp2f((float)e);
-      }
-      gscale[0] = m;
-      gscale[1] = S;
-      gscale[2] = 1.f / S;
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) colmax = fmaxf(colmax, red[i]);
+    const float amax = __uint_as_float(*reinterpret_cast<volatile unsigned int*>(gscale));
+    const float bound = colmax * amax;
+    float S = 1.f;
+    if (bound > 0.f && bound < 3.0e38f) {
+      int e = 8 - (int)ceilf(log2f(bound));
+      e = max(-60, min(60, e));
+      S = exp2f((float)e);
     }
+    gscale[1] = S;
+    gscale[2] = 1.f / S;
   }
 }
 
@@ -906,15 +905,25 @@ static __global__ void __launch_bounds__(256) scale_by_kernel(float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------------------------
-// out[p] = sum_j partial[j][p], fixed order, fp64 accumulator
-static __global__ void __launch_bounds__(128) reduce_blocks_kernel(const float* __restrict__ partial, int nblocks,
+// out[p] = sum_j partial[j][p] in a fixed order: a CTA owns 32 outputs, its 8 warps take the partials j = y, y + 8, ... (fp64),
+// and the eight sub-sums are folded in warp order.  Reads are 128-byte rows of 32 consecutive outputs.
+static __global__ void __launch_bounds__(256) reduce_blocks_kernel(const float* __restrict__ partial, int nblocks,
                                                                    int P, float* __restrict__ out,
                                                                    const float* __restrict__ gscale) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
+  __shared__ double part[8][32];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int p = blockIdx.x * 32 + x;
   double s = 0.0;
-  for (int j = 0; j < nblocks; ++j) s += (double)partial[(long long)j * P + p];
-  out[p] = (float)s * (gscale ? gscale[2] : 1.f);
+  if (p < P)
+    for (int j = y; j < nblocks; j += 8) s += (double)partial[(long long)j * P + p];
+  part[y][x] = s;
+  __syncthreads();
+  if (y == 0 && p < P) {
+    double t = part[0][x];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += part[k][x];
+    out[p] = (float)t * (gscale ? gscale[2] : 1.f);
+  }
 }
 
 // split-K partials [splits][M][N] of several weight-gradient problems -> strided destinations

@@ -487,7 +487,7 @@ static int reduce_blocks(const float* partial, int nblocks, int P, float* scratc
     partial = scratch;
     nblocks = stages;
   }
-  reduce_blocks_kernel<<<ceil_div(P, 128), 128, 0, st>>>(partial, nblocks, P, out, gscale);
+  reduce_blocks_kernel<<<ceil_div(P, 32), 256, 0, st>>>(partial, nblocks, P, out, gscale);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
   return CMWG_OK;
@@ -590,7 +590,10 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   if (TC && f16) {
     gscale = reinterpret_cast<float*>(ws + BL.gscale);
     CMWG_REQUIRE((reinterpret_cast<uintptr_t>(dlst) & 15) == 0, "cmwg_wn_backward: dlst must be 16-byte aligned");
-    grad_scale_kernel<<<1, 1024, 0, st>>>(gscale, dlst, (long long)B * cout * TF, wEnd, cout, d.Cs);
+    CMWG_CHECK_CUDA(cudaMemsetAsync(gscale, 0, 16, st));
+    const long long n_dl = (long long)B * cout * TF;
+    const int nb_gs = (int)std::max<long long>(1, std::min<long long>(ceil_div_ll(n_dl, 256 * 4 * 4), 64));
+    grad_scale_kernel<<<nb_gs, 256, 0, st>>>(gscale, dlst, n_dl, wEnd, cout, d.Cs);
     CMWG_COUNT_LAUNCH();
     CMWG_LAUNCH_CHECK();
   }
@@ -679,21 +682,21 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       } else {
         for (int k = 0; k < gn; ++k) CMWG_PROPAGATE(ff_wgrad_launch(gp[k], B, d.H, T, Lc, st));
       }
-      if (deferred_gather) {
-        // single split per problem: the "reduction" would be a re-layout only -- the weight-norm backward gathers the
-        // tiles itself (WnBwdSrc); anything it cannot take falls through to the reduce kernel below
-        bool all = true;
-        for (int k = 0; k < gn; ++k) all = all && splits[k] == 1;
-        if (all) {
+      // a problem with a single split needs no reduction, only a re-layout: the weight-norm backward gathers its tile
+      // itself (WnBwdSrc); problems with several splits go through the reduce kernel below
+      bool any_reduce = false;
+      for (int k = 0; k < nr; ++k) {
+        if (rs[k].pi < g0 || rs[k].pi >= g0 + gn) continue;
+        const WgradProblem& q = pr[rs[k].pi];
+        if (deferred_gather && splits[rs[k].pi - g0] == 1) {
           pending_gather = true;
-          for (int k = 0; k < nr; ++k) {
-            if (rs[k].pi < g0 || rs[k].pi >= g0 + gn) continue;
-            const WgradProblem& q = pr[rs[k].pi];
-            gather[ngather++] = GatherSpec{rs[k].out, q.partial, q.M, q.N, rs[k].n_valid, rs[k].sm, rs[k].sn, rs[k].off};
-          }
-          continue;
+          gather[ngather++] = GatherSpec{rs[k].out, q.partial, q.M, q.N, rs[k].n_valid, rs[k].sm, rs[k].sn, rs[k].off};
+          rs[k].pi = -1;   // taken
+        } else {
+          any_reduce = true;
         }
       }
+      if (!any_reduce) continue;
       WgReduceTable rt;
       rt.n = 0;
       rt.gscale = gscale;

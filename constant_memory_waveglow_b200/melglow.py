@@ -21,6 +21,7 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
 
+from . import _lib as L
 from .base import FlowBase
 from .efficient_modules import AffineCouplingBlock, InvertibleConv1x1
 from .utils import add_weight_norms
@@ -52,6 +53,40 @@ class Predictor(nn.Module):
         return self.end(s)
 
 
+class _LVCGate(torch.autograd.Function):
+    """Location-variable dilated conv + gate as one kernel each way (``cmwg_lvc_gate_forward`` / ``_backward``,
+    csrc/lvc.cu): reference ``model/melglow.py:72-85`` (pad, unfold, grouped ``F.conv1d`` with one kernel per frame,
+    ``fused_gate``).  x (B, Cr, T), weights (B, frames, 2Cd, Cr, radix) -> g (B, Cd, T)."""
+
+    @staticmethod
+    def forward(ctx, x, weights, dilation):
+        L.require_cuda(x, weights, op="WN_LVC")
+        x = x.detach().float().contiguous()
+        w = weights.detach().float().contiguous()
+        B, frames, o2, cr, radix = w.shape
+        T = x.shape[2]
+        g = torch.empty((B, o2 // 2, T), device=x.device, dtype=torch.float32)
+        L.check(L.load().cmwg_lvc_gate_forward(x.data_ptr(), w.data_ptr(), B, T, frames, o2 // 2, cr, radix, int(dilation),
+                                               g.data_ptr(), L.stream_ptr(x.device)), "lvc_gate_forward")
+        ctx.save_for_backward(x, w)
+        ctx.dilation = int(dilation)
+        return g
+
+    @staticmethod
+    def backward(ctx, dg):
+        x, w = ctx.saved_tensors
+        B, frames, o2, cr, radix = w.shape
+        T = x.shape[2]
+        dg = dg.float().contiguous()
+        dz = torch.empty((B, o2, T), device=x.device, dtype=torch.float32)
+        dx = torch.empty_like(x)
+        dw = torch.empty_like(w)
+        L.check(L.load().cmwg_lvc_gate_backward(x.data_ptr(), w.data_ptr(), dg.data_ptr(), B, T, frames, o2 // 2, cr, radix,
+                                                ctx.dilation, dz.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+                                                L.stream_ptr(x.device)), "lvc_gate_backward")
+        return dx, dw, None
+
+
 class NonCausalLayerLVC(nn.Module):
     """One layer (reference ``model/melglow.py:52-92``): location-variable dilated conv -> gate -> ``W_o`` 1x1 -> residual / skip."""
 
@@ -62,8 +97,9 @@ class NonCausalLayerLVC(nn.Module):
         self.chs_split = [skip_channels] if last_layer else [residual_channels, skip_channels]
         self.W_o = nn.Conv1d(dilation_channels, sum(self.chs_split), 1, bias=bias)
 
-    def forward(self, x: Tensor, weights: Tensor):
-        """x (B, Cr, T); weights (B, frames, 2*Cd, Cr, radix), frame s owns columns [s*T/frames, (s+1)*T/frames)."""
+    def _lvc_gate_torch(self, x: Tensor, weights: Tensor) -> Tensor:
+        """The same computation as torch ops (tap-by-tap einsum): what tests/test_melglow.py checks the kernels against;
+        not on the product path."""
         B, frames, cout, cin, radix = weights.shape
         T = x.shape[2]
         span = T // frames
@@ -74,7 +110,11 @@ class NonCausalLayerLVC(nn.Module):
             term = torch.einsum("bsoc,bcst->bost", weights[..., k], tap)
             z = term if z is None else z + term
         zw, zv = z.reshape(B, cout, T).chunk(2, 1)
-        out = self.W_o(fused_gate(zw, zv))
+        return fused_gate(zw, zv)
+
+    def forward(self, x: Tensor, weights: Tensor):
+        """x (B, Cr, T); weights (B, frames, 2*Cd, Cr, radix), frame s owns columns [s*T/frames, (s+1)*T/frames)."""
+        out = self.W_o(_LVCGate.apply(x, weights, self.dilation))     # raises for CPU tensors: there is no CPU path
         if len(self.chs_split) == 1:
             return None, out
         res, skip = out.split(self.chs_split, 1)
@@ -82,7 +122,8 @@ class NonCausalLayerLVC(nn.Module):
 
 
 class WN_LVC(nn.Module):
-    """Reference ``model/melglow.py:95-159``."""
+    """Reference ``model/melglow.py:95-159``.  The location-variable convolutions and gates run in csrc/lvc.cu; the kernel
+    predictor and the 1x1 ``W_o`` / ``start`` / ``end`` convolutions are PyTorch modules."""
 
     def __init__(self, in_channels, aux_channels, depth, dilation_channels, residual_channels, skip_channels,
                  predict_channels, predict_layers, radix, bias, zero_init=True):

@@ -266,6 +266,19 @@ int cmwg_wsrglow_cond(float* c, int B, int Tc, const float* emb, int E, int n_co
                       const float* window, float* out, int* codes, int* phase_codes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Location-variable convolution + gate of MelGlow's WN_LVC (model/melglow.py:52-92, NonCausalLayerLVC.forward, the F.conv1d
+ * with groups = batch * frames at :81-82 and the fused_gate at :85):
+ *   z[b, oc, t] = sum_{ic, k} w[b, t / span, oc, ic, k] * x[b, ic, t + (k - radix/2) * dilation]   (zero padding), span = T / frames
+ *   g[b, c, t]  = tanh(z[b, c, t]) * sigmoid(z[b, Cd + c, t])
+ * x (B, Cr, T), w (B, frames, 2Cd, Cr, radix), g (B, Cd, T), all fp32 contiguous.  One CTA per (frame, batch item).
+ * Backward: dg (B, Cd, T) -> dx (B, Cr, T), dw (like w), with dz (B, 2Cd, T) as scratch; deterministic.
+ * ------------------------------------------------------------------------------------------- */
+int cmwg_lvc_gate_forward(const float* x, const float* w, int B, int T, int frames, int Cd, int Cr, int radix, int dilation,
+                          float* g, void* stream);
+int cmwg_lvc_gate_backward(const float* x, const float* w, const float* dg, int B, int T, int frames, int Cd, int Cr,
+                           int radix, int dilation, float* dz, float* dx, float* dw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * WaveFlow glue (model/waveflow.py:154-265).  Images are (B, H, W) fp32 contiguous, H = n_group lines;
  * lst = (B, 2, (H-1)*W) is the 2-D WN's output for input lines 0..H-2 (log_s, then t).
  * ------------------------------------------------------------------------------------------- */

@@ -32,24 +32,52 @@ def test_oracle_matches_reference_fixture():
     assert max_abs(xr, fx["x"]) < 5e-6 and rel_l2(ldr, fx["logdet_reverse"]) < 1e-5
 
 
-def test_wn_lvc_module_matches_reference_fixture_on_cpu():
-    """The transform is plain PyTorch (tap-by-tap einsum instead of the reference's unfold + grouped conv): same numbers,
-    same state-dict keys, same BatchNorm bookkeeping."""
+def test_wn_lvc_module_layout_matches_reference_fixture():
+    """Same state-dict keys and parameter order as the reference; no CPU path (the location-variable convolutions run in
+    csrc/lvc.cu like the flow primitives)."""
     import constant_memory_waveglow_b200 as cm
     fx = load_golden("melglow_tiny.pt")
     m = cm.MelGlow(memory_efficient=True, **fx["arch"], **fx["wn_kwargs"]).train()
     assert list(m.state_dict().keys()) == list(fx["state"].keys())
     m.load_state_dict(fx["state"])
     wn = m.WNs[0].F
-    assert [n for n, _ in wn.named_parameters()][:2] == ["start.bias", "start.weight_g"] or \
-        [n for n, _ in wn.named_parameters()][0].startswith("start.")
-    with torch.no_grad():
-        log_s, t = wn(fx["wn_x"], fx["h"][..., :16])
-    assert rel_l2(log_s, fx["wn_log_s"]) < 1e-5 and rel_l2(t, fx["wn_t"]) < 1e-5
+    assert [n for n, _ in wn.named_parameters()][0].startswith("start.")
     from model import MelGlow
     assert MelGlow is cm.MelGlow
     with pytest.raises(RuntimeError):
+        wn(fx["wn_x"], fx["h"][..., :16])
+    with pytest.raises(RuntimeError):
         m(fx["x"].clone(), fx["h"])          # the flow primitives have no CPU path
+
+
+@pytest.mark.gpu
+def test_wn_lvc_kernels_against_fixture_and_torch_ops():
+    """cmwg_lvc_gate_forward / _backward: the WN_LVC transform against the reference fixture, and one layer's forward,
+    input gradient and kernel gradient against the same computation written as torch ops -- dilations 1 .. 64 put the
+    taps' source samples in the same, the neighbouring and the second-next frame."""
+    import constant_memory_waveglow_b200 as cm
+    from constant_memory_waveglow_b200.melglow import NonCausalLayerLVC, _LVCGate
+    fx = load_golden("melglow_tiny.pt")
+    m = cm.MelGlow(memory_efficient=True, **fx["arch"], **fx["wn_kwargs"]).train()
+    m.load_state_dict(fx["state"])
+    wn = m.WNs[0].F.cuda()
+    with torch.no_grad():
+        log_s, t = wn(fx["wn_x"].cuda(), fx["h"][..., :16].cuda())
+    assert rel_l2(log_s, fx["wn_log_s"]) < 1e-5 and rel_l2(t, fx["wn_t"]) < 1e-5
+    g = torch.Generator().manual_seed(0)
+    for (B, frames, span, Cd, Cr, radix, dil) in ((2, 5, 32, 48, 48, 3, 1), (3, 7, 32, 48, 48, 3, 32), (2, 6, 32, 48, 48, 3, 64),
+                                                   (2, 4, 16, 8, 12, 5, 3), (1, 3, 64, 16, 8, 3, 16)):
+        layer = NonCausalLayerLVC(dil, Cd, Cr, Cd, radix, False)
+        x = torch.randn(B, Cr, frames * span, generator=g).cuda().requires_grad_(True)
+        w = (torch.randn(B, frames, 2 * Cd, Cr, radix, generator=g) * 0.2).cuda().requires_grad_(True)
+        dg = torch.randn(B, Cd, frames * span, generator=g).cuda()
+        want = layer._lvc_gate_torch(x, w)
+        gx, gw = torch.autograd.grad(want, [x, w], dg)
+        got = _LVCGate.apply(x, w, dil)
+        hx, hw = torch.autograd.grad(got, [x, w], dg)
+        assert rel_l2(got, want) < 2e-6, (dil, rel_l2(got, want))
+        assert rel_l2(hx, gx) < 5e-6 and rel_l2(hw, gw) < 5e-6, (dil, rel_l2(hx, gx), rel_l2(hw, gw))
+        assert torch.equal(hw, torch.autograd.grad(_LVCGate.apply(x, w, dil), [w], dg)[0])     # deterministic
 
 
 @pytest.mark.gpu
