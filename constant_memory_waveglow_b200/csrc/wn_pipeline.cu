@@ -519,6 +519,7 @@ struct WnBwdQueue {
     }
     return false;
   }
+  void reset() { tb.n = 0; rows = 0; }
   int flush(cudaStream_t st, const float* gscale = nullptr) {
     tb.gscale = gscale;
     if (rows == 0) return CMWG_OK;
@@ -876,6 +877,10 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       CMWG_COUNT_LAUNCH();
       CMWG_LAUNCH_CHECK();
     }
+    // the tiles live in the `partial` workspace, which the start conv backward below reuses for its block partials:
+    // the weight-norm backward of everything queued so far runs NOW; the start conv's own entry follows in a second launch
+    CMWG_PROPAGATE(wq.flush(st, gscale));
+    wq.reset();
   }
 
   if constexpr (TC) {

@@ -61,8 +61,13 @@ def test_wn_lvc_kernels_against_fixture_and_torch_ops():
     m = cm.MelGlow(memory_efficient=True, **fx["arch"], **fx["wn_kwargs"]).train()
     m.load_state_dict(fx["state"])
     wn = m.WNs[0].F.cuda()
-    with torch.no_grad():
-        log_s, t = wn(fx["wn_x"].cuda(), fx["h"][..., :16].cuda())
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False   # the predictor / W_o are torch convs
+    try:
+        with torch.no_grad():
+            log_s, t = wn(fx["wn_x"].cuda(), fx["h"][..., :16].cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     assert rel_l2(log_s, fx["wn_log_s"]) < 1e-5 and rel_l2(t, fx["wn_t"]) < 1e-5
     g = torch.Generator().manual_seed(0)
     for (B, frames, span, Cd, Cr, radix, dil) in ((2, 5, 32, 48, 48, 3, 1), (3, 7, 32, 48, 48, 3, 32), (2, 6, 32, 48, 48, 3, 64),
