@@ -80,6 +80,13 @@ struct alignas(64) MegaParams {
   int dual;                     // 1: warp MEGA_BWARP issues the weight tiles (default), 0: warp 0 issues both operands
   // `end` conv fused into the skip tiles' epilogue (model/waveglow.py:92,105): lst[b][o][t] = sum_c w_end[o][c] * cum_skip[b][t][c].
   // lst == nullptr: off (the fp32 skip slab is written and a separate kernel reads it back).
+  // Residual tiles with DIRECT global loads / stores of the (hi, lo) pairs (row-per-thread 32-byte vectors) instead of TMA
+  // chunks through the staging buffers: the small epilogue transfers no longer queue behind the operand stream in the SM's
+  // TMA unit (res_direct = 0: the TMA path).
+  const uint16_t* hi_ptr[MEGA_D];   // layer inputs, hi halves  [rows][Cr]
+  uint16_t* lo_ptr[MEGA_D];         // layer inputs, lo halves
+  uint16_t* hi_out_ptr[MEGA_D];     // same slabs, writable view (hi_out_ptr[i] = hi_ptr[i])
+  int res_direct;
   float* lst;                   // (B, cout, T) fp32 NCL
   const float* w_end;           // [MEGA_END_MAXC][Cs] fp32, rows >= cout zero
   int cout;
@@ -312,6 +319,75 @@ __device__ __forceinline__ void mega_epilogue_task(const Epi& epi, uint32_t tmem
   tt[0] += c_b - c_a;            // waiting for the accumulator
   tt[1] += c_c - c_b;            // drain + functor + staging + store issue (+ input waits)
   tt[2] += (uint32_t)clock() - c_c;  // store completion + signal
+  tt[3] += 1;
+}
+
+__device__ __forceinline__ void ldg256_cg(const void* p, uint32_t (&r)[8]) {   // L2 only: the slabs are rewritten by other SMs
+  asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// In-place tile (two 16-bit input streams, two output streams, 256 columns) without TMA: thread = accumulator row, a warp owns
+// 64 columns = four 16-column steps of one 32-byte vector per stream; the loads of step k + 2 are in flight while step k is
+// computed.  in0 / in1 / out0 / out1 point at this thread's row (element offset of the warp's first column included) or are
+// nullptr for rows beyond T.  Ends with every lane's stores fenced and ONE release by lane 0.
+template <class Epi>
+__device__ __forceinline__ void mega_inplace_direct(const Epi& epi, uint32_t taddr, uint64_t* tmem_full, uint32_t full_phase,
+                                                    uint32_t tmem_empty_remote, int lane, int col0, const uint16_t* in0,
+                                                    const uint16_t* in1, uint16_t* out0, uint16_t* out1, MegaSig sig,
+                                                    uint32_t* tt) {
+  uint32_t buf[2][2][8];   // [step parity][stream][8]
+  const bool valid = out0 != nullptr;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (Epi::kIn > 0 && valid) {
+      ldg256_cg(in0 + 16 * k, buf[k][0]);
+      ldg256_cg(in1 + 16 * k, buf[k][1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) buf[k][0][j] = buf[k][1][j] = 0u;
+    }
+  }
+  const uint32_t c_a = (uint32_t)clock();
+  mbar_wait(tmem_full, full_phase);
+  tc_fence_after();
+  const uint32_t c_b = (uint32_t)clock();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float v[16];
+    tmem_ld16(taddr + 16 * k, v);
+    if (k == 3) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tmem_empty_remote);
+    }
+    uint32_t o[2][8];
+    if constexpr (Epi::kIn > 0) epi.compute(col0 + 16 * k, v, buf[k & 1], o);
+    else epi.compute(col0 + 16 * k, v, o);
+    if (Epi::kIn > 0 && k + 2 < 4 && valid) {
+      ldg256_cg(in0 + 16 * (k + 2), buf[k & 1][0]);
+      ldg256_cg(in1 + 16 * (k + 2), buf[k & 1][1]);
+    }
+    if (valid) {
+      stg256(out0 + 16 * k, o[0]);
+      stg256(out1 + 16 * k, o[1]);
+    }
+  }
+  const uint32_t c_c = (uint32_t)clock();
+  __threadfence();          // this lane's stores are visible device-wide ...
+  __syncwarp();             // ... before lane 0 publishes the tile
+  if (lane == 0) mega_signal(sig);
+  __syncwarp();
+  tt[0] += c_b - c_a;
+  tt[1] += c_c - c_b;
+  tt[2] += (uint32_t)clock() - c_c;
   tt[3] += 1;
 }
 
@@ -630,6 +706,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
                                                          ibar, it, &p.g_c16[t.layer], &p.a_c16[t.layer], &p.b_c16[t.layer],
                                                          nullptr, nullptr, b, r0, t.nt * (MEGA_BN / 2),
                                                          MegaSig{mega_gflag(p, t.layer, t.rt), dcnt}, prev, p.dbg, tt);
+      } else if (t.type == MEGA_R && p.res_direct) {
+        if (lane == 0 && !(p.dbg & 1)) mega_wait_flag(mega_gflag(p, t.layer, t.rt), gtarget);  // implies R(layer-1, rt) is complete
+        __syncwarp();
+        const int trow = r0 + lane;                      // row within the batch item
+        const bool ok = trow < p.T;
+        const size_t off = ((size_t)b * p.T + trow) * MEGA_BN + cg * (MEGA_BN / 4);
+        mega_inplace_direct<SplitTcEpi<true>>(split_epi, tile + ((uint32_t)(q * 32) << 16) + cg * (MEGA_BN / 4), &s.tmem_full[acc],
+                                              acc_phase, te, lane, cg * (MEGA_BN / 4), ok ? p.hi_ptr[t.layer] + off : nullptr,
+                                              ok ? p.lo_ptr[t.layer] + off : nullptr,
+                                              ok ? p.hi_out_ptr[t.layer + 1] + off : nullptr,
+                                              ok ? p.lo_ptr[t.layer + 1] + off : nullptr,
+                                              MegaSig{mega_rflag(p, t.layer, t.rt), dcnt}, tt + 4);
       } else if (t.type == MEGA_R) {
         if (lane == 0) {  // chunk 0 of the layer input's (hi, lo) pair, ahead of the accumulator
           if (!(p.dbg & 1)) mega_wait_flag(mega_gflag(p, t.layer, t.rt), gtarget);  // implies R(layer-1, rt) is complete
@@ -700,6 +788,13 @@ struct alignas(64) MegaBwdParams {
   uint32_t idesc, desc_lbo, desc_sbo;
   int lag, total_tasks;
   int dual;                       // see MegaParams::dual
+  // direct global loads / stores in the epilogues (see MegaParams::res_direct)
+  const uint16_t* sa_ptr[MEGA_D];   // saved tanh     [rows][Cd]
+  const uint16_t* sb_ptr[MEGA_D];   // saved sigmoid  [rows][Cd]
+  uint16_t* dpre_ptr[MEGA_D];       // dpre_i         [rows][2Cd]
+  uint16_t* dhi_ptr[MEGA_D];        // dh_i hi halves [rows][Cr]
+  uint16_t* dlo_ptr[MEGA_D];        // dh_i lo halves [rows][Cr]
+  int direct;
 };
 
 __host__ __device__ __forceinline__ MegaTask mega_bwd_decode(const MegaBwdParams& p, int idx) {
@@ -913,6 +1008,36 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
       const uint32_t dcnt = smem_u32(done_cnt + (seq++ & 3));
       const bool last = t.layer == p.depth - 1;
       const int c0 = cg * (MEGA_BN / 4);
+      if (p.direct) {
+        const int trow = r0 + lane;
+        const bool ok = trow < p.T;
+        const size_t row = (size_t)b * p.T + trow;
+        const uint32_t ta = tile + ((uint32_t)(q * 32) << 16) + c0;
+        if (t.type == MEGA_DG) {
+          const size_t oi = row * MEGA_BN + c0, oo = row * (2 * MEGA_BN) + c0;
+          mega_inplace_direct<GateBwdTcEpi>(gbwd_epi, ta, &s.tmem_full[acc], acc_phase, te, lane, c0,
+                                            ok ? p.sa_ptr[t.layer] + oi : nullptr, ok ? p.sb_ptr[t.layer] + oi : nullptr,
+                                            ok ? p.dpre_ptr[t.layer] + oo : nullptr,
+                                            ok ? p.dpre_ptr[t.layer] + oo + MEGA_BN : nullptr,
+                                            MegaSig{mega_bwd_gflag(p, t.layer, t.rt), dcnt}, tt);
+        } else if (!last) {
+          if (lane == 0) mega_wait_flag(mega_bwd_xflag(p, t.layer + 1, t.rt), target);   // the upstream (hi, lo) pair is complete
+          __syncwarp();
+          const size_t o = row * MEGA_BN + c0;
+          mega_inplace_direct<SplitTcEpi<true>>(add_epi, ta, &s.tmem_full[acc], acc_phase, te, lane, c0,
+                                                ok ? p.dhi_ptr[t.layer + 1] + o : nullptr, ok ? p.dlo_ptr[t.layer + 1] + o : nullptr,
+                                                ok ? p.dhi_ptr[t.layer] + o : nullptr, ok ? p.dlo_ptr[t.layer] + o : nullptr,
+                                                MegaSig{mega_bwd_xflag(p, t.layer, t.rt), dcnt}, tt);
+        } else {
+          const size_t o = row * MEGA_BN + c0;
+          mega_inplace_direct<SplitTcEpi<false>>(first_epi, ta, &s.tmem_full[acc], acc_phase, te, lane, c0, nullptr, nullptr,
+                                                 ok ? p.dhi_ptr[t.layer] + o : nullptr, ok ? p.dlo_ptr[t.layer] + o : nullptr,
+                                                 MegaSig{mega_bwd_xflag(p, t.layer, t.rt), dcnt}, tt);
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       if (t.type == MEGA_DG) {
         if (lane == 0) {  // chunk 0 of the saved tanh / sigmoid values (written by the forward: always ready)
           fence_proxy_async_all();

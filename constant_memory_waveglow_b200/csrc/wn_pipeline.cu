@@ -222,6 +222,17 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
   // R(u) must come after G(u) and before G(u + RT - 1) (its right-hand neighbour one layer up): lag <= RT - 2
   p.lag = mega_fwd_lag(p.RT);
   p.dual = mega_dual();
+  {
+    // measured SLOWER than the TMA chunks (whole WN forward 0.540 vs 0.503 ms, saving 0.598 vs 0.560: row-per-thread 32-byte
+    // accesses and a device-scope fence per lane cost more than the queueing they avoid): opt-in, kept for the comparison
+    const char* e = getenv("CMWG_MEGA_RDIRECT");
+    p.res_direct = (e && e[0] == '1') ? 1 : 0;
+    for (int i = 0; i < d.depth; ++i) {
+      p.hi_ptr[i] = reinterpret_cast<const uint16_t*>(hin[i]);
+      p.hi_out_ptr[i] = reinterpret_cast<uint16_t*>(hin[i]);
+      p.lo_ptr[i] = reinterpret_cast<uint16_t*>(hlo[i]);
+    }
+  }
   if (mega_end_fused(d)) {
     p.lst = lst;
     p.w_end = reinterpret_cast<const float*>(pk + PL.wEnd);
@@ -286,6 +297,17 @@ static int wn_backward_mega(const WnDims& d, const PackedLayout& PL, const BwdLa
   p.desc_lbo = 1u; p.desc_sbo = 1024u >> 4;
   p.lag = mega_bwd_lag(p.RT);
   p.dual = mega_dual();
+  {
+    const char* e = getenv("CMWG_MEGA_RDIRECT");   // see wn_forward_mega: opt-in, measured slower
+    p.direct = (e && e[0] == '1') ? 1 : 0;
+    for (int i = 0; i < d.depth; ++i) {
+      p.sa_ptr[i] = reinterpret_cast<const uint16_t*>(sa[i]);
+      p.sb_ptr[i] = reinterpret_cast<const uint16_t*>(sb[i]);
+      p.dpre_ptr[i] = reinterpret_cast<uint16_t*>(dpre[i]);
+      p.dhi_ptr[i] = reinterpret_cast<uint16_t*>(dh_hi[i]);
+      p.dlo_ptr[i] = reinterpret_cast<uint16_t*>(dh_lo[i]);
+    }
+  }
   p.total_tasks = p.RT + 2 * (d.depth * p.RT + p.lag);
   p.flags = reinterpret_cast<uint32_t*>(ws + BL.flags);
   CMWG_CHECK_CUDA(cudaMemsetAsync(p.flags, 0, (size_t)d.depth * 2 * p.RT * 4, st));
