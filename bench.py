@@ -38,10 +38,11 @@ FWD_GFLOP_PER_SEGMENT = 214.023  # algorithmic, counted on the reference (BASELI
 # kernel ends), from the `ncu --set full` capture summarised in profiles/r01_v5_ncu_gemm_summary.txt.
 # Algorithmic bytes of the same launch: 48000 x (512 hi + 256 y in, 512 g out) = 61.4 MB.
 GATE_TRAFFIC_BYTES_PER_LAUNCH = 38.9e6
-# dram__bytes_read.sum + dram__bytes_write.sum per wn_fwd_mega_kernel launch at B=24 (ncu --set full): 1143 MB for the forward
-# variant (profiles/r01_v9_ncu_fused_forward_summary.txt), 1760 MB for the recompute variant that also stores tanh / sigmoid
-# (profiles/r01_v13_ncu_task_kernels_summary.txt); a step launches 12 of each
-FUSED_TRAFFIC_BYTES_PER_LAUNCH = 0.5 * (1143.1e6 + 1759.5e6)
+# dram__bytes_read.sum + dram__bytes_write.sum per wn_fwd_mega_kernel launch at B=24, fp16 operands (ncu --set full,
+# profiles/r02_v3_ncu_mega_metrics.txt): 1118 MB for the forward variant (573.5 read + 544.4 written: g per layer, (hi, lo) per
+# layer; the fp32 skip slab is no longer written), 1662 MB for the recompute variant that also stores tanh / sigmoid and the
+# skip slab (701.1 + 960.5); a step launches 12 of each
+FUSED_TRAFFIC_BYTES_PER_LAUNCH = 0.5 * (1117.9e6 + 1661.6e6)
 TRAIN_GFLOP_PER_SEGMENT = 4 * FWD_GFLOP_PER_SEGMENT
 SYNTH_FRAMES = 862               # 10 s at 22.05 kHz -> 220672 samples (model/base.py:47-48)
 GLOBAL_BATCH = 24                # configs/waveglow_LJ_speech.json:31; train.py:51-53 divides it by the GPU count

@@ -87,6 +87,7 @@ struct alignas(64) MegaParams {
   uint16_t* lo_ptr[MEGA_D];         // layer inputs, lo halves
   uint16_t* hi_out_ptr[MEGA_D];     // same slabs, writable view (hi_out_ptr[i] = hi_ptr[i])
   int res_direct;
+  int gate_mix;                 // GateTcEpi::mix
   float* lst;                   // (B, cout, T) fp32 NCL
   const float* w_end;           // [MEGA_END_MAXC][Cs] fp32, rows >= cout zero
   int cout;
@@ -662,7 +663,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
     const uint32_t wbuf = smem_u32(s.epi + e * WB);
     uint64_t* ibar = s.in_bar + e;
     const uint32_t tmem_empty_addr = mapa_shared(smem_u32(&s.tmem_empty[0]), 0);
-    const GateTcEpi<SAVE> gate_epi{nullptr, p.Cd, p.f16};
+    const GateTcEpi<SAVE> gate_epi{nullptr, p.Cd, p.f16, p.gate_mix};
     const SplitTcEpi<true> split_epi{nullptr, p.f16};
     const StoreTcEpi store_epi{nullptr, nullptr};
     int acc = 0;
