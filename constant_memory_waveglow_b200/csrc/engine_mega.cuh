@@ -63,13 +63,14 @@ struct alignas(64) MegaParams {
   CUtensorMap g_op[MEGA_D];     // operand maps: gate outputs
   CUtensorMap cond_op;          // operand map: packed conditioning
   CUtensorMap pa[MEGA_D], pb[MEGA_D], ps;                       // weights (64 x 128-row boxes)
-  CUtensorMap g_c16[MEGA_D], a_c16[MEGA_D], b_c16[MEGA_D];      // 32 x 32 chunk maps: gate outputs (a, b: saved tanh / sigmoid)
+  CUtensorMap g_c16[MEGA_D], b_c16[MEGA_D];                     // 32 x 32 chunk maps: gate outputs, saved sigmoid
   CUtensorMap hi_c16[MEGA_D], lo_c16[MEGA_D];                   // chunk maps: (hi, lo) pair of every layer's INPUT
   CUtensorMap skip_c32;                                         // fp32 chunk map: cumulative skip
   uint32_t* flags;              // [depth][2][RT]: gate-done / residual-done counters (zeroed before the launch)
   int depth, B, T, tiles_per_batch, RT;
   int ngt;                      // gate N tiles
   int taps, kb_h, kb_c, kb_g;   // taps; k-blocks per tap / of the conditioning / of one gate output
+  int kc_last;                  // K = 16 steps of the conditioning's last k-block that hold real channels (1 .. 4)
   int Cd, f16;
   uint32_t idesc, desc_lbo, desc_sbo;
   int lag;                      // residual tiles trail their gate tiles by `lag` row-tile slots (< RT - 1)
@@ -87,6 +88,7 @@ struct alignas(64) MegaParams {
   uint16_t* lo_ptr[MEGA_D];         // layer inputs, lo halves
   uint16_t* hi_out_ptr[MEGA_D];     // same slabs, writable view (hi_out_ptr[i] = hi_ptr[i])
   int res_direct;
+  int res_lo;                   // 1: the residual stream is a (hi, lo) pair of 16-bit slabs; 0: the operand slab alone (AddTcEpi)
   int gate_mix;                 // GateTcEpi::mix
   float* lst;                   // (B, cout, T) fp32 NCL
   const float* w_end;           // [MEGA_END_MAXC][Cs] fp32, rows >= cout zero
@@ -392,6 +394,59 @@ __device__ __forceinline__ void mega_inplace_direct(const Epi& epi, uint32_t tad
   tt[3] += 1;
 }
 
+// Residual tile on a single 16-bit stream (AddTcEpi).  The caller has issued BOTH 32-column chunks of the layer input into the
+// warp's two staging buffers (one mbarrier phase); each chunk is updated in place and stored.
+__device__ __forceinline__ void mega_res1_task(const AddTcEpi& epi, uint32_t tmem_tile, uint64_t* tmem_full, uint32_t full_phase,
+                                               uint32_t tmem_empty_remote, int q, int cg, int lane, uint32_t wbuf, uint64_t* ibar,
+                                               uint32_t& it, const CUtensorMap* om, int b, int r0, MegaSig sig, uint32_t* tt) {
+  const uint32_t taddr = tmem_tile + ((uint32_t)(q * 32) << 16) + cg * (MEGA_BN / 4);
+  const uint32_t c_a = (uint32_t)clock();
+  mbar_wait(tmem_full, full_phase);
+  tc_fence_after();
+  mbar_wait(ibar, it & 1);
+  ++it;
+  const uint32_t c_b = (uint32_t)clock();
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int c0 = cg * (MEGA_BN / 4) + 32 * k;
+    const uint32_t buf = wbuf + k * TC_CHUNK16_BYTES;
+    uint32_t in[16];
+    stage_load16(buf, lane, in);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[16];
+      tmem_ld16(taddr + 32 * k + 16 * h, v);
+      if (h == 1 && k == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_remote);
+      }
+      uint32_t inh[1][8], o[1][8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) inh[0][j] = in[8 * h + j];
+      epi.compute(c0 + 16 * h, v, inh, o);
+      stage_store16h(buf, lane, h, o[0]);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(om, buf, c0, r0, 0, b);
+      bulk_commit();
+    }
+  }
+  const uint32_t c_c = (uint32_t)clock();
+  if (lane == 0) {
+    bulk_wait_all();            // stores COMPLETE: the results are in global memory
+    mega_signal(sig);
+  }
+  __syncwarp();
+  tt[0] += c_b - c_a;
+  tt[1] += c_c - c_b;
+  tt[2] += (uint32_t)clock() - c_c;
+  tt[3] += 1;
+}
+
 constexpr int MEGA_END_MAXC = 16;   // output channels of the fused `end` conv (2 * in_channels; every shipped config has <= 8)
 
 // Skip tile with the `end` 1x1 conv in its epilogue.  A warp owns 32 rows x 64 of the tile's 256 skip channels: it folds its
@@ -633,6 +688,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
         tc_fence_after();
         w_empty += clock64() - c0;
         const uint32_t d_tmem = tmem_base + acc * MEGA_BN;
+        // the conditioning's channels are padded to whole k-blocks with zeros (80 -> 128): the K = 16 steps that would
+        // multiply nothing but padding are not issued (3 of the 56 steps of a gate tile at the LJ config)
+        const int kb_trim = t.type == MEGA_G ? total_kb - 1 : -1;
         for (int kb = 0; kb < total_kb; ++kb) {
           c0 = clock64();
           mbar_wait(&s.full[stage], phase);
@@ -641,9 +699,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
           const uint32_t sa = smem_u32(s.stages + stage * MEGA_STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(sa, p.desc_lbo, p.desc_sbo);
           const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES, p.desc_lbo, p.desc_sbo);
+          const int nk = kb == kb_trim ? p.kc_last : TC_BK / 16;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (k < nk) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&s.empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -665,6 +724,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
     const uint32_t tmem_empty_addr = mapa_shared(smem_u32(&s.tmem_empty[0]), 0);
     const GateTcEpi<SAVE> gate_epi{nullptr, p.Cd, p.f16, p.gate_mix};
     const SplitTcEpi<true> split_epi{nullptr, p.f16};
+    const AddTcEpi add_epi{nullptr, p.f16};
     const StoreTcEpi store_epi{nullptr, nullptr};
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -704,10 +764,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
       prev_alt = alt;
       if (t.type == MEGA_G) {
         mega_epilogue_task<GateTcEpi<SAVE>, MEGA_BN / 2>(gate_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, ubuf,
-                                                         ibar, it, &p.g_c16[t.layer], &p.a_c16[t.layer], &p.b_c16[t.layer],
+                                                         ibar, it, &p.g_c16[t.layer], &p.b_c16[t.layer], nullptr,
                                                          nullptr, nullptr, b, r0, t.nt * (MEGA_BN / 2),
                                                          MegaSig{mega_gflag(p, t.layer, t.rt), dcnt}, prev, p.dbg, tt);
-      } else if (t.type == MEGA_R && p.res_direct) {
+      } else if (t.type == MEGA_R && p.res_direct && p.res_lo) {
         if (lane == 0 && !(p.dbg & 1)) mega_wait_flag(mega_gflag(p, t.layer, t.rt), gtarget);  // implies R(layer-1, rt) is complete
         __syncwarp();
         const int trow = r0 + lane;                      // row within the batch item
@@ -719,6 +779,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
                                               ok ? p.hi_out_ptr[t.layer + 1] + off : nullptr,
                                               ok ? p.lo_ptr[t.layer + 1] + off : nullptr,
                                               MegaSig{mega_rflag(p, t.layer, t.rt), dcnt}, tt + 4);
+      } else if (t.type == MEGA_R && !p.res_lo) {
+        if (lane == 0) {  // the warp's whole share of the layer input (two chunks), ahead of the accumulator
+          mega_wait_flag(mega_gflag(p, t.layer, t.rt), gtarget);  // implies R(layer-1, rt) is complete
+          fence_proxy_async_all();
+          mbar_arrive_expect_tx(ibar, 2 * TC_CHUNK16_BYTES);
+          const int c0 = cg * (MEGA_BN / 4);
+          tma_load_4d_local(wbuf, &p.hi_c16[t.layer], smem_u32(ibar), c0, r0, 0, b);
+          tma_load_4d_local(wbuf + TC_CHUNK16_BYTES, &p.hi_c16[t.layer], smem_u32(ibar), c0 + 32, r0, 0, b);
+        }
+        __syncwarp();
+        mega_res1_task(add_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf, ibar, it, &p.hi_c16[t.layer + 1], b, r0,
+                       MegaSig{mega_rflag(p, t.layer, t.rt), dcnt}, tt + 4);
       } else if (t.type == MEGA_R) {
         if (lane == 0) {  // chunk 0 of the layer input's (hi, lo) pair, ahead of the accumulator
           if (!(p.dbg & 1)) mega_wait_flag(mega_gflag(p, t.layer, t.rt), gtarget);  // implies R(layer-1, rt) is complete
@@ -779,7 +851,7 @@ struct alignas(64) MegaBwdParams {
   CUtensorMap dskip_op;           // operand map: gradient of the cumulative skip
   CUtensorMap dpre_op[MEGA_D];    // operand maps: dpre_i [rows][2Cd]
   CUtensorMap q1[MEGA_D], q2[MEGA_D];                       // W_o^T and W^T (per tap) weights
-  CUtensorMap sa_c16[MEGA_D], sb_c16[MEGA_D];               // chunk maps: saved tanh / sigmoid
+  CUtensorMap sa_c16[MEGA_D], sb_c16[MEGA_D];               // chunk maps: gate output g / saved sigmoid (GateBwdTcEpi)
   CUtensorMap dpt_c16[MEGA_D], dps_c16[MEGA_D];             // chunk maps: tanh / sigmoid halves of dpre_i
   CUtensorMap dhi_c16[MEGA_D], dlo_c16[MEGA_D];             // chunk maps: (hi, lo) pair of dh_i
   uint32_t* flags;                // [depth][2][RT]: DG-done / DX-done counters (zeroed before the launch)
@@ -790,12 +862,13 @@ struct alignas(64) MegaBwdParams {
   int lag, total_tasks;
   int dual;                       // see MegaParams::dual
   // direct global loads / stores in the epilogues (see MegaParams::res_direct)
-  const uint16_t* sa_ptr[MEGA_D];   // saved tanh     [rows][Cd]
+  const uint16_t* sa_ptr[MEGA_D];   // gate output g  [rows][Cd]
   const uint16_t* sb_ptr[MEGA_D];   // saved sigmoid  [rows][Cd]
   uint16_t* dpre_ptr[MEGA_D];       // dpre_i         [rows][2Cd]
   uint16_t* dhi_ptr[MEGA_D];        // dh_i hi halves [rows][Cr]
   uint16_t* dlo_ptr[MEGA_D];        // dh_i lo halves [rows][Cr]
   int direct;
+  int res_lo;                       // see MegaParams::res_lo (here: the residual GRADIENT stream)
 };
 
 __host__ __device__ __forceinline__ MegaTask mega_bwd_decode(const MegaBwdParams& p, int idx) {
@@ -993,6 +1066,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
     const GateBwdTcEpi gbwd_epi{p.f16};
     const SplitTcEpi<true> add_epi{nullptr, p.f16};
     const SplitTcEpi<false> first_epi{nullptr, p.f16};
+    const AddTcEpi add1_epi{nullptr, p.f16};
+    const RoundTcEpi round_epi{p.f16};
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t it = 0, seq = 0;
@@ -1009,7 +1084,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
       const uint32_t dcnt = smem_u32(done_cnt + (seq++ & 3));
       const bool last = t.layer == p.depth - 1;
       const int c0 = cg * (MEGA_BN / 4);
-      if (p.direct) {
+      if (p.direct && p.res_lo) {
         const int trow = r0 + lane;
         const bool ok = trow < p.T;
         const size_t row = (size_t)b * p.T + trow;
@@ -1040,7 +1115,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
         continue;
       }
       if (t.type == MEGA_DG) {
-        if (lane == 0) {  // chunk 0 of the saved tanh / sigmoid values (written by the forward: always ready)
+        if (lane == 0) {  // chunk 0 of the gate output / saved sigmoid (written by the forward: always ready)
           fence_proxy_async_all();
           mbar_arrive_expect_tx(ibar, 2 * TC_CHUNK16_BYTES);
           tma_load_4d_local(wbuf, &p.sa_c16[t.layer], smem_u32(ibar), c0, r0, 0, b);
@@ -1051,6 +1126,21 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
                                                   &p.dpt_c16[t.layer], &p.dps_c16[t.layer], nullptr, &p.sa_c16[t.layer],
                                                   &p.sb_c16[t.layer], b, r0, 0,
                                                   MegaSig{mega_bwd_gflag(p, t.layer, t.rt), dcnt}, nullptr, 0, tt);
+      } else if (!last && !p.res_lo) {
+        if (lane == 0) {  // the warp's whole share of the upstream residual gradient (two chunks of one stream)
+          mega_wait_flag(mega_bwd_xflag(p, t.layer + 1, t.rt), target);
+          fence_proxy_async_all();
+          mbar_arrive_expect_tx(ibar, 2 * TC_CHUNK16_BYTES);
+          tma_load_4d_local(wbuf, &p.dhi_c16[t.layer + 1], smem_u32(ibar), c0, r0, 0, b);
+          tma_load_4d_local(wbuf + TC_CHUNK16_BYTES, &p.dhi_c16[t.layer + 1], smem_u32(ibar), c0 + 32, r0, 0, b);
+        }
+        __syncwarp();
+        mega_res1_task(add1_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf, ibar, it, &p.dhi_c16[t.layer], b, r0,
+                       MegaSig{mega_bwd_xflag(p, t.layer, t.rt), dcnt}, tt);
+      } else if (!p.res_lo) {
+        mega_epilogue_task<RoundTcEpi, MEGA_BN>(round_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf, ibar, it,
+                                                &p.dhi_c16[t.layer], nullptr, nullptr, nullptr, nullptr, b, r0, 0,
+                                                MegaSig{mega_bwd_xflag(p, t.layer, t.rt), dcnt}, nullptr, 0, tt);
       } else if (!last) {
         if (lane == 0) {  // chunk 0 of the upstream residual gradient's (hi, lo) pair
           mega_wait_flag(mega_bwd_xflag(p, t.layer + 1, t.rt), target);

@@ -18,11 +18,14 @@
 namespace cmwg {
 
 // ---- gate: g = tanh(pre_t) * sigmoid(pre_s)  (model/waveglow.py:13-15,42-44) ---------------------
-// SAVE additionally stores tanh(pre_t) and sigmoid(pre_s) for the backward pass.
+// SAVE additionally stores sigmoid(pre_s) for the backward pass.  tanh(pre_t) is NOT stored: the backward recovers it as
+// g / sigmoid (GateBwdTcEpi), so a saving gate tile writes two 16-bit streams instead of three -- both fit the two staging
+// buffers of an epilogue warp at once (no wait for the first stores before the third stream can be staged) and a WN
+// forward with saves writes 25 % fewer bytes.
 template <bool SAVE>
 struct GateTcEpi {
   static constexpr bool kPaired = true, kOutF32 = false;
-  static constexpr int kOut = SAVE ? 3 : 1, kIn = 0, kOutBufs = 1, kColGroups = 4;
+  static constexpr int kOut = SAVE ? 2 : 1, kIn = 0, kOutBufs = 1, kColGroups = 4;
   const float* bias;  // nullptr or [2][Cd]
   int Cd, f16;
   int mix;            // fp16 path: odd columns take e^(-y) from the FMA pipe (exp2_fma), even columns from MUFU.EX2
@@ -44,7 +47,7 @@ struct GateTcEpi {
           gate_ex2<SAVE, false>(lo[j], hi[j], a0, b0, g0);
           gate_ex2<SAVE, true>(lo[j + 1], hi[j + 1], a1, b1, g1);
           o[0][j >> 1] = pack2(g0, g1, 1);
-          if constexpr (SAVE) { o[1][j >> 1] = pack2(a0, a1, 1); o[2][j >> 1] = pack2(b0, b1, 1); }
+          if constexpr (SAVE) o[1][j >> 1] = pack2(b0, b1, 1);
         }
       } else {
 #pragma unroll
@@ -53,7 +56,7 @@ struct GateTcEpi {
           gate_ex2<SAVE>(lo[j], hi[j], a0, b0, g0);
           gate_ex2<SAVE>(lo[j + 1], hi[j + 1], a1, b1, g1);
           o[0][j >> 1] = pack2(g0, g1, 1);
-          if constexpr (SAVE) { o[1][j >> 1] = pack2(a0, a1, 1); o[2][j >> 1] = pack2(b0, b1, 1); }
+          if constexpr (SAVE) o[1][j >> 1] = pack2(b0, b1, 1);
         }
       }
     } else {
@@ -62,7 +65,7 @@ struct GateTcEpi {
         float a0 = tanh_f<true>(lo[j]), a1 = tanh_f<true>(lo[j + 1]);
         float b0 = sigmoid_f<true>(hi[j]), b1 = sigmoid_f<true>(hi[j + 1]);
         o[0][j >> 1] = pack2(a0 * b0, a1 * b1, 0);
-        if constexpr (SAVE) { o[1][j >> 1] = pack2(a0, a1, 0); o[2][j >> 1] = pack2(b0, b1, 0); }
+        if constexpr (SAVE) o[1][j >> 1] = pack2(b0, b1, 0);
       }
     }
   }
@@ -130,10 +133,73 @@ struct SplitTcEpi {
   }
 };
 
+// ---- residual add on ONE 16-bit stream: out = rn16(acc + in) ---------------------------------------
+// fp16 operands: the residual stream (forward) and its gradient (backward) are carried as the operand slab alone.  The extra rounding per layer
+// (2^-12 relative, on a stream every dilated conv re-reads rounded to fp16 anyway) measures as +20 % on the error of the WN
+// output (profiles/r02_precision.json), and a residual tile moves half the bytes: its whole input fits the warp's two staging
+// buffers, so nothing is loaded while the accumulator waits.  bf16 operands (8 mantissa bits) keep the (hi, lo) pair.
+template <int CG = 4>
+struct AddTcEpiT {
+  static constexpr bool kPaired = false, kOutF32 = false;
+  static constexpr int kOut = 1, kIn = 1, kOutBufs = 1, kColGroups = CG;
+  const float* bias;
+  int f16;
+  __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
+  __device__ __forceinline__ int in_col(int, int c0) const { return c0; }
+  __device__ __forceinline__ void compute(int col0, float (&v)[16], const uint32_t (&in)[1][8], uint32_t (&o)[1][8]) const {
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + col0 + j);
+    }
+    if (f16) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        float h0, h1;
+        unpack2(in[0][j >> 1], 1, h0, h1);
+        o[0][j >> 1] = pack2(v[j] + h0, v[j + 1] + h1, 1);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        float h0, h1;
+        unpack2(in[0][j >> 1], 0, h0, h1);
+        o[0][j >> 1] = pack2(v[j] + h0, v[j + 1] + h1, 0);
+      }
+    }
+  }
+};
+
+using AddTcEpi = AddTcEpiT<4>;
+
+// ---- plain 16-bit store: out = rn16(acc)  (first tile of a single-stream chain: nothing to add) ----
+struct RoundTcEpi {
+  static constexpr bool kPaired = false, kOutF32 = false;
+  static constexpr int kOut = 1, kIn = 0, kOutBufs = 1, kColGroups = 4;
+  int f16;
+  __device__ __forceinline__ int out_col(int, int c0) const { return c0; }
+  __device__ __forceinline__ int in_col(int, int c0) const { return c0; }
+  __device__ __forceinline__ void compute(int, float (&v)[16], uint32_t (&o)[1][8]) const {
+    if (f16) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) o[0][j >> 1] = pack2(v[j], v[j + 1], 1);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) o[0][j >> 1] = pack2(v[j], v[j + 1], 0);
+    }
+  }
+};
+
 // ---- gate backward: dpre = dg * d(tanh * sigmoid) ------------------------------------------------
-// inputs: saved tanh / sigmoid values; outputs: the tanh-half and sigmoid-half gradients, columns
-// [0, Cd) and [Cd, 2Cd) of the dpre slab (two tensor maps, one per column window).  With fp16 operands
-// the accumulator holds S * dg (gradient scale, wn_kernels.cuh); the functor is linear in it.
+// inputs: the gate output g = tanh * sigmoid and the saved sigmoid (both 16-bit slabs of the recompute); tanh = g / sigmoid
+// (one MUFU.RCP; where the sigmoid has underflowed to 0 so has g, and both gradient halves carry a factor sigmoid = 0);
+// outputs: the tanh-half and sigmoid-half gradients, columns [0, Cd) and [Cd, 2Cd) of the dpre slab (two tensor maps, one
+// per column window).  With fp16 operands the accumulator holds S * dg (gradient scale, wn_kernels.cuh); the functor is
+// linear in it.
+__device__ __forceinline__ float tanh_from_gate(float g, float s) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaxf(s, 5.9604645e-8f)));   // smallest fp16 subnormal: s = 0 -> g = 0 -> 0
+  return fminf(fmaxf(g * r, -1.f), 1.f);
+}
 struct GateBwdTcEpi {
   static constexpr bool kPaired = false, kOutF32 = false;
   static constexpr int kOut = 2, kIn = 2, kOutBufs = 1, kColGroups = 4;
@@ -144,9 +210,10 @@ struct GateBwdTcEpi {
   __device__ __forceinline__ void run(float (&v)[16], const uint32_t (&in)[2][8], uint32_t (&o)[2][8]) const {
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
-      float a0, a1, b0, b1;
-      unpack2(in[0][j >> 1], F16, a0, a1);
+      float g0, g1, b0, b1;
+      unpack2(in[0][j >> 1], F16, g0, g1);
       unpack2(in[1][j >> 1], F16, b0, b1);
+      const float a0 = tanh_from_gate(g0, b0), a1 = tanh_from_gate(g1, b1);
       float t0 = v[j] * b0, t1 = v[j + 1] * b1;  // dg * sigmoid
       o[0][j >> 1] = pack2(t0 * (1.f - a0 * a0), t1 * (1.f - a1 * a1), F16);
       o[1][j >> 1] = pack2(t0 * a0 * (1.f - b0), t1 * a1 * (1.f - b1), F16);

@@ -18,10 +18,10 @@ __device__ __forceinline__ float block_sum128(float v, float* red) {
 __global__ void __launch_bounds__(128) upsample_fwd_kernel(const float* __restrict__ h, const float* __restrict__ g,
                                                            const float* __restrict__ v,
                                                            const float* __restrict__ bias, int C, int F, int K,
-                                                           int stride, int pad, int Tout, float* __restrict__ y) {
+                                                           int stride, int pad, int Tout, float* __restrict__ y,
+                                                           int stage_h) {
   extern __shared__ float sm[];
   float* w = sm;       // [K]
-  float* hs = sm + K;  // [F]
   __shared__ float red[4];
   int b = blockIdx.x / C, c = blockIdx.x % C;
   float ss = 0.f;
@@ -30,7 +30,14 @@ __global__ void __launch_bounds__(128) upsample_fwd_kernel(const float* __restri
     w[k] = vv;
     ss = fmaf(vv, vv, ss);
   }
-  for (int f = threadIdx.x; f < F; f += 128) hs[f] = h[((long long)b * C + c) * F + f];
+  // the row of frames is staged in shared memory when it fits (stage_h); a longer row (full-utterance super-resolution:
+  // F = T / 16 frames with upsample factor 1) is read in place -- consecutive outputs touch consecutive frames, L1 serves them
+  const float* hs = h + ((long long)b * C + c) * F;
+  if (stage_h) {
+    float* hsm = sm + K;  // [F]
+    for (int f = threadIdx.x; f < F; f += 128) hsm[f] = hs[f];
+    hs = hsm;
+  }
   ss = block_sum128(ss, red);
   float scale = g ? g[c] / sqrtf(ss) : 1.f;
   float bv = bias ? bias[c] : 0.f;
@@ -195,8 +202,10 @@ int cmwg_upsample_fwd(const float* h, const float* g, const float* v, const floa
                stride, pad);
   if (B == 0 || C == 0) return CMWG_OK;
   size_t smem = (size_t)(K + F) * sizeof(float);
-  CMWG_REQUIRE(smem <= 48 * 1024, "cmwg_upsample_fwd: F=%d frames exceed the shared-memory staging buffer", F);
-  upsample_fwd_kernel<<<B * C, 128, smem, (cudaStream_t)stream>>>(h, g, v, bias, C, F, K, stride, pad, Tout, y);
+  const int stage_h = smem <= 48 * 1024 ? 1 : 0;
+  if (!stage_h) smem = (size_t)K * sizeof(float);
+  CMWG_REQUIRE(smem <= 48 * 1024, "cmwg_upsample_fwd: K=%d taps exceed the shared-memory staging buffer", K);
+  upsample_fwd_kernel<<<B * C, 128, smem, (cudaStream_t)stream>>>(h, g, v, bias, C, F, K, stride, pad, Tout, y, stage_h);
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
   return CMWG_OK;

@@ -481,7 +481,8 @@ static __global__ void __launch_bounds__(256) start_bwd_kernel(const float* __re
     if (t < T) {
       long long off = ((long long)b * T + t) * Cr + o;
       // tc engine: dh_0 arrives as a (hi, lo) 16-bit pair, scaled by the gradient scale
-      val = dh0 ? dh0[off] : (op16_to_f32(dh_hi[off], is_fp16) + op16_to_f32(dh_lo[off], is_fp16)) * inv_scale;
+      val = dh0 ? dh0[off]
+                : (op16_to_f32(dh_hi[off], is_fp16) + (dh_lo ? op16_to_f32(dh_lo[off], is_fp16) : 0.f)) * inv_scale;
     }
     dhs[r * LD + o] = val;
   }
@@ -533,8 +534,9 @@ __device__ __forceinline__ void load_row8(const float* __restrict__ p32, const u
     const float4 a = *reinterpret_cast<const float4*>(p32 + off), b = *reinterpret_cast<const float4*>(p32 + off + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   } else {
-    // (hi, lo) 16-bit pair: value = hi + lo
-    const uint4 h = *reinterpret_cast<const uint4*>(hi + off), l = *reinterpret_cast<const uint4*>(lo + off);
+    // (hi, lo) 16-bit pair: value = hi + lo  (lo == nullptr: single-stream residual gradient, value = hi)
+    const uint4 h = *reinterpret_cast<const uint4*>(hi + off);
+    const uint4 l = lo ? *reinterpret_cast<const uint4*>(lo + off) : make_uint4(0u, 0u, 0u, 0u);
     const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
     if (is_fp16) {
 #pragma unroll

@@ -208,7 +208,7 @@ inline void make_fwd_layout(const WnDims& d, int B, int T, FwdLayout* L) {
   for (int i = 0; i < d.depth; ++i) {
     L->s_hin[i] = take(rows * d.Cr * d.opsize);
     L->s_g[i] = take(rows * d.Cd * d.opsize);
-    L->s_a[i] = take(rows * d.Cd * d.opsize);
+    L->s_a[i] = d.tc ? L->s_g[i] : take(rows * d.Cd * d.opsize);   // tcgen05 engine: tanh is not saved (= g / sigmoid)
     L->s_b[i] = take(rows * d.Cd * d.opsize);
   }
   L->s_skip = take(rows * d.Cs * 4);

@@ -168,6 +168,15 @@ static inline int gate_mix() {
   return v;
 }
 
+// Residual stream of the tcgen05 engine (forward) and its gradient (backward): (hi, lo) pair of 16-bit slabs, or the operand
+// slab alone (AddTcEpi: fp16 operands only -- bf16's 8 mantissa bits need the pair).  CMWG_RES_LO=1 keeps the pair with fp16
+// too (read at every call).
+static inline bool fwd_res_lo(const WnDims& d) {
+  if (d.prec != CMWG_PREC_FP16) return true;
+  const char* e = getenv("CMWG_RES_LO");
+  return e && e[0] == '1';
+}
+
 static inline bool mega_shapes_ok(const WnDims& d, int B, int T) {
   return d.tc && d.H == 1 && !d.bias && d.depth >= 1 && d.depth <= MEGA_D && d.Cr == 256 && d.Cs == 256 &&
          d.Cd % 128 == 0 && d.bn_gate == 256 && (((d.radix - 1) / 2) << (d.depth - 1)) <= 2 * TC_BM && d.radix <= 7 &&
@@ -192,7 +201,7 @@ static int mega_launch(const MegaParams& p, cudaStream_t st) {
   return CMWG_OK;
 }
 
-// hin(i) / hlo(i): (hi, lo) slabs of layer i's input; gop(i), sa(i), sb(i): gate output and saved tanh / sigmoid
+// hin(i) / hlo(i): (hi, lo) slabs of layer i's input; gop(i), sb(i): gate output and saved sigmoid
 static inline bool mega_end_fused(const WnDims& d) {  // CMWG_MEGA_END=0: separate end conv kernel (read at every call: tests flip it)
   const char* e = getenv("CMWG_MEGA_END");
   return !(e && e[0] == '0') && 2 * d.cin <= MEGA_END_MAXC && !d.bias && d.Cs == MEGA_BN;
@@ -200,21 +209,20 @@ static inline bool mega_end_fused(const WnDims& d) {  // CMWG_MEGA_END=0: separa
 
 static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLayout& FL, const uint8_t* pk, uint8_t* ws,
                            const void* ycl, int B, int T, bool save, int f16, void* const* hin, void* const* hlo,
-                           void* const* gop, void* const* sa, void* const* sb, float* skip32, float* lst, cudaStream_t st) {
+                           void* const* gop, void* const* sb, float* skip32, float* lst, cudaStream_t st) {
   MegaParams p;
   memset(&p, 0, sizeof(p));
+  const bool res_lo = fwd_res_lo(d);
+  p.res_lo = res_lo ? 1 : 0;
   for (int i = 0; i < d.depth; ++i) {
     CMWG_PROPAGATE(get_slab_map(&p.hin_op[i], hin[i], d.Cr, d.Cr, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
     CMWG_PROPAGATE(get_slab_map(&p.g_op[i], gop[i], d.Cd, d.Cd, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
     CMWG_PROPAGATE(get_matrix_map(&p.pa[i], pk + PL.PA[i], d.KA, d.npadA, MEGA_BN / 2, f16));
     if (i < d.depth - 1) CMWG_PROPAGATE(get_matrix_map(&p.pb[i], pk + PL.PB[i], d.ldPB, d.nb(i), MEGA_BN / 2, f16));
     CMWG_PROPAGATE(get_slab_map(&p.g_c16[i], gop[i], d.Cd, d.Cd, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
-    if (save) {
-      CMWG_PROPAGATE(get_slab_map(&p.a_c16[i], sa[i], d.Cd, d.Cd, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
-      CMWG_PROPAGATE(get_slab_map(&p.b_c16[i], sb[i], d.Cd, d.Cd, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
-    }
+    if (save) CMWG_PROPAGATE(get_slab_map(&p.b_c16[i], sb[i], d.Cd, d.Cd, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
     CMWG_PROPAGATE(get_slab_map(&p.hi_c16[i], hin[i], d.Cr, d.Cr, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
-    CMWG_PROPAGATE(get_slab_map(&p.lo_c16[i], hlo[i], d.Cr, d.Cr, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+    if (res_lo) CMWG_PROPAGATE(get_slab_map(&p.lo_c16[i], hlo[i], d.Cr, d.Cr, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
   }
   CMWG_PROPAGATE(get_slab_map(&p.cond_op, ycl, d.auxp, d.auxp, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
   CMWG_PROPAGATE(get_matrix_map(&p.ps, pk + PL.PS, d.ldPS, d.Cs, MEGA_BN / 2, f16));
@@ -225,6 +233,11 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
   p.ngt = d.npadA / MEGA_BN;
   p.taps = d.R; p.kb_h = d.Crp / TC_BK; p.kb_c = d.auxp / TC_BK; p.kb_g = d.Cdp / TC_BK;
   p.Cd = d.Cd; p.f16 = f16;
+  {
+    const char* e = getenv("CMWG_MEGA_KTRIM");   // CMWG_MEGA_KTRIM=0: issue the padded K steps too (A/B timing)
+    const int real_last = d.aux - (p.kb_c - 1) * TC_BK;
+    p.kc_last = (e && e[0] == '0') ? TC_BK / 16 : std::max(1, std::min(TC_BK / 16, ceil_div(real_last, 16)));
+  }
   p.idesc = make_idesc(f16, 2 * TC_BM, MEGA_BN, 0, 0);
   p.desc_lbo = 1u; p.desc_sbo = 1024u >> 4;
   // R(u) must come after G(u) and before G(u + RT - 1) (its right-hand neighbour one layer up): lag <= RT - 2
@@ -282,6 +295,7 @@ static int wn_backward_mega(const WnDims& d, const PackedLayout& PL, const BwdLa
                             void* const* dpre, const void* const* sa, const void* const* sb, cudaStream_t st) {
   MegaBwdParams p;
   memset(&p, 0, sizeof(p));
+  p.res_lo = fwd_res_lo(d) ? 1 : 0;
   for (int i = 0; i < d.depth; ++i) {
     CMWG_PROPAGATE(get_slab_map(&p.dh_op[i], dh_hi[i], d.Cr, d.Cr, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
     CMWG_PROPAGATE(get_slab_map(&p.dpre_op[i], dpre[i], 2 * d.Cd, 2 * d.Cd, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
@@ -294,7 +308,7 @@ static int wn_backward_mega(const WnDims& d, const PackedLayout& PL, const BwdLa
     CMWG_PROPAGATE(get_slab_map(&p.dps_c16[i], (const uint16_t*)dpre[i] + d.Cd, d.Cd, 2 * d.Cd, T, 1, B, 32, 32, f16,
                                 TC_MAP_CHUNK16));
     CMWG_PROPAGATE(get_slab_map(&p.dhi_c16[i], dh_hi[i], d.Cr, d.Cr, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
-    CMWG_PROPAGATE(get_slab_map(&p.dlo_c16[i], dh_lo[i], d.Cr, d.Cr, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
+    if (p.res_lo) CMWG_PROPAGATE(get_slab_map(&p.dlo_c16[i], dh_lo[i], d.Cr, d.Cr, T, 1, B, 32, 32, f16, TC_MAP_CHUNK16));
   }
   CMWG_PROPAGATE(get_slab_map(&p.dskip_op, dskip, d.Cs, d.Cs, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
   p.depth = d.depth; p.B = B; p.T = T;
@@ -378,7 +392,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
     // tc: (hi, lo) 16-bit pair; ff inference: h32 only (operand aliases it); ff training: fp32 copy per layer
     float* o32 = (!TC && !keep) ? h32 : nullptr;
     OpT* oop = (TC || keep) ? hin_op(0) : nullptr;
-    OpT* olo = TC ? hlo_op(0) : nullptr;
+    OpT* olo = (TC && fwd_res_lo(d)) ? hlo_op(0) : nullptr;
     CMWG_PROPAGATE(smallk_to_slab<OpT>(x, x_bs, reinterpret_cast<const float*>(pk + PL.wStart), d.cin, 1,
                                        d.bias ? reinterpret_cast<const float*>(pk + PL.biasStart) : nullptr, d.cin,
                                        d.Cr, B, d.H * T, o32, oop, olo, f16, st, t_off, t_n));
@@ -387,12 +401,12 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
   bool fused = false;
   if constexpr (TC) {
     if (mega_enabled() && !stt && lw.nh == 0 && mega_shapes_ok(d, B, T)) {
-      void *hin[MEGA_D], *hlo[MEGA_D], *gop[MEGA_D], *sa[MEGA_D], *sb[MEGA_D];
+      void *hin[MEGA_D], *hlo[MEGA_D], *gop[MEGA_D], *sb[MEGA_D];
       for (int i = 0; i < d.depth; ++i) {
         hin[i] = hin_op(i); hlo[i] = hlo_op(i); gop[i] = g_op(i);
-        sa[i] = save ? sv + FL.s_a[i] : nullptr; sb[i] = save ? sv + FL.s_b[i] : nullptr;
+        sb[i] = save ? sv + FL.s_b[i] : nullptr;
       }
-      CMWG_PROPAGATE(wn_forward_mega(d, PL, FL, pk, ws, ycl, B, T, save, f16, hin, hlo, gop, sa, sb, skip32, lst, st));
+      CMWG_PROPAGATE(wn_forward_mega(d, PL, FL, pk, ws, ycl, B, T, save, f16, hin, hlo, gop, sb, skip32, lst, st));
       fused = true;
     }
   }
@@ -420,8 +434,7 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
         memset(&io, 0, sizeof(io));
         io.out[0] = op_stream(g_op(i), d.Cd);
         if (save) {
-          io.out[1] = op_stream(sv + FL.s_a[i], d.Cd);
-          io.out[2] = op_stream(sv + FL.s_b[i], d.Cd);
+          io.out[1] = op_stream(sv + FL.s_b[i], d.Cd);   // the backward recovers tanh as g / sigmoid (GateBwdTcEpi)
           GateTcEpi<true> epi{biasA, d.Cd, f16, gate_mix()};
           CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
         } else {
@@ -450,12 +463,18 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
         g.B = B; g.T = T; g.H = d.H; g.h0 = lw.h0; g.nh = lw.nh; g.bn = pick_bn(d.Cr); g.is_fp16 = f16; g.tag = CMWG_KCLASS_RESSKIP;
         TcIo io;
         memset(&io, 0, sizeof(io));
+        const float* biasB = d.bias ? reinterpret_cast<const float*>(pk + PL.biasB[i]) : nullptr;
         io.in[0] = op_stream(hin_op(i), d.Cr);
-        io.in[1] = op_stream(hlo_op(i), d.Cr);
         io.out[0] = op_stream(hin_op(i + 1), d.Cr);
-        io.out[1] = op_stream(hlo_op(i + 1), d.Cr);
-        SplitTcEpi<true> epi{d.bias ? reinterpret_cast<const float*>(pk + PL.biasB[i]) : nullptr, f16};
-        CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+        if (fwd_res_lo(d)) {
+          io.in[1] = op_stream(hlo_op(i), d.Cr);
+          io.out[1] = op_stream(hlo_op(i + 1), d.Cr);
+          SplitTcEpi<true> epi{biasB, f16};
+          CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+        } else {
+          AddTcEpi epi{biasB, f16};   // fp16 operands: the residual stream is the operand slab alone
+          CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+        }
       }
     } else {
       // ---- residual / skip GEMM (fp32 engine: read-modify-write epilogue)
@@ -678,7 +697,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       const void *sa[MEGA_D], *sb[MEGA_D];
       for (int i = 0; i < d.depth; ++i) {
         hh[i] = dhi(i); hl[i] = dlo(i); dp[i] = dpre_l(i);
-        sa[i] = sv + FL.s_a[i]; sb[i] = sv + FL.s_b[i];
+        sa[i] = sv + FL.s_g[i]; sb[i] = sv + FL.s_b[i];   // gate output and saved sigmoid (tanh = g / sigmoid)
       }
       CMWG_PROPAGATE(wn_backward_mega(d, PL, BL, pk, ws, B, T, f16, hh, hl, dskip_op, dp, sa, sb, st));
     }
@@ -771,7 +790,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       if constexpr (TC) {
         TcIo io;
         memset(&io, 0, sizeof(io));
-        io.in[0] = op_stream(sv + FL.s_a[i], d.Cd);
+        io.in[0] = op_stream(sv + FL.s_g[i], d.Cd);    // gate output; tanh = g / sigmoid
         io.in[1] = op_stream(sv + FL.s_b[i], d.Cd);
         // two column windows of the dpre slab: each map exposes only its own Cd channels, so a partial
         // N tile (Cd < BN) is clipped instead of spilling into the other half
@@ -871,15 +890,26 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
         TcIo io;
         memset(&io, 0, sizeof(io));
         io.out[0] = op_stream(dhi(i), d.Cr);
-        io.out[1] = op_stream(dlo(i), d.Cr);
-        if (!last) {  // the upstream residual gradient (hi, lo) is added in the epilogue
-          io.in[0] = op_stream(dhi(i + 1), d.Cr);
-          io.in[1] = op_stream(dlo(i + 1), d.Cr);
-          SplitTcEpi<true, 2> epi{nullptr, f16};  // K = R*2Cd is long: trade epilogue width for operand stages
-          CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+        if (!fwd_res_lo(d)) {   // fp16 operands: the residual gradient is the operand slab alone
+          if (!last) {
+            io.in[0] = op_stream(dhi(i + 1), d.Cr);
+            AddTcEpiT<2> epi{nullptr, f16};
+            CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+          } else {
+            RoundTcEpi epi{f16};
+            CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+          }
         } else {
-          SplitTcEpi<false> epi{nullptr, f16};
-          CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+          io.out[1] = op_stream(dlo(i), d.Cr);
+          if (!last) {  // the upstream residual gradient (hi, lo) is added in the epilogue
+            io.in[0] = op_stream(dhi(i + 1), d.Cr);
+            io.in[1] = op_stream(dlo(i + 1), d.Cr);
+            SplitTcEpi<true, 2> epi{nullptr, f16};  // K = R*2Cd is long: trade epilogue width for operand stages
+            CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+          } else {
+            SplitTcEpi<false> epi{nullptr, f16};
+            CMWG_PROPAGATE(tc_gemm_launch(g, io, epi, st));
+          }
         }
       } else {
         DxEpi<OpT> epi;
@@ -949,7 +979,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     float* scratch = pb + (size_t)nblk * d.Cr;
     const float* a32 = TC ? nullptr : dh32;
     const uint16_t* ahi = TC ? reinterpret_cast<const uint16_t*>(dhi(0)) : nullptr;
-    const uint16_t* alo = TC ? reinterpret_cast<const uint16_t*>(dlo(0)) : nullptr;
+    const uint16_t* alo = (TC && fwd_res_lo(d)) ? reinterpret_cast<const uint16_t*>(dlo(0)) : nullptr;
     float* pbs = (d.bias && gr->start.bias) ? pb : nullptr;
     int nblk_s = nblk;
     if (d.Cr == 256 && d.cin >= 1 && d.cin <= 8) {

@@ -14,13 +14,21 @@ natural bucket is "one flow" (~17.9 MB fp32 at the LJ config) plus one bucket fo
   * a post-accumulate-grad hook counts arrivals; when a bucket is complete its all-reduce is issued
     immediately with ``async_op=True`` -- NCCL runs it on its own stream over NVLink/NVSwitch while
     the compute stream proceeds with the next flow's recompute + gradient GEMMs;
-  * ``finish()`` waits for the outstanding collectives and averages.
+  * ``finish()`` waits for the outstanding collectives and averages (NCCL: the collective itself averages,
+    ``ReduceOp.AVG``; other backends: one fused multiply over all buckets);
+  * all buckets are windows of ONE flat buffer, so the exchange can also be issued as a single all-reduce at
+    the end of the backward: ``mode="deferred"`` (or ``CMWG_GRAD_SYNC=deferred``).  The persistent tensor-core
+    kernels of the WN hold every SM with one CTA each and need all their CTA pairs resident; an NCCL kernel
+    that gets an SM first delays the whole grid by its own run time, once per bucket (measured, 8 x B200: the
+    forward task kernel slows 0.46 -> 0.55 ms per launch under the overlapped exchange).  One 215 MB all-reduce
+    over NVSwitch is ~0.5 ms unhidden; which of the two is cheaper is a measurement (``bench.py``).
 
 Works with any process group backend (``nccl`` on the B200 box, ``gloo`` in the CPU tests).
 Inference shards independent utterances across ranks and needs no collective (``shard_utterances``).
 """
 from __future__ import annotations
 
+import os
 from typing import Iterable, List, Optional, Sequence
 
 import torch
@@ -57,19 +65,39 @@ def flow_buckets(model) -> List[List[torch.nn.Parameter]]:
 
 
 class FlowGradSync:
-    def __init__(self, buckets: Sequence[Sequence[torch.nn.Parameter]], process_group=None):
+    def __init__(self, buckets: Sequence[Sequence[torch.nn.Parameter]], process_group=None, mode: Optional[str] = None):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.mode = (mode or os.environ.get("CMWG_GRAD_SYNC", "overlap")).lower()
+        if self.mode not in ("overlap", "deferred"):
+            raise ValueError(f"FlowGradSync: mode must be 'overlap' or 'deferred', got {self.mode!r}")
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then one fused multiply
+        self._avg_in_collective = bool(dist.is_initialized() and dist.get_backend(process_group) == "nccl")
         self.buckets = [list(b) for b in buckets]
         self.flat: List[torch.Tensor] = []
         self._pending: List[int] = []
         self._works = []
         self._launch_order: List[int] = []
         self._handles = []
+        # one allocation for all buckets (each window starts on a 256-byte boundary) when they share device and dtype
+        sizes = [sum(p.numel() for p in params) for params in self.buckets]
+        firsts = [params[0] for params in self.buckets]
+        uniform = len({(p.device, p.dtype) for p in firsts}) <= 1
+        self.whole: Optional[torch.Tensor] = None
+        starts: List[int] = []
+        if uniform and firsts:
+            off = 0
+            for n in sizes:
+                starts.append(off)
+                off += (n + 63) // 64 * 64
+            self.whole = torch.zeros(off, device=firsts[0].device, dtype=firsts[0].dtype)
+        elif self.mode == "deferred":
+            raise ValueError("FlowGradSync: mode='deferred' needs all parameters on one device with one dtype")
         for bi, params in enumerate(self.buckets):
-            n = sum(p.numel() for p in params)
+            n = sizes[bi]
             p0 = params[0]
-            flat = torch.zeros(n, device=p0.device, dtype=p0.dtype)
+            flat = self.whole[starts[bi]:starts[bi] + n] if self.whole is not None else \
+                torch.zeros(n, device=p0.device, dtype=p0.dtype)
             self.flat.append(flat)
             off = 0
             for p in params:
@@ -101,10 +129,13 @@ class FlowGradSync:
                 self._launch(bi)
         return hook
 
+    def _reduce_op(self):
+        return dist.ReduceOp.AVG if self._avg_in_collective else dist.ReduceOp.SUM
+
     def _launch(self, bi: int) -> None:
         self._launch_order.append(bi)
-        if self.world > 1:
-            self._works.append(dist.all_reduce(self.flat[bi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if self.world > 1 and self.mode == "overlap":
+            self._works.append(dist.all_reduce(self.flat[bi], op=self._reduce_op(), group=self.group, async_op=True))
 
     def zero_grad(self) -> None:
         """Drop all gradients (``p.grad = None``) so that the next backward writes / adopts them in place;
@@ -127,13 +158,17 @@ class FlowGradSync:
                     self._adopt(p)
                 if self.world > 1:
                     self._launch(bi)
+        if self.world > 1 and self.mode == "deferred":
+            self._works.append(dist.all_reduce(self.whole, op=self._reduce_op(), group=self.group, async_op=True))
         for w in self._works:
             w.wait()
         self._works.clear()
-        if self.world > 1:
+        if self.world > 1 and not self._avg_in_collective:
             inv = 1.0 / self.world
-            for f in self.flat:
-                f.mul_(inv)
+            if self.whole is not None:
+                self.whole.mul_(inv)
+            else:
+                torch._foreach_mul_(self.flat, inv)
 
     @property
     def launch_order(self) -> List[int]:

@@ -122,7 +122,8 @@ def test_nll_loss_and_gradient(B, T, mean):
     assert rel_l2(zc.grad, gz) < 1e-6 and rel_l2(lc.grad, gl) < 1e-6
 
 
-@pytest.mark.parametrize("C,F_,K,stride,pad", [(80, 63, 65, 32, 16), (8, 8, 65, 32, 16), (5, 40, 3, 1, 1), (3, 7, 9, 4, 2)])
+@pytest.mark.parametrize("C,F_,K,stride,pad", [(80, 63, 65, 32, 16), (8, 8, 65, 32, 16), (5, 40, 3, 1, 1), (3, 7, 9, 4, 2),
+                                                 (2, 13000, 3, 1, 1)])   # a frame row longer than the 48 KB staging buffer
 def test_upsampler_forward_backward(C, F_, K, stride, pad):
     g0 = torch.Generator().manual_seed(C + K)
     B = 2

@@ -37,7 +37,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, mode="overlap"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -58,7 +58,8 @@ def _worker(rank, world, port, out):
 
         buckets = flow_buckets(model)
         assert len(buckets) == 4 and len(buckets[0]) == 5       # flow 2 first, upsampler last
-        sync = FlowGradSync(buckets)
+        sync = FlowGradSync(buckets, mode=mode)
+        assert sync.whole is not None and all(f.data_ptr() >= sync.whole.data_ptr() for f in sync.flat)
         for step in range(2):
             sync.zero_grad()
             model(xs[rank]).backward()
@@ -75,12 +76,13 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_flow_grad_sync_two_ranks_gloo():
+@pytest.mark.parametrize("mode", ["overlap", "deferred"])   # per-flow all-reduces during the backward / one at its end
+def test_flow_grad_sync_two_ranks_gloo(mode):
     world = 2
     port = _free_port()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, out, mode), nprocs=world, join=True)
     assert dict(out) == {0: 1, 1: 1}
 
 
