@@ -71,6 +71,12 @@ struct alignas(64) MegaParams {
   int ngt;                      // gate N tiles
   int taps, kb_h, kb_c, kb_g;   // taps; k-blocks per tap / of the conditioning / of one gate output
   int kc_last;                  // K = 16 steps of the conditioning's last k-block that hold real channels (1 .. 4)
+  // layer 0 with the start conv folded in (PackedLayout::PA0f / PB0f): its gate tiles read only the conditioning slab (whose
+  // padding columns carry the taps of x_a), its residual tiles add one k-block of that slab (W_start x_a = h_0) to W_res g_0
+  // and have nothing to load in their epilogue
+  int fold0;
+  int kc_last0;                 // as kc_last, counting the x_a columns too
+  CUtensorMap pa0f, pb0f;
   int Cd, f16;
   uint32_t idesc, desc_lbo, desc_sbo;
   int lag;                      // residual tiles trail their gate tiles by `lag` row-tile slots (< RT - 1)
@@ -605,17 +611,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
           if (!(p.dbg & 16)) fence_proxy_async_all();
         }
         w_flag += clock64() - cf;
+        const bool f0 = p.fold0 && t.layer == 0;
         if (t.type == MEGA_G) {
           const int n0 = t.nt * MEGA_BN + nrow;
-          for (int sg = 0; sg < p.taps; ++sg) {
-            const int shift = (sg - (p.taps - 1) / 2) * (1 << t.layer);
-            for (int kb = 0; kb < p.kb_h; ++kb)
-              load(&p.hin_op[t.layer], kb * TC_BK, t0 + shift, b, &p.pa[t.layer], sg * Crp + kb * TC_BK, n0);
+          if (f0) {
+            for (int kb = 0; kb < p.kb_c; ++kb) load(&p.cond_op, kb * TC_BK, t0, b, &p.pa0f, kb * TC_BK, n0);
+          } else {
+            for (int sg = 0; sg < p.taps; ++sg) {
+              const int shift = (sg - (p.taps - 1) / 2) * (1 << t.layer);
+              for (int kb = 0; kb < p.kb_h; ++kb)
+                load(&p.hin_op[t.layer], kb * TC_BK, t0 + shift, b, &p.pa[t.layer], sg * Crp + kb * TC_BK, n0);
+            }
+            for (int kb = 0; kb < p.kb_c; ++kb)
+              load(&p.cond_op, kb * TC_BK, t0, b, &p.pa[t.layer], p.taps * Crp + kb * TC_BK, n0);
           }
-          for (int kb = 0; kb < p.kb_c; ++kb)
-            load(&p.cond_op, kb * TC_BK, t0, b, &p.pa[t.layer], p.taps * Crp + kb * TC_BK, n0);
         } else if (t.type == MEGA_R) {
-          for (int kb = 0; kb < p.kb_g; ++kb) load(&p.g_op[t.layer], kb * TC_BK, t0, b, &p.pb[t.layer], kb * TC_BK, nrow);
+          const CUtensorMap* bm = f0 ? &p.pb0f : &p.pb[t.layer];
+          for (int kb = 0; kb < p.kb_g; ++kb) load(&p.g_op[t.layer], kb * TC_BK, t0, b, bm, kb * TC_BK, nrow);
+          if (f0) load(&p.cond_op, (p.kb_c - 1) * TC_BK, t0, b, bm, p.kb_g * TC_BK, nrow);
         } else {
           for (int j = 0; j < p.depth; ++j)
             for (int kb = 0; kb < p.kb_g; ++kb)
@@ -660,12 +673,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
         const MegaTask t = mega_decode(p, task);
         if (t.type == MEGA_NONE) continue;
         const int nrow = rank * (MEGA_BN / 2);
+        const bool f0 = p.fold0 && t.layer == 0;
         if (t.type == MEGA_G) {
           const int n0 = t.nt * MEGA_BN + nrow;
-          const int nkb = p.taps * p.kb_h + p.kb_c;
-          for (int kb = 0; kb < nkb; ++kb) loadb(&p.pa[t.layer], kb * TC_BK, n0);
+          const int nkb = f0 ? p.kb_c : p.taps * p.kb_h + p.kb_c;
+          const CUtensorMap* bm = f0 ? &p.pa0f : &p.pa[t.layer];
+          for (int kb = 0; kb < nkb; ++kb) loadb(bm, kb * TC_BK, n0);
         } else if (t.type == MEGA_R) {
-          for (int kb = 0; kb < p.kb_g; ++kb) loadb(&p.pb[t.layer], kb * TC_BK, nrow);
+          const CUtensorMap* bm = f0 ? &p.pb0f : &p.pb[t.layer];
+          for (int kb = 0; kb < p.kb_g + (f0 ? 1 : 0); ++kb) loadb(bm, kb * TC_BK, nrow);
         } else {
           for (int kb = 0; kb < p.depth * p.kb_g; ++kb) loadb(&p.ps, kb * TC_BK, nrow);
         }
@@ -682,7 +698,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
       for (int task = pair; task < p.total_tasks; task += npairs) {
         const MegaTask t = mega_decode(p, task);
         if (t.type == MEGA_NONE) continue;
-        const int total_kb = t.type == MEGA_G ? p.taps * p.kb_h + p.kb_c : (t.type == MEGA_R ? p.kb_g : p.depth * p.kb_g);
+        const bool f0 = p.fold0 && t.layer == 0;
+        const int total_kb = t.type == MEGA_G ? (f0 ? p.kb_c : p.taps * p.kb_h + p.kb_c)
+                                              : (t.type == MEGA_R ? p.kb_g + (f0 ? 1 : 0) : p.depth * p.kb_g);
         long long c0 = clock64();
         mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -690,7 +708,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
         const uint32_t d_tmem = tmem_base + acc * MEGA_BN;
         // the conditioning's channels are padded to whole k-blocks with zeros (80 -> 128): the K = 16 steps that would
         // multiply nothing but padding are not issued (3 of the 56 steps of a gate tile at the LJ config)
-        const int kb_trim = t.type == MEGA_G ? total_kb - 1 : -1;
+        const int kb_trim = (t.type == MEGA_G || (t.type == MEGA_R && f0)) ? total_kb - 1 : -1;
+        const int nk_trim = f0 ? p.kc_last0 : p.kc_last;
         for (int kb = 0; kb < total_kb; ++kb) {
           c0 = clock64();
           mbar_wait(&s.full[stage], phase);
@@ -699,7 +718,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
           const uint32_t sa = smem_u32(s.stages + stage * MEGA_STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(sa, p.desc_lbo, p.desc_sbo);
           const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES, p.desc_lbo, p.desc_sbo);
-          const int nk = kb == kb_trim ? p.kc_last : TC_BK / 16;
+          const int nk = kb == kb_trim ? nk_trim : TC_BK / 16;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             if (k < nk) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -725,6 +744,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
     const GateTcEpi<SAVE> gate_epi{nullptr, p.Cd, p.f16, p.gate_mix};
     const SplitTcEpi<true> split_epi{nullptr, p.f16};
     const AddTcEpi add_epi{nullptr, p.f16};
+    const RoundTcEpi round_epi{p.f16};
     const StoreTcEpi store_epi{nullptr, nullptr};
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -779,6 +799,11 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_fwd_mega_kernel(const __gr
                                               ok ? p.hi_out_ptr[t.layer + 1] + off : nullptr,
                                               ok ? p.lo_ptr[t.layer + 1] + off : nullptr,
                                               MegaSig{mega_rflag(p, t.layer, t.rt), dcnt}, tt + 4);
+      } else if (t.type == MEGA_R && p.fold0 && t.layer == 0) {
+        // h_1 = W_res g_0 + W_start x_a, all of it from the tensor core: nothing to load, one 16-bit stream to store
+        mega_epilogue_task<RoundTcEpi, MEGA_BN>(round_epi, tile, &s.tmem_full[acc], acc_phase, te, q, cg, lane, wbuf, ibar, it,
+                                                &p.hi_c16[1], nullptr, nullptr, nullptr, nullptr, b, r0, 0,
+                                                MegaSig{mega_rflag(p, 0, t.rt), dcnt}, prev, p.dbg, tt + 4);
       } else if (t.type == MEGA_R && !p.res_lo) {
         if (lane == 0) {  // the warp's whole share of the layer input (two chunks), ahead of the accumulator
           mega_wait_flag(mega_gflag(p, t.layer, t.rt), gtarget);  // implies R(layer-1, rt) is complete

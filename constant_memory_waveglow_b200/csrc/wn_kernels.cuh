@@ -221,6 +221,100 @@ static __global__ void __launch_bounds__(256) pack_operands_kernel(const PackPar
   }
 }
 
+// Layer 0 with the start conv folded in (wn_layout.cuh: PA0f / PB0f).  Column aux + tap * cin + c of the conditioning slab
+// holds x_a[c] at the tap's time offset, so
+//   PA0f[n][aux + tap * cin + c] = sum_ic W_0[oc(n)][ic][tap] * W_start[ic][c]      (gate rows in PA's interleaved order)
+//   PB0f[n][Cdp + j]             = W_start[n][c]  where column (auxp - kb) + j is the centre tap's channel c
+// and everything else is PA's conditioning block / PB's W_o block / zero.
+struct Fold0Params {
+  WnDims d;
+  const float* wV;      // [depth * 2Cd][aux]
+  const float* wW0;     // [2Cd][Cr][R]
+  const float* wWo0;    // [nb(0)][Cd]
+  const float* wStart;  // [Cr][cin]
+  uint16_t* PA0f;
+  uint16_t* PB0f;
+  int is_fp16;
+};
+static __global__ void __launch_bounds__(256) pack_fold0_kernel(const Fold0Params p) {
+  const WnDims& d = p.d;
+  const long long nA = (long long)d.npadA * d.auxp, ldB = d.Cdp + d.kb, nB = (long long)d.Cr * ldB;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < nA + nB; idx += (long long)gridDim.x * 256) {
+    float val = 0.f;
+    if (idx < nA) {
+      const int n = (int)(idx / d.auxp), k = (int)(idx % d.auxp);
+      const int tile = n / d.bn_gate, r = n % d.bn_gate;
+      const int half = r / d.G, ch = tile * d.G + (r % d.G);
+      if (ch < d.Cd) {
+        const int oc = half * d.Cd + ch;
+        if (k < d.aux) {
+          val = p.wV[(long long)oc * d.aux + k];
+        } else if (k < d.aux + d.R * d.cin) {
+          const int tap = (k - d.aux) / d.cin, c = (k - d.aux) % d.cin;
+          const float* w = p.wW0 + (long long)oc * d.Cr * d.R + tap;
+          for (int ic = 0; ic < d.Cr; ++ic) val = fmaf(w[(long long)ic * d.R], p.wStart[ic * d.cin + c], val);
+        }
+      }
+      p.PA0f[idx] = f32_to_op16(val, p.is_fp16);
+    } else {
+      const long long j = idx - nA;
+      const int n = (int)(j / ldB), k = (int)(j % ldB);
+      if (k < d.Cd) {
+        val = p.wWo0[(long long)n * d.Cd + k];
+      } else if (k >= d.Cdp) {
+        const int col = d.auxp - d.kb + (k - d.Cdp);               // column of the conditioning slab
+        const int c = col - d.aux - ((d.R - 1) / 2) * d.cin;       // channel under the centre tap
+        if (c >= 0 && c < d.cin) val = p.wStart[n * d.cin + c];
+      }
+      p.PB0f[j] = f32_to_op16(val, p.is_fp16);
+    }
+  }
+}
+
+// taps of x_a into the padding columns of the conditioning slab: ycl[row][aux + tap * cin + c] = x[b][c][t + (tap - centre)]
+// (zero outside [0, T): the dilated conv's 'same' padding of h_0 = W_start x_a, which has no bias here)
+static __global__ void __launch_bounds__(256) cond_aug_kernel(const float* __restrict__ x, long long x_bs, int cin, int R,
+                                                              int B, int T, uint16_t* __restrict__ ycl, int aux, int auxp,
+                                                              int is_fp16) {
+  pdl_trigger();
+  pdl_wait();
+  const long long rows = (long long)B * T;
+  const int per = R * cin, ct = (R - 1) / 2;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < rows * per; idx += (long long)gridDim.x * 256) {
+    // consecutive threads walk consecutive time steps of one (tap, channel): coalesced reads
+    const long long row = idx % rows;
+    const int j = (int)(idx / rows), tap = j / cin, c = j % cin;
+    const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+    const int ts = t + tap - ct;
+    const float v = (ts >= 0 && ts < T) ? x[b * x_bs + (long long)c * T + ts] : 0.f;
+    ycl[row * auxp + aux + j] = f32_to_op16(v, is_fp16);
+  }
+}
+
+// Weight gradient of layer 0's dilated conv through the fold.  With h_0 = W_start x_a never materialised,
+//   dW_0[oc][ic][tap] = sum_t dpre_0[t][oc] h_0[t + shift_tap][ic] = sum_c D[oc][tap * cin + c] W_start[ic][c],
+//   D[oc][tap * cin + c] = sum_t dpre_0[t][oc] x_a[c][t + shift_tap]
+// and D is what the conditioning weight-gradient GEMM of layer 0 (dV_0 = dpre_0^T ycond) leaves in the columns of its tile
+// that face the x_a taps in the conditioning slab: columns [aux, aux + R * cin).  One CTA per output channel.
+static __global__ void __launch_bounds__(256) fold0_dw_kernel(const float* __restrict__ tile, int splits, int M, int N, int aux,
+                                                              int cin, int R, int Cr, const float* __restrict__ wStart,
+                                                              const float* __restrict__ gscale, float* __restrict__ dW) {
+  __shared__ float Drow[64];
+  const int oc = blockIdx.x, per = R * cin;
+  if (threadIdx.x < per) {
+    float sacc = 0.f;
+    for (int j = 0; j < splits; ++j) sacc += tile[((long long)j * M + oc) * N + aux + threadIdx.x];   // fixed order
+    Drow[threadIdx.x] = sacc * (gscale ? gscale[2] : 1.f);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < Cr * R; idx += 256) {
+    const int ic = idx / R, tap = idx - ic * R;
+    float a = 0.f;
+    for (int c = 0; c < cin; ++c) a = fmaf(Drow[tap * cin + c], wStart[ic * cin + c], a);
+    dW[(long long)oc * Cr * R + idx] = a;
+  }
+}
+
 struct BiasPackParams {
   WnDims d;
   const float* bV;

@@ -117,8 +117,18 @@ struct PackedLayout {
   size_t Q1[CMWG_MAX_DEPTH];  // dgate GEMM     [Cd][k1(i)]          = W_o^T
   size_t Q2[CMWG_MAX_DEPTH];  // dx GEMM        [Cr][ldQ2]           = W^T per tap
   size_t QV[CMWG_MAX_DEPTH];  // dy GEMM        [auxp][ldQV] shared; QV[i] points at column i*Cd2p
+  // layer 0 with the start conv folded in (fold0_ok): h_0 = W_start x_a has K = in_channels, so layer 0's dilated conv is
+  // a K = taps * in_channels GEMM in disguise.  The taps of x_a ride in the padding columns of the conditioning slab.
+  size_t PA0f;                // gate GEMM of layer 0   [npadA][auxp]: V_0 | W_0,tap W_start per tap | 0
+  size_t PB0f;                // residual GEMM of layer 0 [Cr][Cdp + kb]: W_res,0 | W_start under the centre tap's columns
   size_t total;
 };
+
+// Layer 0 can run without the start conv when the taps of x_a fit behind the conditioning channels in the LAST k-block of the
+// padded conditioning slab (1-D WN on the tcgen05 engine, no bias, at least one residual layer).
+inline bool fold0_shapes_ok(const WnDims& d) {
+  return d.tc && d.H == 1 && !d.bias && d.depth >= 2 && d.aux - (d.auxp - d.kb) + d.R * d.cin <= d.kb;
+}
 
 inline PackedLayout make_packed_layout(const WnDims& d) {
   PackedLayout L;
@@ -147,6 +157,8 @@ inline PackedLayout make_packed_layout(const WnDims& d) {
     L.Q2[i] = take((size_t)d.Cr * d.ldQ2 * d.opsize);
     L.QV[i] = qv_base + (size_t)i * d.Cd2p * d.opsize;
   }
+  L.PA0f = take((size_t)d.npadA * d.auxp * d.opsize);
+  L.PB0f = take((size_t)d.Cr * (d.Cdp + d.kb) * d.opsize);
   L.total = off;
   return L;
 }

@@ -98,6 +98,22 @@ static int wn_pack_impl(const WnDims& d, const cmwg_wn_params* prm, void* packed
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
 
+  if (fold0_shapes_ok(d)) {   // layer 0 with the start conv folded in (used by the task kernel's forward)
+    Fold0Params fp;
+    fp.d = d;
+    fp.wV = reinterpret_cast<const float*>(base + L.wV);
+    fp.wW0 = reinterpret_cast<const float*>(base + L.wW[0]);
+    fp.wWo0 = reinterpret_cast<const float*>(base + L.wWo[0]);
+    fp.wStart = reinterpret_cast<const float*>(base + L.wStart);
+    fp.PA0f = reinterpret_cast<uint16_t*>(base + L.PA0f);
+    fp.PB0f = reinterpret_cast<uint16_t*>(base + L.PB0f);
+    fp.is_fp16 = d.prec == CMWG_PREC_FP16;
+    const long long n = (long long)d.npadA * d.auxp + (long long)d.Cr * (d.Cdp + d.kb);
+    pack_fold0_kernel<<<(int)ceil_div_ll(n, 256), 256, 0, st>>>(fp);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+  }
+
   if (d.bias) {
     BiasPackParams bp;
     bp.d = d;
@@ -177,6 +193,18 @@ static inline bool fwd_res_lo(const WnDims& d) {
   return e && e[0] == '1';
 }
 
+// Layer 0 without the start conv (PackedLayout::PA0f / PB0f) in the task kernel's forward -- both variants: the first pass
+// and the recompute of the reversible backward must produce the SAME log_s / t, or the input reconstructed from the output
+// (efficient_modules.py:127-136) drifts by the difference, flow after flow.  h_0 is then never materialised; the one
+// consumer besides layer 0 itself, the weight gradient of layer 0's dilated conv, goes through the fold as well
+// (fold0_dw_kernel).  Needs the single-stream residual (the first residual tile has nothing to add).
+// CMWG_FOLD0=0 turns it off (read at every call -- forward and backward of one step must see the same value).
+static inline bool fold0_enabled(const WnDims& d) {
+  if (!fold0_shapes_ok(d) || fwd_res_lo(d)) return false;
+  const char* e = getenv("CMWG_FOLD0");
+  return !(e && e[0] == '0');
+}
+
 static inline bool mega_shapes_ok(const WnDims& d, int B, int T) {
   return d.tc && d.H == 1 && !d.bias && d.depth >= 1 && d.depth <= MEGA_D && d.Cr == 256 && d.Cs == 256 &&
          d.Cd % 128 == 0 && d.bn_gate == 256 && (((d.radix - 1) / 2) << (d.depth - 1)) <= 2 * TC_BM && d.radix <= 7 &&
@@ -208,7 +236,7 @@ static inline bool mega_end_fused(const WnDims& d) {  // CMWG_MEGA_END=0: separa
 }
 
 static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLayout& FL, const uint8_t* pk, uint8_t* ws,
-                           const void* ycl, int B, int T, bool save, int f16, void* const* hin, void* const* hlo,
+                           const void* ycl, int B, int T, bool save, bool fold0, int f16, void* const* hin, void* const* hlo,
                            void* const* gop, void* const* sb, float* skip32, float* lst, cudaStream_t st) {
   MegaParams p;
   memset(&p, 0, sizeof(p));
@@ -237,6 +265,13 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
     const char* e = getenv("CMWG_MEGA_KTRIM");   // CMWG_MEGA_KTRIM=0: issue the padded K steps too (A/B timing)
     const int real_last = d.aux - (p.kb_c - 1) * TC_BK;
     p.kc_last = (e && e[0] == '0') ? TC_BK / 16 : std::max(1, std::min(TC_BK / 16, ceil_div(real_last, 16)));
+  }
+  if (fold0) {
+    p.fold0 = 1;
+    const int real_last0 = d.aux + d.R * d.cin - (p.kb_c - 1) * TC_BK;
+    p.kc_last0 = p.kc_last == TC_BK / 16 ? p.kc_last : std::max(1, std::min(TC_BK / 16, ceil_div(real_last0, 16)));
+    CMWG_PROPAGATE(get_matrix_map(&p.pa0f, pk + PL.PA0f, d.auxp, d.npadA, MEGA_BN / 2, f16));
+    CMWG_PROPAGATE(get_matrix_map(&p.pb0f, pk + PL.PB0f, d.Cdp + d.kb, d.Cr, MEGA_BN / 2, f16));
   }
   p.idesc = make_idesc(f16, 2 * TC_BM, MEGA_BN, 0, 0);
   p.desc_lbo = 1u; p.desc_sbo = 1024u >> 4;
@@ -387,8 +422,21 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
   };
   const int bpb = ceil_div(T, ROWS_PER_BLOCK);
 
-  // ---- start conv
-  {
+  bool use_mega = false, fold0 = false;
+  if constexpr (TC) {
+    use_mega = mega_enabled() && !stt && lw.nh == 0 && mega_shapes_ok(d, B, T);
+    fold0 = use_mega && fold0_enabled(d);
+  }
+
+  // ---- start conv (folded into layer 0's GEMM tiles when fold0: the taps of x_a go into the conditioning slab's padding)
+  if (fold0) {
+    const long long n = (long long)B * T * d.R * d.cin;
+    const int nb_aug = (int)std::min<long long>(ceil_div_ll(n, 256), 4 * 148 * 8);
+    CMWG_CHECK_CUDA(launch_pdl(cond_aug_kernel, dim3(nb_aug), dim3(256), 0, st, x, x_bs, d.cin, d.R, B, T,
+                               reinterpret_cast<uint16_t*>(const_cast<void*>(ycl)), d.aux, d.auxp, f16));
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+  } else {
     // tc: (hi, lo) 16-bit pair; ff inference: h32 only (operand aliases it); ff training: fp32 copy per layer
     float* o32 = (!TC && !keep) ? h32 : nullptr;
     OpT* oop = (TC || keep) ? hin_op(0) : nullptr;
@@ -400,13 +448,13 @@ static int wn_forward_impl(const WnDims& d, const void* packed, const float* x, 
 
   bool fused = false;
   if constexpr (TC) {
-    if (mega_enabled() && !stt && lw.nh == 0 && mega_shapes_ok(d, B, T)) {
+    if (use_mega) {
       void *hin[MEGA_D], *hlo[MEGA_D], *gop[MEGA_D], *sb[MEGA_D];
       for (int i = 0; i < d.depth; ++i) {
         hin[i] = hin_op(i); hlo[i] = hlo_op(i); gop[i] = g_op(i);
         sb[i] = save ? sv + FL.s_b[i] : nullptr;
       }
-      CMWG_PROPAGATE(wn_forward_mega(d, PL, FL, pk, ws, ycl, B, T, save, f16, hin, hlo, gop, sb, skip32, lst, st));
+      CMWG_PROPAGATE(wn_forward_mega(d, PL, FL, pk, ws, ycl, B, T, save, fold0, f16, hin, hlo, gop, sb, skip32, lst, st));
       fused = true;
     }
   }
@@ -627,6 +675,11 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     return reinterpret_cast<OpT*>(ws + BL.dhi2[i & 1]);
   };
   auto dlo = [&](int i) -> OpT* { return reinterpret_cast<OpT*>(ws + BL.dlo2[i & 1]); };
+  // the saved state came from a forward with the start conv folded into layer 0 (same predicate as wn_forward_impl): no h_0 slab
+  bool fold0 = false;
+  if constexpr (TC) fold0 = mega_enabled() && mega_shapes_ok(d, B, T) && fold0_enabled(d);
+  int fold_pi = -1;                 // index of layer 0's conditioning weight-gradient problem (its tile holds D, fold0_dw_kernel)
+  int splits_of[TC_MAX_WG];
   float* partial = reinterpret_cast<float*>(ws + BL.partial);
   float* dweff = reinterpret_cast<float*>(ws + BL.dweff);
   const float* skip32 = reinterpret_cast<const float*>(sv + FL.s_skip);
@@ -725,6 +778,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       float* pcur = partial;
       for (int k = 0; k < gn; ++k) {
         gp[k].partial = pcur;
+        splits_of[g0 + k] = splits[k];
         pcur += (size_t)splits[k] * gp[k].M * gp[k].N;
       }
       CMWG_REQUIRE((size_t)((uint8_t*)pcur - (uint8_t*)partial) <= BL.partial_bytes, "wgrad partial buffer overflow");
@@ -831,12 +885,16 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
         if (!last) red(add(dh_next, d.Cr, d.Cr, gsv, d.Cd, d.Cd, 0, 0, 0), dWo, d.Cd, 1, 0, d.Cd);
         red(add(dskip_op, d.Cs, d.Cs, gsv, d.Cd, d.Cd, 0, 0, 0), dWo, d.Cd, 1, (long long)d.cr_eff(i) * d.Cd, d.Cd);
       }
-      if (want_w)
+      const bool folded = fold0 && i == 0;   // no h_0 slab: dW_0 comes out of the conditioning problem's tile (fold0_dw_kernel)
+      if (want_w && !folded)
         for (int s = 0; s < d.R; ++s)
           red(add(dpre_i, 2 * d.Cd, 2 * d.Cd, hin, d.Cr, d.Cr, d.tap_dt(i, s), d.tap_dh(i, s), 0), dW,
               (long long)d.Cr * d.R, d.R, s, d.Cr);
-      if (want_v)
-        red(add(dpre_i, 2 * d.Cd, 2 * d.Cd, ycl, d.auxp, d.auxp, 0, 0, d.H > 1), dV, d.aux, 1, 0, d.aux);
+      if (want_v || (folded && want_w)) {
+        const int pi = add(dpre_i, 2 * d.Cd, 2 * d.Cd, ycl, d.auxp, d.auxp, 0, 0, d.H > 1);
+        if (want_v) red(pi, dV, d.aux, 1, 0, d.aux);
+        if (folded && want_w) fold_pi = pi;
+      }
       if (!wg_batched) CMWG_PROPAGATE(flush_wgrad(TC_WG_GROUP));
       if (np > np_before) {
         if (want_wo)
@@ -921,6 +979,14 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   }
 
   if (wg_batched) CMWG_PROPAGATE(flush_wgrad(TC_MAX_WG));
+  if (fold_pi >= 0) {
+    // layer 0's group was the last one flushed: its tiles are still in the `partial` workspace
+    const WgradProblem& q = pr[fold_pi];
+    fold0_dw_kernel<<<2 * d.Cd, 256, 0, st>>>(q.partial, splits_of[fold_pi], q.M, q.N, d.aux, d.cin, d.R, d.Cr, wStart, gscale,
+                                              dweff + (size_t)d.nb(0) * d.Cd);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+  }
   if (pending_gather) {
     // every destination matrix has its weight-norm entry by now: attach the tiles; leftovers go through one reduce launch
     WgReduceTable rt;

@@ -1,5 +1,6 @@
 """One LJ training step (or one synthesis call) between cudaProfilerStart/Stop, for
-`ncu --profile-from-start off ...`.  Usage: python tools/profile_step.py [train|synth] [precision] [batch]"""
+`ncu --profile-from-start off ...`.  Usage: python tools/profile_step.py [train|trainopt|synth] [precision] [batch]
+(trainopt: with the fused Adam step, so the weight packs of all flows are rebuilt inside the profiled step, as in bench.py)"""
 import os
 import sys
 
@@ -19,8 +20,9 @@ torch.manual_seed(0)
 dev = torch.device("cuda", 0)
 model = cm.WaveGlow(memory_efficient=True, zero_init=False, **bench.LJ, **bench.LJ_WN).to(dev)
 loss_fn = cm.WaveGlowLoss(bench.SIGMA)
-if mode == "train":
+if mode in ("train", "trainopt"):
     model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True) if mode == "trainopt" else None
     x = torch.rand(B, bench.SEGMENT, device=dev) * 2 - 1
     h = torch.randn(B, 80, bench.FRAMES, device=dev)
 
@@ -28,6 +30,8 @@ if mode == "train":
         model.zero_grad(set_to_none=True)
         z, ld = model(x, h)
         loss_fn(z, ld).backward()
+        if opt is not None:
+            opt.step()
 else:
     model.eval()
     hs = torch.randn(B, 80, bench.SYNTH_FRAMES, device=dev)
