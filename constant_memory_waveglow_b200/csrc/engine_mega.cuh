@@ -894,6 +894,12 @@ struct alignas(64) MegaBwdParams {
   uint16_t* dlo_ptr[MEGA_D];        // dh_i lo halves [rows][Cr]
   int direct;
   int res_lo;                       // see MegaParams::res_lo (here: the residual GRADIENT stream)
+  // `end` conv folded into the dgate GEMM (PackedLayout::Q1f): instead of the kb_s k-blocks of dskip = W_end^T d(log_s, t), a
+  // dgate tile reads ONE k-block of the slab dl = S * d(log_s, t) (2 in_channels real columns) against (W_end W_skip)^T
+  int fold_end;
+  int kdl;                          // K = 16 steps of that k-block that hold real columns
+  CUtensorMap dl_op;
+  CUtensorMap q1f[MEGA_D];
 };
 
 __host__ __device__ __forceinline__ MegaTask mega_bwd_decode(const MegaBwdParams& p, int idx) {
@@ -994,10 +1000,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
           fence_proxy_async_all();
         }
         if (t.type == MEGA_DG) {
+          const CUtensorMap* bm = p.fold_end ? &p.q1f[t.layer] : &p.q1[t.layer];
           if (!last)
-            for (int kb = 0; kb < p.kb_r; ++kb) load(&p.dh_op[t.layer + 1], kb * TC_BK, t0, b, &p.q1[t.layer], kb * TC_BK, nrow);
-          for (int kb = 0; kb < p.kb_s; ++kb)
-            load(&p.dskip_op, kb * TC_BK, t0, b, &p.q1[t.layer], (last ? 0 : Crp) + kb * TC_BK, nrow);
+            for (int kb = 0; kb < p.kb_r; ++kb) load(&p.dh_op[t.layer + 1], kb * TC_BK, t0, b, bm, kb * TC_BK, nrow);
+          if (p.fold_end) {
+            load(&p.dl_op, 0, t0, b, bm, last ? 0 : Crp, nrow);
+          } else {
+            for (int kb = 0; kb < p.kb_s; ++kb) load(&p.dskip_op, kb * TC_BK, t0, b, bm, (last ? 0 : Crp) + kb * TC_BK, nrow);
+          }
         } else {
           for (int sg = 0; sg < p.taps; ++sg) {
             const int shift = -(sg - (p.taps - 1) / 2) * (1 << t.layer);
@@ -1042,8 +1052,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
         if (t.type == MEGA_NONE) continue;
         const int nrow = rank * (MEGA_BN / 2);
         if (t.type == MEGA_DG) {
-          const int nkb = (t.layer == p.depth - 1) ? p.kb_s : p.kb_r + p.kb_s;
-          for (int kb = 0; kb < nkb; ++kb) loadb(&p.q1[t.layer], kb * TC_BK, nrow);
+          const int ks = p.fold_end ? 1 : p.kb_s;
+          const int nkb = (t.layer == p.depth - 1) ? ks : p.kb_r + ks;
+          const CUtensorMap* bm = p.fold_end ? &p.q1f[t.layer] : &p.q1[t.layer];
+          for (int kb = 0; kb < nkb; ++kb) loadb(bm, kb * TC_BK, nrow);
         } else {
           for (int kb = 0; kb < p.taps * p.kb_d2; ++kb) loadb(&p.q2[t.layer], kb * TC_BK, nrow);
         }
@@ -1060,7 +1072,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
         if (task < 0) continue;
         const MegaTask t = mega_bwd_decode(p, task);
         if (t.type == MEGA_NONE) continue;
-        const int total_kb = t.type == MEGA_DX ? p.taps * p.kb_d2 : (t.layer == p.depth - 1 ? p.kb_s : p.kb_r + p.kb_s);
+        const int ks = p.fold_end ? 1 : p.kb_s;
+        const int total_kb = t.type == MEGA_DX ? p.taps * p.kb_d2 : (t.layer == p.depth - 1 ? ks : p.kb_r + ks);
+        const int kb_trim = (t.type == MEGA_DG && p.fold_end) ? total_kb - 1 : -1;   // the dl k-block: 2 in_channels real columns
         mbar_wait(&s.tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * MEGA_BN;
@@ -1070,9 +1084,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) wn_bwd_mega_kernel(const __gr
           const uint32_t sa = smem_u32(s.stages + stage * MEGA_STAGE_BYTES);
           const uint64_t adesc = make_smem_desc(sa, p.desc_lbo, p.desc_sbo);
           const uint64_t bdesc = make_smem_desc(sa + TC_A_BYTES, p.desc_lbo, p.desc_sbo);
+          const int nk = kb == kb_trim ? p.kdl : TC_BK / 16;
 #pragma unroll
           for (int kk = 0; kk < TC_BK / 16; ++kk)
-            umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, p.idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            if (kk < nk) umma_f16(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, p.idesc, (kb > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&s.empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }

@@ -221,6 +221,118 @@ static __global__ void __launch_bounds__(256) pack_operands_kernel(const PackPar
   }
 }
 
+// 16-bit operands: the same matrices, 8 or 16 destination-contiguous elements per thread (16 / 32-byte stores) with the work
+// items ordered so that a warp's READS are contiguous too -- for the transposing matrices (Q1, Q2, QV) the lanes walk the
+// source's fast axis and every lane writes its own full 32-byte sector.  (One element per thread took 56 us per WN at the LJ
+// config, every training step, for 20 MB of output.)  Bit-identical to pack_operands_kernel<uint16_t>.
+__device__ __forceinline__ void pack_store8(uint16_t* dst, const float (&v)[8], int f16) {
+  *reinterpret_cast<uint4*>(dst) =
+      make_uint4(pack2(v[0], v[1], f16), pack2(v[2], v[3], f16), pack2(v[4], v[5], f16), pack2(v[6], v[7], f16));
+}
+static __global__ void __launch_bounds__(256) pack_operands16_kernel(const PackParams p) {
+  const WnDims& d = p.d;
+  const int i = blockIdx.y;     // layer
+  const int kind = blockIdx.z;  // 0 PA, 1 PB, 2 Q1, 3 Q2, 4 QV, 5 PS
+  const int nb = d.nb(i), k1 = d.k1(i), cr_eff = d.cr_eff(i), f16 = p.is_fp16;
+  const float* __restrict__ wW = p.wW[i];
+  const float* __restrict__ wWo = p.wWo[i];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long w0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (kind == 0) {
+    uint16_t* dst = reinterpret_cast<uint16_t*>(p.PA[i]);
+    const int wa = d.Crp / 8, per_row = wa + d.auxp / 8;
+    for (long long w = w0; w < (long long)d.npadA * per_row; w += stride) {
+      const int n = (int)(w / per_row), r = (int)(w % per_row);
+      const int tile = n / d.bn_gate, rr = n % d.bn_gate;
+      const int half = rr / d.G, ch = tile * d.G + (rr % d.G);
+      const bool live = ch < d.Cd;
+      const int oc = half * d.Cd + ch;
+      float v[8];
+      if (r < wa) {          // the taps of 8 consecutive input channels: 8 * R consecutive source floats
+        const int ic0 = r * 8;
+        for (int tap = 0; tap < d.R; ++tap) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[j] = (live && ic0 + j < d.Cr) ? wW[((long long)oc * d.Cr + ic0 + j) * d.R + tap] : 0.f;
+          pack_store8(dst + (long long)n * d.KA + tap * d.Crp + ic0, v, f16);
+        }
+      } else {               // conditioning columns
+        const int kk0 = (r - wa) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          v[j] = (live && kk0 + j < d.aux) ? p.wV[((long long)i * 2 * d.Cd + oc) * d.aux + kk0 + j] : 0.f;
+        pack_store8(dst + (long long)n * d.KA + d.R * d.Crp + kk0, v, f16);
+      }
+    }
+  } else if (kind == 1 || kind == 5) {
+    if (kind == 5 && !d.tc) return;
+    const int rows = kind == 1 ? nb : d.Cs, ld = kind == 1 ? d.ldPB : d.Cdp, per_row = ld / 8;
+    const int row_off = kind == 1 ? 0 : cr_eff;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(kind == 1 ? p.PB[i] : p.PS);
+    for (long long w = w0; w < (long long)rows * per_row; w += stride) {
+      const int n = (int)(w / per_row), k0 = (int)(w % per_row) * 8;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (k0 + j < d.Cd) ? wWo[((long long)row_off + n) * d.Cd + k0 + j] : 0.f;
+      pack_store8(dst + (kind == 1 ? (long long)n * d.ldPB + k0 : (long long)n * d.ldPS + (long long)i * d.Cdp + k0), v, f16);
+    }
+  } else if (kind == 2) {    // Q1 = W_o^T: lanes walk n (the source's fast axis), 16 k per thread
+    uint16_t* dst = reinterpret_cast<uint16_t*>(p.Q1[i]);
+    for (long long w = w0; w < (long long)d.Cd * (k1 / 16); w += stride) {
+      const int n = (int)(w % d.Cd), k0 = (int)(w / d.Cd) * 16;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = k0 + 8 * h + j;
+          int ro = -1;
+          if (cr_eff > 0) {
+            if (k < d.Crp) { if (k < d.Cr) ro = k; }
+            else { const int kk = k - d.Crp; if (kk < d.Cs) ro = d.Cr + kk; }
+          } else {
+            if (k < d.Cs) ro = k;
+          }
+          v[j] = ro >= 0 ? wWo[(long long)ro * d.Cd + n] : 0.f;
+        }
+        pack_store8(dst + (long long)n * k1 + k0 + 8 * h, v, f16);
+      }
+    }
+  } else if (kind == 3) {    // Q2 = W^T per tap: lanes walk n, 16 output channels x R taps per thread
+    uint16_t* dst = reinterpret_cast<uint16_t*>(p.Q2[i]);
+    for (long long w = w0; w < (long long)d.Cr * (d.Cd2p / 16); w += stride) {
+      const int n = (int)(w % d.Cr), oc0 = (int)(w / d.Cr) * 16;
+      for (int tap = 0; tap < d.R; ++tap) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int oc = oc0 + 8 * h + j;
+            v[j] = oc < 2 * d.Cd ? wW[((long long)oc * d.Cr + n) * d.R + tap] : 0.f;
+          }
+          pack_store8(dst + (long long)n * d.ldQ2 + tap * d.Cd2p + oc0 + 8 * h, v, f16);
+        }
+      }
+    }
+  } else {                   // QV = V^T, K-concatenated over layers: lanes walk n
+    uint16_t* dst = reinterpret_cast<uint16_t*>(p.QV);
+    for (long long w = w0; w < (long long)d.auxp * (d.Cd2p / 16); w += stride) {
+      const int n = (int)(w % d.auxp), k0 = (int)(w / d.auxp) * 16;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = k0 + 8 * h + j;
+          v[j] = (n < d.aux && k < 2 * d.Cd) ? p.wV[((long long)i * 2 * d.Cd + k) * d.aux + n] : 0.f;
+        }
+        pack_store8(dst + (long long)n * d.ldQV + (long long)i * d.Cd2p + k0 + 8 * h, v, f16);
+      }
+    }
+  }
+}
+
 // Layer 0 with the start conv folded in (wn_layout.cuh: PA0f / PB0f).  Column aux + tap * cin + c of the conditioning slab
 // holds x_a[c] at the tap's time offset, so
 //   PA0f[n][aux + tap * cin + c] = sum_ic W_0[oc(n)][ic][tap] * W_start[ic][c]      (gate rows in PA's interleaved order)
@@ -236,10 +348,35 @@ struct Fold0Params {
   uint16_t* PB0f;
   int is_fp16;
 };
+// PA0f[n][aux + tap * cin + c] = sum_ic W_0[oc(n)][ic][tap] * W_start[ic][c]: one warp per element, lanes stride the input
+// channels (fixed shuffle order: deterministic)
+__device__ __forceinline__ void pack_fold0_dot(const Fold0Params& p, int block) {
+  const WnDims& d = p.d;
+  const int per = d.R * d.cin, lane = threadIdx.x & 31;
+  const long long wid = (block * 256ll + threadIdx.x) >> 5;
+  if (wid >= (long long)d.npadA * per) return;
+  const int n = (int)(wid / per), j = (int)(wid % per), tap = j / d.cin, c = j % d.cin;
+  const int tile = n / d.bn_gate, r = n % d.bn_gate;
+  const int half = r / d.G, ch = tile * d.G + (r % d.G);
+  float val = 0.f;
+  if (ch < d.Cd) {
+    const float* w = p.wW0 + (long long)(half * d.Cd + ch) * d.Cr * d.R + tap;
+    for (int ic = lane; ic < d.Cr; ic += 32) val = fmaf(w[(long long)ic * d.R], p.wStart[ic * d.cin + c], val);
+    val = warp_sum(val);
+  }
+  if (lane == 0) p.PA0f[(long long)n * d.auxp + d.aux + j] = f32_to_op16(val, p.is_fp16);
+}
+
 static __global__ void __launch_bounds__(256) pack_fold0_kernel(const Fold0Params p) {
   const WnDims& d = p.d;
   const long long nA = (long long)d.npadA * d.auxp, ldB = d.Cdp + d.kb, nB = (long long)d.Cr * ldB;
-  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < nA + nB; idx += (long long)gridDim.x * 256) {
+  // blocks [0, nb_elem): one element per thread; blocks behind them: the folded columns, one warp per element
+  const int nb_elem = (int)((nA + nB + 255) / 256);
+  if ((int)blockIdx.x >= nb_elem) {
+    pack_fold0_dot(p, blockIdx.x - nb_elem);
+    return;
+  }
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < nA + nB; idx += (long long)nb_elem * 256) {
     float val = 0.f;
     if (idx < nA) {
       const int n = (int)(idx / d.auxp), k = (int)(idx % d.auxp);
@@ -249,13 +386,9 @@ static __global__ void __launch_bounds__(256) pack_fold0_kernel(const Fold0Param
         const int oc = half * d.Cd + ch;
         if (k < d.aux) {
           val = p.wV[(long long)oc * d.aux + k];
-        } else if (k < d.aux + d.R * d.cin) {
-          const int tap = (k - d.aux) / d.cin, c = (k - d.aux) % d.cin;
-          const float* w = p.wW0 + (long long)oc * d.Cr * d.R + tap;
-          for (int ic = 0; ic < d.Cr; ++ic) val = fmaf(w[(long long)ic * d.R], p.wStart[ic * d.cin + c], val);
-        }
+        }   // the folded columns [aux, aux + R * cin) are 256-term dot products: pack_fold0_dot_kernel, one warp each
       }
-      p.PA0f[idx] = f32_to_op16(val, p.is_fp16);
+      if (k < d.aux || k >= d.aux + d.R * d.cin) p.PA0f[idx] = f32_to_op16(val, p.is_fp16);
     } else {
       const long long j = idx - nA;
       const int n = (int)(j / ldB), k = (int)(j % ldB);
@@ -268,6 +401,67 @@ static __global__ void __launch_bounds__(256) pack_fold0_kernel(const Fold0Param
       }
       p.PB0f[j] = f32_to_op16(val, p.is_fp16);
     }
+  }
+}
+
+// dgate weights with the `end` conv folded in (wn_layout.cuh: Q1f):  Q1f[i][n][k] = W_o,i[k][n] for k < Cr (layers with a
+// residual half), and behind them one k-block whose first 2 in_channels columns hold
+//   F_i[n][o] = sum_k W_o,i[cr_eff + k][n] * W_end[o][k]        (one warp per element, fixed shuffle order)
+struct FoldEndParams {
+  WnDims d;
+  const float* wWo[CMWG_MAX_DEPTH];
+  const float* wEnd;   // [2 cin][Cs]
+  uint16_t* Q1f[CMWG_MAX_DEPTH];
+  int is_fp16;
+};
+static __global__ void __launch_bounds__(256) pack_foldend_kernel(const FoldEndParams p) {
+  const WnDims& d = p.d;
+  const int i = blockIdx.y, cout = 2 * d.cin, cr_eff = d.cr_eff(i), ld = (i < d.depth - 1 ? d.Crp : 0) + d.kb;
+  const int kres = ld - d.kb;
+  const float* __restrict__ wWo = p.wWo[i];
+  uint16_t* dst = p.Q1f[i];
+  // elementwise part: lanes walk n (the source's fast axis), one k per thread row
+  const long long n_elem = (long long)d.Cd * ld;
+  const int nb_elem = (int)((n_elem + 255) / 256);
+  if ((int)blockIdx.x < nb_elem) {
+    const long long idx = blockIdx.x * 256ll + threadIdx.x;
+    if (idx >= n_elem) return;
+    const int n = (int)(idx % d.Cd), k = (int)(idx / d.Cd);
+    if (k >= kres && k < kres + cout) return;            // the folded columns: below
+    const float val = (k < kres && k < d.Cr) ? wWo[(long long)k * d.Cd + n] : 0.f;
+    dst[(long long)n * ld + k] = f32_to_op16(val, p.is_fp16);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const long long wid = (((long long)blockIdx.x - nb_elem) * 256 + threadIdx.x) >> 5;
+  if (wid >= (long long)d.Cd * cout) return;
+  const int n = (int)(wid % d.Cd), o = (int)(wid / d.Cd);
+  float val = 0.f;
+  for (int k = lane; k < d.Cs; k += 32) val = fmaf(wWo[((long long)cr_eff + k) * d.Cd + n], p.wEnd[(long long)o * d.Cs + k], val);
+  val = warp_sum(val);
+  if (lane == 0) dst[(long long)n * ld + kres + o] = f32_to_op16(val, p.is_fp16);
+}
+
+// S * d(log_s, t) as a [rows][kb] operand slab: the first 2 in_channels columns, zeros behind (folded `end` conv backward)
+static __global__ void __launch_bounds__(256) dl_slab_kernel(const float* __restrict__ dlst, int cout, int T, long long rows,
+                                                             int kb, uint16_t* __restrict__ dl, int is_fp16,
+                                                             const float* __restrict__ gscale) {
+  pdl_trigger();
+  pdl_wait();
+  const float sc = gscale ? gscale[1] : 1.f;
+  const int groups = kb / 8;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < rows * groups; idx += (long long)gridDim.x * 256) {
+    // consecutive threads walk consecutive rows of one 8-column group: coalesced reads of dlst (B, cout, T)
+    const long long row = idx % rows;
+    const int gi = (int)(idx / rows);
+    const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = gi * 8 + j;
+      v[j] = o < cout ? dlst[((long long)b * cout + o) * T + t] * sc : 0.f;
+    }
+    pack_store8(dl + row * kb + gi * 8, v, is_fp16);
   }
 }
 
@@ -619,7 +813,10 @@ static __global__ void __launch_bounds__(256) start_bwd_kernel(const float* __re
 // weight-gradient outer products accumulate in registers.  Warps fold into one partial per CTA in warp order and a
 // CTA's row range is fixed by its index, so results are bitwise reproducible.
 // ------------------------------------------------------------------------------------------------
-constexpr int FAST_ROWS_PER_CTA = 256;  // 8 warps x 32 rows
+// 8 warps x 16 rows.  (32 rows per warp left ~10 warps per SM at the LJ training shape: the per-row dependent chains -- a
+// 32-byte load, CIN warp reductions -- had nothing to overlap with; measured 34 us for a 25 MB read.)
+constexpr int FAST_ROWS_PER_WARP = 16;
+constexpr int FAST_ROWS_PER_CTA = 8 * FAST_ROWS_PER_WARP;
 
 __device__ __forceinline__ void load_row8(const float* __restrict__ p32, const uint16_t* __restrict__ hi,
                                           const uint16_t* __restrict__ lo, long long off, float (&v)[8],
@@ -699,9 +896,9 @@ static __global__ void __launch_bounds__(256) start_bwd256_kernel(const float* _
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int i = 0; i < CIN; ++i) wreg[c][i] = ws[(lane * 8 + c) * CIN + i];
-  const long long g0 = (long long)blockIdx.x * FAST_ROWS_PER_CTA + warp * 32;
+  const long long g0 = (long long)blockIdx.x * FAST_ROWS_PER_CTA + warp * FAST_ROWS_PER_WARP;
   if (g0 < rows) {
-    const int nrows = (int)min(32LL, rows - g0);
+    const int nrows = (int)min((long long)FAST_ROWS_PER_WARP, rows - g0);
     const bool valid = lane < nrows;
     int b = 0, t = 0;
     if (valid) {
@@ -762,9 +959,9 @@ static __global__ void __launch_bounds__(256) end_bwd_dw256_kernel(const float* 
   float acc[8 * COUT + COUT];
 #pragma unroll
   for (int a = 0; a < 8 * COUT + COUT; ++a) acc[a] = 0.f;
-  const long long g0 = (long long)blockIdx.x * FAST_ROWS_PER_CTA + warp * 32;
+  const long long g0 = (long long)blockIdx.x * FAST_ROWS_PER_CTA + warp * FAST_ROWS_PER_WARP;
   if (g0 < rows) {
-    const int nrows = (int)min(32LL, rows - g0);
+    const int nrows = (int)min((long long)FAST_ROWS_PER_WARP, rows - g0);
     float dl[COUT];
     if (lane < nrows) {
       const int b = (int)((g0 + lane) / TF);
@@ -978,6 +1175,9 @@ static __global__ void __launch_bounds__(256) grad_scale_kernel(float* __restric
     float S = 1.f;
     if (bound > 0.f && bound < 3.0e38f) {
       int e = 8 - (int)ceilf(log2f(bound));
+      // S * dlst itself is an fp16 operand when the `end` conv is folded into the dgate GEMM (dl_slab_kernel): keep it
+      // below 2^14 (only a nearly-zero `end` weight makes this the binding bound)
+      e = min(e, 14 - (int)ceilf(log2f(amax)));
       e = max(-60, min(60, e));
       S = exp2f((float)e);
     }

@@ -121,8 +121,13 @@ struct PackedLayout {
   // a K = taps * in_channels GEMM in disguise.  The taps of x_a ride in the padding columns of the conditioning slab.
   size_t PA0f;                // gate GEMM of layer 0   [npadA][auxp]: V_0 | W_0,tap W_start per tap | 0
   size_t PB0f;                // residual GEMM of layer 0 [Cr][Cdp + kb]: W_res,0 | W_start under the centre tap's columns
+  // dgate GEMM with the `end` conv folded in (foldend_shapes_ok): dskip = W_end^T d(log_s, t) has K = 2 in_channels, so the
+  // skip half of the dgate GEMM is a K = 2 in_channels GEMM in disguise:  dg_i = W_res,i^T dh_{i+1} + (W_end W_skip,i)^T d(log_s, t)
+  size_t Q1f[CMWG_MAX_DEPTH]; // [Cd][k1f(i)] = W_res,i^T | (W_end W_skip,i)^T in the first 2 in_channels columns of one k-block
   size_t total;
 };
+inline int k1f(const WnDims& d, int i) { return (i < d.depth - 1 ? d.Crp : 0) + d.kb; }
+inline bool foldend_shapes_ok(const WnDims& d) { return d.tc && d.H == 1 && !d.bias && 2 * d.cin <= 16; }
 
 // Layer 0 can run without the start conv when the taps of x_a fit behind the conditioning channels in the LAST k-block of the
 // padded conditioning slab (1-D WN on the tcgen05 engine, no bias, at least one residual layer).
@@ -159,6 +164,7 @@ inline PackedLayout make_packed_layout(const WnDims& d) {
   }
   L.PA0f = take((size_t)d.npadA * d.auxp * d.opsize);
   L.PB0f = take((size_t)d.Cr * (d.Cdp + d.kb) * d.opsize);
+  for (int i = 0; i < d.depth; ++i) L.Q1f[i] = take((size_t)d.Cd * k1f(d, i) * d.opsize);
   L.total = off;
   return L;
 }
@@ -195,10 +201,13 @@ struct BwdLayout {
   size_t dprel[CMWG_MAX_DEPTH];     // tc: per-layer dpre
   size_t partial;    // split-K partials / block partials
   size_t partial_bytes;
+  size_t partial_start;  // block partials of the start conv backward (its own region: the gathered weight-gradient tiles in
+                         // `partial` stay alive until the single weight-norm backward launch at the end)
   size_t dycl_lines; // [B][H][T][auxp] fp32 per-line conditioning gradient (2-D WN only; summed over lines afterwards)
   size_t dweff;      // fp32 effective-weight gradients of every conv (consumed by ONE weight-norm backward launch)
   size_t dweff_layer, dweff_start, dweff_end;  // in floats: per-layer stride, offsets of the start / end conv
   size_t gscale;     // 4 floats: gradient scale of the fp16-operand backward {max|dlst| bits, S, 1/S} (wn_kernels.cuh)
+  size_t dl16;       // [rows][kb] operand: S * d(log_s, t) in the first 2 in_channels columns, zeros behind (folded `end` conv)
   size_t total;
 };
 
@@ -274,6 +283,7 @@ inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
   size_t p2 = (blocks32 + blocks32 / 64 + 2) * per_block * 4;  // + second-stage scratch
   L->partial_bytes = p1 > p2 ? p1 : p2;
   L->partial = take(L->partial_bytes);
+  L->partial_start = take(p2);
   L->dycl_lines = d.H > 1 ? take(rows * d.auxp * 4) : 0;
   // effective-weight gradients: per layer dW_o, dW, dV_i side by side, then the start and end convs
   size_t per = (size_t)(d.Cr + d.Cs) * d.Cd + (size_t)2 * d.Cd * d.Cr * d.R + (size_t)2 * d.Cd * d.aux;
@@ -284,6 +294,7 @@ inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
   size_t total_f = L->dweff_end + align_up((size_t)2 * d.cin * d.Cs, 64);
   L->dweff = take(total_f * 4 + 4096);
   L->gscale = take(64);
+  L->dl16 = d.tc ? take(rows * d.kb * 2) : 0;
   L->total = off;
 }
 

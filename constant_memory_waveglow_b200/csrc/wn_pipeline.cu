@@ -93,8 +93,18 @@ static int wn_pack_impl(const WnDims& d, const cmwg_wn_params* prm, void* packed
   if (q2 > biggest) biggest = q2;
   int gx = (int)std::min<long long>(ceil_div_ll(biggest, 256 * 4), 1024);
   dim3 grid(gx, d.depth, d.tc ? 6 : 5);
-  if (d.tc) pack_operands_kernel<uint16_t><<<grid, 256, 0, st>>>(pp);
-  else pack_operands_kernel<float><<<grid, 256, 0, st>>>(pp);
+  const char* pse = getenv("CMWG_PACK_SCALAR");   // =1: the one-element-per-thread kernel (tests compare the two)
+  const bool pack_scalar = pse && pse[0] == '1';
+  if (d.tc && !pack_scalar) {
+    // vector form: the largest matrix (PA) has npadA * (Crp + auxp) / 8 work items
+    const long long items = (long long)d.npadA * ((d.Crp + d.auxp) / 8);
+    grid.x = (unsigned)std::max<long long>(1, std::min<long long>(ceil_div_ll(items, 256), 1024));
+    pack_operands16_kernel<<<grid, 256, 0, st>>>(pp);
+  } else if (d.tc) {
+    pack_operands_kernel<uint16_t><<<grid, 256, 0, st>>>(pp);
+  } else {
+    pack_operands_kernel<float><<<grid, 256, 0, st>>>(pp);
+  }
   CMWG_COUNT_LAUNCH();
   CMWG_LAUNCH_CHECK();
 
@@ -109,7 +119,24 @@ static int wn_pack_impl(const WnDims& d, const cmwg_wn_params* prm, void* packed
     fp.PB0f = reinterpret_cast<uint16_t*>(base + L.PB0f);
     fp.is_fp16 = d.prec == CMWG_PREC_FP16;
     const long long n = (long long)d.npadA * d.auxp + (long long)d.Cr * (d.Cdp + d.kb);
-    pack_fold0_kernel<<<(int)ceil_div_ll(n, 256), 256, 0, st>>>(fp);
+    const int nb_dot = (int)ceil_div_ll((long long)d.npadA * d.R * d.cin * 32, 256);
+    pack_fold0_kernel<<<(int)ceil_div_ll(n, 256) + nb_dot, 256, 0, st>>>(fp);
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+  }
+
+  if (foldend_shapes_ok(d)) {   // dgate weights with the `end` conv folded in (used by the task kernel's backward chain)
+    FoldEndParams ep;
+    ep.d = d;
+    ep.wEnd = reinterpret_cast<const float*>(base + L.wEnd);
+    ep.is_fp16 = d.prec == CMWG_PREC_FP16;
+    for (int i = 0; i < d.depth; ++i) {
+      ep.wWo[i] = reinterpret_cast<const float*>(base + L.wWo[i]);
+      ep.Q1f[i] = reinterpret_cast<uint16_t*>(base + L.Q1f[i]);
+    }
+    const int nb_elem = (int)ceil_div_ll((long long)d.Cd * k1f(d, 0), 256);
+    const int nb_dot = (int)ceil_div_ll((long long)d.Cd * 2 * d.cin * 32, 256);
+    pack_foldend_kernel<<<dim3(nb_elem + nb_dot, d.depth), 256, 0, st>>>(ep);
     CMWG_COUNT_LAUNCH();
     CMWG_LAUNCH_CHECK();
   }
@@ -202,6 +229,13 @@ static inline bool fwd_res_lo(const WnDims& d) {
 static inline bool fold0_enabled(const WnDims& d) {
   if (!fold0_shapes_ok(d) || fwd_res_lo(d)) return false;
   const char* e = getenv("CMWG_FOLD0");
+  return !(e && e[0] == '0');
+}
+
+// `end` conv folded into the dgate tiles of the backward task kernel (PackedLayout::Q1f).  CMWG_FOLD_END=0 turns it off.
+static inline bool foldend_enabled(const WnDims& d) {
+  if (!foldend_shapes_ok(d)) return false;
+  const char* e = getenv("CMWG_FOLD_END");
   return !(e && e[0] == '0');
 }
 
@@ -327,9 +361,17 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
 // single-kernel backward chain (engine_mega.cuh): dgate + dx GEMM tiles of all layers as one task list
 static int wn_backward_mega(const WnDims& d, const PackedLayout& PL, const BwdLayout& BL, const uint8_t* pk, uint8_t* ws,
                             int B, int T, int f16, void* const* dh_hi, void* const* dh_lo, const void* dskip,
-                            void* const* dpre, const void* const* sa, const void* const* sb, cudaStream_t st) {
+                            const void* dl16, void* const* dpre, const void* const* sa, const void* const* sb,
+                            cudaStream_t st) {
   MegaBwdParams p;
   memset(&p, 0, sizeof(p));
+  if (dl16 != nullptr) {
+    p.fold_end = 1;
+    p.kdl = std::max(1, ceil_div(2 * d.cin, 16));
+    CMWG_PROPAGATE(get_slab_map(&p.dl_op, dl16, d.kb, d.kb, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
+    for (int i = 0; i < d.depth; ++i)
+      CMWG_PROPAGATE(get_matrix_map(&p.q1f[i], pk + PL.Q1f[i], k1f(d, i), d.Cd, MEGA_BN / 2, f16));
+  }
   p.res_lo = fwd_res_lo(d) ? 1 : 0;
   for (int i = 0; i < d.depth; ++i) {
     CMWG_PROPAGATE(get_slab_map(&p.dh_op[i], dh_hi[i], d.Cr, d.Cr, T, 1, B, TC_BK, TC_BM, f16, TC_MAP_OPERAND));
@@ -752,7 +794,17 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
         hh[i] = dhi(i); hl[i] = dlo(i); dp[i] = dpre_l(i);
         sa[i] = sv + FL.s_g[i]; sb[i] = sv + FL.s_b[i];   // gate output and saved sigmoid (tanh = g / sigmoid)
       }
-      CMWG_PROPAGATE(wn_backward_mega(d, PL, BL, pk, ws, B, T, f16, hh, hl, dskip_op, dp, sa, sb, st));
+      const void* dl16 = nullptr;
+      if (foldend_enabled(d)) {   // S * dlst as a one-k-block operand slab for the folded dgate tiles
+        uint16_t* dl = reinterpret_cast<uint16_t*>(ws + BL.dl16);
+        const int nb_dl = (int)std::min<long long>(ceil_div_ll(rows * (d.kb / 8), 256), 4 * 148 * 8);
+        CMWG_CHECK_CUDA(launch_pdl(dl_slab_kernel, dim3(nb_dl), dim3(256), 0, st, dlst, cout, TF, rows, d.kb, dl, f16,
+                                   (const float*)gscale));
+        CMWG_COUNT_LAUNCH();
+        CMWG_LAUNCH_CHECK();
+        dl16 = dl;
+      }
+      CMWG_PROPAGATE(wn_backward_mega(d, PL, BL, pk, ws, B, T, f16, hh, hl, dskip_op, dl16, dp, sa, sb, st));
     }
   }
 
@@ -1004,10 +1056,8 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       CMWG_COUNT_LAUNCH();
       CMWG_LAUNCH_CHECK();
     }
-    // the tiles live in the `partial` workspace, which the start conv backward below reuses for its block partials:
-    // the weight-norm backward of everything queued so far runs NOW; the start conv's own entry follows in a second launch
-    CMWG_PROPAGATE(wq.flush(st, gscale));
-    wq.reset();
+    // the tiles live in the `partial` workspace until the weight-norm backward at the end gathers them: the start conv
+    // backward below keeps its block partials in a region of its own (BwdLayout::partial_start)
   }
 
   if constexpr (TC) {
@@ -1040,8 +1090,8 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   // ---- start conv backward
   {
     size_t smem = ((size_t)ROWS_PER_BLOCK * (d.Cr + 1) + (size_t)d.cin * ROWS_PER_BLOCK) * sizeof(float);
-    float* pw = partial;
-    float* pb = partial + (size_t)nblk * d.Cr * d.cin;
+    float* pw = reinterpret_cast<float*>(ws + BL.partial_start);
+    float* pb = pw + (size_t)nblk * d.Cr * d.cin;
     float* scratch = pb + (size_t)nblk * d.Cr;
     const float* a32 = TC ? nullptr : dh32;
     const uint16_t* ahi = TC ? reinterpret_cast<const uint16_t*>(dhi(0)) : nullptr;

@@ -37,6 +37,7 @@ def _both(fn):
     (test_fused_end_conv_matches_separate_kernel)."""
     os.environ["CMWG_MEGA_END"] = "0"
     os.environ["CMWG_FOLD0"] = "0"      # ... and the start conv in its own kernel (test_folded_start_conv_matches_separate_kernel)
+    os.environ["CMWG_FOLD_END"] = "0"   # ... and the backward chain's dgate tiles on the dskip slab (layered pipeline's operands)
     os.environ["CMWG_MEGA"] = "1"
     try:
         a = fn()
@@ -46,6 +47,7 @@ def _both(fn):
         os.environ["CMWG_MEGA"] = "1"
         os.environ.pop("CMWG_MEGA_END", None)
         os.environ.pop("CMWG_FOLD0", None)
+        os.environ.pop("CMWG_FOLD_END", None)
     return a, b
 
 
@@ -226,6 +228,46 @@ def test_training_step_gradients_equal_layered_pipeline(prec):
     # ... and with fp16 operands layer 0 runs without the start conv (x_a and W_0 W_start are rounded to 16 bits instead of
     # h_0; the weight gradient of its dilated conv goes through the fold as well)
     for a, c in zip(ga, gc):
-        assert rel_l2(c, a) < (6e-4 if prec == "fp16" else 2e-3), rel_l2(c, a)
+        assert rel_l2(c, a) < (6e-4 if prec == "fp16" else 4e-3), rel_l2(c, a)
     gd = run()
     assert all(torch.equal(c, d) for c, d in zip(gc, gd))      # the default arrangement is deterministic too
+
+
+@pytest.mark.parametrize("end_scale", [1.0, 1e-5])
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_folded_end_conv_backward_matches_dskip_slab(prec, end_scale):
+    """Backward chain with the `end` conv folded into the dgate tiles ((W_end W_skip)^T against a one-k-block slab of
+    S * d(log_s, t); the default) against the tiles that read the 256-channel dskip slab: the same function with other 16-bit
+    roundings.  A nearly-zero `end` weight (zero_init models a few steps into training) makes S * d(log_s, t) itself the
+    binding magnitude for the power-of-two gradient scale."""
+    torch.manual_seed(1)
+    blk = cm.AffineCouplingBlock(cm.WN, True, in_channels=4, aux_channels=80, zero_init=False, dilation_channels=256,
+                                 residual_channels=256, skip_channels=256, depth=8).cuda()
+    with torch.no_grad():
+        blk.F.end.weight.mul_(end_scale)
+    x0 = torch.rand(3, 8, 1800, device="cuda") * 2 - 1
+    y = torch.randn(3, 80, 1800, device="cuda")
+    precision.set_precision(prec)
+
+    def run():
+        for p in blk.parameters():
+            p.grad = None
+        x = x0.clone().requires_grad_(True)
+        z, log_s = blk(x * 1.0, y)
+        (z.square().mean() + log_s.mean()).backward()
+        torch.cuda.synchronize()
+        return [x.grad.clone()] + [p.grad.clone() for p in blk.parameters()]
+
+    folded = run()
+    os.environ["CMWG_FOLD_END"] = "0"
+    try:
+        slab = run()
+    finally:
+        os.environ.pop("CMWG_FOLD_END", None)
+    assert all(torch.isfinite(a).all() for a in folded)
+    num = sum((a.double() - b.double()).square().sum() for a, b in zip(folded, slab)).sqrt()
+    den = sum(b.double().square().sum() for b in slab).sqrt()
+    assert num / den < (6e-4 if prec == "fp16" else 4e-3), float(num / den)
+    assert any(not torch.equal(a, b) for a, b in zip(folded, slab))      # the fold is on by default
+    again = run()
+    assert all(torch.equal(a, b) for a, b in zip(folded, again))          # deterministic

@@ -215,3 +215,29 @@ def test_generic_transform_falls_back_to_module_call():
     assert torch.allclose(res[0][1], res[1][1], atol=1e-5)
     for a, b in zip(res[0][2], res[1][2]):
         assert torch.allclose(a, b, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("cin,aux,ch,depth,radix,height", [(4, 80, 256, 8, 3, 0), (3, 20, 64, 2, 5, 0), (8, 100, 128, 3, 3, 0),
+                                                          (1, 80, 64, 3, 3, 8)])
+def test_vector_operand_pack_equals_scalar_pack(cin, aux, ch, depth, radix, height, prec):
+    """csrc/wn_kernels.cuh: pack_operands16_kernel (8 / 16 elements per thread, coalesced reads for the transposed
+    matrices) writes the same bytes as the one-element-per-thread kernel; 1-D and 2-D (WaveFlow) weight layouts."""
+    import os
+    torch.manual_seed(cin * 100 + aux)
+    if height:
+        from constant_memory_waveglow_b200.waveflow import WN2D
+        wn = WN2D(height, aux, dilation_channels=ch, residual_channels=ch, skip_channels=ch, zero_init=False).cuda()
+    else:
+        wn = cm.WN(cin, aux, dilation_channels=ch, residual_channels=ch, skip_channels=ch, depth=depth, radix=radix,
+                   zero_init=False).cuda()
+    cm.invalidate_packs()
+    a = wn._prepare(prec, torch.device("cuda", 0), height)[1].clone()
+    os.environ["CMWG_PACK_SCALAR"] = "1"
+    try:
+        cm.invalidate_packs()
+        b = wn._prepare(prec, torch.device("cuda", 0), height)[1].clone()
+    finally:
+        os.environ.pop("CMWG_PACK_SCALAR", None)
+        cm.invalidate_packs()
+    assert a.numel() == b.numel() and torch.equal(a, b)
