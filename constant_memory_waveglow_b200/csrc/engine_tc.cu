@@ -165,11 +165,20 @@ static int wgrad_group_splits(const WgradProblem* probs, int nprob, int bn, int 
   int tiles = 0;
   for (int i = 0; i < nprob; ++i) tiles += ceil_div(probs[i].M, 2 * TC_BM) * ceil_div(probs[i].N, bn);
   const int total_units = B * ceil_div(T, TC_BK);
-  int s = tiles > 0 ? TC_PLAN_PAIRS / tiles : 1;
-  if (s < 1) s = 1;
-  if (s > total_units) s = total_units;
+  if (tiles <= 0) return 1;
+  // The launch takes ceil(tiles * s / pairs) rounds of ceil(units / s) k-blocks: 49 tiles on 74 pairs are ONE round of the
+  // full K with s = 1 (a third of the pairs idle), two rounds of a third of K with s = 3.  Every split costs a partial tile
+  // (written, then read by the reduce pass): charged as a few k-blocks so that equal round counts prefer fewer splits.
+  const int smax = std::min(total_units, 80);
+  int best = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= smax; ++s) {
+    const long long rounds = ceil_div(tiles * s, TC_PLAN_PAIRS);
+    const long long cost = rounds * ceil_div(total_units, s) + 8ll * s * rounds;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
   // whole units per split; drop splits that would be empty
-  const int ups = ceil_div(total_units, s);
+  const int ups = ceil_div(total_units, best);
   return ceil_div(total_units, ups);
 }
 

@@ -417,29 +417,68 @@ struct FoldEndParams {
 static __global__ void __launch_bounds__(256) pack_foldend_kernel(const FoldEndParams p) {
   const WnDims& d = p.d;
   const int i = blockIdx.y, cout = 2 * d.cin, cr_eff = d.cr_eff(i), ld = (i < d.depth - 1 ? d.Crp : 0) + d.kb;
-  const int kres = ld - d.kb;
+  const int kres = ld - d.kb, f16 = p.is_fp16;
   const float* __restrict__ wWo = p.wWo[i];
   uint16_t* dst = p.Q1f[i];
-  // elementwise part: lanes walk n (the source's fast axis), one k per thread row
-  const long long n_elem = (long long)d.Cd * ld;
-  const int nb_elem = (int)((n_elem + 255) / 256);
-  if ((int)blockIdx.x < nb_elem) {
-    const long long idx = blockIdx.x * 256ll + threadIdx.x;
-    if (idx >= n_elem) return;
-    const int n = (int)(idx % d.Cd), k = (int)(idx / d.Cd);
-    if (k >= kres && k < kres + cout) return;            // the folded columns: below
-    const float val = (k < kres && k < d.Cr) ? wWo[(long long)k * d.Cd + n] : 0.f;
-    dst[(long long)n * ld + k] = f32_to_op16(val, p.is_fp16);
+  // blocks [0, nb_t): the transposed residual rows, lanes walk n (the source's fast axis), 16 k per thread (one 32-byte
+  // sector); columns behind the residual rows are zero except the folded ones
+  const int nb_t = (d.Cd * (ld / 16) + 255) / 256;
+  if ((int)blockIdx.x < nb_t) {
+    const int w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= d.Cd * (ld / 16)) return;
+    const int n = w % d.Cd, k0 = (w / d.Cd) * 16;
+    if (k0 >= kres && k0 < kres + 16) return;          // the k-group that holds the folded columns: written below
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = k0 + 8 * h + j;
+        v[j] = (k < kres && k < d.Cr) ? wWo[(long long)k * d.Cd + n] : 0.f;
+      }
+      pack_store8(dst + (long long)n * ld + k0 + 8 * h, v, f16);
+    }
     return;
   }
-  const int lane = threadIdx.x & 31;
-  const long long wid = (((long long)blockIdx.x - nb_elem) * 256 + threadIdx.x) >> 5;
-  if (wid >= (long long)d.Cd * cout) return;
-  const int n = (int)(wid % d.Cd), o = (int)(wid / d.Cd);
-  float val = 0.f;
-  for (int k = lane; k < d.Cs; k += 32) val = fmaf(wWo[((long long)cr_eff + k) * d.Cd + n], p.wEnd[(long long)o * d.Cs + k], val);
-  val = warp_sum(val);
-  if (lane == 0) dst[(long long)n * ld + kres + o] = f32_to_op16(val, p.is_fp16);
+  // blocks behind them: F_i[n][o] for 32 consecutive n.  Thread (n, kg) sums its 32 skip rows for every o (coalesced
+  // reads over n, W_end from shared memory), the 8 row groups fold in a fixed order.
+  __shared__ float wend[16 * 32 * 8];     // [o][k within the group][kg]  (<= 16 outputs)
+  __shared__ float part[8][16][33];
+  const int nblk = blockIdx.x - nb_t;     // 32-wide n chunk
+  const int nl = threadIdx.x & 31, kg = threadIdx.x >> 5;
+  const int n = nblk * 32 + nl;
+  const int per = d.Cs / 8;               // skip rows per group (Cs is a multiple of 64)
+  float acc[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+  for (int k0 = 0; k0 < per; k0 += 32) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < cout * 32 * 8; idx += 256) {
+      const int o = idx / 256, r = idx % 256, kk = r / 8, g = r % 8;
+      const int k = g * per + k0 + kk;
+      wend[idx] = (k0 + kk < per) ? p.wEnd[(long long)o * d.Cs + k] : 0.f;
+    }
+    __syncthreads();
+    if (n < d.Cd) {
+      for (int kk = 0; kk < 32 && k0 + kk < per; ++kk) {
+        const float w = wWo[((long long)cr_eff + kg * per + k0 + kk) * d.Cd + n];
+#pragma unroll
+        for (int o = 0; o < 16; ++o)
+          if (o < cout) acc[o] = fmaf(w, wend[(o * 32 + kk) * 8 + kg], acc[o]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 16; ++o) part[kg][o][nl] = acc[o];
+  __syncthreads();
+  // 32 n x 16 columns of the folded k-group: thread (n, o) folds the 8 groups and the warp-wide store order is irrelevant
+  for (int idx = threadIdx.x; idx < 32 * 16; idx += 256) {
+    const int nn = idx & 31, o = idx >> 5;
+    float sacc = 0.f;
+    if (o < cout)
+      for (int g = 0; g < 8; ++g) sacc += part[g][o][nn];
+    if (nblk * 32 + nn < d.Cd) dst[(long long)(nblk * 32 + nn) * ld + kres + o] = f32_to_op16(sacc, f16);
+  }
 }
 
 // S * d(log_s, t) as a [rows][kb] operand slab: the first 2 in_channels columns, zeros behind (folded `end` conv backward)
@@ -462,6 +501,63 @@ static __global__ void __launch_bounds__(256) dl_slab_kernel(const float* __rest
       v[j] = o < cout ? dlst[((long long)b * cout + o) * T + t] * sc : 0.f;
     }
     pack_store8(dl + row * kb + gi * 8, v, is_fp16);
+  }
+}
+
+// Weight gradients through the folded `end` conv.  The skip rows of every W_o and the `end` weight itself only ever see
+// dskip = W_end^T d(log_s, t), so with  P_i[n][o] = sum_t g_i[t][n] * S d(log_s, t)[t][o]  (one small weight-gradient problem
+// per layer, N = 2 in_channels instead of 256):
+//   dW_o,i[cr_eff + k][n] = (1/S) sum_o W_end[o][k] P_i[n][o]
+//   dW_end[o][k]          = (1/S) sum_i sum_n P_i[n][o] W_o,i[cr_eff + k][n]       (partials per layer, folded afterwards)
+// neither the 256-channel dskip slab nor the saved fp32 skip sum is read.  grid (Cs / 32, depth), 256 threads.
+struct FoldEndDwParams {
+  const float* ptile[CMWG_MAX_DEPTH];   // [splits][Cd][pn] fp32 tiles of the P problems
+  int splits[CMWG_MAX_DEPTH];
+  const float* wWo[CMWG_MAX_DEPTH];     // effective W_o, [nb(i)][Cd]
+  float* dWo_skip[CMWG_MAX_DEPTH];      // [Cs][Cd] skip rows of the effective-weight gradient
+  const float* wEnd;                    // [cout][Cs]
+  float* dEnd_part;                     // [depth][cout][Cs] or nullptr
+  const float* gscale;
+  int depth, Cd, Cs, Cr, cout, pn;
+};
+constexpr int FOLDEND_DW_ROWS = 16;    // skip rows (k) per CTA
+static __global__ void __launch_bounds__(256) foldend_dw_kernel(const FoldEndDwParams p) {
+  __shared__ float Ps[256 * 16];                  // [n][o], summed over the splits, times 1 / S   (Cd == 256, cout <= 16)
+  __shared__ float Wt[FOLDEND_DW_ROWS][257];      // W_o,i skip rows of this block's k range, [k][n]
+  const int i = blockIdx.y, kc = blockIdx.x * FOLDEND_DW_ROWS, cr_eff = i < p.depth - 1 ? p.Cr : 0;
+  const float inv = p.gscale ? p.gscale[2] : 1.f;
+  for (int idx = threadIdx.x; idx < p.Cd * 16; idx += 256) {
+    const int n = idx >> 4, o = idx & 15;
+    float sacc = 0.f;
+    if (o < p.cout)
+      for (int j = 0; j < p.splits[i]; ++j) sacc += p.ptile[i][((long long)j * p.Cd + n) * p.pn + o];   // fixed order
+    Ps[idx] = sacc * inv;
+  }
+  for (int idx = threadIdx.x; idx < FOLDEND_DW_ROWS * p.Cd; idx += 256) {
+    const int k = idx / p.Cd, n = idx - k * p.Cd;
+    Wt[k][n] = p.wWo[i][((long long)cr_eff + kc + k) * p.Cd + n];
+  }
+  __syncthreads();
+  // skip rows of dW_o,i: thread = n
+  {
+    const int n = threadIdx.x;
+    float pr[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) pr[o] = Ps[n * 16 + o];
+    for (int k = 0; k < FOLDEND_DW_ROWS; ++k) {
+      float a = 0.f;
+#pragma unroll
+      for (int o = 0; o < 16; ++o)
+        if (o < p.cout) a = fmaf(p.wEnd[(long long)o * p.Cs + kc + k], pr[o], a);
+      p.dWo_skip[i][((long long)kc + k) * p.Cd + n] = a;
+    }
+  }
+  // this layer's share of dW_end[o][kc .. kc + 16): thread = (k, o), the n sum runs in a fixed order
+  if (p.dEnd_part) {
+    const int k = threadIdx.x >> 4, o = threadIdx.x & 15;
+    float a = 0.f;
+    for (int n = 0; n < p.Cd; ++n) a = fmaf(Ps[n * 16 + o], Wt[k][n], a);
+    if (o < p.cout) p.dEnd_part[((long long)i * p.cout + o) * p.Cs + kc + k] = a;
   }
 }
 

@@ -134,9 +134,8 @@ static int wn_pack_impl(const WnDims& d, const cmwg_wn_params* prm, void* packed
       ep.wWo[i] = reinterpret_cast<const float*>(base + L.wWo[i]);
       ep.Q1f[i] = reinterpret_cast<uint16_t*>(base + L.Q1f[i]);
     }
-    const int nb_elem = (int)ceil_div_ll((long long)d.Cd * k1f(d, 0), 256);
-    const int nb_dot = (int)ceil_div_ll((long long)d.Cd * 2 * d.cin * 32, 256);
-    pack_foldend_kernel<<<dim3(nb_elem + nb_dot, d.depth), 256, 0, st>>>(ep);
+    const int nb_t = ceil_div(d.Cd * (k1f(d, 0) / 16), 256);     // layer 0 has the widest matrix (depth >= 2) or the only one
+    pack_foldend_kernel<<<dim3(nb_t + ceil_div(d.Cd, 32), d.depth), 256, 0, st>>>(ep);
     CMWG_COUNT_LAUNCH();
     CMWG_LAUNCH_CHECK();
   }
@@ -744,8 +743,37 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     CMWG_LAUNCH_CHECK();
   }
 
+  // weight-gradient GEMMs of all layers in ONE launch after the single-kernel chain
+  const bool wg_batched = fusedb && d.depth * (d.R + 3) <= TC_MAX_WG &&
+                          !(getenv("CMWG_WGRAD_BATCH") && getenv("CMWG_WGRAD_BATCH")[0] == '0');
+  // `end` conv folded into the backward: fe_dg -- the dgate tiles of the chain read S * dlst (one k-block) against
+  // (W_end W_skip)^T instead of the 256-channel dskip slab; fe_full -- the weight gradients that dskip feeds (skip rows of every
+  // W_o, the `end` weight) go through the fold as well (foldend_dw_kernel), so dskip is never formed.  CMWG_FOLD_END_W=0
+  // keeps the slab for the weight gradients.
+  const bool fe_dg = fusedb && foldend_enabled(d);
+  const bool fe_full = fe_dg && wg_batched && !(getenv("CMWG_FOLD_END_W") && getenv("CMWG_FOLD_END_W")[0] == '0');
+  uint16_t* dl16 = nullptr;
+  int p_pi[CMWG_MAX_DEPTH];
+  for (int i = 0; i < CMWG_MAX_DEPTH; ++i) p_pi[i] = -1;
+  if (fe_dg) {   // S * dlst as a one-k-block operand slab
+    dl16 = reinterpret_cast<uint16_t*>(ws + BL.dl16);
+    const int nb_dl = (int)std::min<long long>(ceil_div_ll(rows * (d.kb / 8), 256), 4 * 148 * 8);
+    CMWG_CHECK_CUDA(launch_pdl(dl_slab_kernel, dim3(nb_dl), dim3(256), 0, st, dlst, cout, TF, rows, d.kb, dl16, f16,
+                               (const float*)gscale));
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+  }
+
   // ---- end conv backward: dskip, d end.weight, d end.bias
-  {
+  if (fe_full) {
+    if (gr->end.v) {   // the matrix is written by foldend_dw_kernel + one reduction after the weight-gradient launch
+      cmwg_conv_grad ge = gr->end;
+      ge.g = nullptr;
+      cmwg_conv_param pe = prm->end;
+      pe.g = nullptr;
+      wq.add(dweff + BL.dweff_end, pe, nullptr, ge, cout, d.Cs);
+    }
+  } else {
     CMWG_PROPAGATE(smallk_to_slab<OpT>(dlst, (long long)cout * TF, wEnd, 1, d.Cs, nullptr, cout, d.Cs, B, TF, nullptr,
                                        dskip_op, (OpT*)nullptr, f16, st, 0, -1, gscale));
     if (gr->end.v || gr->end.bias) {
@@ -794,31 +822,19 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
         hh[i] = dhi(i); hl[i] = dlo(i); dp[i] = dpre_l(i);
         sa[i] = sv + FL.s_g[i]; sb[i] = sv + FL.s_b[i];   // gate output and saved sigmoid (tanh = g / sigmoid)
       }
-      const void* dl16 = nullptr;
-      if (foldend_enabled(d)) {   // S * dlst as a one-k-block operand slab for the folded dgate tiles
-        uint16_t* dl = reinterpret_cast<uint16_t*>(ws + BL.dl16);
-        const int nb_dl = (int)std::min<long long>(ceil_div_ll(rows * (d.kb / 8), 256), 4 * 148 * 8);
-        CMWG_CHECK_CUDA(launch_pdl(dl_slab_kernel, dim3(nb_dl), dim3(256), 0, st, dlst, cout, TF, rows, d.kb, dl, f16,
-                                   (const float*)gscale));
-        CMWG_COUNT_LAUNCH();
-        CMWG_LAUNCH_CHECK();
-        dl16 = dl;
-      }
       CMWG_PROPAGATE(wn_backward_mega(d, PL, BL, pk, ws, B, T, f16, hh, hl, dskip_op, dl16, dp, sa, sb, st));
     }
   }
 
   // weight-gradient problems: launched per layer, or -- after the single-kernel chain -- for all layers at once
   // (63 full-K tiles fill one wave of CTA pairs without any split-K partials)
-  struct RedSpec { int pi; float* out; long long sm, sn, off; int n_valid; };
+  struct RedSpec { int pi; float* out; long long sm, sn, off; int n_valid; bool no_gather; };
   struct GatherSpec { float* out; const float* tile; int M, N, n_valid; long long sm, sn, off; };
   WgradProblem pr[TC_MAX_WG];
   RedSpec rs[TC_MAX_WG];
   GatherSpec gather[TC_MAX_WG];
   int np = 0, nr = 0, ngather = 0;
   bool pending_gather = false;
-  const bool wg_batched = fusedb && d.depth * (d.R + 3) <= TC_MAX_WG &&
-                          !(getenv("CMWG_WGRAD_BATCH") && getenv("CMWG_WGRAD_BATCH")[0] == '0');
   const bool deferred_gather = wg_batched && !(getenv("CMWG_WGRAD_GATHER") && getenv("CMWG_WGRAD_GATHER")[0] == '0');
   auto flush_wgrad = [&](int group) -> int {
     for (int g0 = 0; g0 < np; g0 += group) {
@@ -845,7 +861,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       for (int k = 0; k < nr; ++k) {
         if (rs[k].pi < g0 || rs[k].pi >= g0 + gn) continue;
         const WgradProblem& q = pr[rs[k].pi];
-        if (deferred_gather && splits[rs[k].pi - g0] == 1) {
+        if (deferred_gather && splits[rs[k].pi - g0] == 1 && !rs[k].no_gather) {
           pending_gather = true;
           gather[ngather++] = GatherSpec{rs[k].out, q.partial, q.M, q.N, rs[k].n_valid, rs[k].sm, rs[k].sn, rs[k].off};
           rs[k].pi = -1;   // taken
@@ -927,16 +943,21 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
       float* dWo = dweff + BL.dweff_layer * (size_t)i;
       float* dW = dWo + (size_t)d.nb(i) * d.Cd;
       float* dV = dW + (size_t)2 * d.Cd * d.Cr * d.R;
-      auto red = [&](int pi, float* out, long long sm, long long sn, long long off, int n_valid) {
-        rs[nr++] = RedSpec{pi, out, sm, sn, off, n_valid};
+      auto red = [&](int pi, float* out, long long sm, long long sn, long long off, int n_valid, bool no_gather = false) {
+        rs[nr++] = RedSpec{pi, out, sm, sn, off, n_valid, no_gather};
       };
       const bool want_wo = gr->W_o[i].g || gr->W_o[i].v;
       const bool want_w = gr->W[i].g || gr->W[i].v;
       const bool want_v = gr->V.g || gr->V.v;
       if (want_wo) {
-        if (!last) red(add(dh_next, d.Cr, d.Cr, gsv, d.Cd, d.Cd, 0, 0, 0), dWo, d.Cd, 1, 0, d.Cd);
-        red(add(dskip_op, d.Cs, d.Cs, gsv, d.Cd, d.Cd, 0, 0, 0), dWo, d.Cd, 1, (long long)d.cr_eff(i) * d.Cd, d.Cd);
+        // fe_full: the skip rows are written into dWo by foldend_dw_kernel, so the residual rows are materialised too
+        // (reduce pass) instead of gathered from their tile by the weight-norm backward
+        if (!last) red(add(dh_next, d.Cr, d.Cr, gsv, d.Cd, d.Cd, 0, 0, 0), dWo, d.Cd, 1, 0, d.Cd, fe_full);
+        if (!fe_full)
+          red(add(dskip_op, d.Cs, d.Cs, gsv, d.Cd, d.Cd, 0, 0, 0), dWo, d.Cd, 1, (long long)d.cr_eff(i) * d.Cd, d.Cd);
       }
+      if (fe_full && (want_wo || gr->end.v))   // P_i = g_i^T (S dlst): tile [Cd][kb], 2 in_channels real columns
+        p_pi[i] = add(gsv, d.Cd, d.Cd, dl16, d.kb, d.kb, 0, 0, 0);
       const bool folded = fold0 && i == 0;   // no h_0 slab: dW_0 comes out of the conditioning problem's tile (fold0_dw_kernel)
       if (want_w && !folded)
         for (int s = 0; s < d.R; ++s)
@@ -1031,6 +1052,30 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   }
 
   if (wg_batched) CMWG_PROPAGATE(flush_wgrad(TC_MAX_WG));
+  if (fe_full) {
+    FoldEndDwParams fp;
+    memset(&fp, 0, sizeof(fp));
+    bool all = true;
+    for (int i = 0; i < d.depth; ++i) {
+      if (p_pi[i] < 0) { all = false; break; }
+      fp.ptile[i] = pr[p_pi[i]].partial;
+      fp.splits[i] = splits_of[p_pi[i]];
+      fp.wWo[i] = reinterpret_cast<const float*>(pk + PL.wWo[i]);
+      fp.dWo_skip[i] = dweff + BL.dweff_layer * (size_t)i + (size_t)d.cr_eff(i) * d.Cd;
+    }
+    if (all) {   // (all or none: every W_o and the `end` weight of a WN are trained together)
+      float* dEnd_part = reinterpret_cast<float*>(ws + BL.partial_start);   // [depth][cout][Cs], folded below
+      fp.wEnd = wEnd; fp.gscale = gscale;
+      fp.dEnd_part = gr->end.v ? dEnd_part : nullptr;
+      fp.depth = d.depth; fp.Cd = d.Cd; fp.Cs = d.Cs; fp.Cr = d.Cr; fp.cout = cout; fp.pn = d.kb;
+      foldend_dw_kernel<<<dim3(d.Cs / FOLDEND_DW_ROWS, d.depth), 256, 0, st>>>(fp);
+      CMWG_COUNT_LAUNCH();
+      CMWG_LAUNCH_CHECK();
+      if (gr->end.v)
+        CMWG_PROPAGATE(reduce_blocks(dEnd_part, d.depth, cout * d.Cs, dEnd_part + (size_t)d.depth * cout * d.Cs,
+                                     dweff + BL.dweff_end, st));
+    }
+  }
   if (fold_pi >= 0) {
     // layer 0's group was the last one flushed: its tiles are still in the `partial` workspace
     const WgradProblem& q = pr[fold_pi];
