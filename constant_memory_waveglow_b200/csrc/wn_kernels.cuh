@@ -94,7 +94,7 @@ constexpr int WN_BWD_MAX_L = 7 * 256;   // longest conv row gathered through sha
 
 static __global__ void __launch_bounds__(128) weight_norm_bwd_kernel(const __grid_constant__ WnBwdTable tb) {
   __shared__ float red[4];
-  __shared__ float rowbuf[WN_BWD_MAX_L];
+  __shared__ __align__(16) float rowbuf[WN_BWD_MAX_L];
   int row = blockIdx.x;
   int ci = 0;
   while (ci + 1 < tb.n && row >= tb.e[ci + 1].row_begin) ++ci;
@@ -119,15 +119,33 @@ static __global__ void __launch_bounds__(128) weight_norm_bwd_kernel(const __gri
     return;
   }
   const float* vo = e.v + (long long)o * L;
+  float* dvo = e.dv ? e.dv + (long long)o * L : nullptr;
+  // rows of whole, 16-byte aligned float4 (every conv of the shipped configs but the start conv): a quarter of the instructions
+  const bool vec = (L & 3) == 0 && (((uintptr_t)vo | (uintptr_t)dwo | (uintptr_t)dvo) & 15) == 0;
   float dot = 0.f;
-  for (int l = threadIdx.x; l < L; l += 128) dot = fmaf(dwo[l], vo[l], dot);
+  if (vec) {
+    for (int l = threadIdx.x * 4; l < L; l += 512) {
+      const float4 a = *reinterpret_cast<const float4*>(dwo + l), b = *reinterpret_cast<const float4*>(vo + l);
+      dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot); dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+    }
+  } else {
+    for (int l = threadIdx.x; l < L; l += 128) dot = fmaf(dwo[l], vo[l], dot);
+  }
   dot = block_sum_128(dot, red);
   float inv = e.inv_norm[o];
   if (threadIdx.x == 0 && e.dg) e.dg[o] = dot * inv;
-  if (e.dv) {
+  if (dvo) {
     float gs = e.g[o] * inv;
     float k = dot * inv * inv;
-    for (int l = threadIdx.x; l < L; l += 128) e.dv[(long long)o * L + l] = gs * (dwo[l] - vo[l] * k);
+    if (vec) {
+      for (int l = threadIdx.x * 4; l < L; l += 512) {
+        const float4 a = *reinterpret_cast<const float4*>(dwo + l), b = *reinterpret_cast<const float4*>(vo + l);
+        *reinterpret_cast<float4*>(dvo + l) =
+            make_float4(gs * (a.x - b.x * k), gs * (a.y - b.y * k), gs * (a.z - b.z * k), gs * (a.w - b.w * k));
+      }
+    } else {
+      for (int l = threadIdx.x; l < L; l += 128) dvo[l] = gs * (dwo[l] - vo[l] * k);
+    }
   }
 }
 
@@ -511,27 +529,24 @@ static __global__ void __launch_bounds__(256) dl_slab_kernel(const float* __rest
 //   dW_end[o][k]          = (1/S) sum_i sum_n P_i[n][o] W_o,i[cr_eff + k][n]       (partials per layer, folded afterwards)
 // neither the 256-channel dskip slab nor the saved fp32 skip sum is read.  grid (Cs / 32, depth), 256 threads.
 struct FoldEndDwParams {
-  const float* ptile[CMWG_MAX_DEPTH];   // [splits][Cd][pn] fp32 tiles of the P problems
-  int splits[CMWG_MAX_DEPTH];
+  const float* pred;                    // [depth][Cd][cout]: the P problems, split-K partials folded and 1 / S applied
+                                        // (the reduce pass of the weight-gradient launch writes them)
   const float* wWo[CMWG_MAX_DEPTH];     // effective W_o, [nb(i)][Cd]
   float* dWo_skip[CMWG_MAX_DEPTH];      // [Cs][Cd] skip rows of the effective-weight gradient
   const float* wEnd;                    // [cout][Cs]
   float* dEnd_part;                     // [depth][cout][Cs] or nullptr
-  const float* gscale;
-  int depth, Cd, Cs, Cr, cout, pn;
+  int depth, Cd, Cs, Cr, cout;
 };
 constexpr int FOLDEND_DW_ROWS = 16;    // skip rows (k) per CTA
 static __global__ void __launch_bounds__(256) foldend_dw_kernel(const FoldEndDwParams p) {
-  __shared__ float Ps[256 * 16];                  // [n][o], summed over the splits, times 1 / S   (Cd == 256, cout <= 16)
+  __shared__ float Ps[256 * 16];                  // [n][o]   (Cd == 256, cout <= 16)
   __shared__ float Wt[FOLDEND_DW_ROWS][257];      // W_o,i skip rows of this block's k range, [k][n]
   const int i = blockIdx.y, kc = blockIdx.x * FOLDEND_DW_ROWS, cr_eff = i < p.depth - 1 ? p.Cr : 0;
-  const float inv = p.gscale ? p.gscale[2] : 1.f;
+  const float* __restrict__ pred = p.pred + (long long)i * p.Cd * p.cout;
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < p.Cd * 16; idx += 256) {
     const int n = idx >> 4, o = idx & 15;
-    float sacc = 0.f;
-    if (o < p.cout)
-      for (int j = 0; j < p.splits[i]; ++j) sacc += p.ptile[i][((long long)j * p.Cd + n) * p.pn + o];   // fixed order
-    Ps[idx] = sacc * inv;
+    Ps[idx] = o < p.cout ? pred[n * p.cout + o] : 0.f;
   }
   for (int idx = threadIdx.x; idx < FOLDEND_DW_ROWS * p.Cd; idx += 256) {
     const int k = idx / p.Cd, n = idx - k * p.Cd;
@@ -1343,8 +1358,26 @@ static __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgReduce
     int m = (int)(idx / nv4), n = (int)(idx % nv4) * 4;
     const float* p = e.partial + (long long)m * e.N + n;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < e.splits; ++j) {  // fixed order: deterministic
-      float4 v = *reinterpret_cast<const float4*>(p + j * stride);
+    int j = 0;
+    for (; j + 4 <= e.splits; j += 4) {  // four loads in flight, summed in split order: deterministic
+      const float4 v0 = *reinterpret_cast<const float4*>(p + j * stride);
+      const float4 v1 = *reinterpret_cast<const float4*>(p + (j + 1) * stride);
+      const float4 v2 = *reinterpret_cast<const float4*>(p + (j + 2) * stride);
+      const float4 v3 = *reinterpret_cast<const float4*>(p + (j + 3) * stride);
+      s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
+      s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
+      s.x += v2.x; s.y += v2.y; s.z += v2.z; s.w += v2.w;
+      s.x += v3.x; s.y += v3.y; s.z += v3.z; s.w += v3.w;
+    }
+    if (j + 2 <= e.splits) {
+      const float4 v0 = *reinterpret_cast<const float4*>(p + j * stride);
+      const float4 v1 = *reinterpret_cast<const float4*>(p + (j + 1) * stride);
+      s.x += v0.x; s.y += v0.y; s.z += v0.z; s.w += v0.w;
+      s.x += v1.x; s.y += v1.y; s.z += v1.z; s.w += v1.w;
+      j += 2;
+    }
+    if (j < e.splits) {
+      const float4 v = *reinterpret_cast<const float4*>(p + j * stride);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     float* o = e.out + e.off + m * e.sm + n * e.sn;

@@ -208,6 +208,7 @@ struct BwdLayout {
   size_t dweff_layer, dweff_start, dweff_end;  // in floats: per-layer stride, offsets of the start / end conv
   size_t gscale;     // 4 floats: gradient scale of the fp16-operand backward {max|dlst| bits, S, 1/S} (wn_kernels.cuh)
   size_t dl16;       // [rows][kb] operand: S * d(log_s, t) in the first 2 in_channels columns, zeros behind (folded `end` conv)
+  size_t pred;       // [depth][Cd][2 in_channels] fp32: P_i = g_i^T d(log_s, t) (foldend_dw_kernel)
   size_t total;
 };
 
@@ -295,6 +296,7 @@ inline void make_bwd_layout(const WnDims& d, int B, int T, BwdLayout* L) {
   L->dweff = take(total_f * 4 + 4096);
   L->gscale = take(64);
   L->dl16 = d.tc ? take(rows * d.kb * 2) : 0;
+  L->pred = take((size_t)d.depth * d.Cd * 2 * d.cin * 4);
   L->total = off;
 }
 

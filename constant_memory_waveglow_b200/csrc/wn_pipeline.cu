@@ -238,6 +238,22 @@ static inline bool foldend_enabled(const WnDims& d) {
   return !(e && e[0] == '0');
 }
 
+static inline bool mega_shapes_ok(const WnDims& d, int B, int T);
+// The backward will run the single-kernel chain / batch all weight-gradient GEMMs / fold the `end` conv completely
+// (wn_backward_impl); the saving forward asks the last one to know whether anything will read the fp32 skip sum.
+static inline bool bwd_fused_chain(const WnDims& d, int B, int T) {
+  const char* e = getenv("CMWG_MEGA_BWD");
+  return d.tc && mega_enabled() && mega_shapes_ok(d, B, T) && d.Cd == 256 && !(e && e[0] == '0');
+}
+static inline bool bwd_wgrad_batched(const WnDims& d, int B, int T) {
+  const char* e = getenv("CMWG_WGRAD_BATCH");
+  return bwd_fused_chain(d, B, T) && d.depth * (d.R + 3) <= TC_MAX_WG && !(e && e[0] == '0');
+}
+static inline bool bwd_foldend_full(const WnDims& d, int B, int T) {
+  const char* e = getenv("CMWG_FOLD_END_W");
+  return bwd_wgrad_batched(d, B, T) && foldend_enabled(d) && !(e && e[0] == '0');
+}
+
 static inline bool mega_shapes_ok(const WnDims& d, int B, int T) {
   return d.tc && d.H == 1 && !d.bias && d.depth >= 1 && d.depth <= MEGA_D && d.Cr == 256 && d.Cs == 256 &&
          d.Cd % 128 == 0 && d.bn_gate == 256 && (((d.radix - 1) / 2) << (d.depth - 1)) <= 2 * TC_BM && d.radix <= 7 &&
@@ -327,7 +343,8 @@ static int wn_forward_mega(const WnDims& d, const PackedLayout& PL, const FwdLay
     p.lst = lst;
     p.w_end = reinterpret_cast<const float*>(pk + PL.wEnd);
     p.cout = 2 * d.cin;
-    p.store_skip = save ? 1 : 0;
+    // training: the `end` weight gradient reads the fp32 skip sum -- unless the backward folds the `end` conv completely
+    p.store_skip = (save && !bwd_foldend_full(d, B, T)) ? 1 : 0;
   }
   p.total_tasks = (d.depth * p.RT + p.lag) * (p.ngt + 1) + p.RT;
   // timing experiments that SKIP synchronisation or epilogue work (wrong results by design) exist only in builds made
@@ -709,7 +726,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   auto dpre_l = [&](int i) -> OpT* { return TC ? reinterpret_cast<OpT*>(ws + BL.dprel[i]) : dpre_op; };
   // single-kernel chain: dgate + dx tiles of all layers in one launch; the weight-gradient GEMMs follow, so dh keeps
   // a hi slab per layer
-  const bool fusedb = TC && mega_enabled() && mega_shapes_ok(d, B, T) && d.Cd == 256 && !(getenv("CMWG_MEGA_BWD") && getenv("CMWG_MEGA_BWD")[0] == '0');
+  const bool fusedb = TC && bwd_fused_chain(d, B, T);
   auto dhi = [&](int i) -> OpT* {
     if (!TC) return dh_op;
     if (fusedb) return reinterpret_cast<OpT*>(ws + BL.dhi_l[i < d.depth ? i : d.depth - 1]);
@@ -744,14 +761,13 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   }
 
   // weight-gradient GEMMs of all layers in ONE launch after the single-kernel chain
-  const bool wg_batched = fusedb && d.depth * (d.R + 3) <= TC_MAX_WG &&
-                          !(getenv("CMWG_WGRAD_BATCH") && getenv("CMWG_WGRAD_BATCH")[0] == '0');
+  const bool wg_batched = TC && bwd_wgrad_batched(d, B, T);
   // `end` conv folded into the backward: fe_dg -- the dgate tiles of the chain read S * dlst (one k-block) against
   // (W_end W_skip)^T instead of the 256-channel dskip slab; fe_full -- the weight gradients that dskip feeds (skip rows of every
   // W_o, the `end` weight) go through the fold as well (foldend_dw_kernel), so dskip is never formed.  CMWG_FOLD_END_W=0
   // keeps the slab for the weight gradients.
   const bool fe_dg = fusedb && foldend_enabled(d);
-  const bool fe_full = fe_dg && wg_batched && !(getenv("CMWG_FOLD_END_W") && getenv("CMWG_FOLD_END_W")[0] == '0');
+  const bool fe_full = TC && bwd_foldend_full(d, B, T);
   uint16_t* dl16 = nullptr;
   int p_pi[CMWG_MAX_DEPTH];
   for (int i = 0; i < CMWG_MAX_DEPTH; ++i) p_pi[i] = -1;
@@ -956,8 +972,10 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
         if (!fe_full)
           red(add(dskip_op, d.Cs, d.Cs, gsv, d.Cd, d.Cd, 0, 0, 0), dWo, d.Cd, 1, (long long)d.cr_eff(i) * d.Cd, d.Cd);
       }
-      if (fe_full && (want_wo || gr->end.v))   // P_i = g_i^T (S dlst): tile [Cd][kb], 2 in_channels real columns
-        p_pi[i] = add(gsv, d.Cd, d.Cd, dl16, d.kb, d.kb, 0, 0, 0);
+      if (fe_full && (want_wo || gr->end.v)) {   // P_i = g_i^T (S dlst): tile [Cd][kb], 2 in_channels real columns, folded
+        p_pi[i] = add(gsv, d.Cd, d.Cd, dl16, d.kb, d.kb, 0, 0, 0);   // (and unscaled) into pred[i][Cd][cout] by the reduce pass
+        red(p_pi[i], reinterpret_cast<float*>(ws + BL.pred) + (size_t)i * d.Cd * cout, cout, 1, 0, cout, true);
+      }
       const bool folded = fold0 && i == 0;   // no h_0 slab: dW_0 comes out of the conditioning problem's tile (fold0_dw_kernel)
       if (want_w && !folded)
         for (int s = 0; s < d.R; ++s)
@@ -1058,16 +1076,15 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
     bool all = true;
     for (int i = 0; i < d.depth; ++i) {
       if (p_pi[i] < 0) { all = false; break; }
-      fp.ptile[i] = pr[p_pi[i]].partial;
-      fp.splits[i] = splits_of[p_pi[i]];
       fp.wWo[i] = reinterpret_cast<const float*>(pk + PL.wWo[i]);
       fp.dWo_skip[i] = dweff + BL.dweff_layer * (size_t)i + (size_t)d.cr_eff(i) * d.Cd;
     }
     if (all) {   // (all or none: every W_o and the `end` weight of a WN are trained together)
       float* dEnd_part = reinterpret_cast<float*>(ws + BL.partial_start);   // [depth][cout][Cs], folded below
-      fp.wEnd = wEnd; fp.gscale = gscale;
+      fp.wEnd = wEnd;
+      fp.pred = reinterpret_cast<const float*>(ws + BL.pred);
       fp.dEnd_part = gr->end.v ? dEnd_part : nullptr;
-      fp.depth = d.depth; fp.Cd = d.Cd; fp.Cs = d.Cs; fp.Cr = d.Cr; fp.cout = cout; fp.pn = d.kb;
+      fp.depth = d.depth; fp.Cd = d.Cd; fp.Cs = d.Cs; fp.Cr = d.Cr; fp.cout = cout;
       foldend_dw_kernel<<<dim3(d.Cs / FOLDEND_DW_ROWS, d.depth), 256, 0, st>>>(fp);
       CMWG_COUNT_LAUNCH();
       CMWG_LAUNCH_CHECK();

@@ -1,20 +1,31 @@
 #!/bin/bash
-# ncu --set full of the slow small kernels of the backward, with per-line stall samples (run under gpurun)
-O=gpurun_out; T=${1:-r03_small}
+# ncu --set full of the slow small kernels of the backward: one compact line per kernel + the top stall lines (run under gpurun)
+O=gpurun_out; T=${1:-r03_small}; PAT=${2:-'start_bwd256|foldend_dw|wgrad_reduce|weight_norm_bwd'}; N=${3:-4}
 mkdir -p $O
-ncu --profile-from-start off --clock-control none --set full --import-source on -k 'regex:start_bwd256|end_bwd_dw256|weight_norm_bwd|smallk_to_slab|cond_unpack|pack_foldend|weight_eff' -c 9 -f -o $O/${T} python tools/profile_step.py trainopt fp16 24 > $O/${T}.log 2>&1
+ncu --profile-from-start off --clock-control none --set full --import-source on -k "regex:$PAT" -c $N -f -o $O/${T} python tools/profile_step.py trainopt fp16 24 > $O/${T}.log 2>&1
 ncu -i $O/${T}.ncu-rep --page raw --csv > $O/${T}_raw.csv 2>/dev/null
-python tools/ncu_raw_summary.py $O/${T}_raw.csv > $O/${T}_summary.txt 2>&1
-ncu -i $O/${T}.ncu-rep --page source --csv --print-source sass,cuda > $O/${T}_source.csv 2>/dev/null
-python tools/ncu_lines.py $O/${T}_source.csv 60 >> $O/${T}_summary.txt 2>&1
-python - <<'PY' >> $O/${T}_summary.txt
-import csv,sys,os
-T=os.environ.get("T","r03_small")
+T=$T python - <<'PY' > $O/${T}_summary.txt
+import csv,os
+T=os.environ["T"]
 rows=list(csv.reader(open("gpurun_out/%s_raw.csv"%T)))
 hdr=rows[0]
-want=[i for i,h in enumerate(hdr) if any(k in h for k in ("Kernel Name","achieved_occupancy","warps_active.avg.pct","issue_active.avg.pct","stalled_long_scoreboard","stalled_barrier","stalled_short_scoreboard","stalled_lg_throttle","stalled_math_pipe","stalled_wait.","stalled_mio_throttle","inst_executed.sum","l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum","registers_per_thread","shared_mem_per_block"))]
+def col(name):
+    for i,h in enumerate(hdr):
+        if h==name: return i
+    for i,h in enumerate(hdr):
+        if name in h: return i
+    return None
+keys=[("Kernel Name","name"),("gpu__time_duration.sum","ns"),("smsp__inst_executed.sum","inst"),("sm__issue_active.avg.pct_of_peak_sustained_elapsed","issue%"),
+("sm__warps_active.avg.pct_of_peak_sustained_active","occ%"),("dram__bytes_read.sum","rdB"),("dram__bytes_write.sum","wrB"),("lts__t_bytes.sum","l2B"),
+("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio","long_sb"),("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio","short_sb"),
+("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio","barrier"),("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio","mio"),
+("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio","lg"),("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio","wait"),
+("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio","math"),("launch__registers_per_thread","regs"),("launch__grid_size","grid")]
+idx=[(col(k),n) for k,n in keys]
 for r in rows[2:]:
-    print([ (hdr[i][:60], r[i][:40]) for i in want])
+    print("  ".join("%s=%s"%(n,(r[i][:46] if i is not None else "?")) for i,n in idx))
 PY
-rm -f $O/${T}_source.csv $O/${T}.ncu-rep
-tail -100 $O/${T}_summary.txt
+ncu -i $O/${T}.ncu-rep --page source --csv --print-source sass,cuda > $O/${T}_source.csv 2>/dev/null
+python tools/ncu_lines.py $O/${T}_source.csv 28 >> $O/${T}_summary.txt 2>&1
+rm -f $O/${T}_source.csv $O/${T}.ncu-rep $O/${T}_raw.csv
+cat $O/${T}_summary.txt
