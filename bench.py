@@ -798,8 +798,7 @@ def run_b200(args):
         model.train()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish_ranks(world)
         return
 
     pk = peaks()
@@ -878,8 +877,28 @@ def run_b200(args):
         r = reference_subprocess("train", ["--steps", "6", "--warmup", "1"])   # ~15-25 s of CPU work
         line["cpu_baseline"] = r.get("cpu_baseline", r)
     print(json.dumps(line), flush=True)
-    if world > 1:
+    finish_ranks(world)
+
+
+def finish_ranks(world):
+    """End of a multi-rank run: the ranks meet once more, then tear the process group down -- under a watchdog.  One N = 2
+    run of this round printed its line and then sat in `destroy_process_group()` until the box's time limit (one rank had
+    left, the other waited inside NCCL's teardown); the measurement is complete by then, so a teardown that does not return
+    within 20 s ends the process instead of the run."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    wd = threading.Timer(20.0, lambda: os._exit(0))
+    wd.daemon = True
+    wd.start()
+    try:
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+    finally:
+        wd.cancel()
 
 
 def parity_leg(model, loss_fn, dev, args):

@@ -17,11 +17,13 @@ natural bucket is "one flow" (~17.9 MB fp32 at the LJ config) plus one bucket fo
   * ``finish()`` waits for the outstanding collectives and averages (NCCL: the collective itself averages,
     ``ReduceOp.AVG``; other backends: one fused multiply over all buckets);
   * all buckets are windows of ONE flat buffer, so the exchange can also be issued as a single all-reduce at
-    the end of the backward: ``mode="deferred"`` (or ``CMWG_GRAD_SYNC=deferred``).  The persistent tensor-core
-    kernels of the WN hold every SM with one CTA each and need all their CTA pairs resident; an NCCL kernel
-    that gets an SM first delays the whole grid by its own run time, once per bucket (measured, 8 x B200: the
-    forward task kernel slows 0.46 -> 0.55 ms per launch under the overlapped exchange).  One 215 MB all-reduce
-    over NVSwitch is ~0.5 ms unhidden; which of the two is cheaper is a measurement (``bench.py``).
+    the end of the backward: ``mode="deferred"`` (``CMWG_GRAD_SYNC=deferred``), the DEFAULT.  The persistent
+    tensor-core kernels of the WN hold every SM with one CTA each and need all their CTA pairs resident; an NCCL
+    kernel that gets an SM first delays the whole grid by its own run time, once per bucket (measured: on
+    8 x B200 the forward task kernel slows 0.46 -> 0.55 ms per launch under the overlapped exchange, 5 % of the
+    step; on 2 x B200 10.0 -> 11.8 ms per step of forward task kernels in eager steps, and the graphed step is
+    24.55 ms deferred against 24.79 ms overlapped).  One 215 MB all-reduce over NVSwitch is 0.3-0.5 ms
+    unhidden.  ``mode="overlap"`` (``CMWG_GRAD_SYNC=overlap``) keeps the per-flow exchange during the backward.
 
 Works with any process group backend (``nccl`` on the B200 box, ``gloo`` in the CPU tests).
 Inference shards independent utterances across ranks and needs no collective (``shard_utterances``).
@@ -68,7 +70,7 @@ class FlowGradSync:
     def __init__(self, buckets: Sequence[Sequence[torch.nn.Parameter]], process_group=None, mode: Optional[str] = None):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        self.mode = (mode or os.environ.get("CMWG_GRAD_SYNC", "overlap")).lower()
+        self.mode = (mode or os.environ.get("CMWG_GRAD_SYNC", "deferred")).lower()
         if self.mode not in ("overlap", "deferred"):
             raise ValueError(f"FlowGradSync: mode must be 'overlap' or 'deferred', got {self.mode!r}")
         # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then one fused multiply
