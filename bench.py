@@ -39,10 +39,11 @@ FWD_GFLOP_PER_SEGMENT = 214.023  # algorithmic, counted on the reference (BASELI
 # Algorithmic bytes of the same launch: 48000 x (512 hi + 256 y in, 512 g out) = 61.4 MB.
 GATE_TRAFFIC_BYTES_PER_LAUNCH = 38.9e6
 # dram__bytes_read.sum + dram__bytes_write.sum per wn_fwd_mega_kernel launch at B=24, fp16 operands (ncu --set full,
-# profiles/r02_v3_ncu_mega_metrics.txt): 1118 MB for the forward variant (573.5 read + 544.4 written: g per layer, (hi, lo) per
-# layer; the fp32 skip slab is no longer written), 1662 MB for the recompute variant that also stores tanh / sigmoid and the
-# skip slab (701.1 + 960.5); a step launches 12 of each
-FUSED_TRAFFIC_BYTES_PER_LAUNCH = 0.5 * (1117.9e6 + 1661.6e6)
+# profiles/r02_s2_v5_ncu_task_kernels_summary.txt): 656.5 MB for the forward variant (290.5 read + 366.0 written: g per
+# layer and the single-stream residual per layer; neither h_0, a `lo` slab nor the fp32 skip sum exists), 901.0 MB for the
+# recompute variant that also stores the sigmoid (330.9 + 570.1); a step launches 12 of each.  (Round 2's first session:
+# 1118 / 1662 MB; round 1: 1143 / 1760 MB.)
+FUSED_TRAFFIC_BYTES_PER_LAUNCH = 0.5 * (656.5e6 + 901.0e6)
 TRAIN_GFLOP_PER_SEGMENT = 4 * FWD_GFLOP_PER_SEGMENT
 SYNTH_FRAMES = 862               # 10 s at 22.05 kHz -> 220672 samples (model/base.py:47-48)
 GLOBAL_BATCH = 24                # configs/waveglow_LJ_speech.json:31; train.py:51-53 divides it by the GPU count

@@ -116,7 +116,9 @@ def test_fp16_gradient_scale_is_magnitude_independent(scale):
 # <= 8, end_bwd_dw256_kernel for in_channels <= 4); row counts that are not multiples of 32 make the 32-row warp
 # groups straddle batch items and leave ragged tails
 FAST256 = [(4, 80, 256, 2, 2, 333), (3, 80, 256, 1, 3, 200), (2, 16, 256, 1, 2, 97), (7, 24, 256, 1, 2, 150),
-           (2, 80, 256, 1, 1, 2000)]
+           (2, 80, 256, 1, 1, 2000),
+           (8, 200, 256, 2, 2, 300)]   # WSRGlow-like: 8 input channels (16 outputs of `end`), four conditioning k-blocks -- the
+                                       # widest shapes the folded start / end convs take (csrc/wn_pipeline.cu: fold0, fe_full)
 
 
 @pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
