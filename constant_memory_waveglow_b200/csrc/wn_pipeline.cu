@@ -736,6 +736,17 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
   // the saved state came from a forward with the start conv folded into layer 0 (same predicate as wn_forward_impl): no h_0 slab
   bool fold0 = false;
   if constexpr (TC) fold0 = mega_enabled() && mega_shapes_ok(d, B, T) && fold0_enabled(d);
+  if (fold0) {
+    // The taps of x_a ride in the padding columns of the conditioning slab, which all flows share: in the constant-memory mode
+    // the recompute has just written them, but an activation-storing model (memory_efficient=False) ran every flow's forward
+    // before the first backward, and the columns hold the LAST flow's taps by now.  They are cheap (7 us): write them again.
+    const long long n = (long long)B * T * d.R * d.cin;
+    const int nb_aug = (int)std::min<long long>(ceil_div_ll(n, 256), 4 * 148 * 8);
+    CMWG_CHECK_CUDA(launch_pdl(cond_aug_kernel, dim3(nb_aug), dim3(256), 0, st, x, x_bs, d.cin, d.R, B, T,
+                               reinterpret_cast<uint16_t*>(const_cast<void*>(ycl)), d.aux, d.auxp, f16));
+    CMWG_COUNT_LAUNCH();
+    CMWG_LAUNCH_CHECK();
+  }
   int fold_pi = -1;                 // index of layer 0's conditioning weight-gradient problem (its tile holds D, fold0_dw_kernel)
   int splits_of[TC_MAX_WG];
   float* partial = reinterpret_cast<float*>(ws + BL.partial);
@@ -972,7 +983,7 @@ static int wn_backward_impl(const WnDims& d, const cmwg_wn_params* prm, const vo
         if (!fe_full)
           red(add(dskip_op, d.Cs, d.Cs, gsv, d.Cd, d.Cd, 0, 0, 0), dWo, d.Cd, 1, (long long)d.cr_eff(i) * d.Cd, d.Cd);
       }
-      if (fe_full && (want_wo || gr->end.v)) {   // P_i = g_i^T (S dlst): tile [Cd][kb], 2 in_channels real columns, folded
+      if (fe_full) {   // (every layer, wanted or not: dW_end sums over all of them) P_i = g_i^T (S dlst): tile [Cd][kb], folded
         p_pi[i] = add(gsv, d.Cd, d.Cd, dl16, d.kb, d.kb, 0, 0, 0);   // (and unscaled) into pred[i][Cd][cout] by the reduce pass
         red(p_pi[i], reinterpret_cast<float*>(ws + BL.pred) + (size_t)i * d.Cd * cout, cout, 1, 0, cout, true);
       }

@@ -271,3 +271,27 @@ def test_folded_end_conv_backward_matches_dskip_slab(prec, end_scale):
     assert any(not torch.equal(a, b) for a, b in zip(folded, slab))      # the fold is on by default
     again = run()
     assert all(torch.equal(a, b) for a, b in zip(folded, again))          # deterministic
+
+
+def test_activation_storing_model_shares_the_conditioning_slab():
+    """memory_efficient=False runs every flow's forward (with saves) before the first backward.  The taps of x_a that the folded
+    start conv reads ride in padding columns of the conditioning slab ALL flows share, so by the time flow 0's backward runs
+    they hold the last flow's taps -- the backward writes them again (csrc/wn_pipeline.cu).  Same weights, same inputs: the
+    activation-storing model and the constant-memory model must produce the same gradients."""
+    precision.set_precision("fp16")
+    wn_kw = dict(dilation_channels=256, residual_channels=256, skip_channels=256, depth=3)
+    torch.manual_seed(4)
+    stored = cm.WaveGlow(3, 8, 2, 2, 256, 80, False, zero_init=False, **wn_kw).cuda().train()
+    const = cm.WaveGlow(3, 8, 2, 2, 256, 80, True, zero_init=False, **wn_kw).cuda().train()
+    const.load_state_dict(stored.state_dict())
+    x = torch.rand(2, 8192, device="cuda") * 2 - 1
+    h = torch.randn(2, 80, 32, device="cuda")
+    grads = []
+    for m in (stored, const):
+        z, logdet = m(x.clone(), h.clone())
+        cm.WaveGlowLoss(0.7)(z, logdet).backward()
+        torch.cuda.synchronize()
+        grads.append({n: p.grad.clone() for n, p in m.named_parameters()})
+    for n in grads[0]:
+        assert torch.isfinite(grads[0][n]).all(), n
+        assert rel_l2(grads[0][n], grads[1][n]) < 1e-4, (n, rel_l2(grads[0][n], grads[1][n]))
