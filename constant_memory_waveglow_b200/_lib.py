@@ -103,6 +103,7 @@ SIGNATURES = {
     "cmwg_profile_collect": (_I, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "cmwg_mega_clk_read": (_I, [C.POINTER(C.c_longlong), _I]),
     "cmwg_debug_counter": (C.c_ulonglong, [_I]),
+    "cmwg_wgrad_plan_splits": (_I, [_I, _I, _I, _I]),
     "cmwg_mega_task_list": (_I, [_I, _I, _I, _I, C.POINTER(C.c_int), _I, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cmwg_selftest_tc_gemm": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
 }

@@ -268,6 +268,16 @@ int tc_wgrad_launch(const WgradProblem* probs, int nprob, int B, int H, int T, i
 
 using namespace cmwg;
 
+extern "C" int cmwg_wgrad_plan_splits(int tiles, int bn, int B, int T) {
+  if (tiles < 1 || B < 1 || T < 1 || (bn != 128 && bn != 256)) return -1;
+  WgradProblem pr[TC_MAX_WG];
+  // `tiles` problems of one (256 x bn) tile each
+  const int n = tiles < TC_MAX_WG ? tiles : TC_MAX_WG;
+  for (int i = 0; i < n; ++i) { pr[i].M = 2 * TC_BM; pr[i].N = bn; }
+  if (tiles > TC_MAX_WG) pr[0].M = 2 * TC_BM * (tiles - TC_MAX_WG + 1);   // the rest as more row tiles of the first problem
+  return wgrad_group_splits(pr, n, bn, B, T);
+}
+
 extern "C" unsigned long long cmwg_debug_counter(int which) {
   return which == 0 ? cmwg::g_map_misses : cmwg::g_map_clears;
 }

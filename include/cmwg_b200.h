@@ -184,6 +184,9 @@ size_t cmwg_wn_workspace_bytes(const cmwg_wn_config* cfg, int B, int T);
 /* host-side listing of the single-kernel WN forward (backward = 0) / backward chain (1) task lists, for the dependency-order
  * tests: entry i -> out[4i..4i+3] = (type, layer, row tile, N tile); *total entries, *lag row-tile slots */
 int cmwg_mega_task_list(int backward, int depth, int B, int T, int* out, int cap, int* total, int* lag);
+/* host-side split-K plan of a batched weight-gradient launch (for the plan's tests): `tiles` output tiles of `bn` columns
+ * whose K runs over B batch items x T time steps -> number of splits (rounds x K per round, minimised) */
+int cmwg_wgrad_plan_splits(int tiles, int bn, int B, int T);
 /* tools only: 0 = TMA descriptor encodes so far (cache misses), 1 = descriptor cache clears */
 unsigned long long cmwg_debug_counter(int which);
 /* tools only: cycle accumulators [CTA][18 warps][16] of the last single-kernel WN forward launched with CMWG_MEGA_CLK=1 */

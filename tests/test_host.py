@@ -242,3 +242,25 @@ def test_task_lists_are_in_dependency_order(depth, B, T):
             deps = [(0, layer, r) for r in neighbours(rt)]
         for d in deps:
             assert d in pos and pos[d] < i, ((typ, layer, rt), d)
+
+
+# ---- split-K plan of the batched weight-gradient launch (csrc/engine_tc.cu: wgrad_group_splits) -------------------------
+def test_weight_gradient_split_plan_minimises_rounds_times_k():
+    """74 CTA pairs take ceil(tiles * s / 74) rounds of ceil(units / s) k-blocks.  The LJ training shape has 24 x 32 = 768
+    time units; 49 tiles (the batched launch with both folds) are ONE round of the full K with s = 1 and two rounds of a
+    third with s = 3; 63 tiles (no folds) gain too little from any split to pay for its partial tiles at s <= 6."""
+    lib = _lib.load()
+    units = 24 * 32
+
+    def rounds_times_k(tiles, s):
+        return -(-tiles * s // 74) * -(-units // s)
+
+    s49 = lib.cmwg_wgrad_plan_splits(49, 256, 24, 2000)
+    assert s49 == 3 and rounds_times_k(49, s49) * 3 <= rounds_times_k(49, 1) * 2 + 3
+    for tiles in (1, 8, 24, 37, 49, 57, 63, 74, 100):
+        s = lib.cmwg_wgrad_plan_splits(tiles, 256, 24, 2000)
+        assert 1 <= s <= 80
+        assert rounds_times_k(tiles, s) <= rounds_times_k(tiles, 1)          # never worse than no split
+    assert lib.cmwg_wgrad_plan_splits(24, 128, 24, 2000) == 3                 # the N = 128 group: one round of a third of K
+    assert lib.cmwg_wgrad_plan_splits(2, 256, 1, 64) == 1                     # a single time unit cannot be split
+    assert lib.cmwg_wgrad_plan_splits(0, 256, 1, 64) == -1 and lib.cmwg_wgrad_plan_splits(4, 64, 1, 64) == -1
