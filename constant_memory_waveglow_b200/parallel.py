@@ -70,7 +70,8 @@ class FlowGradSync:
     def __init__(self, buckets: Sequence[Sequence[torch.nn.Parameter]], process_group=None, mode: Optional[str] = None):
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
-        self.mode = (mode or os.environ.get("CMWG_GRAD_SYNC", "deferred")).lower()
+        requested = mode or os.environ.get("CMWG_GRAD_SYNC")
+        self.mode = (requested or "deferred").lower()
         if self.mode not in ("overlap", "deferred"):
             raise ValueError(f"FlowGradSync: mode must be 'overlap' or 'deferred', got {self.mode!r}")
         # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then one fused multiply
@@ -94,7 +95,9 @@ class FlowGradSync:
                 off += (n + 63) // 64 * 64
             self.whole = torch.zeros(off, device=firsts[0].device, dtype=firsts[0].dtype)
         elif self.mode == "deferred":
-            raise ValueError("FlowGradSync: mode='deferred' needs all parameters on one device with one dtype")
+            if requested:
+                raise ValueError("FlowGradSync: mode='deferred' needs all parameters on one device with one dtype")
+            self.mode = "overlap"       # mixed devices / dtypes: no single flat buffer, exchange per bucket
         for bi, params in enumerate(self.buckets):
             n = sizes[bi]
             p0 = params[0]
