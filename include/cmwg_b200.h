@@ -170,7 +170,11 @@ int cmwg_wn_aux_padded(const cmwg_wn_config* cfg);
 /* y (B, aux, T) fp32 with arbitrary element strides -> slab [B][T][aux_padded] in the operand type
  * of cfg->precision (zero padded).  Done once per conditioning tensor and shared by all flows.
  * Replaces nothing in the reference (its V conv reads y directly, model/waveglow.py:100); it is the
- * layout change that lets V be folded into the dilated-conv GEMM as extra K rows. */
+ * layout change that lets V be folded into the dilated-conv GEMM as extra K rows.
+ * The PADDING columns [aux, aux_padded) of the slab belong to the library afterwards: cmwg_wn_forward and
+ * cmwg_wn_backward keep the taps of xa there when they fold the start conv into layer 0, although they take
+ * the slab as `const void*` (its conditioning columns are never written).  One slab must therefore not be used by
+ * concurrent calls on different streams; sequential calls (the flows of one model) may share it. */
 int cmwg_cond_pack(const cmwg_wn_config* cfg, const float* y, long long y_bstride, long long y_cstride,
                    long long y_tstride, int B, int T, void* ycl, void* stream);
 /* dy (B, aux, T) contiguous fp32 <- slab gradient [B][T][aux_padded] fp32 */
